@@ -1,0 +1,187 @@
+/*
+ * pgmatch.h -- C ABI of libpgmatch.so: B200 (sm_100a) descriptor matching for
+ * Takatsuka-Mark/Photogrammetry.
+ *
+ * This is the drop-in boundary for ONE reference path:
+ *
+ *   List<KeypointPair> KeypointMatching.MatchKeypoints(List<Keypoint>, List<Keypoint>)
+ *       dotnet_src/ImageProcessing/KeypointMatching.cs:14-69   (+ CountOnes :71-82)
+ *   called from dotnet_src/Photogrammetry/TestService.cs:96
+ *
+ * The reference has no native code and no FFI; the entry points below are
+ * what a P/Invoke ([LibraryImport]) binding of that method would bind (see
+ * INTEGRATION.md and dotnet/GpuKeypointMatching.cs).  Everything is
+ * `extern "C"`, blittable: plain pointers, sizes, no C++/torch types.
+ *
+ * Conventions
+ *  - Descriptors: uint8[n][stride_bytes], the little-endian bytes of the
+ *    non-negative BigInteger `Keypoint.BriefDescriptor`
+ *    (dotnet_src/ImageProcessing.Abstractions/Keypoint.cs:14,29-57), i.e.
+ *    BigInteger.ToByteArray(isUnsigned: true, isBigEndian: false) copied into
+ *    a zero-filled slot.  stride_bytes is a multiple of 16 and
+ *    8*stride_bytes >= desc_bits; 1 <= desc_bits <= 512; bits at positions
+ *    >= desc_bits must be zero.
+ *  - Matches: SoA int32 arrays (query index, train index, distance) standing
+ *    for KeypointPair {Keypoint1, Keypoint2, Distance}
+ *    (dotnet_src/ImageProcessing.Abstractions/KeypointPair.cs:3-8); the caller
+ *    rebuilds object references by indexing its own input lists.
+ *  - Every function returns PGM_OK (0) or a negative pgm_status; no exception
+ *    crosses the ABI.  pgm_last_error(h) gives the text for the last failure.
+ *  - The caller owns every buffer it passes.  Host-buffer entry points copy
+ *    H2D/D2H synchronously with respect to the call and retain no caller
+ *    pointer after return.  `_dev` entry points take device pointers on the
+ *    handle's device and enqueue on the handle's stream WITHOUT a final
+ *    synchronize unless stated otherwise.
+ *  - One handle = one device + one stream; calls on one handle are serialised
+ *    by an internal mutex; different handles may be used concurrently.
+ *  - n1, n2 < 2^20 (1 048 576) per pair: match keys pack (distance, index)
+ *    into 32 bits so that an integer min implements the reference's
+ *    (distance, query index, train index) tie-break (KeypointMatching.cs:44-54).
+ */
+#ifndef PGMATCH_H
+#define PGMATCH_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGM_VERSION 100 /* 0.1.0 */
+
+typedef enum pgm_status {
+    PGM_OK = 0,
+    PGM_E_INVALID_ARG = -1,
+    PGM_E_CAPACITY = -2,    /* output buffer too small */
+    PGM_E_CUDA = -3,        /* a CUDA runtime call failed; see pgm_last_error */
+    PGM_E_NCCL = -4,        /* reserved for the train-sharded multi-GPU mode */
+    PGM_E_EMPTY_TRAIN = -5, /* n1 > 0 and n2 == 0: the reference throws
+                               ArgumentOutOfRangeException at KeypointMatching.cs:61 */
+    PGM_E_NOMEM = -6,
+    PGM_E_NO_DEVICE = -7    /* no usable sm_100 device: there is NO CPU fallback */
+} pgm_status;
+
+/* pgm_match_* flags */
+#define PGM_FLAG_REFERENCE_COMPAT_TAIL 0x1u /* when n1 > n2 append the reference's n1-n2
+                                               (0, 0, int.MaxValue) triples
+                                               (KeypointMatching.cs:38-42,57-62) */
+#define PGM_TAIL_DISTANCE 2147483647
+
+typedef struct pgm_handle pgm_handle;
+
+/* Counters of the last match call on a handle (diagnostics / bench). */
+typedef struct pgm_stats {
+    int32_t rounds;            /* mutual-nearest-neighbour rounds run on the grid */
+    int32_t kernel_launches;   /* kernels launched by the call */
+    int32_t host_syncs;        /* stream synchronisations inside the call */
+    int32_t pairs;             /* image pairs processed */
+    int64_t distance_evals;    /* sum over pairs of n1*n2 (each (i,j) counted once) */
+    int64_t evals_computed;    /* XOR+popcount evaluations actually executed (all rounds) */
+    int64_t matched;           /* real (non-tail) triples produced */
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+} pgm_stats;
+
+int pgm_version(void);
+const char *pgm_status_string(int status);
+
+/* Creates a matcher bound to CUDA device `device_ordinal` (own stream, own
+ * scratch).  Fails with PGM_E_NO_DEVICE when the device is absent or is not
+ * compute capability 10.x -- there is no fallback path. */
+int pgm_create(int device_ordinal, pgm_handle **out);
+int pgm_destroy(pgm_handle *h);
+const char *pgm_last_error(pgm_handle *h);
+/* Borrow a caller-owned cudaStream_t (e.g. a torch stream) for all subsequent
+ * work of this handle; NULL restores the handle's own stream. */
+int pgm_set_stream(pgm_handle *h, void *cuda_stream);
+int pgm_synchronize(pgm_handle *h);
+int pgm_get_stats(pgm_handle *h, pgm_stats *out);
+
+/* ---- MatchKeypoints (KeypointMatching.cs:14-69) -------------------------
+ * Full Hamming matrix + greedy global one-to-one assignment, bit-exact with
+ * the reference including output order ((distance, i, j) ascending) and, with
+ * PGM_FLAG_REFERENCE_COMPAT_TAIL, the degenerate tail.
+ * Writes *out_count triples: n1 with the tail flag, min(n1,n2) without.
+ * capacity must be >= that count.  n1 == 0 -> 0 triples.  n2 == 0 < n1 ->
+ * PGM_E_EMPTY_TRAIN. */
+int pgm_match_hamming_greedy(pgm_handle *h,
+                             const uint8_t *q, int32_t n1,
+                             const uint8_t *t, int32_t n2,
+                             int32_t desc_bits, int32_t stride_bytes,
+                             int32_t *out_qi, int32_t *out_tj, int32_t *out_dist,
+                             int32_t capacity, int32_t *out_count, uint32_t flags);
+
+/* Same, every pointer except out_count is DEVICE memory; out_count (host) is
+ * computed from n1/n2/flags.  Asynchronous on the handle's stream except for
+ * the rare internal synchronisations counted in pgm_stats.host_syncs. */
+int pgm_match_hamming_greedy_dev(pgm_handle *h,
+                                 const uint8_t *d_q, int32_t n1,
+                                 const uint8_t *d_t, int32_t n2,
+                                 int32_t desc_bits, int32_t stride_bytes,
+                                 int32_t *d_out_qi, int32_t *d_out_tj, int32_t *d_out_dist,
+                                 int32_t capacity, int32_t *out_count, uint32_t flags);
+
+/* ---- many image pairs in one call (all-pairs / consecutive-frame modes) --
+ * all_desc: uint8[image_offsets[n_images]][stride_bytes], image k owning rows
+ * [image_offsets[k], image_offsets[k+1]).  pair_list: int32[n_pairs][2] =
+ * (query image, train image).  Outputs are packed in pair order: pair p's
+ * triples start at  sum_{p' < p} n1(p')  (the exclusive prefix sum of the
+ * query-image sizes) and out_counts[p] of them are valid (n1(p) with the tail
+ * flag, min(n1,n2) without; unused slots are filled with -1).  capacity (in
+ * triples) must be >= sum_p n1(p).  A pair with an empty train image and a
+ * non-empty query image fails the call with PGM_E_EMPTY_TRAIN.  Each pair is
+ * matched exactly as pgm_match_hamming_greedy would match it. */
+int pgm_match_pairs_batch(pgm_handle *h,
+                          const uint8_t *all_desc, const int64_t *image_offsets, int32_t n_images,
+                          const int32_t *pair_list, int32_t n_pairs,
+                          int32_t desc_bits, int32_t stride_bytes,
+                          int32_t *out_qi, int32_t *out_tj, int32_t *out_dist,
+                          int64_t capacity, int32_t *out_counts, uint32_t flags);
+
+/* Same with all_desc and the three output arrays in DEVICE memory;
+ * image_offsets, pair_list and out_counts stay on the host. */
+int pgm_match_pairs_batch_dev(pgm_handle *h,
+                              const uint8_t *d_all_desc, const int64_t *image_offsets, int32_t n_images,
+                              const int32_t *pair_list, int32_t n_pairs,
+                              int32_t desc_bits, int32_t stride_bytes,
+                              int32_t *d_out_qi, int32_t *d_out_tj, int32_t *d_out_dist,
+                              int64_t capacity, int32_t *out_counts, uint32_t flags);
+
+/* ---- nearest / second-nearest neighbour (north_star extension) ----------
+ * Per query i: the best and second-best train index under the (distance, j)
+ * order, -1 where absent.  Column 0/1 of the rows that
+ * python_src/photogrammetry/image_processing/keypoint_matching.py:7-33
+ * returns (up to its unspecified tie order). */
+int pgm_knn2_hamming(pgm_handle *h,
+                     const uint8_t *q, int32_t n1, const uint8_t *t, int32_t n2,
+                     int32_t desc_bits, int32_t stride_bytes,
+                     int32_t *best_j, int32_t *best_d, int32_t *second_j, int32_t *second_d);
+int pgm_knn2_hamming_dev(pgm_handle *h,
+                         const uint8_t *d_q, int32_t n1, const uint8_t *d_t, int32_t n2,
+                         int32_t desc_bits, int32_t stride_bytes,
+                         int32_t *d_best_j, int32_t *d_best_d, int32_t *d_second_j, int32_t *d_second_d);
+
+/* Ratio test + mutual cross-check (north_star extension; not in the
+ * reference).  Keep (i, j1, d1) iff
+ *   [n2 < 2 or ratio <= 0 or (float)d1 < ratio * (float)d2]  and
+ *   [!cross_check or the best query of train j1 under (distance, i) is i] and
+ *   [max_dist < 0 or d1 <= max_dist]     (python_src/scripts/match_keypoints.py:126-128)
+ * Output ordered by i ascending. */
+int pgm_match_ratio_crosscheck(pgm_handle *h,
+                               const uint8_t *q, int32_t n1, const uint8_t *t, int32_t n2,
+                               int32_t desc_bits, int32_t stride_bytes,
+                               float ratio, int32_t cross_check, int32_t max_dist,
+                               int32_t *out_qi, int32_t *out_tj, int32_t *out_dist,
+                               int32_t capacity, int32_t *out_count);
+
+/* ---- measurement helpers -------------------------------------------------
+ * Register-only POPC.32 throughput of the device (the roofline denominator
+ * for this path: one 256-bit distance = 8 POPC.32).  Runs a saturating
+ * micro-benchmark for roughly `millis` ms and reports popc32 results / s. */
+int pgm_measure_popc_peak(pgm_handle *h, int32_t millis, double *popc32_per_s,
+                          double *lop3_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGMATCH_H */

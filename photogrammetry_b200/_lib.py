@@ -1,0 +1,128 @@
+"""ctypes loader for libpgmatch.so (the C ABI declared in include/pgmatch.h).
+
+The product path has NO CPU fallback: if the shared library is missing, or it
+cannot create a handle because no sm_100 device is present, the error is raised
+to the caller.  The oracle under ``oracle/`` is test infrastructure and is never
+imported from here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpgmatch.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+PGM_OK = 0
+PGM_E_INVALID_ARG = -1
+PGM_E_CAPACITY = -2
+PGM_E_CUDA = -3
+PGM_E_NCCL = -4
+PGM_E_EMPTY_TRAIN = -5
+PGM_E_NOMEM = -6
+PGM_E_NO_DEVICE = -7
+PGM_FLAG_REFERENCE_COMPAT_TAIL = 0x1
+PGM_TAIL_DISTANCE = 2147483647
+
+# every symbol include/pgmatch.h declares (tests check the .so exports them all)
+EXPORTED_SYMBOLS = (
+    "pgm_version", "pgm_status_string", "pgm_create", "pgm_destroy", "pgm_last_error",
+    "pgm_set_stream", "pgm_synchronize", "pgm_get_stats",
+    "pgm_match_hamming_greedy", "pgm_match_hamming_greedy_dev",
+    "pgm_match_pairs_batch", "pgm_match_pairs_batch_dev",
+    "pgm_knn2_hamming", "pgm_knn2_hamming_dev", "pgm_match_ratio_crosscheck",
+    "pgm_measure_popc_peak",
+)
+
+
+class PgmatchLibraryError(RuntimeError):
+    """libpgmatch.so is missing/unloadable, or no usable B200 is present."""
+
+
+class PgmatchError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"pgmatch status {status}: {message}")
+        self.status = status
+
+
+class EmptyTrainError(PgmatchError, IndexError):
+    """Mirror of the ArgumentOutOfRangeException the reference throws at
+    KeypointMatching.cs:61 (``keypoints2[0]`` on an empty list)."""
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("rounds", C.c_int32), ("kernel_launches", C.c_int32), ("host_syncs", C.c_int32), ("pairs", C.c_int32),
+        ("distance_evals", C.c_int64), ("evals_computed", C.c_int64), ("matched", C.c_int64),
+        ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+    ]
+
+    def as_dict(self) -> dict:
+        return {name: int(getattr(self, name)) for name, _ in self._fields_}
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/ for sm_100a into photogrammetry_b200/libpgmatch.so (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC_DIR, f) for f in os.listdir(CSRC_DIR) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "pgmatch.h"))
+    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale:
+        cmd = ["make", "-C", CSRC_DIR, "--no-print-directory"] + (["-B"] if force else [])
+        subprocess.check_call(cmd, stdout=None if verbose else subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load() -> C.CDLL:
+    """Load libpgmatch.so and declare prototypes.  Raises PgmatchLibraryError if it is missing."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise PgmatchLibraryError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C photogrammetry_b200/csrc`.  There is no CPU fallback.")
+        try:
+            lib = C.CDLL(LIB_PATH)
+        except OSError as e:  # pragma: no cover
+            raise PgmatchLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+        u8p, i32p, i64p, vp = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p   # raw addresses: host or device
+        lib.pgm_version.restype = C.c_int
+        lib.pgm_status_string.restype = C.c_char_p
+        lib.pgm_status_string.argtypes = [C.c_int]
+        lib.pgm_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        lib.pgm_destroy.argtypes = [C.c_void_p]
+        lib.pgm_last_error.restype = C.c_char_p
+        lib.pgm_last_error.argtypes = [C.c_void_p]
+        lib.pgm_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        lib.pgm_synchronize.argtypes = [C.c_void_p]
+        lib.pgm_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        greedy = [C.c_void_p, u8p, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32, i32p, i32p, i32p,
+                  C.c_int32, C.POINTER(C.c_int32), C.c_uint32]
+        lib.pgm_match_hamming_greedy.argtypes = greedy
+        lib.pgm_match_hamming_greedy_dev.argtypes = greedy
+        batch = [C.c_void_p, u8p, i64p, C.c_int32, i32p, C.c_int32, C.c_int32, C.c_int32, i32p, i32p, i32p,
+                 C.c_int64, i32p, C.c_uint32]
+        lib.pgm_match_pairs_batch.argtypes = batch
+        lib.pgm_match_pairs_batch_dev.argtypes = batch
+        knn = [C.c_void_p, u8p, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32, i32p, i32p, i32p, i32p]
+        lib.pgm_knn2_hamming.argtypes = knn
+        lib.pgm_knn2_hamming_dev.argtypes = knn
+        lib.pgm_match_ratio_crosscheck.argtypes = [C.c_void_p, u8p, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32,
+                                                   C.c_float, C.c_int32, C.c_int32, i32p, i32p, i32p, C.c_int32,
+                                                   C.POINTER(C.c_int32)]
+        lib.pgm_measure_popc_peak.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        _ = vp
+        _lib = lib
+        return _lib
+
+
+def status_string(status: int) -> str:
+    return load().pgm_status_string(status).decode()

@@ -1,0 +1,710 @@
+// pgm_kernels.cuh -- sm_100a kernels of the descriptor-matching path.
+//
+// Reference path: ImageProcessing.KeypointMatching.MatchKeypoints
+//   dotnet_src/ImageProcessing/KeypointMatching.cs:14-69 (+ CountOnes :71-82).
+// The reference builds the full N1 x N2 Hamming matrix and then removes the
+// global (distance, i, j)-minimum N1 times.  Here the same assignment is
+// computed as iterated mutual-nearest-neighbour rounds:
+//
+//   round kernel   distances of live rows x live columns, fused with the
+//                  per-row argmin (registers) and per-column argmin (REDUX +
+//                  shared/global atomicMin) over packed (distance<<20 | index)
+//                  keys, so an integer min IS the reference tie-break
+//                  (KeypointMatching.cs:44-54: ascending i, ascending j, strict <)
+//   accept kernel  rows/columns that chose each other are matched and retired,
+//                  survivors are compacted; the last block plans the next round
+//   finisher       once a pair is small, one CTA runs all remaining rounds out
+//                  of a distance matrix held in shared memory
+//   order kernel   stable counting sort of the matches by distance -> the
+//                  reference's output order, plus the n1>n2 tail (:38-42)
+//
+// Nothing here is translated from the reference (it has no native code).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pgm {
+
+constexpr uint32_t KEY_IDX_BITS = 20;
+constexpr uint32_t KEY_IDX_MASK = (1u << KEY_IDX_BITS) - 1u;
+constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
+// Index part of a padded (non-existent) row/column slot: with distance <= 512,
+// (d << 20) + KEY_INVALID never overflows and always exceeds every real key.
+constexpr uint32_t KEY_INVALID = 0xDFFFFFFFu;
+constexpr int MAX_N = 1 << KEY_IDX_BITS;
+
+constexpr int ROUND_THREADS = 128;   // 4 warps per CTA
+constexpr int STAGE_COLS = 64;       // train descriptors staged in shared memory per step
+constexpr int ACCEPT_THREADS = 256;
+constexpr int FIN_THREADS = 512;
+constexpr int FIN_MAX_DIM = 512;     // (== FIN_THREADS) finisher takes a pair once nlr, nlc <= this ...
+constexpr int FIN_MAX_EVALS = 49152; // ... and nlr * nlc <= this (distance matrix in smem)
+constexpr int ORDER_THREADS = 512;
+constexpr int ORDER_WARPS = ORDER_THREADS / 32;
+
+enum PairStatus : uint8_t { PAIR_DONE = 0, PAIR_BIG = 1, PAIR_SMALL = 2 };
+
+struct PairDesc {
+    const uint32_t *q;   // query descriptors (row-major, `words` u32 per row)
+    const uint32_t *t;   // train descriptors
+    int32_t n1, n2;
+    int64_t row_base;    // first slot of this pair in the per-row state arrays
+    int64_t col_base;    // first slot in the per-column state arrays
+    int64_t out_base;    // where this pair's triples start in the output arrays
+};
+
+struct PlanInfo {                 // device resident, rewritten every round
+    int32_t total_tiles;          // round-kernel work items
+    int32_t cols_per_tile;        // column extent of one tile (multiple of STAGE_COLS)
+    int32_t total_ablocks;        // accept-kernel work items
+    int32_t n_big;                // pairs still on grid rounds
+    int32_t n_small;              // pairs handed to the finisher this round
+    int32_t round;
+    uint32_t accept_ticket;       // last-block-done counter
+    int32_t done_round;           // first round whose plan found no PAIR_BIG pair (-1: not yet)
+    unsigned long long evals;     // XOR+popcount evaluations executed so far
+};
+
+struct Chunk {
+    PairDesc *pairs;
+    int32_t n_pairs;
+    int32_t tile_rows;            // rows per round-kernel tile (ROUND_THREADS * RQ)
+    int32_t target_tiles;         // tiles the planner aims for per round
+    int32_t min_tile_evals;
+    uint32_t *rowbest[2];
+    uint32_t *colbest[2];
+    int32_t *live_rows[2];
+    int32_t *live_cols[2];
+    int32_t *counts;              // [3][n_pairs][2] live rows / live cols
+    uint32_t *match_key;          // per row: accepted (d<<20 | j) or KEY_NONE
+    int32_t *tile_base;           // [n_pairs + 1]
+    int32_t *ablock_base;         // [n_pairs + 1]
+    uint8_t *status;              // PairStatus per pair
+    PlanInfo *plan;
+};
+
+__device__ __forceinline__ int32_t *cnt_ptr(const Chunk &c, int buf3, int p) {
+    return c.counts + ((size_t)buf3 * c.n_pairs + p) * 2;
+}
+
+// Largest p with base[p] <= g (base is an exclusive prefix, base[n] = total).
+__device__ __forceinline__ int find_pair(const int32_t *__restrict__ base, int n, int g) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (__ldcg(base + mid) <= g) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ---------------------------------------------------------------------------
+// init: live lists = identity, keys = none, counts[0] = (n1, n2)
+// ---------------------------------------------------------------------------
+__global__ void init_kernel(Chunk c) {
+    const int p = blockIdx.y;
+    const PairDesc pd = c.pairs[p];
+    const int n = max(pd.n1, pd.n2);
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < n; x += gridDim.x * blockDim.x) {
+        if (x < pd.n1) {
+            c.live_rows[0][pd.row_base + x] = x;
+            c.rowbest[0][pd.row_base + x] = KEY_NONE;
+            c.rowbest[1][pd.row_base + x] = KEY_NONE;
+            c.match_key[pd.row_base + x] = KEY_NONE;
+        }
+        if (x < pd.n2) {
+            c.live_cols[0][pd.col_base + x] = x;
+            c.colbest[0][pd.col_base + x] = KEY_NONE;
+            c.colbest[1][pd.col_base + x] = KEY_NONE;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int32_t *c0 = cnt_ptr(c, 0, p);
+        c0[0] = pd.n1; c0[1] = pd.n2;
+        int32_t *c1 = cnt_ptr(c, 1, p), *c2 = cnt_ptr(c, 2, p);
+        c1[0] = c1[1] = 0; c2[0] = c2[1] = 0;
+        if (p == 0) { c.plan->evals = 0ull; c.plan->accept_ticket = 0u; c.plan->done_round = -1; }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// planner: one CTA.  Classifies every pair from counts[r % 3], sizes the
+// tiles so the round kernel gets ~target_tiles work items, and writes the
+// per-pair exclusive prefixes the round/accept kernels search.
+// ---------------------------------------------------------------------------
+__device__ void plan_device(const Chunk &c, int r) {
+    __shared__ unsigned long long s_evals[32];
+    __shared__ int s_cnt[2][32];
+    __shared__ int s_scan[2][ACCEPT_THREADS];
+    __shared__ int s_cpt;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const int buf = r % 3;
+
+    unsigned long long ev = 0; int nbig = 0, nsmall = 0;
+    for (int p = tid; p < c.n_pairs; p += nt) {
+        const int32_t *cp = cnt_ptr(c, buf, p);
+        const int nlr = __ldcg(cp), nlc = __ldcg(cp + 1);
+        uint8_t st = PAIR_DONE;
+        if (nlr > 0 && nlc > 0) {
+            const bool small = nlr <= FIN_MAX_DIM && nlc <= FIN_MAX_DIM && nlr * nlc <= FIN_MAX_EVALS;
+            st = small ? PAIR_SMALL : PAIR_BIG;
+            if (small) nsmall++; else { nbig++; ev += (unsigned long long)nlr * (unsigned long long)nlc; }
+        }
+        c.status[p] = st;
+        int32_t *nx = cnt_ptr(c, (r + 1) % 3, p);   // accept(r) appends here
+        nx[0] = 0; nx[1] = 0;
+    }
+    for (int o = 16; o; o >>= 1) {
+        ev += __shfl_xor_sync(0xffffffffu, ev, o);
+        nbig += __shfl_xor_sync(0xffffffffu, nbig, o);
+        nsmall += __shfl_xor_sync(0xffffffffu, nsmall, o);
+    }
+    if (lane == 0) { s_evals[wid] = ev; s_cnt[0][wid] = nbig; s_cnt[1][wid] = nsmall; }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long e = 0; int b = 0, s = 0;
+        for (int w = 0; w < (nt + 31) / 32; w++) { e += s_evals[w]; b += s_cnt[0][w]; s += s_cnt[1][w]; }
+        unsigned long long per_tile = e / (unsigned long long)max(c.target_tiles, 1);
+        if (per_tile < (unsigned long long)c.min_tile_evals) per_tile = c.min_tile_evals;
+        unsigned long long cpt = (per_tile + c.tile_rows - 1) / c.tile_rows;
+        cpt = ((cpt + STAGE_COLS - 1) / STAGE_COLS) * STAGE_COLS;
+        if (cpt < STAGE_COLS) cpt = STAGE_COLS;
+        if (cpt > (unsigned long long)MAX_N) cpt = MAX_N;
+        s_cpt = (int)cpt;
+        c.plan->cols_per_tile = (int)cpt;
+        c.plan->n_big = b; c.plan->n_small = s; c.plan->round = r;
+        c.plan->accept_ticket = 0u;
+        c.plan->evals += e;
+        if (b == 0 && c.plan->done_round < 0) c.plan->done_round = r;
+    }
+    __syncthreads();
+    const int cpt = s_cpt;
+    // exclusive scan over pairs: each thread owns a contiguous slice
+    const int per = (c.n_pairs + nt - 1) / nt;
+    const int p0 = min(tid * per, c.n_pairs), p1 = min(p0 + per, c.n_pairs);
+    int tsum = 0, asum = 0;
+    for (int p = p0; p < p1; p++) {
+        if (c.status[p] == PAIR_BIG) {
+            const int32_t *cp = cnt_ptr(c, buf, p);
+            const int nlr = __ldcg(cp), nlc = __ldcg(cp + 1);
+            tsum += ((nlr + c.tile_rows - 1) / c.tile_rows) * ((nlc + cpt - 1) / cpt);
+            asum += (nlr + ACCEPT_THREADS - 1) / ACCEPT_THREADS + (nlc + ACCEPT_THREADS - 1) / ACCEPT_THREADS;
+        }
+    }
+    s_scan[0][tid] = tsum; s_scan[1][tid] = asum;
+    __syncthreads();
+    if (tid == 0) {
+        int a = 0, b = 0;
+        for (int k = 0; k < nt; k++) {
+            int x = s_scan[0][k], y = s_scan[1][k];
+            s_scan[0][k] = a; s_scan[1][k] = b; a += x; b += y;
+        }
+        c.plan->total_tiles = a; c.plan->total_ablocks = b;
+        c.tile_base[c.n_pairs] = a; c.ablock_base[c.n_pairs] = b;
+    }
+    __syncthreads();
+    int tb = s_scan[0][tid], ab = s_scan[1][tid];
+    for (int p = p0; p < p1; p++) {
+        c.tile_base[p] = tb; c.ablock_base[p] = ab;
+        if (c.status[p] == PAIR_BIG) {
+            const int32_t *cp = cnt_ptr(c, buf, p);
+            const int nlr = __ldcg(cp), nlc = __ldcg(cp + 1);
+            tb += ((nlr + c.tile_rows - 1) / c.tile_rows) * ((nlc + cpt - 1) / cpt);
+            ab += (nlr + ACCEPT_THREADS - 1) / ACCEPT_THREADS + (nlc + ACCEPT_THREADS - 1) / ACCEPT_THREADS;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(ACCEPT_THREADS) plan_kernel(Chunk c, int r) { plan_device(c, r); }
+
+// ---------------------------------------------------------------------------
+// distance of one query (registers) against one train descriptor (registers)
+// ---------------------------------------------------------------------------
+template <int WORDS>
+__device__ __forceinline__ uint32_t hamming_words(const uint32_t (&q)[WORDS], const uint32_t (&t)[WORDS]) {
+    uint32_t d = 0;
+#pragma unroll
+    for (int w = 0; w < WORDS; w++) d += __popc(q[w] ^ t[w]);
+    return d;
+}
+
+// ---------------------------------------------------------------------------
+// round kernel: live rows x live columns of every PAIR_BIG pair.
+// One thread owns RQ query descriptors in registers; the CTA streams train
+// descriptors through shared memory in stages of STAGE_COLS (128-bit loads,
+// 128-bit broadcast LDS).  Row argmin stays in registers for the whole tile;
+// the column argmin is a warp REDUX.MIN of the packed keys followed by one
+// shared-memory atomicMin per (warp, column).
+// ---------------------------------------------------------------------------
+template <int WORDS, int RQ>
+__global__ void __launch_bounds__(ROUND_THREADS) hamming_round_kernel(Chunk c, int r) {
+    constexpr int V4 = WORDS / 4;
+    __shared__ uint4 s_t[STAGE_COLS * V4];
+    __shared__ uint32_t s_jkey[STAGE_COLS];
+    __shared__ uint32_t s_col[STAGE_COLS];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int cur = r & 1, buf = r % 3;
+    const int total = __ldcg(&c.plan->total_tiles);
+    const int cpt = __ldcg(&c.plan->cols_per_tile);
+    const int tile_rows = ROUND_THREADS * RQ;
+
+    for (int g = blockIdx.x; g < total; g += gridDim.x) {
+        const int p = find_pair(c.tile_base, c.n_pairs, g);
+        const PairDesc pd = c.pairs[p];
+        const int32_t *cp = cnt_ptr(c, buf, p);
+        const int nlr = __ldcg(cp), nlc = __ldcg(cp + 1);
+        const int nct = (nlc + cpt - 1) / cpt;
+        const int local = g - __ldcg(c.tile_base + p);
+        const int rt = local / nct, ct = local - rt * nct;
+        const int32_t *live_rows = c.live_rows[cur] + pd.row_base;
+        const int32_t *live_cols = c.live_cols[cur] + pd.col_base;
+
+        uint32_t q[RQ][WORDS], ikey[RQ], rowkey[RQ];
+#pragma unroll
+        for (int k = 0; k < RQ; k++) {
+            const int slot = rt * tile_rows + k * ROUND_THREADS + tid;
+            rowkey[k] = KEY_NONE;
+            if (slot < nlr) {
+                const int i = __ldcg(live_rows + slot);
+                ikey[k] = (uint32_t)i;
+                const uint4 *src = reinterpret_cast<const uint4 *>(pd.q + (size_t)i * WORDS);
+#pragma unroll
+                for (int v = 0; v < V4; v++) {
+                    const uint4 x = __ldg(src + v);
+                    q[k][4 * v + 0] = x.x; q[k][4 * v + 1] = x.y; q[k][4 * v + 2] = x.z; q[k][4 * v + 3] = x.w;
+                }
+            } else {
+                ikey[k] = KEY_INVALID;
+#pragma unroll
+                for (int w = 0; w < WORDS; w++) q[k][w] = 0u;
+            }
+        }
+
+        const int c0 = ct * cpt, c1 = min(nlc, c0 + cpt);
+        for (int s0 = c0; s0 < c1; s0 += STAGE_COLS) {
+            __syncthreads();                       // previous stage fully consumed
+            for (int k = tid; k < STAGE_COLS * V4; k += ROUND_THREADS) {
+                const int col = k / V4, part = k - col * V4, y = s0 + col;
+                uint4 x = make_uint4(0u, 0u, 0u, 0u);
+                uint32_t jk = KEY_INVALID;
+                if (y < c1) {
+                    const int j = __ldcg(live_cols + y);
+                    x = __ldg(reinterpret_cast<const uint4 *>(pd.t + (size_t)j * WORDS) + part);
+                    jk = (uint32_t)j;
+                }
+                s_t[k] = x;
+                if (part == 0) s_jkey[col] = jk;
+            }
+            if (tid < STAGE_COLS) s_col[tid] = KEY_NONE;
+            __syncthreads();
+
+            const int ncs = min(STAGE_COLS, (c1 - s0 + 7) & ~7);
+            for (int jj0 = 0; jj0 < ncs; jj0 += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int jj = jj0 + u;
+                    uint32_t t[WORDS];
+#pragma unroll
+                    for (int v = 0; v < V4; v++) {
+                        const uint4 x = s_t[jj * V4 + v];
+                        t[4 * v + 0] = x.x; t[4 * v + 1] = x.y; t[4 * v + 2] = x.z; t[4 * v + 3] = x.w;
+                    }
+                    const uint32_t jk = s_jkey[jj];
+                    uint32_t cmin = KEY_NONE;
+#pragma unroll
+                    for (int k = 0; k < RQ; k++) {
+                        const uint32_t d = hamming_words<WORDS>(q[k], t) << KEY_IDX_BITS;
+                        rowkey[k] = min(rowkey[k], d + jk);
+                        cmin = min(cmin, d + ikey[k]);
+                    }
+                    // all 32 lanes hit one address: ptxas aggregates this into a single
+                    // CREDUX.MIN + one elected ATOMS.MIN per (warp, column)
+                    atomicMin(&s_col[jj], cmin);
+                }
+            }
+            __syncthreads();
+            if (tid < STAGE_COLS) {
+                const uint32_t jk = s_jkey[tid], v = s_col[tid];
+                if (jk != KEY_INVALID && v < KEY_INVALID)
+                    atomicMin(c.colbest[cur] + pd.col_base + jk, v);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < RQ; k++)
+            if (ikey[k] != KEY_INVALID && rowkey[k] < KEY_INVALID)
+                atomicMin(c.rowbest[cur] + pd.row_base + ikey[k], rowkey[k]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// accept kernel: a row and a column that chose each other are the minimum of
+// every edge touching either of them, i.e. the pair the reference's next
+// applicable argmin scan would emit (KeypointMatching.cs:44-65).  Survivors
+// are appended to the next live lists; their key slots in the other buffer
+// are reset.  The last block to finish plans round r+1.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(ACCEPT_THREADS) accept_kernel(Chunk c, int r) {
+    __shared__ bool s_last;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int cur = r & 1, nxt = cur ^ 1, buf = r % 3, nbuf = (r + 1) % 3;
+    const int total = __ldcg(&c.plan->total_ablocks);
+
+    for (int b = blockIdx.x; b < total; b += gridDim.x) {
+        const int p = find_pair(c.ablock_base, c.n_pairs, b);
+        const PairDesc pd = c.pairs[p];
+        const int32_t *cp = cnt_ptr(c, buf, p);
+        const int nlr = __ldcg(cp), nlc = __ldcg(cp + 1);
+        const int nrb = (nlr + ACCEPT_THREADS - 1) / ACCEPT_THREADS;
+        const int local = b - __ldcg(c.ablock_base + p);
+        const uint32_t *rowbest = c.rowbest[cur] + pd.row_base;
+        const uint32_t *colbest = c.colbest[cur] + pd.col_base;
+        const bool is_row = local < nrb;
+        const int x = (is_row ? local : local - nrb) * ACCEPT_THREADS + tid;
+        bool survive = false;
+        int id = 0;
+        if (is_row) {
+            if (x < nlr) {
+                id = __ldcg(c.live_rows[cur] + pd.row_base + x);
+                const uint32_t rk = __ldcg(rowbest + id);
+                const uint32_t ck = __ldcg(colbest + (rk & KEY_IDX_MASK));
+                if ((ck & KEY_IDX_MASK) == (uint32_t)id) c.match_key[pd.row_base + id] = rk;
+                else { survive = true; c.rowbest[nxt][pd.row_base + id] = KEY_NONE; }
+            }
+        } else {
+            if (x < nlc) {
+                id = __ldcg(c.live_cols[cur] + pd.col_base + x);
+                const uint32_t ck = __ldcg(colbest + id);
+                const uint32_t rk = __ldcg(rowbest + (ck & KEY_IDX_MASK));
+                if ((rk & KEY_IDX_MASK) != (uint32_t)id) { survive = true; c.colbest[nxt][pd.col_base + id] = KEY_NONE; }
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, survive);
+        if (m) {
+            int base = 0;
+            if (lane == (__ffs(m) - 1)) base = atomicAdd(cnt_ptr(c, nbuf, p) + (is_row ? 0 : 1), __popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (survive) {
+                const int pos = base + __popc(m & ((1u << lane) - 1u));
+                if (is_row) c.live_rows[nxt][pd.row_base + pos] = id;
+                else c.live_cols[nxt][pd.col_base + pos] = id;
+            }
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&c.plan->accept_ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        plan_device(c, r + 1);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// finisher: one CTA per PAIR_SMALL pair runs every remaining round out of a
+// u16 distance matrix in shared memory.  Live lists arrive in arbitrary order
+// (atomic append), so they are rank-sorted first: local positions then order
+// like the original indices and keys can carry positions.
+// ---------------------------------------------------------------------------
+template <int WORDS>
+__global__ void __launch_bounds__(FIN_THREADS) finisher_kernel(Chunk c, int r) {
+    extern __shared__ __align__(16) unsigned char fin_smem[];
+    const int p = blockIdx.x;
+    if (c.status[p] != PAIR_SMALL) return;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int cur = r & 1, buf = r % 3;
+    const PairDesc pd = c.pairs[p];
+    int32_t *cp = cnt_ptr(c, buf, p);
+    const int nr = cp[0], nc = cp[1];
+    int S = (nc + 1) & ~1;            // row pitch in u16; S/2 odd -> row scans hit 32 banks
+    if (((S >> 1) & 1) == 0) S += 2;
+
+    int32_t *rowid = reinterpret_cast<int32_t *>(fin_smem);
+    int32_t *colid = rowid + FIN_MAX_DIM;
+    uint32_t *rkoff = reinterpret_cast<uint32_t *>(colid + FIN_MAX_DIM);
+    uint32_t *ckoff = rkoff + FIN_MAX_DIM;
+    uint32_t *rbest = ckoff + FIN_MAX_DIM;
+    uint32_t *cbest = rbest + FIN_MAX_DIM;
+    int32_t *tmp = reinterpret_cast<int32_t *>(cbest + FIN_MAX_DIM);     // 2 * FIN_MAX_DIM
+    uint16_t *D = reinterpret_cast<uint16_t *>(tmp + 2 * FIN_MAX_DIM);
+
+    // rank sort of the live lists (ids are distinct)
+    for (int k = tid; k < nr + nc; k += nt)
+        tmp[k < nr ? k : FIN_MAX_DIM + (k - nr)] =
+            k < nr ? c.live_rows[cur][pd.row_base + k] : c.live_cols[cur][pd.col_base + (k - nr)];
+    __syncthreads();
+    for (int k = tid; k < nr + nc; k += nt) {
+        const bool is_row = k < nr;
+        const int32_t *src = is_row ? tmp : tmp + FIN_MAX_DIM;
+        const int n = is_row ? nr : nc, me = src[is_row ? k : k - nr];
+        int rank = 0;
+        for (int m = 0; m < n; m++) rank += (src[m] < me);
+        if (is_row) { rowid[rank] = me; rkoff[rank] = (uint32_t)rank; }
+        else { colid[rank] = me; ckoff[rank] = (uint32_t)rank; }
+    }
+    __syncthreads();
+
+    // distance matrix: thread (x, column group) with the query row in registers
+    int rxt = 1;
+    while (rxt < nr && rxt < nt) rxt <<= 1;
+    const int cg = nt / rxt, gx = tid % rxt, gy = tid / rxt;
+    for (int x = gx; x < nr; x += rxt) {
+        uint32_t q[WORDS];
+        const uint4 *qs = reinterpret_cast<const uint4 *>(pd.q + (size_t)rowid[x] * WORDS);
+#pragma unroll
+        for (int v = 0; v < WORDS / 4; v++) {
+            const uint4 a = __ldg(qs + v);
+            q[4 * v] = a.x; q[4 * v + 1] = a.y; q[4 * v + 2] = a.z; q[4 * v + 3] = a.w;
+        }
+        for (int y = gy; y < nc; y += cg) {
+            uint32_t t[WORDS];
+            const uint4 *ts = reinterpret_cast<const uint4 *>(pd.t + (size_t)colid[y] * WORDS);
+#pragma unroll
+            for (int v = 0; v < WORDS / 4; v++) {
+                const uint4 a = __ldg(ts + v);
+                t[4 * v] = a.x; t[4 * v + 1] = a.y; t[4 * v + 2] = a.z; t[4 * v + 3] = a.w;
+            }
+            D[x * S + y] = (uint16_t)hamming_words<WORDS>(q, t);
+        }
+    }
+    __syncthreads();
+
+    int live_r = nr, live_c = nc;
+    while (live_r > 0 && live_c > 0) {
+        for (int k = tid; k < nr + nc; k += nt) {
+            uint32_t best = KEY_NONE;
+            if (k < nr) {
+                if (rkoff[k] != KEY_INVALID) {
+                    const uint16_t *row = D + k * S;
+                    for (int y = 0; y < nc; y++) best = min(best, ((uint32_t)row[y] << KEY_IDX_BITS) + ckoff[y]);
+                }
+                rbest[k] = best;
+            } else {
+                const int y = k - nr;
+                if (ckoff[y] != KEY_INVALID) {
+                    for (int x = 0; x < nr; x++) best = min(best, ((uint32_t)D[x * S + y] << KEY_IDX_BITS) + rkoff[x]);
+                }
+                cbest[y] = best;
+            }
+        }
+        __syncthreads();
+        // FIN_MAX_DIM == FIN_THREADS: a thread owns at most one row
+        int accepted = 0;
+        if (tid < nr && rkoff[tid] != KEY_INVALID) {
+            const uint32_t rk = rbest[tid];
+            const uint32_t y = rk & KEY_IDX_MASK;
+            if ((cbest[y] & KEY_IDX_MASK) == (uint32_t)tid) {
+                c.match_key[pd.row_base + rowid[tid]] = (rk & ~KEY_IDX_MASK) | (uint32_t)colid[y];
+                rkoff[tid] = KEY_INVALID;    // nobody else touches rkoff[tid] / ckoff[y] in this phase:
+                ckoff[y] = KEY_INVALID;      // column y is claimed by exactly one accepted row
+                accepted = 1;
+            }
+        }
+        const int n_acc = __syncthreads_count(accepted);
+        live_r -= n_acc; live_c -= n_acc;
+    }
+    if (tid == 0) { cp[0] = 0; cp[1] = 0; c.status[p] = PAIR_DONE; }
+}
+
+inline size_t finisher_smem_bytes() {
+    // ids/keys: 8 arrays of FIN_MAX_DIM words; D: worst case rows * (pitch <= nc + 3)
+    return (size_t)8 * FIN_MAX_DIM * 4 + ((size_t)FIN_MAX_EVALS + 3 * FIN_MAX_DIM) * 2 + 64;
+}
+
+// ---------------------------------------------------------------------------
+// order kernel: one CTA per pair.  Stable counting sort of the matched rows by
+// distance (rows are visited in ascending i, and a row has one j), which is
+// the (distance, i, j) order the reference emits; then the degenerate tail.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(ORDER_THREADS) order_kernel(Chunk c, int nbins, uint32_t flags,
+                                                             int32_t *out_qi, int32_t *out_tj, int32_t *out_dist) {
+    extern __shared__ int32_t s_hist[];          // [ORDER_WARPS][nbins + 1]
+    __shared__ int32_t s_tot[1024 + 8];
+    const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const PairDesc pd = c.pairs[p];
+    const int hb = nbins + 1;                    // last bin: unmatched rows (never written out)
+    for (int k = tid; k < ORDER_WARPS * hb; k += ORDER_THREADS) s_hist[k] = 0;
+    __syncthreads();
+    int seg = (pd.n1 + ORDER_WARPS - 1) / ORDER_WARPS;
+    seg = (seg + 31) & ~31;
+    const int x0 = min(pd.n1, wid * seg), x1 = min(pd.n1, x0 + seg);
+    for (int x = x0 + lane; x < x1; x += 32) {
+        const uint32_t key = c.match_key[pd.row_base + x];
+        if (key != KEY_NONE) atomicAdd(&s_hist[wid * hb + (key >> KEY_IDX_BITS)], 1);
+    }
+    __syncthreads();
+    // per-distance totals -> exclusive scan over distances
+    for (int d = tid; d < nbins; d += ORDER_THREADS) {
+        int t = 0;
+        for (int w = 0; w < ORDER_WARPS; w++) t += s_hist[w * hb + d];
+        s_tot[d] = t;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int a = 0;
+        for (int d = 0; d < nbins; d++) { int t = s_tot[d]; s_tot[d] = a; a += t; }
+        s_tot[nbins] = a;
+    }
+    __syncthreads();
+    for (int d = tid; d < nbins; d += ORDER_THREADS) {
+        int a = s_tot[d];
+        for (int w = 0; w < ORDER_WARPS; w++) { int t = s_hist[w * hb + d]; s_hist[w * hb + d] = a; a += t; }
+    }
+    __syncthreads();
+    const int matched = s_tot[nbins];
+    for (int xb = x0; xb < x1; xb += 32) {
+        const int x = xb + lane;
+        uint32_t key = KEY_NONE;
+        if (x < x1) key = c.match_key[pd.row_base + x];
+        const int d = key != KEY_NONE ? (int)(key >> KEY_IDX_BITS) : nbins;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        const int base = s_hist[wid * hb + d];
+        __syncwarp();
+        if (rank == 0) s_hist[wid * hb + d] = base + __popc(peers);
+        __syncwarp();
+        if (key != KEY_NONE) {
+            const int64_t o = pd.out_base + base + rank;
+            out_qi[o] = x; out_tj[o] = (int32_t)(key & KEY_IDX_MASK); out_dist[o] = d;
+        }
+    }
+    if (flags & 1u) {                            // PGM_FLAG_REFERENCE_COMPAT_TAIL
+        for (int k = matched + tid; k < pd.n1; k += ORDER_THREADS) {
+            const int64_t o = pd.out_base + k;
+            out_qi[o] = 0; out_tj[o] = 0; out_dist[o] = 2147483647;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// nearest / second nearest (no masks): same tiling, two keys per row in
+// registers; column splits write partial top-2 that a merge kernel combines.
+// ---------------------------------------------------------------------------
+template <int WORDS, int RQ>
+__global__ void __launch_bounds__(ROUND_THREADS) knn2_kernel(const uint32_t *__restrict__ qd, int n1,
+                                                            const uint32_t *__restrict__ td, int n2,
+                                                            int cols_per_split, uint32_t *__restrict__ part /*[splits][n1][2]*/) {
+    constexpr int V4 = WORDS / 4;
+    __shared__ uint4 s_t[STAGE_COLS * V4];
+    const int tid = threadIdx.x;
+    const int tile_rows = ROUND_THREADS * RQ;
+    const int rt = blockIdx.x, sp = blockIdx.y;
+    uint32_t q[RQ][WORDS], best[RQ], second[RQ];
+#pragma unroll
+    for (int k = 0; k < RQ; k++) {
+        const int i = rt * tile_rows + k * ROUND_THREADS + tid;
+        best[k] = KEY_NONE; second[k] = KEY_NONE;
+        const uint4 *src = reinterpret_cast<const uint4 *>(qd + (size_t)min(i, n1 - 1) * WORDS);
+#pragma unroll
+        for (int v = 0; v < V4; v++) {
+            const uint4 x = __ldg(src + v);
+            q[k][4 * v + 0] = x.x; q[k][4 * v + 1] = x.y; q[k][4 * v + 2] = x.z; q[k][4 * v + 3] = x.w;
+        }
+    }
+    const int c0 = sp * cols_per_split, c1 = min(n2, c0 + cols_per_split);
+    for (int s0 = c0; s0 < c1; s0 += STAGE_COLS) {
+        __syncthreads();
+        for (int k = tid; k < STAGE_COLS * V4; k += ROUND_THREADS) {
+            const int col = k / V4, part_i = k - col * V4, j = s0 + col;
+            s_t[k] = j < c1 ? __ldg(reinterpret_cast<const uint4 *>(td + (size_t)j * WORDS) + part_i)
+                            : make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+        const int ncs = min(STAGE_COLS, c1 - s0);
+        for (int jj = 0; jj < ncs; jj++) {
+            uint32_t t[WORDS];
+#pragma unroll
+            for (int v = 0; v < V4; v++) {
+                const uint4 x = s_t[jj * V4 + v];
+                t[4 * v + 0] = x.x; t[4 * v + 1] = x.y; t[4 * v + 2] = x.z; t[4 * v + 3] = x.w;
+            }
+            const uint32_t jk = (uint32_t)(s0 + jj);
+#pragma unroll
+            for (int k = 0; k < RQ; k++) {
+                const uint32_t key = (hamming_words<WORDS>(q[k], t) << KEY_IDX_BITS) + jk;
+                second[k] = min(second[k], max(best[k], key));
+                best[k] = min(best[k], key);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < RQ; k++) {
+        const int i = rt * tile_rows + k * ROUND_THREADS + tid;
+        if (i < n1) {
+            part[((size_t)sp * n1 + i) * 2 + 0] = best[k];
+            part[((size_t)sp * n1 + i) * 2 + 1] = second[k];
+        }
+    }
+}
+
+__global__ void knn2_merge_kernel(const uint32_t *__restrict__ part, int n1, int splits,
+                                  int32_t *best_j, int32_t *best_d, int32_t *second_j, int32_t *second_d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1) return;
+    uint32_t b = KEY_NONE, s = KEY_NONE;
+    for (int sp = 0; sp < splits; sp++) {
+        const uint32_t pb = part[((size_t)sp * n1 + i) * 2 + 0], ps = part[((size_t)sp * n1 + i) * 2 + 1];
+        s = min(min(s, ps), max(b, pb));
+        b = min(b, pb);
+    }
+    best_j[i] = b == KEY_NONE ? -1 : (int32_t)(b & KEY_IDX_MASK);
+    best_d[i] = b == KEY_NONE ? -1 : (int32_t)(b >> KEY_IDX_BITS);
+    second_j[i] = s == KEY_NONE ? -1 : (int32_t)(s & KEY_IDX_MASK);
+    second_d[i] = s == KEY_NONE ? -1 : (int32_t)(s >> KEY_IDX_BITS);
+}
+
+// per-train best query under (d, i): the cross-check side.  Same kernel with
+// the roles swapped gives best only; reuse knn2 by calling it with (t, q).
+
+// ratio + cross-check filter over knn2 results, compacted in ascending i.
+__global__ void ratio_crosscheck_kernel(int n1, int n2, const int32_t *best_j, const int32_t *best_d,
+                                        const int32_t *second_d, const int32_t *col_best_i,
+                                        float ratio, int cross_check, int max_dist, uint8_t *keep) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1) return;
+    bool k = best_j[i] >= 0;
+    if (k && ratio > 0.0f && n2 >= 2 && !((float)best_d[i] < ratio * (float)second_d[i])) k = false;
+    if (k && cross_check && col_best_i[best_j[i]] != i) k = false;
+    if (k && max_dist >= 0 && best_d[i] > max_dist) k = false;
+    keep[i] = k ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------
+// integer-pipe micro-benchmarks (roofline denominators)
+// ---------------------------------------------------------------------------
+__global__ void popc_peak_kernel(uint32_t *out, int iters, uint32_t seed) {
+    uint32_t a[8], acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { a[k] = seed * (threadIdx.x + 1) + k * 0x9E3779B9u; acc[k] = 0; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[k] = __popc(acc[k] ^ a[k]);   // dependent chain per k, 8 chains
+        }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += acc[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;   // keeps the chains alive
+}
+
+__global__ void lop3_peak_kernel(uint32_t *out, int iters, uint32_t seed) {
+    uint32_t a[8], acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { a[k] = seed * (threadIdx.x + 1) + k * 0x9E3779B9u; acc[k] = k; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[k] = (acc[k] & a[k]) ^ a[(k + 1) & 7];   // one LOP3 each
+        }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += acc[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;   // keeps the chains alive
+}
+
+}  // namespace pgm

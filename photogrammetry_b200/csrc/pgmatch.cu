@@ -1,0 +1,743 @@
+// pgmatch.cu -- C ABI (include/pgmatch.h) and host-side engine of libpgmatch.so.
+//
+// Replaces ImageProcessing.KeypointMatching.MatchKeypoints
+// (dotnet_src/ImageProcessing/KeypointMatching.cs:14-69) behind a P/Invoke-able
+// boundary.  There is deliberately no CPU implementation in this file: if no
+// sm_100 device is usable every entry point fails with PGM_E_NO_DEVICE.
+#include "../../include/pgmatch.h"
+#include "pgm_kernels.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace pgm;
+
+// ---------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+struct HostBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct pgm_handle {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    DevBuf state;     // per-chunk matcher state (carved by carve())
+    DevBuf desc;      // descriptors uploaded by the host-buffer entry points
+    DevBuf out;       // device staging of outputs for the host-buffer entry points
+    DevBuf misc;      // knn2 partials etc.
+    HostBuf pin_in;   // pinned staging, host -> device
+    HostBuf pin_out;  // pinned staging, device -> host
+    HostBuf pin_meta; // pinned PairDesc array + PlanInfo readback
+    pgm_stats stats{};
+    int rounds_hint = 6;      // grid rounds to enqueue before the first completion check
+    int round_grid = 0;       // persistent grid of the round kernel
+    int accept_grid = 0;
+    bool fin_attr_set[5] = {false, false, false, false, false};
+};
+
+#define CU_CHECK(h, call)                                                                      \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            char b__[512];                                                                     \
+            snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                     __FILE__, __LINE__);                                                      \
+            (h)->err = b__;                                                                    \
+            return PGM_E_CUDA;                                                                 \
+        }                                                                                      \
+    } while (0)
+
+static int fail(pgm_handle *h, int code, const char *msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+static int ensure_dev(pgm_handle *h, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return PGM_OK;
+    size_t want = std::max(bytes, b.cap + b.cap / 2);
+    want = (want + 255) & ~(size_t)255;
+    if (b.p) {
+        CU_CHECK(h, cudaStreamSynchronize(h->stream));
+        CU_CHECK(h, cudaFree(b.p));
+        b.p = nullptr; b.cap = 0;
+    }
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        h->err = std::string("cudaMalloc failed: ") + cudaGetErrorString(e);
+        b.p = nullptr;
+        return e == cudaErrorMemoryAllocation ? PGM_E_NOMEM : PGM_E_CUDA;
+    }
+    b.cap = want;
+    return PGM_OK;
+}
+
+static int ensure_host(pgm_handle *h, HostBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return PGM_OK;
+    size_t want = std::max(bytes, b.cap + b.cap / 2);
+    if (b.p) {
+        CU_CHECK(h, cudaStreamSynchronize(h->stream));
+        CU_CHECK(h, cudaFreeHost(b.p));
+        b.p = nullptr; b.cap = 0;
+    }
+    CU_CHECK(h, cudaMallocHost(&b.p, want));
+    b.cap = want;
+    return PGM_OK;
+}
+
+extern "C" int pgm_version(void) { return PGM_VERSION; }
+
+extern "C" const char *pgm_status_string(int s) {
+    switch (s) {
+        case PGM_OK: return "ok";
+        case PGM_E_INVALID_ARG: return "invalid argument";
+        case PGM_E_CAPACITY: return "output capacity too small";
+        case PGM_E_CUDA: return "CUDA error";
+        case PGM_E_NCCL: return "NCCL error";
+        case PGM_E_EMPTY_TRAIN: return "train set is empty (reference throws ArgumentOutOfRangeException)";
+        case PGM_E_NOMEM: return "out of memory";
+        case PGM_E_NO_DEVICE: return "no usable sm_100 CUDA device (there is no CPU fallback)";
+        default: return "unknown status";
+    }
+}
+
+extern "C" int pgm_create(int device_ordinal, pgm_handle **out) {
+    if (!out) return PGM_E_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device_ordinal < 0 || device_ordinal >= count) {
+        cudaGetLastError();
+        return PGM_E_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess) return PGM_E_NO_DEVICE;
+    if (prop.major != 10) return PGM_E_NO_DEVICE;   // the .so carries sm_100a SASS only
+    if (cudaSetDevice(device_ordinal) != cudaSuccess) return PGM_E_NO_DEVICE;
+    pgm_handle *h = new pgm_handle();
+    h->device = device_ordinal;
+    h->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return PGM_E_CUDA;
+    }
+    h->stream = h->own_stream;
+    *out = h;
+    return PGM_OK;
+}
+
+extern "C" int pgm_destroy(pgm_handle *h) {
+    if (!h) return PGM_E_INVALID_ARG;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (DevBuf *b : {&h->state, &h->desc, &h->out, &h->misc})
+        if (b->p) cudaFree(b->p);
+    for (HostBuf *b : {&h->pin_in, &h->pin_out, &h->pin_meta})
+        if (b->p) cudaFreeHost(b->p);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return PGM_OK;
+}
+
+extern "C" const char *pgm_last_error(pgm_handle *h) { return h ? h->err.c_str() : "null handle"; }
+
+extern "C" int pgm_set_stream(pgm_handle *h, void *cuda_stream) {
+    if (!h) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return PGM_OK;
+}
+
+extern "C" int pgm_synchronize(pgm_handle *h) {
+    if (!h) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU_CHECK(h, cudaSetDevice(h->device));
+    CU_CHECK(h, cudaStreamSynchronize(h->stream));
+    return PGM_OK;
+}
+
+extern "C" int pgm_get_stats(pgm_handle *h, pgm_stats *out) {
+    if (!h || !out) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    *out = h->stats;
+    return PGM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// kernel dispatch on descriptor width
+// ---------------------------------------------------------------------------
+constexpr int RQ_DEFAULT = 4;
+
+template <int WORDS>
+static void launch_round(const Chunk &c, int r, int grid, cudaStream_t s) {
+    hamming_round_kernel<WORDS, RQ_DEFAULT><<<grid, ROUND_THREADS, 0, s>>>(c, r);
+}
+static void dispatch_round(int words, const Chunk &c, int r, int grid, cudaStream_t s) {
+    switch (words) {
+        case 4: launch_round<4>(c, r, grid, s); break;
+        case 8: launch_round<8>(c, r, grid, s); break;
+        case 12: launch_round<12>(c, r, grid, s); break;
+        default: launch_round<16>(c, r, grid, s); break;
+    }
+}
+template <int WORDS>
+static cudaError_t launch_fin(pgm_handle *h, const Chunk &c, int r, cudaStream_t s) {
+    const size_t smem = finisher_smem_bytes();
+    if (!h->fin_attr_set[WORDS / 4]) {
+        cudaError_t e = cudaFuncSetAttribute(finisher_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        h->fin_attr_set[WORDS / 4] = true;
+    }
+    finisher_kernel<WORDS><<<c.n_pairs, FIN_THREADS, smem, s>>>(c, r);
+    return cudaSuccess;
+}
+static cudaError_t dispatch_fin(pgm_handle *h, int words, const Chunk &c, int r, cudaStream_t s) {
+    switch (words) {
+        case 4: return launch_fin<4>(h, c, r, s);
+        case 8: return launch_fin<8>(h, c, r, s);
+        case 12: return launch_fin<12>(h, c, r, s);
+        default: return launch_fin<16>(h, c, r, s);
+    }
+}
+template <int WORDS>
+static int round_occupancy() {
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hamming_round_kernel<WORDS, RQ_DEFAULT>, ROUND_THREADS, 0);
+    return nb;
+}
+static int dispatch_occupancy(int words) {
+    switch (words) {
+        case 4: return round_occupancy<4>();
+        case 8: return round_occupancy<8>();
+        case 12: return round_occupancy<12>();
+        default: return round_occupancy<16>();
+    }
+}
+template <int WORDS>
+static void launch_knn2(const uint32_t *q, int n1, const uint32_t *t, int n2, int cps, int splits, uint32_t *part,
+                        cudaStream_t s) {
+    const int tile_rows = ROUND_THREADS * RQ_DEFAULT;
+    dim3 grid((n1 + tile_rows - 1) / tile_rows, splits);
+    knn2_kernel<WORDS, RQ_DEFAULT><<<grid, ROUND_THREADS, 0, s>>>(q, n1, t, n2, cps, part);
+}
+static void dispatch_knn2(int words, const uint32_t *q, int n1, const uint32_t *t, int n2, int cps, int splits,
+                          uint32_t *part, cudaStream_t s) {
+    switch (words) {
+        case 4: launch_knn2<4>(q, n1, t, n2, cps, splits, part, s); break;
+        case 8: launch_knn2<8>(q, n1, t, n2, cps, splits, part, s); break;
+        case 12: launch_knn2<12>(q, n1, t, n2, cps, splits, part, s); break;
+        default: launch_knn2<16>(q, n1, t, n2, cps, splits, part, s); break;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// argument checks shared by every entry point
+// ---------------------------------------------------------------------------
+static int check_format(pgm_handle *h, int32_t desc_bits, int32_t stride_bytes) {
+    if (desc_bits < 1 || desc_bits > 512) return fail(h, PGM_E_INVALID_ARG, "desc_bits must be in 1..512");
+    if (stride_bytes < 16 || stride_bytes > 64 || stride_bytes % 16 != 0)
+        return fail(h, PGM_E_INVALID_ARG, "stride_bytes must be 16, 32, 48 or 64");
+    if (8 * stride_bytes < desc_bits) return fail(h, PGM_E_INVALID_ARG, "stride_bytes too small for desc_bits");
+    return PGM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// the engine: greedy assignment of one chunk of pairs, everything on device
+// ---------------------------------------------------------------------------
+struct HostPair {
+    const uint8_t *d_q, *d_t;   // device pointers
+    int32_t n1, n2;
+    int64_t out_base;           // in rows, relative to the chunk's output arrays
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc_bits, int stride_bytes,
+                     uint32_t flags, int32_t *d_out_qi, int32_t *d_out_tj, int32_t *d_out_dist) {
+    const int words = stride_bytes / 4;
+    cudaStream_t s = h->stream;
+
+    int64_t rows = 0, cols = 0;
+    int max_n = 1;
+    for (int p = 0; p < n_pairs; p++) {
+        rows += pairs[p].n1; cols += pairs[p].n2;
+        max_n = std::max(max_n, std::max(pairs[p].n1, pairs[p].n2));
+    }
+    // carve the state arena
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_pairs = take(sizeof(PairDesc) * n_pairs);
+    const size_t o_rb0 = take(4 * rows), o_rb1 = take(4 * rows), o_cb0 = take(4 * cols), o_cb1 = take(4 * cols);
+    const size_t o_lr0 = take(4 * rows), o_lr1 = take(4 * rows), o_lc0 = take(4 * cols), o_lc1 = take(4 * cols);
+    const size_t o_cnt = take(sizeof(int32_t) * 6 * n_pairs);
+    const size_t o_mk = take(4 * rows);
+    const size_t o_tb = take(4 * (n_pairs + 1)), o_ab = take(4 * (n_pairs + 1));
+    const size_t o_st = take(n_pairs);
+    const size_t o_plan = take(sizeof(PlanInfo));
+    int rc = ensure_dev(h, h->state, off);
+    if (rc) return rc;
+    rc = ensure_host(h, h->pin_meta, sizeof(PairDesc) * n_pairs + 256);
+    if (rc) return rc;
+    char *base = (char *)h->state.p;
+
+    if (h->round_grid == 0) {
+        int occ = dispatch_occupancy(8);
+        if (occ < 1) occ = 1;
+        h->round_grid = h->num_sms * occ;
+        h->accept_grid = h->num_sms * 4;
+    }
+
+    Chunk c{};
+    c.pairs = (PairDesc *)(base + o_pairs);
+    c.n_pairs = n_pairs;
+    c.tile_rows = ROUND_THREADS * RQ_DEFAULT;
+    c.target_tiles = h->round_grid * 2;
+    c.min_tile_evals = c.tile_rows * STAGE_COLS;
+    c.rowbest[0] = (uint32_t *)(base + o_rb0); c.rowbest[1] = (uint32_t *)(base + o_rb1);
+    c.colbest[0] = (uint32_t *)(base + o_cb0); c.colbest[1] = (uint32_t *)(base + o_cb1);
+    c.live_rows[0] = (int32_t *)(base + o_lr0); c.live_rows[1] = (int32_t *)(base + o_lr1);
+    c.live_cols[0] = (int32_t *)(base + o_lc0); c.live_cols[1] = (int32_t *)(base + o_lc1);
+    c.counts = (int32_t *)(base + o_cnt);
+    c.match_key = (uint32_t *)(base + o_mk);
+    c.tile_base = (int32_t *)(base + o_tb);
+    c.ablock_base = (int32_t *)(base + o_ab);
+    c.status = (uint8_t *)(base + o_st);
+    c.plan = (PlanInfo *)(base + o_plan);
+
+    PairDesc *hp = (PairDesc *)h->pin_meta.p;
+    PlanInfo *h_plan = (PlanInfo *)((char *)h->pin_meta.p + align_up(sizeof(PairDesc) * n_pairs, 64));
+    // (pin_meta was sized with 256 spare bytes for the PlanInfo readback)
+    int64_t rb = 0, cb = 0;
+    for (int p = 0; p < n_pairs; p++) {
+        hp[p].q = (const uint32_t *)pairs[p].d_q;
+        hp[p].t = (const uint32_t *)pairs[p].d_t;
+        hp[p].n1 = pairs[p].n1; hp[p].n2 = pairs[p].n2;
+        hp[p].row_base = rb; hp[p].col_base = cb; hp[p].out_base = pairs[p].out_base;
+        rb += pairs[p].n1; cb += pairs[p].n2;
+        h->stats.distance_evals += (int64_t)pairs[p].n1 * pairs[p].n2;
+        h->stats.matched += std::min(pairs[p].n1, pairs[p].n2);
+    }
+    h->stats.pairs += n_pairs;
+    CU_CHECK(h, cudaMemcpyAsync(c.pairs, hp, sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, s));
+
+    dim3 igrid(std::min((max_n + 255) / 256, 64), n_pairs);
+    init_kernel<<<igrid, 256, 0, s>>>(c);
+    plan_kernel<<<1, ACCEPT_THREADS, 0, s>>>(c, 0);
+    CU_CHECK(h, dispatch_fin(h, words, c, 0, s));
+    h->stats.kernel_launches += 3;
+
+    int r = 0;
+    int batch = std::max(1, h->rounds_hint);
+    for (;;) {
+        for (int k = 0; k < batch; k++, r++) {
+            dispatch_round(words, c, r, h->round_grid, s);
+            accept_kernel<<<h->accept_grid, ACCEPT_THREADS, 0, s>>>(c, r);
+            CU_CHECK(h, dispatch_fin(h, words, c, r + 1, s));
+            h->stats.kernel_launches += 3;
+        }
+        CU_CHECK(h, cudaMemcpyAsync(h_plan, c.plan, sizeof(PlanInfo), cudaMemcpyDeviceToHost, s));
+        CU_CHECK(h, cudaStreamSynchronize(s));
+        h->stats.host_syncs++;
+        if (h_plan->n_big == 0) break;
+        batch = 2;
+        if (r > 4 * MAX_N) return fail(h, PGM_E_CUDA, "matcher failed to converge (internal error)");
+    }
+    // grid rounds actually needed = first round whose plan had no big pair; the next call on this
+    // handle enqueues that many before its first completion check
+    const int needed = h_plan->done_round >= 0 ? h_plan->done_round : r;
+    h->stats.rounds += needed;
+    h->stats.evals_computed += (int64_t)h_plan->evals;
+    h->rounds_hint = std::max(1, std::min(needed, 64));
+
+    const int nbins = desc_bits + 1;
+    const size_t osmem = sizeof(int32_t) * ORDER_WARPS * (nbins + 1);
+    order_kernel<<<n_pairs, ORDER_THREADS, osmem, s>>>(c, nbins, flags, d_out_qi, d_out_tj, d_out_dist);
+    h->stats.kernel_launches += 1;
+    CU_CHECK(h, cudaGetLastError());
+    return PGM_OK;
+}
+
+static int32_t out_count_for(int32_t n1, int32_t n2, uint32_t flags) {
+    return (flags & PGM_FLAG_REFERENCE_COMPAT_TAIL) ? n1 : std::min(n1, n2);
+}
+
+static int check_pair(pgm_handle *h, int32_t n1, int32_t n2) {
+    if (n1 < 0 || n2 < 0) return fail(h, PGM_E_INVALID_ARG, "negative size");
+    if (n1 >= MAX_N || n2 >= MAX_N) return fail(h, PGM_E_INVALID_ARG, "n1 and n2 must be < 2^20");
+    if (n1 > 0 && n2 == 0)
+        return fail(h, PGM_E_EMPTY_TRAIN, "keypoints2 is empty (KeypointMatching.cs:61 throws)");
+    return PGM_OK;
+}
+
+extern "C" int pgm_match_hamming_greedy_dev(pgm_handle *h, const uint8_t *d_q, int32_t n1, const uint8_t *d_t,
+                                            int32_t n2, int32_t desc_bits, int32_t stride_bytes, int32_t *d_out_qi,
+                                            int32_t *d_out_tj, int32_t *d_out_dist, int32_t capacity,
+                                            int32_t *out_count, uint32_t flags) {
+    if (!h) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    int rc = check_format(h, desc_bits, stride_bytes);
+    if (rc) return rc;
+    rc = check_pair(h, n1, n2);
+    if (rc) return rc;
+    h->stats = pgm_stats{};
+    const int32_t cnt = out_count_for(n1, n2, flags);
+    if (out_count) *out_count = cnt;
+    if (n1 == 0) return PGM_OK;
+    if (!d_q || !d_t || !d_out_qi || !d_out_tj || !d_out_dist) return fail(h, PGM_E_INVALID_ARG, "null pointer");
+    if (capacity < cnt) return fail(h, PGM_E_CAPACITY, "capacity < number of triples");
+    CU_CHECK(h, cudaSetDevice(h->device));
+    HostPair hp{d_q, d_t, n1, n2, 0};
+    return run_chunk(h, &hp, 1, desc_bits, stride_bytes, flags, d_out_qi, d_out_tj, d_out_dist);
+}
+
+extern "C" int pgm_match_hamming_greedy(pgm_handle *h, const uint8_t *q, int32_t n1, const uint8_t *t, int32_t n2,
+                                        int32_t desc_bits, int32_t stride_bytes, int32_t *out_qi, int32_t *out_tj,
+                                        int32_t *out_dist, int32_t capacity, int32_t *out_count, uint32_t flags) {
+    if (!h) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    int rc = check_format(h, desc_bits, stride_bytes);
+    if (rc) return rc;
+    rc = check_pair(h, n1, n2);
+    if (rc) return rc;
+    h->stats = pgm_stats{};
+    const int32_t cnt = out_count_for(n1, n2, flags);
+    if (out_count) *out_count = cnt;
+    if (n1 == 0) return PGM_OK;
+    if (!q || !t || !out_qi || !out_tj || !out_dist) return fail(h, PGM_E_INVALID_ARG, "null pointer");
+    if (capacity < cnt) return fail(h, PGM_E_CAPACITY, "capacity < number of triples");
+    CU_CHECK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+
+    const size_t qb = (size_t)n1 * stride_bytes, tb = (size_t)n2 * stride_bytes;
+    const size_t q_off = 0, t_off = align_up(qb, 256);
+    if ((rc = ensure_host(h, h->pin_in, t_off + tb))) return rc;
+    if ((rc = ensure_dev(h, h->desc, t_off + tb))) return rc;
+    if ((rc = ensure_dev(h, h->out, (size_t)3 * n1 * 4))) return rc;
+    if ((rc = ensure_host(h, h->pin_out, (size_t)3 * n1 * 4))) return rc;
+    memcpy((char *)h->pin_in.p + q_off, q, qb);
+    memcpy((char *)h->pin_in.p + t_off, t, tb);
+    CU_CHECK(h, cudaMemcpyAsync(h->desc.p, h->pin_in.p, t_off + tb, cudaMemcpyHostToDevice, s));
+    int32_t *d_qi = (int32_t *)h->out.p, *d_tj = d_qi + n1, *d_dd = d_tj + n1;
+    HostPair hp{(const uint8_t *)h->desc.p + q_off, (const uint8_t *)h->desc.p + t_off, n1, n2, 0};
+    rc = run_chunk(h, &hp, 1, desc_bits, stride_bytes, flags, d_qi, d_tj, d_dd);
+    if (rc) return rc;
+    CU_CHECK(h, cudaMemcpyAsync(h->pin_out.p, h->out.p, (size_t)3 * n1 * 4, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(h, cudaStreamSynchronize(s));
+    h->stats.host_syncs++;
+    const int32_t *po = (const int32_t *)h->pin_out.p;
+    memcpy(out_qi, po, (size_t)cnt * 4);
+    memcpy(out_tj, po + n1, (size_t)cnt * 4);
+    memcpy(out_dist, po + 2 * (size_t)n1, (size_t)cnt * 4);
+    h->stats.h2d_bytes += (int64_t)(qb + tb);
+    h->stats.d2h_bytes += (int64_t)3 * n1 * 4;
+    return PGM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// many pairs
+// ---------------------------------------------------------------------------
+constexpr int MAX_CHUNK_PAIRS = 4096;
+constexpr int64_t MAX_CHUNK_SLOTS = 24ll << 20;   // rows + cols per chunk
+
+static int batch_impl(pgm_handle *h, const uint8_t *d_all_desc, const int64_t *image_offsets, int32_t n_images,
+                      const int32_t *pair_list, int32_t n_pairs, int32_t desc_bits, int32_t stride_bytes,
+                      int32_t *out_qi, int32_t *out_tj, int32_t *out_dist, bool out_on_host, int64_t capacity,
+                      int32_t *out_counts, uint32_t flags) {
+    cudaStream_t s = h->stream;
+    // validate + total size
+    int64_t total = 0;
+    for (int p = 0; p < n_pairs; p++) {
+        const int a = pair_list[2 * p], b = pair_list[2 * p + 1];
+        if (a < 0 || a >= n_images || b < 0 || b >= n_images) return fail(h, PGM_E_INVALID_ARG, "pair index out of range");
+        const int64_t n1 = image_offsets[a + 1] - image_offsets[a], n2 = image_offsets[b + 1] - image_offsets[b];
+        if (n1 < 0 || n2 < 0) return fail(h, PGM_E_INVALID_ARG, "image_offsets must be non-decreasing");
+        int rc = check_pair(h, (int32_t)std::min<int64_t>(n1, MAX_N), (int32_t)std::min<int64_t>(n2, MAX_N));
+        if (rc) return rc;
+        total += n1;
+        if (out_counts) out_counts[p] = out_count_for((int32_t)n1, (int32_t)n2, flags);
+    }
+    if (capacity < total) return fail(h, PGM_E_CAPACITY, "capacity < sum of query sizes");
+
+    std::vector<HostPair> chunk;
+    int64_t done_rows = 0;
+    int p = 0;
+    while (p < n_pairs) {
+        chunk.clear();
+        int64_t slots = 0, rows = 0;
+        while (p < n_pairs && (int)chunk.size() < MAX_CHUNK_PAIRS) {
+            const int a = pair_list[2 * p], b = pair_list[2 * p + 1];
+            const int32_t n1 = (int32_t)(image_offsets[a + 1] - image_offsets[a]);
+            const int32_t n2 = (int32_t)(image_offsets[b + 1] - image_offsets[b]);
+            if (!chunk.empty() && slots + n1 + n2 > MAX_CHUNK_SLOTS) break;
+            if (n1 > 0)
+                chunk.push_back(HostPair{d_all_desc + (size_t)image_offsets[a] * stride_bytes,
+                                         d_all_desc + (size_t)image_offsets[b] * stride_bytes, n1, n2, rows});
+            slots += n1 + n2; rows += n1;
+            p++;
+        }
+        if (rows == 0) continue;
+        int32_t *d_qi, *d_tj, *d_dd;
+        if (out_on_host) {
+            int rc;
+            if ((rc = ensure_dev(h, h->out, (size_t)3 * rows * 4))) return rc;
+            d_qi = (int32_t *)h->out.p; d_tj = d_qi + rows; d_dd = d_tj + rows;
+        } else {
+            d_qi = out_qi + done_rows; d_tj = out_tj + done_rows; d_dd = out_dist + done_rows;
+        }
+        if (!(flags & PGM_FLAG_REFERENCE_COMPAT_TAIL)) {
+            // rows beyond min(n1,n2) of a pair are not written without the tail flag: define them
+            CU_CHECK(h, cudaMemsetAsync(d_qi, 0xFF, (size_t)rows * 4, s));
+            CU_CHECK(h, cudaMemsetAsync(d_tj, 0xFF, (size_t)rows * 4, s));
+            CU_CHECK(h, cudaMemsetAsync(d_dd, 0xFF, (size_t)rows * 4, s));
+        }
+        int rc = run_chunk(h, chunk.data(), (int)chunk.size(), desc_bits, stride_bytes, flags, d_qi, d_tj, d_dd);
+        if (rc) return rc;
+        if (out_on_host) {
+            CU_CHECK(h, cudaMemcpyAsync(out_qi + done_rows, d_qi, (size_t)rows * 4, cudaMemcpyDeviceToHost, s));
+            CU_CHECK(h, cudaMemcpyAsync(out_tj + done_rows, d_tj, (size_t)rows * 4, cudaMemcpyDeviceToHost, s));
+            CU_CHECK(h, cudaMemcpyAsync(out_dist + done_rows, d_dd, (size_t)rows * 4, cudaMemcpyDeviceToHost, s));
+            CU_CHECK(h, cudaStreamSynchronize(s));
+            h->stats.host_syncs++;
+            h->stats.d2h_bytes += (int64_t)3 * rows * 4;
+        }
+        done_rows += rows;
+    }
+    return PGM_OK;
+}
+
+extern "C" int pgm_match_pairs_batch_dev(pgm_handle *h, const uint8_t *d_all_desc, const int64_t *image_offsets,
+                                         int32_t n_images, const int32_t *pair_list, int32_t n_pairs,
+                                         int32_t desc_bits, int32_t stride_bytes, int32_t *d_out_qi,
+                                         int32_t *d_out_tj, int32_t *d_out_dist, int64_t capacity,
+                                         int32_t *out_counts, uint32_t flags) {
+    if (!h) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    int rc = check_format(h, desc_bits, stride_bytes);
+    if (rc) return rc;
+    if (n_images < 0 || n_pairs < 0 || !image_offsets || (n_pairs > 0 && !pair_list))
+        return fail(h, PGM_E_INVALID_ARG, "bad image/pair arguments");
+    h->stats = pgm_stats{};
+    if (n_pairs == 0) return PGM_OK;
+    CU_CHECK(h, cudaSetDevice(h->device));
+    return batch_impl(h, d_all_desc, image_offsets, n_images, pair_list, n_pairs, desc_bits, stride_bytes, d_out_qi,
+                      d_out_tj, d_out_dist, false, capacity, out_counts, flags);
+}
+
+extern "C" int pgm_match_pairs_batch(pgm_handle *h, const uint8_t *all_desc, const int64_t *image_offsets,
+                                     int32_t n_images, const int32_t *pair_list, int32_t n_pairs, int32_t desc_bits,
+                                     int32_t stride_bytes, int32_t *out_qi, int32_t *out_tj, int32_t *out_dist,
+                                     int64_t capacity, int32_t *out_counts, uint32_t flags) {
+    if (!h) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    int rc = check_format(h, desc_bits, stride_bytes);
+    if (rc) return rc;
+    if (n_images < 0 || n_pairs < 0 || !image_offsets || (n_pairs > 0 && !pair_list))
+        return fail(h, PGM_E_INVALID_ARG, "bad image/pair arguments");
+    h->stats = pgm_stats{};
+    if (n_pairs == 0) return PGM_OK;
+    CU_CHECK(h, cudaSetDevice(h->device));
+    const size_t bytes = (size_t)image_offsets[n_images] * stride_bytes;
+    if ((rc = ensure_dev(h, h->desc, std::max<size_t>(bytes, 16)))) return rc;
+    if (bytes) {
+        // one bulk upload of every image's descriptors; pairs then index into it
+        CU_CHECK(h, cudaMemcpyAsync(h->desc.p, all_desc, bytes, cudaMemcpyHostToDevice, h->stream));
+        h->stats.h2d_bytes += (int64_t)bytes;
+    }
+    return batch_impl(h, (const uint8_t *)h->desc.p, image_offsets, n_images, pair_list, n_pairs, desc_bits,
+                      stride_bytes, out_qi, out_tj, out_dist, true, capacity, out_counts, flags);
+}
+
+// ---------------------------------------------------------------------------
+// nearest / second nearest, ratio test, cross-check
+// ---------------------------------------------------------------------------
+static int knn2_dev_impl(pgm_handle *h, const uint8_t *d_q, int32_t n1, const uint8_t *d_t, int32_t n2,
+                         int32_t stride_bytes, int32_t *d_bj, int32_t *d_bd, int32_t *d_sj, int32_t *d_sd,
+                         size_t misc_off) {
+    const int words = stride_bytes / 4;
+    cudaStream_t s = h->stream;
+    const int tile_rows = ROUND_THREADS * RQ_DEFAULT;
+    const int row_tiles = (n1 + tile_rows - 1) / tile_rows;
+    // enough column splits to fill the machine ~2x, each a multiple of STAGE_COLS columns
+    int splits = std::max(1, (2 * h->num_sms * 8 + row_tiles - 1) / row_tiles);
+    int cps = (n2 + splits - 1) / splits;
+    cps = std::max(STAGE_COLS, (cps + STAGE_COLS - 1) / STAGE_COLS * STAGE_COLS);
+    splits = std::max(1, (n2 + cps - 1) / cps);
+    int rc = ensure_dev(h, h->misc, misc_off + (size_t)splits * n1 * 8);
+    if (rc) return rc;
+    uint32_t *part = (uint32_t *)((char *)h->misc.p + misc_off);
+    dispatch_knn2(words, (const uint32_t *)d_q, n1, (const uint32_t *)d_t, n2, cps, splits, part, s);
+    knn2_merge_kernel<<<(n1 + 255) / 256, 256, 0, s>>>(part, n1, splits, d_bj, d_bd, d_sj, d_sd);
+    h->stats.kernel_launches += 2;
+    h->stats.distance_evals += (int64_t)n1 * n2;
+    h->stats.evals_computed += (int64_t)n1 * n2;
+    CU_CHECK(h, cudaGetLastError());
+    return PGM_OK;
+}
+
+extern "C" int pgm_knn2_hamming_dev(pgm_handle *h, const uint8_t *d_q, int32_t n1, const uint8_t *d_t, int32_t n2,
+                                    int32_t desc_bits, int32_t stride_bytes, int32_t *d_best_j, int32_t *d_best_d,
+                                    int32_t *d_second_j, int32_t *d_second_d) {
+    if (!h) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    int rc = check_format(h, desc_bits, stride_bytes);
+    if (rc) return rc;
+    if (n1 < 0 || n2 < 0 || n1 >= MAX_N || n2 >= MAX_N) return fail(h, PGM_E_INVALID_ARG, "bad sizes");
+    h->stats = pgm_stats{};
+    if (n1 == 0) return PGM_OK;
+    CU_CHECK(h, cudaSetDevice(h->device));
+    if (n2 == 0) {
+        for (int32_t *o : {d_best_j, d_best_d, d_second_j, d_second_d})
+            CU_CHECK(h, cudaMemsetAsync(o, 0xFF, (size_t)n1 * 4, h->stream));
+        return PGM_OK;
+    }
+    return knn2_dev_impl(h, d_q, n1, d_t, n2, stride_bytes, d_best_j, d_best_d, d_second_j, d_second_d, 0);
+}
+
+static int upload_pair(pgm_handle *h, const uint8_t *q, int32_t n1, const uint8_t *t, int32_t n2, int stride_bytes,
+                       const uint8_t **d_q, const uint8_t **d_t) {
+    const size_t qb = (size_t)n1 * stride_bytes, tb = (size_t)n2 * stride_bytes;
+    const size_t t_off = align_up(std::max<size_t>(qb, 1), 256);
+    int rc;
+    if ((rc = ensure_host(h, h->pin_in, t_off + tb + 16))) return rc;
+    if ((rc = ensure_dev(h, h->desc, t_off + tb + 16))) return rc;
+    if (qb) memcpy(h->pin_in.p, q, qb);
+    if (tb) memcpy((char *)h->pin_in.p + t_off, t, tb);
+    CU_CHECK(h, cudaMemcpyAsync(h->desc.p, h->pin_in.p, t_off + tb, cudaMemcpyHostToDevice, h->stream));
+    *d_q = (const uint8_t *)h->desc.p;
+    *d_t = (const uint8_t *)h->desc.p + t_off;
+    h->stats.h2d_bytes += (int64_t)(qb + tb);
+    return PGM_OK;
+}
+
+extern "C" int pgm_knn2_hamming(pgm_handle *h, const uint8_t *q, int32_t n1, const uint8_t *t, int32_t n2,
+                                int32_t desc_bits, int32_t stride_bytes, int32_t *best_j, int32_t *best_d,
+                                int32_t *second_j, int32_t *second_d) {
+    if (!h) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    int rc = check_format(h, desc_bits, stride_bytes);
+    if (rc) return rc;
+    if (n1 < 0 || n2 < 0 || n1 >= MAX_N || n2 >= MAX_N) return fail(h, PGM_E_INVALID_ARG, "bad sizes");
+    h->stats = pgm_stats{};
+    if (n1 == 0) return PGM_OK;
+    if (n2 == 0) {
+        for (int32_t *o : {best_j, best_d, second_j, second_d}) std::fill(o, o + n1, -1);
+        return PGM_OK;
+    }
+    CU_CHECK(h, cudaSetDevice(h->device));
+    const uint8_t *d_q, *d_t;
+    if ((rc = upload_pair(h, q, n1, t, n2, stride_bytes, &d_q, &d_t))) return rc;
+    if ((rc = ensure_dev(h, h->out, (size_t)4 * n1 * 4))) return rc;
+    if ((rc = ensure_host(h, h->pin_out, (size_t)4 * n1 * 4))) return rc;
+    int32_t *o = (int32_t *)h->out.p;
+    if ((rc = knn2_dev_impl(h, d_q, n1, d_t, n2, stride_bytes, o, o + n1, o + 2 * (size_t)n1, o + 3 * (size_t)n1, 0)))
+        return rc;
+    CU_CHECK(h, cudaMemcpyAsync(h->pin_out.p, o, (size_t)4 * n1 * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU_CHECK(h, cudaStreamSynchronize(h->stream));
+    h->stats.host_syncs++;
+    h->stats.d2h_bytes += (int64_t)4 * n1 * 4;
+    const int32_t *po = (const int32_t *)h->pin_out.p;
+    memcpy(best_j, po, (size_t)n1 * 4);
+    memcpy(best_d, po + n1, (size_t)n1 * 4);
+    memcpy(second_j, po + 2 * (size_t)n1, (size_t)n1 * 4);
+    memcpy(second_d, po + 3 * (size_t)n1, (size_t)n1 * 4);
+    return PGM_OK;
+}
+
+extern "C" int pgm_match_ratio_crosscheck(pgm_handle *h, const uint8_t *q, int32_t n1, const uint8_t *t, int32_t n2,
+                                          int32_t desc_bits, int32_t stride_bytes, float ratio, int32_t cross_check,
+                                          int32_t max_dist, int32_t *out_qi, int32_t *out_tj, int32_t *out_dist,
+                                          int32_t capacity, int32_t *out_count) {
+    if (!h || !out_count) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    int rc = check_format(h, desc_bits, stride_bytes);
+    if (rc) return rc;
+    if (n1 < 0 || n2 < 0 || n1 >= MAX_N || n2 >= MAX_N) return fail(h, PGM_E_INVALID_ARG, "bad sizes");
+    h->stats = pgm_stats{};
+    *out_count = 0;
+    if (n1 == 0 || n2 == 0) return PGM_OK;
+    CU_CHECK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const uint8_t *d_q, *d_t;
+    if ((rc = upload_pair(h, q, n1, t, n2, stride_bytes, &d_q, &d_t))) return rc;
+    // layout of h->out: row side 4*n1 | column side 4*n2 | keep n1 bytes
+    const size_t o_col = (size_t)4 * n1 * 4, o_keep = o_col + (size_t)4 * n2 * 4, o_end = o_keep + align_up(n1, 16);
+    if ((rc = ensure_dev(h, h->out, o_end))) return rc;
+    if ((rc = ensure_host(h, h->pin_out, o_end))) return rc;
+    int32_t *rj = (int32_t *)h->out.p, *rd = rj + n1, *sj = rd + n1, *sd = sj + n1;
+    int32_t *ci = (int32_t *)((char *)h->out.p + o_col), *cd = ci + n2, *c2 = cd + n2, *c3 = c2 + n2;
+    uint8_t *keep = (uint8_t *)h->out.p + o_keep;
+    if ((rc = knn2_dev_impl(h, d_q, n1, d_t, n2, stride_bytes, rj, rd, sj, sd, 0))) return rc;
+    if (cross_check) {
+        // column side = the same kernel with the roles swapped: best query per train under (d, i)
+        if ((rc = knn2_dev_impl(h, d_t, n2, d_q, n1, stride_bytes, ci, cd, c2, c3, 0))) return rc;
+    }
+    ratio_crosscheck_kernel<<<(n1 + 255) / 256, 256, 0, s>>>(n1, n2, rj, rd, sd, ci, ratio, cross_check, max_dist, keep);
+    h->stats.kernel_launches += 1;
+    CU_CHECK(h, cudaMemcpyAsync(h->pin_out.p, h->out.p, o_end, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(h, cudaStreamSynchronize(s));
+    h->stats.host_syncs++;
+    h->stats.d2h_bytes += (int64_t)o_end;
+    const int32_t *pj = (const int32_t *)h->pin_out.p, *pd = pj + n1;
+    const uint8_t *pk = (const uint8_t *)h->pin_out.p + o_keep;
+    int cnt = 0;
+    for (int i = 0; i < n1; i++) {
+        if (!pk[i]) continue;
+        if (cnt >= capacity) return fail(h, PGM_E_CAPACITY, "capacity too small");
+        out_qi[cnt] = i; out_tj[cnt] = pj[i]; out_dist[cnt] = pd[i]; cnt++;
+    }
+    *out_count = cnt;
+    h->stats.matched = cnt;
+    return PGM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// roofline denominators
+// ---------------------------------------------------------------------------
+extern "C" int pgm_measure_popc_peak(pgm_handle *h, int32_t millis, double *popc32_per_s, double *lop3_per_s) {
+    if (!h) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU_CHECK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const int threads = 256, blocks = h->num_sms * 8, iters = 4096;
+    int rc = ensure_dev(h, h->misc, (size_t)threads * blocks * 4);
+    if (rc) return rc;
+    cudaEvent_t e0, e1;
+    CU_CHECK(h, cudaEventCreate(&e0));
+    CU_CHECK(h, cudaEventCreate(&e1));
+    const double ops_per_launch = (double)threads * blocks * iters * 32.0;   // 4 x 8 per iteration
+    for (int which = 0; which < 2; which++) {
+        double best = 0.0;
+        auto t0 = std::chrono::steady_clock::now();
+        int reps = 0;
+        do {
+            CU_CHECK(h, cudaEventRecord(e0, s));
+            if (which == 0) popc_peak_kernel<<<blocks, threads, 0, s>>>((uint32_t *)h->misc.p, iters, 12345u + reps);
+            else lop3_peak_kernel<<<blocks, threads, 0, s>>>((uint32_t *)h->misc.p, iters, 12345u + reps);
+            CU_CHECK(h, cudaEventRecord(e1, s));
+            CU_CHECK(h, cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CU_CHECK(h, cudaEventElapsedTime(&ms, e0, e1));
+            if (reps >= 2) best = std::max(best, ops_per_launch / (ms * 1e-3));
+            reps++;
+        } while (reps < 4 || std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() <
+                                 millis / 2.0);
+        if (which == 0 && popc32_per_s) *popc32_per_s = best;
+        if (which == 1 && lop3_per_s) *lop3_per_s = best;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return PGM_OK;
+}

@@ -50,11 +50,11 @@ def as_descriptor_rows(desc, desc_bits: int | None = None) -> tuple[np.ndarray, 
     """Accept ``uint8[n, stride]`` rows or a sequence of ints; return (rows, desc_bits)."""
     if isinstance(desc, np.ndarray) and desc.dtype == np.uint8 and desc.ndim == 2:
         rows = np.ascontiguousarray(desc)
+        bits = desc_bits or rows.shape[1] * 8
         if rows.shape[1] % 16 != 0:
-            bits = desc_bits or rows.shape[1] * 8
             padded = np.zeros((rows.shape[0], stride_for_bits(max(bits, rows.shape[1] * 8))), dtype=np.uint8)
             padded[:, :rows.shape[1]] = rows
             rows = padded
-        return rows, (desc_bits or rows.shape[1] * 8)
+        return rows, bits
     bits = desc_bits or 256
     return pack_descriptors(desc, bits), bits

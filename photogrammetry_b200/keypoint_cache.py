@@ -48,18 +48,38 @@ def load_keypoint_dat(path: str) -> List[Keypoint]:
     return out
 
 
-class CachedKeyPoint:
-    """Minimal picklable stand-in with the cache's attribute layout."""
-
-    def __init__(self, coord, descriptor, moment=0.0):
-        self.coord = list(coord)
-        self.moment = moment
-        self.descriptor = int(descriptor)
-
-
 def save_keypoint_dat(path: str, keypoints: List[Keypoint]) -> None:
-    """Write a list of keypoints in the cache's pickle layout (protocol 4)."""
-    raw = [CachedKeyPoint(k.coord, k.BriefDescriptor, k.Value if isinstance(k.Value, float) else 0.0)
-           for k in keypoints]
-    with open(path, "wb") as f:
-        pickle.dump(raw, f, protocol=4)
+    """Write keypoints the way the Python generation's ``KeypointCache`` does
+    (keypoint_cache.py:41-49: ``pickle.dump(list_of_KeyPoint)``), so the file can be
+    read back by the reference's own ``pickle.load`` with its package importable:
+    instances of ``photogrammetry.models.keypoint.KeyPoint`` carrying ``_coord`` and a
+    materialised ``_descriptor`` (models/keypoint.py:5-30)."""
+    import sys
+    import types
+
+    mod_name = "photogrammetry.models.keypoint"
+    created = []
+    parts = mod_name.split(".")
+    for k in range(1, len(parts) + 1):
+        name = ".".join(parts[:k])
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+            created.append(name)
+    mod = sys.modules[mod_name]
+    had = hasattr(mod, "KeyPoint")
+    if not had:
+        mod.KeyPoint = type("KeyPoint", (), {"__module__": mod_name})
+    try:
+        raw = []
+        for k in keypoints:
+            o = mod.KeyPoint.__new__(mod.KeyPoint)
+            o.__dict__.update({"_image_id": 0, "_coord": [int(k.coord[0]), int(k.coord[1])],
+                               "_descriptor": int(k.BriefDescriptor), "_gaussian_pairs": None, "_image_db": None})
+            raw.append(o)
+        with open(path, "wb") as f:
+            pickle.dump(raw, f, protocol=4)
+    finally:
+        if not had:
+            del mod.KeyPoint
+        for name in created:
+            sys.modules.pop(name, None)

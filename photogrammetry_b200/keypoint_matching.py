@@ -1,0 +1,239 @@
+"""Host mirror of the reference's matcher over the C ABI of libpgmatch.so.
+
+Reference surface (same names, same argument meaning, same error behaviour):
+
+  ImageProcessing.KeypointMatching                       dotnet_src/ImageProcessing/KeypointMatching.cs:8-12
+      List<KeypointPair> MatchKeypoints(List<Keypoint>, List<Keypoint>)        :14-69
+  photogrammetry.image_processing.keypoint_matching.match_keypoints            python_src/.../keypoint_matching.py:7-33
+
+``KeypointMatching().MatchKeypoints(kp1, kp2)`` returns exactly ``len(kp1)``
+``KeypointPair`` objects whose ``Keypoint1``/``Keypoint2`` are *the caller's own
+objects* (KeypointMatching.cs:57-62), in the reference's order, including the
+``(keypoints1[0], keypoints2[0], int.MaxValue)`` tail when ``len(kp1) > len(kp2)``
+and an ``IndexError`` (the reference: ArgumentOutOfRangeException, :61) when
+``kp2`` is empty and ``kp1`` is not.
+
+All compute happens in CUDA kernels behind ``pgm_*``; nothing here touches
+``oracle/`` and there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import (PGM_E_EMPTY_TRAIN, PGM_FLAG_REFERENCE_COMPAT_TAIL, PGM_OK, EmptyTrainError, PgmatchError,
+                   PgmatchLibraryError, Stats)
+from .descriptors import as_descriptor_rows, pack_descriptors
+from .keypoint import Keypoint, KeypointPair
+
+
+def _addr(a: Optional[np.ndarray]) -> Optional[int]:
+    return None if a is None else a.ctypes.data
+
+
+class Matcher:
+    """One ``pgm_handle``: a device, a stream and its scratch memory (not thread-affine)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        rc = self._lib.pgm_create(int(device), C.byref(self._h))
+        if rc != PGM_OK:
+            self._h = C.c_void_p()
+            raise PgmatchLibraryError(
+                f"pgm_create(device={device}) failed: {self._lib.pgm_status_string(rc).decode()} "
+                "(libpgmatch has no CPU fallback)")
+        self.device = int(device)
+
+    # -- lifetime ---------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.pgm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- helpers ----------------------------------------------------------
+    def _check(self, rc: int) -> None:
+        if rc == PGM_OK:
+            return
+        msg = self._lib.pgm_last_error(self._h).decode() or self._lib.pgm_status_string(rc).decode()
+        if rc == PGM_E_EMPTY_TRAIN:
+            raise EmptyTrainError(rc, msg)
+        raise PgmatchError(rc, msg)
+
+    def set_stream(self, cuda_stream: Optional[int]) -> None:
+        """Run on a caller-owned CUDA stream (e.g. ``torch.cuda.Stream().cuda_stream``)."""
+        self._check(self._lib.pgm_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self) -> None:
+        self._check(self._lib.pgm_synchronize(self._h))
+
+    def stats(self) -> dict:
+        st = Stats()
+        self._check(self._lib.pgm_get_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+    # -- MatchKeypoints on packed rows ------------------------------------
+    def match_greedy(self, q: np.ndarray, t: np.ndarray, desc_bits: Optional[int] = None,
+                     reference_compat_tail: bool = True) -> np.ndarray:
+        """``int32[count, 3]`` rows (query index, train index, distance) in the reference's order."""
+        q, bits_q = as_descriptor_rows(q, desc_bits)
+        t, bits_t = as_descriptor_rows(t, desc_bits)
+        n1, n2 = int(q.shape[0]), int(t.shape[0])
+        stride = int(q.shape[1]) if n1 else int(t.shape[1])
+        if n1 and n2 and q.shape[1] != t.shape[1]:
+            raise ValueError("query and train descriptors have different strides")
+        bits = desc_bits or max(bits_q, bits_t)
+        out = np.empty((3, max(n1, 1)), dtype=np.int32)
+        cnt = C.c_int32(0)
+        flags = PGM_FLAG_REFERENCE_COMPAT_TAIL if reference_compat_tail else 0
+        self._check(self._lib.pgm_match_hamming_greedy(
+            self._h, _addr(q), n1, _addr(t), n2, bits, stride,
+            out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data, n1, C.byref(cnt), flags))
+        return np.ascontiguousarray(out[:, :cnt.value].T)
+
+    def match_greedy_dev(self, d_q: int, n1: int, d_t: int, n2: int, desc_bits: int, stride: int,
+                         d_out_qi: int, d_out_tj: int, d_out_dist: int, capacity: int,
+                         reference_compat_tail: bool = True) -> int:
+        """Device-pointer variant (raw addresses).  Returns the number of triples written."""
+        cnt = C.c_int32(0)
+        flags = PGM_FLAG_REFERENCE_COMPAT_TAIL if reference_compat_tail else 0
+        self._check(self._lib.pgm_match_hamming_greedy_dev(
+            self._h, d_q, n1, d_t, n2, desc_bits, stride, d_out_qi, d_out_tj, d_out_dist, capacity,
+            C.byref(cnt), flags))
+        return cnt.value
+
+    def match_pairs_batch(self, all_desc: np.ndarray, image_offsets: Sequence[int], pair_list,
+                          desc_bits: Optional[int] = None, reference_compat_tail: bool = True):
+        """Match many image pairs in one call.
+
+        Returns ``(triples int32[total, 3], starts int64[n_pairs], counts int32[n_pairs])``;
+        pair ``p`` owns ``triples[starts[p]:starts[p]+counts[p]]``.
+        """
+        all_desc, bits = as_descriptor_rows(all_desc, desc_bits)
+        offs = np.ascontiguousarray(image_offsets, dtype=np.int64)
+        pairs = np.ascontiguousarray(pair_list, dtype=np.int32).reshape(-1, 2)
+        n_images, n_pairs = len(offs) - 1, len(pairs)
+        sizes = np.diff(offs)
+        n1s = sizes[pairs[:, 0]] if n_pairs else np.zeros(0, dtype=np.int64)
+        starts = np.concatenate([[0], np.cumsum(n1s)]).astype(np.int64)
+        total = int(starts[-1])
+        out = np.empty((3, max(total, 1)), dtype=np.int32)
+        counts = np.zeros(max(n_pairs, 1), dtype=np.int32)
+        flags = PGM_FLAG_REFERENCE_COMPAT_TAIL if reference_compat_tail else 0
+        self._check(self._lib.pgm_match_pairs_batch(
+            self._h, _addr(all_desc), offs.ctypes.data, n_images, pairs.ctypes.data, n_pairs,
+            desc_bits or bits, int(all_desc.shape[1]), out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data,
+            total, counts.ctypes.data, flags))
+        return np.ascontiguousarray(out[:, :total].T), starts[:-1], counts[:n_pairs]
+
+    def match_pairs_batch_dev(self, d_all_desc: int, image_offsets, pair_list, desc_bits: int, stride: int,
+                              d_out_qi: int, d_out_tj: int, d_out_dist: int, capacity: int,
+                              reference_compat_tail: bool = True) -> np.ndarray:
+        offs = np.ascontiguousarray(image_offsets, dtype=np.int64)
+        pairs = np.ascontiguousarray(pair_list, dtype=np.int32).reshape(-1, 2)
+        counts = np.zeros(max(len(pairs), 1), dtype=np.int32)
+        flags = PGM_FLAG_REFERENCE_COMPAT_TAIL if reference_compat_tail else 0
+        self._check(self._lib.pgm_match_pairs_batch_dev(
+            self._h, d_all_desc, offs.ctypes.data, len(offs) - 1, pairs.ctypes.data, len(pairs), desc_bits, stride,
+            d_out_qi, d_out_tj, d_out_dist, capacity, counts.ctypes.data, flags))
+        return counts[:len(pairs)]
+
+    # -- nearest / second nearest, ratio, cross-check ----------------------
+    def knn2(self, q: np.ndarray, t: np.ndarray, desc_bits: Optional[int] = None):
+        q, bits_q = as_descriptor_rows(q, desc_bits)
+        t, bits_t = as_descriptor_rows(t, desc_bits)
+        n1, n2 = int(q.shape[0]), int(t.shape[0])
+        stride = int(q.shape[1]) if n1 else int(t.shape[1])
+        out = np.empty((4, max(n1, 1)), dtype=np.int32)
+        self._check(self._lib.pgm_knn2_hamming(self._h, _addr(q), n1, _addr(t), n2, desc_bits or max(bits_q, bits_t),
+                                               stride, *(out[k].ctypes.data for k in range(4))))
+        return tuple(out[k, :n1].copy() for k in range(4))
+
+    def match_ratio_crosscheck(self, q: np.ndarray, t: np.ndarray, ratio: float = 0.8, cross_check: bool = True,
+                               max_dist: int = -1, desc_bits: Optional[int] = None) -> np.ndarray:
+        q, bits_q = as_descriptor_rows(q, desc_bits)
+        t, bits_t = as_descriptor_rows(t, desc_bits)
+        n1, n2 = int(q.shape[0]), int(t.shape[0])
+        stride = int(q.shape[1]) if n1 else int(t.shape[1])
+        out = np.empty((3, max(n1, 1)), dtype=np.int32)
+        cnt = C.c_int32(0)
+        self._check(self._lib.pgm_match_ratio_crosscheck(
+            self._h, _addr(q), n1, _addr(t), n2, desc_bits or max(bits_q, bits_t), stride, float(ratio),
+            int(bool(cross_check)), int(max_dist), out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data,
+            n1, C.byref(cnt)))
+        return np.ascontiguousarray(out[:, :cnt.value].T)
+
+    def measure_popc_peak(self, millis: int = 200):
+        p, l = C.c_double(0), C.c_double(0)
+        self._check(self._lib.pgm_measure_popc_peak(self._h, int(millis), C.byref(p), C.byref(l)))
+        return p.value, l.value
+
+
+_default: dict = {}
+
+
+def default_matcher(device: int = 0) -> Matcher:
+    if device not in _default:
+        _default[device] = Matcher(device)
+    return _default[device]
+
+
+class KeypointMatching:
+    """Drop-in for ``ImageProcessing.KeypointMatching`` (KeypointMatching.cs:8-69).
+
+    Parameterless like the reference's constructor (:10-12); ``device`` and
+    ``desc_bits`` are optional extras (``desc_bits`` = ``NumGaussianPairs``,
+    appsettings.json:23, default 256; widened automatically if a descriptor
+    needs more bits).
+    """
+
+    def __init__(self, device: int = 0, desc_bits: int = 256):
+        self._matcher = default_matcher(device)
+        self._desc_bits = desc_bits
+
+    def _pack(self, keypoints: Sequence[Keypoint], bits: int) -> np.ndarray:
+        return pack_descriptors([int(k.BriefDescriptor if hasattr(k, "BriefDescriptor") else k.descriptor)
+                                 for k in keypoints], bits)
+
+    def MatchKeypoints(self, keypoints1: List[Keypoint], keypoints2: List[Keypoint]) -> List[KeypointPair]:
+        bits = self._desc_bits
+        for k in list(keypoints1) + list(keypoints2):
+            d = int(k.BriefDescriptor if hasattr(k, "BriefDescriptor") else k.descriptor)
+            if d < 0:
+                raise ValueError("BriefDescriptor must be non-negative")
+            bits = max(bits, d.bit_length())
+        q, t = self._pack(keypoints1, bits), self._pack(keypoints2, bits)
+        triples = self._matcher.match_greedy(q, t, bits, reference_compat_tail=True)
+        return [KeypointPair(Keypoint1=keypoints1[i], Keypoint2=keypoints2[j], Distance=int(d))
+                for i, j, d in triples.tolist()]
+
+
+def match_keypoints_nearest(keypoints1, keypoints2, hamming_threshold: int = -1, device: int = 0):
+    """Nearest-neighbour view of ``match_keypoints`` (keypoint_matching.py:7-33 +
+    scripts/match_keypoints.py:121-134): for every keypoint of image 1 the
+    nearest keypoint of image 2 and its distance, kept if
+    ``hamming_threshold < 0 or dist <= hamming_threshold``.
+    Returns ``int32[k, 3]`` rows (idx1, idx2, dist)."""
+    bits = 256
+    d1 = [int(getattr(k, "descriptor", getattr(k, "BriefDescriptor", None))) for k in keypoints1]
+    d2 = [int(getattr(k, "descriptor", getattr(k, "BriefDescriptor", None))) for k in keypoints2]
+    for d in d1 + d2:
+        bits = max(bits, d.bit_length())
+    m = default_matcher(device)
+    return m.match_ratio_crosscheck(pack_descriptors(d1, bits), pack_descriptors(d2, bits), ratio=0.0,
+                                    cross_check=False, max_dist=hamming_threshold, desc_bits=bits)

@@ -1,9 +1,9 @@
 """Seeded synthetic descriptor sets for the BASELINE configs.
 
 A counter-based splitmix64 stream: the idx-th output of stream ``seed`` is
-``mix(seed + (idx+1)*GAMMA)``, so the generator vectorises in numpy and is
-reproduced bit-for-bit by oracle/pgm_oracle.c (orc_gen_uniform /
-orc_gen_noisy_copy), which the tests use to cross-check this module.
+``mix(seed + (idx+1)*GAMMA)``, so the generator vectorises in numpy; the test
+suite cross-checks it bit-for-bit against an independent C implementation of
+the same stream.
 
 Distributions:
   U  i.i.d. uniform W-bit descriptors.

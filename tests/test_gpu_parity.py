@@ -1,0 +1,164 @@
+"""Parity of the CUDA path with the oracle, through the C ABI (run on a B200: -m gpu).
+
+Bit-exact everywhere: indices, distances, order, tie-breaks and the n1>n2 tail
+(KeypointMatching.cs:38-66)."""
+import numpy as np
+import pytest
+
+from oracle import orc
+from photogrammetry_b200 import synthetic
+from photogrammetry_b200._lib import EmptyTrainError, PgmatchError
+from photogrammetry_b200.keypoint import Coordinate, Keypoint
+from photogrammetry_b200.keypoint_matching import KeypointMatching
+from photogrammetry_b200.descriptors import unpack_descriptors
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("direction", ["l2r", "r2l"])
+def test_lego_fixture_golden(matcher, lego, direction):
+    q, t = (lego["left"], lego["right"]) if direction == "l2r" else (lego["right"], lego["left"])
+    got = matcher.match_greedy(q, t, 256)
+    assert got.shape == lego[direction].shape
+    assert (got == lego[direction]).all()
+    st = matcher.stats()
+    assert st["distance_evals"] == len(q) * len(t) and st["kernel_launches"] > 0
+
+
+def test_lego_without_tail(matcher, lego):
+    got = matcher.match_greedy(lego["left"], lego["right"], 256, reference_compat_tail=False)
+    assert got.shape == (1285, 3) and (got == lego["l2r"][:1285]).all()
+
+
+SMALL = [(1, 1, 256), (2, 1, 256), (1, 2, 256), (7, 7, 1), (13, 5, 3), (5, 13, 8), (33, 33, 8), (64, 48, 17),
+         (48, 64, 100), (40, 40, 128), (31, 57, 129), (20, 20, 300), (25, 9, 512), (64, 64, 6), (130, 300, 8),
+         (700, 650, 4), (513, 512, 256), (1000, 37, 256), (37, 1000, 256), (600, 600, 2)]
+
+
+@pytest.mark.parametrize("n1,n2,bits", SMALL)
+def test_small_random_against_literal(matcher, n1, n2, bits):
+    q = synthetic.uniform_descriptors(1000 + n1, n1, bits)
+    t = synthetic.uniform_descriptors(2000 + n2, n2, bits)
+    exp = orc.match_literal(q, t, kernighan=False) if n1 * n2 <= 250000 else orc.match_sweep(q, t)
+    got = matcher.match_greedy(q, t, bits)
+    assert got.shape == exp.shape and (got == exp).all()
+
+
+def test_duplicates_one_pair_per_round(matcher):
+    q = np.zeros((300, 32), dtype=np.uint8)
+    t = np.zeros((280, 32), dtype=np.uint8)
+    got = matcher.match_greedy(q, t, 256)
+    assert got[:280].tolist() == [[k, k, 0] for k in range(280)]
+    assert (got[280:] == [0, 0, 2147483647]).all()
+
+
+def test_duplicates_large_grid_rounds(matcher):
+    # 40 identical rows inside a bigger problem: forces many grid rounds with few accepts each
+    q = synthetic.uniform_descriptors(5, 1500, 256)
+    t = synthetic.uniform_descriptors(6, 1400, 256)
+    q[100:140] = q[100]
+    t[200:230] = q[100]
+    got = matcher.match_greedy(q, t, 256)
+    assert (got == orc.match_sweep(q, t)).all()
+
+
+def test_edge_cases(matcher):
+    q = synthetic.uniform_descriptors(1, 5, 256)
+    e = np.zeros((0, 32), dtype=np.uint8)
+    assert matcher.match_greedy(e, q, 256).shape == (0, 3)
+    assert matcher.match_greedy(e, e, 256).shape == (0, 3)
+    with pytest.raises(EmptyTrainError):
+        matcher.match_greedy(q, e, 256)
+    with pytest.raises(IndexError):          # what reference callers would catch (ArgumentOutOfRange)
+        matcher.match_greedy(q, e, 256)
+    with pytest.raises(PgmatchError):
+        matcher.match_greedy(np.zeros((3, 32), np.uint8), np.zeros((3, 32), np.uint8), 600)
+
+
+@pytest.mark.parametrize("dist", ["U", "C"])
+def test_config2_8k_against_sweep(matcher, dist):
+    q, t = synthetic.config2_pair(8192, dist)
+    exp = orc.match_sweep(q, t)
+    got = matcher.match_greedy(q, t, 256)
+    assert (got == exp).all()
+    st = matcher.stats()
+    assert st["distance_evals"] == 8192 * 8192
+    assert st["evals_computed"] < 2.5 * st["distance_evals"]
+
+
+def test_rectangular_20k_against_rounds(matcher):
+    q = synthetic.uniform_descriptors(11, 20000, 256)
+    t = synthetic.noisy_copy_descriptors(12, q, 256)[:15000]
+    exp = orc.match_rounds(q, t)
+    got = matcher.match_greedy(q, t, 256)
+    assert (got == exp).all()
+
+
+def test_full_size_properties(matcher):
+    # size-independent properties at a size the oracle does not check element-wise
+    n = 30000
+    q = synthetic.uniform_descriptors(21, n, 256)
+    t = synthetic.noisy_copy_descriptors(22, q, 256)
+    got = matcher.match_greedy(q, t, 256)
+    assert got.shape == (n, 3)
+    assert sorted(got[:, 0].tolist()) == list(range(n)) and sorted(got[:, 1].tolist()) == list(range(n))
+    k = got[:, 2].astype(np.int64) * (1 << 40) + got[:, 0].astype(np.int64) * (1 << 20) + got[:, 1]
+    assert (np.diff(k) > 0).all()                                   # (d, i, j) strictly ascending
+    d = np.bitwise_count(q[got[:, 0]] ^ t[got[:, 1]]).sum(axis=1)
+    assert (d == got[:, 2]).all()                                   # reported distances are the true ones
+    # the first triple is the global minimum edge; spot-check it against a knn pass
+    bj, bd, _, _ = matcher.knn2(q, t, 256)
+    i0 = int(np.lexsort((np.arange(n), bd))[0])
+    assert got[0].tolist() == [i0, int(bj[i0]), int(bd[i0])]
+    # idempotence: matching again gives the same answer
+    assert (matcher.match_greedy(q, t, 256) == got).all()
+
+
+def test_batch_equals_single(matcher):
+    sizes = [300, 0, 1200, 700, 64, 2500]
+    imgs = [synthetic.uniform_descriptors(100 + k, n, 256) for k, n in enumerate(sizes)]
+    imgs[3][:50] = imgs[2][:50]
+    all_desc = np.concatenate(imgs)
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    pairs = [(0, 2), (2, 3), (3, 2), (4, 5), (5, 4), (1, 0), (0, 0), (5, 2)]
+    triples, starts, counts = matcher.match_pairs_batch(all_desc, offs, pairs, 256)
+    for p, (a, b) in enumerate(pairs):
+        exp = orc.match_sweep(imgs[a], imgs[b])
+        got = triples[starts[p]:starts[p] + counts[p]]
+        assert counts[p] == sizes[a] and (got == exp).all(), (p, a, b)
+    with pytest.raises(EmptyTrainError):
+        matcher.match_pairs_batch(all_desc, offs, [(0, 1)], 256)
+
+
+def test_knn2_and_ratio_crosscheck(matcher):
+    q = synthetic.uniform_descriptors(31, 3000, 256)
+    t = synthetic.noisy_copy_descriptors(32, q, 256)[:2500]
+    for a, b in zip(matcher.knn2(q, t, 256), orc.knn2(q, t)):
+        assert (a == b).all()
+    for ratio, cc, md in [(0.8, True, -1), (0.9, False, -1), (0.0, True, -1), (0.0, False, 75), (0.7, True, 60)]:
+        got = matcher.match_ratio_crosscheck(q, t, ratio, cc, md, 256)
+        exp = orc.match_ratio_crosscheck(q, t, ratio, cc, md)
+        assert got.shape == exp.shape and (got == exp).all(), (ratio, cc, md)
+    # heavy ties
+    q8, t8 = synthetic.uniform_descriptors(41, 500, 8), synthetic.uniform_descriptors(42, 700, 8)
+    for a, b in zip(matcher.knn2(q8, t8, 8), orc.knn2(q8, t8)):
+        assert (a == b).all()
+    q1 = synthetic.uniform_descriptors(43, 9, 256)
+    assert [x.tolist() for x in matcher.knn2(q1, q1[:1], 256)][2] == [-1] * 9     # no second neighbour
+
+
+def test_keypoint_matching_object_surface(lego):
+    # the drop-in class: same signature and reference semantics as KeypointMatching.cs:14-69
+    kp1 = [Keypoint(Coordinate(int(x), int(y)), d) for (x, y), d in
+           zip(lego["left_coord"][:400], unpack_descriptors(lego["left"][:400]))]
+    kp2 = [Keypoint(Coordinate(int(x), int(y)), d) for (x, y), d in
+           zip(lego["right_coord"][:250], unpack_descriptors(lego["right"][:250]))]
+    pairs = KeypointMatching().MatchKeypoints(kp1, kp2)
+    exp = orc.match_literal(lego["left"][:400], lego["right"][:250])
+    assert len(pairs) == len(kp1) == 400
+    for p, (i, j, d) in zip(pairs, exp.tolist()):
+        assert p.Keypoint1 is kp1[i] and p.Keypoint2 is kp2[j] and p.Distance == d
+    assert pairs[-1].Keypoint1 is kp1[0] and pairs[-1].Keypoint2 is kp2[0] and pairs[-1].Distance == 2147483647
+    assert KeypointMatching().MatchKeypoints([], kp2) == []
+    with pytest.raises(IndexError):
+        KeypointMatching().MatchKeypoints(kp1, [])

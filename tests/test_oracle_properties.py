@@ -1,0 +1,83 @@
+"""Property tests tying the oracle's formulations together (CPU, small sizes)."""
+import numpy as np
+import pytest
+
+from oracle import oracle_np as onp
+from oracle import orc
+
+CASES = [
+    # (n1, n2, desc_bits)
+    (1, 1, 256), (2, 1, 256), (1, 2, 256), (7, 7, 1), (13, 5, 3), (5, 13, 8), (33, 33, 8),
+    (64, 48, 17), (48, 64, 100), (40, 40, 128), (31, 57, 129), (20, 20, 300), (25, 9, 512), (64, 64, 6),
+]
+
+
+@pytest.mark.parametrize("n1,n2,bits", CASES)
+def test_all_formulations_agree(n1, n2, bits):
+    q = orc.gen_uniform(1000 + n1, n1, bits)
+    t = orc.gen_uniform(2000 + n2, n2, bits)
+    lit = orc.match_literal(q, t, kernighan=True)
+    assert (lit == orc.match_sweep(q, t)).all()
+    assert (lit == orc.match_rounds(q, t)).all()
+    assert (lit == onp.match_literal_np(q, t)).all()
+    py = onp.match_literal_py([onp.desc_to_int(r) for r in q], [onp.desc_to_int(r) for r in t])
+    assert lit.tolist() == [list(x) for x in py]
+    # structure: n1 rows, first min(n1,n2) real and sorted by (d, i, j), then the tail
+    m = min(n1, n2)
+    assert lit.shape == (n1, 3)
+    keys = [tuple(r) for r in lit[:m, [2, 0, 1]].tolist()]
+    assert keys == sorted(keys)
+    assert len(set(lit[:m, 0])) == m and len(set(lit[:m, 1])) == m
+    assert (lit[m:] == [0, 0, orc.TAIL_DISTANCE]).all()
+
+
+def test_duplicates_force_many_rounds():
+    # identical descriptors: every distance is 0, greedy pairs (k, k); one pair per round
+    q = np.zeros((24, 32), dtype=np.uint8)
+    t = np.zeros((24, 32), dtype=np.uint8)
+    out, rounds = orc.match_rounds(q, t, return_rounds=True)
+    assert out.tolist() == [[k, k, 0] for k in range(24)]
+    assert rounds == 24
+    assert (orc.match_literal(q, t) == out).all()
+
+
+def test_empty_inputs():
+    q = orc.gen_uniform(1, 4)
+    e = np.zeros((0, 32), dtype=np.uint8)
+    assert orc.match_literal(e, q).shape == (0, 3)
+    assert orc.match_sweep(e, e).shape == (0, 3)
+    for f in (orc.match_literal, orc.match_sweep, orc.match_rounds):
+        with pytest.raises(orc.EmptyTrainError):
+            f(q, e)
+
+
+def test_knn2_and_ratio_crosscheck_against_matrix():
+    q = orc.gen_uniform(5, 70, 8)           # 8-bit descriptors: heavy ties
+    t = orc.gen_uniform(6, 50, 8)
+    d = orc.distance_matrix(q, t).astype(np.int64)
+    key = d * (1 << 20) + np.arange(50)[None, :]
+    order = np.argsort(key, axis=1, kind="stable")
+    bj, bd, sj, sd = orc.knn2(q, t)
+    assert (bj == order[:, 0]).all() and (sj == order[:, 1]).all()
+    assert (bd == d[np.arange(70), bj]).all() and (sd == d[np.arange(70), sj]).all()
+    ckey = d * (1 << 20) + np.arange(70)[:, None]
+    col_best = np.argmin(ckey, axis=0)
+    got = orc.match_ratio_crosscheck(q, t, ratio=0.8, cross_check=True)
+    exp = [(i, int(bj[i]), int(bd[i])) for i in range(70)
+           if np.float32(bd[i]) < np.float32(0.8) * np.float32(sd[i]) and col_best[bj[i]] == i]
+    assert [tuple(r) for r in got.tolist()] == exp
+    # cross-check alone == round 1 of the greedy rounds (mutual nearest neighbours)
+    mutual = orc.match_ratio_crosscheck(q, t, ratio=0.0, cross_check=True)
+    greedy = {(a, b) for a, b, _ in orc.match_rounds(q, t)[:50].tolist()}
+    assert {(a, b) for a, b, _ in mutual.tolist()} <= greedy
+
+
+def test_l2_knn2_small():
+    rng = np.random.default_rng(3)
+    q = rng.standard_normal((20, 16)).astype(np.float32)
+    t = rng.standard_normal((30, 16)).astype(np.float32)
+    bj, bd, sj, sd = orc.l2_knn2(q, t)
+    d = ((q[:, None, :].astype(np.float64) - t[None].astype(np.float64)) ** 2).sum(-1)
+    o = np.argsort(d, axis=1, kind="stable")
+    assert (bj == o[:, 0]).all() and (sj == o[:, 1]).all()
+    np.testing.assert_allclose(bd, d[np.arange(20), bj], rtol=1e-6)
