@@ -175,6 +175,16 @@ int pgm_match_ratio_crosscheck(pgm_handle *h,
                                int32_t capacity, int32_t *out_count);
 
 /* ---- measurement helpers -------------------------------------------------
+ * Profiling mode brackets every launch of the dominant kernel (the round
+ * kernel) with CUDA events on the handle's stream and records how many
+ * XOR+popcount evaluations each launch executed.  It adds event records to
+ * the stream, so bench.py uses it in a separate pass from the timed steps. */
+int pgm_set_profiling(pgm_handle *h, int32_t enabled);
+/* Per round-kernel launch of the last greedy call: duration in ms and
+ * evaluations executed.  Synchronises the stream. */
+int pgm_get_round_profile(pgm_handle *h, float *ms, int64_t *evals, int32_t capacity, int32_t *out_n);
+
+/*
  * Register-only POPC.32 throughput of the device (the roofline denominator
  * for this path: one 256-bit distance = 8 POPC.32).  Runs a saturating
  * micro-benchmark for roughly `millis` ms and reports popc32 results / s. */

@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = (
     "pgm_match_hamming_greedy", "pgm_match_hamming_greedy_dev",
     "pgm_match_pairs_batch", "pgm_match_pairs_batch_dev",
     "pgm_knn2_hamming", "pgm_knn2_hamming_dev", "pgm_match_ratio_crosscheck",
-    "pgm_measure_popc_peak",
+    "pgm_set_profiling", "pgm_get_round_profile", "pgm_measure_popc_peak",
 )
 
 
@@ -118,6 +118,8 @@ def load() -> C.CDLL:
         lib.pgm_match_ratio_crosscheck.argtypes = [C.c_void_p, u8p, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32,
                                                    C.c_float, C.c_int32, C.c_int32, i32p, i32p, i32p, C.c_int32,
                                                    C.POINTER(C.c_int32)]
+        lib.pgm_set_profiling.argtypes = [C.c_void_p, C.c_int32]
+        lib.pgm_get_round_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
         lib.pgm_measure_popc_peak.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         _ = vp
         _lib = lib

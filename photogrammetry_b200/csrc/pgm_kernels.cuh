@@ -34,14 +34,19 @@ constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
 constexpr uint32_t KEY_INVALID = 0xDFFFFFFFu;
 constexpr int MAX_N = 1 << KEY_IDX_BITS;
 
-constexpr int ROUND_THREADS = 128;   // 4 warps per CTA
-constexpr int STAGE_COLS = 64;       // train descriptors staged in shared memory per step
+constexpr int ROUND_THREADS = 128;    // 4 warps per CTA
+constexpr int RQ_LARGE = 4;           // query rows per thread, large tiles
+constexpr int STAGE_LARGE = 64;       // train descriptors staged in smem per step, large tiles
+constexpr int RQ_SMALL = 1;           // small tiles: late rounds, where the machine would otherwise idle
+constexpr int STAGE_SMALL = 32;
+constexpr int STAGE_COLS = STAGE_LARGE;
 constexpr int ACCEPT_THREADS = 256;
 constexpr int FIN_THREADS = 512;
-constexpr int FIN_MAX_DIM = 512;     // (== FIN_THREADS) finisher takes a pair once nlr, nlc <= this ...
-constexpr int FIN_MAX_EVALS = 49152; // ... and nlr * nlc <= this (distance matrix in smem)
+constexpr int FIN_MAX_DIM = 512;      // (== FIN_THREADS) finisher takes a pair once nlr, nlc <= this ...
+constexpr int FIN_MAX_EVALS = 49152;  // ... and nlr * nlc <= this (u16 distance matrix in smem)
 constexpr int ORDER_THREADS = 512;
 constexpr int ORDER_WARPS = ORDER_THREADS / 32;
+constexpr int ORDER_KEY_CACHE = 16384;  // match keys cached in smem by the order kernel
 
 enum PairStatus : uint8_t { PAIR_DONE = 0, PAIR_BIG = 1, PAIR_SMALL = 2 };
 
@@ -54,24 +59,30 @@ struct PairDesc {
     int64_t out_base;    // where this pair's triples start in the output arrays
 };
 
+struct SmallInfo {       // written when the planner hands a pair to the finisher
+    int32_t nlr, nlc, parity, pad;
+};
+
 struct PlanInfo {                 // device resident, rewritten every round
     int32_t total_tiles;          // round-kernel work items
-    int32_t cols_per_tile;        // column extent of one tile (multiple of STAGE_COLS)
+    int32_t cols_per_tile;        // column extent of one tile (multiple of the stage size)
     int32_t total_ablocks;        // accept-kernel work items
     int32_t n_big;                // pairs still on grid rounds
-    int32_t n_small;              // pairs handed to the finisher this round
+    int32_t n_small;              // pairs waiting for the finisher
     int32_t round;
-    uint32_t accept_ticket;       // last-block-done counter
+    uint32_t ticket;              // last-block-done counter (init and accept kernels)
     int32_t done_round;           // first round whose plan found no PAIR_BIG pair (-1: not yet)
-    unsigned long long evals;     // XOR+popcount evaluations executed so far
+    int32_t rq;                   // rows per thread this round (RQ_LARGE or RQ_SMALL)
+    int32_t pad;
+    unsigned long long evals;     // XOR+popcount evaluations planned so far (grid rounds)
 };
 
 struct Chunk {
     PairDesc *pairs;
     int32_t n_pairs;
-    int32_t tile_rows;            // rows per round-kernel tile (ROUND_THREADS * RQ)
-    int32_t target_tiles;         // tiles the planner aims for per round
-    int32_t min_tile_evals;
+    int32_t num_sms;
+    int32_t ctas_per_sm;          // resident round-kernel CTAs per SM
+    int32_t pad;
     uint32_t *rowbest[2];
     uint32_t *colbest[2];
     int32_t *live_rows[2];
@@ -81,6 +92,7 @@ struct Chunk {
     int32_t *tile_base;           // [n_pairs + 1]
     int32_t *ablock_base;         // [n_pairs + 1]
     uint8_t *status;              // PairStatus per pair
+    SmallInfo *small;             // per pair
     PlanInfo *plan;
 };
 
@@ -99,9 +111,140 @@ __device__ __forceinline__ int find_pair(const int32_t *__restrict__ base, int n
 }
 
 // ---------------------------------------------------------------------------
-// init: live lists = identity, keys = none, counts[0] = (n1, n2)
+// planner: one CTA of ACCEPT_THREADS threads.  Classifies every pair from
+// counts[r % 3], picks the tile shape so the round kernel gets enough work
+// items to cover the machine, and writes the per-pair exclusive prefixes the
+// round/accept kernels search.
 // ---------------------------------------------------------------------------
-__global__ void init_kernel(Chunk c) {
+__device__ __forceinline__ int tiles_of(int nlr, int nlc, int tile_rows, int cpt) {
+    return ((nlr + tile_rows - 1) / tile_rows) * ((nlc + cpt - 1) / cpt);
+}
+__device__ __forceinline__ int ablocks_of(int nlr, int nlc) {
+    return (nlr + ACCEPT_THREADS - 1) / ACCEPT_THREADS + (nlc + ACCEPT_THREADS - 1) / ACCEPT_THREADS;
+}
+
+__device__ void plan_device(const Chunk &c, int r) {
+    constexpr int NW = ACCEPT_THREADS / 32;
+    __shared__ unsigned long long s_evals[NW];
+    __shared__ int s_w[4][NW];
+    __shared__ int s_cpt, s_tile_rows;
+    const int tid = threadIdx.x, nt = ACCEPT_THREADS, lane = tid & 31, wid = tid >> 5;
+    const int buf = r % 3;
+
+    unsigned long long ev = 0; int nbig = 0, nsmall = 0;
+    for (int p = tid; p < c.n_pairs; p += nt) {
+        uint8_t st = c.status[p];
+        if (st == PAIR_SMALL) { nsmall++; }
+        else {
+            const int32_t *cp = cnt_ptr(c, buf, p);
+            const int nlr = __ldcg(cp), nlc = __ldcg(cp + 1);
+            st = PAIR_DONE;
+            if (nlr > 0 && nlc > 0) {
+                const bool small = nlr <= FIN_MAX_DIM && nlc <= FIN_MAX_DIM && nlr * nlc <= FIN_MAX_EVALS;
+                if (small) {
+                    st = PAIR_SMALL; nsmall++;
+                    c.small[p] = SmallInfo{nlr, nlc, r & 1, 0};
+                } else {
+                    st = PAIR_BIG; nbig++;
+                    ev += (unsigned long long)nlr * (unsigned long long)nlc;
+                }
+            }
+            c.status[p] = st;
+        }
+        int32_t *nx = cnt_ptr(c, (r + 1) % 3, p);   // accept(r) appends here
+        nx[0] = 0; nx[1] = 0;
+    }
+    for (int o = 16; o; o >>= 1) {
+        ev += __shfl_xor_sync(0xffffffffu, ev, o);
+        nbig += __shfl_xor_sync(0xffffffffu, nbig, o);
+        nsmall += __shfl_xor_sync(0xffffffffu, nsmall, o);
+    }
+    if (lane == 0) { s_evals[wid] = ev; s_w[0][wid] = nbig; s_w[1][wid] = nsmall; }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long e = 0; int b = 0, s = 0;
+        for (int w = 0; w < NW; w++) { e += s_evals[w]; b += s_w[0][w]; s += s_w[1][w]; }
+        // tile shape: large tiles while they still cover the machine ~4x over, else small ones
+        const unsigned long long slots = (unsigned long long)c.num_sms * c.ctas_per_sm;
+        const unsigned long long large_tile = (unsigned long long)ROUND_THREADS * RQ_LARGE * STAGE_LARGE;
+        int rq, stage;
+        if (e >= 4ull * c.num_sms * large_tile) { rq = RQ_LARGE; stage = STAGE_LARGE; }
+        else { rq = RQ_SMALL; stage = STAGE_SMALL; }
+        const int tile_rows = ROUND_THREADS * rq;
+        unsigned long long per_tile = e / (2ull * slots);
+        const unsigned long long min_tile = (unsigned long long)tile_rows * stage;
+        if (per_tile < min_tile) per_tile = min_tile;
+        unsigned long long cpt = (per_tile + tile_rows - 1) / tile_rows;
+        cpt = ((cpt + stage - 1) / stage) * stage;
+        if (cpt > (unsigned long long)MAX_N) cpt = MAX_N;
+        s_cpt = (int)cpt; s_tile_rows = tile_rows;
+        PlanInfo *pl = c.plan;
+        pl->cols_per_tile = (int)cpt; pl->rq = rq;
+        pl->n_big = b; pl->n_small = s; pl->round = r;
+        pl->ticket = 0u;
+        pl->evals += e;
+        if (b == 0 && pl->done_round < 0) pl->done_round = r;
+    }
+    __syncthreads();
+    const int cpt = s_cpt, tile_rows = s_tile_rows;
+    // exclusive scan over pairs: each thread owns a contiguous slice
+    const int per = (c.n_pairs + nt - 1) / nt;
+    const int p0 = min(tid * per, c.n_pairs), p1 = min(p0 + per, c.n_pairs);
+    int tsum = 0, asum = 0;
+    for (int p = p0; p < p1; p++) {
+        if (c.status[p] == PAIR_BIG) {
+            const int32_t *cp = cnt_ptr(c, buf, p);
+            const int nlr = __ldcg(cp), nlc = __ldcg(cp + 1);
+            tsum += tiles_of(nlr, nlc, tile_rows, cpt);
+            asum += ablocks_of(nlr, nlc);
+        }
+    }
+    int tinc = tsum, ainc = asum;                    // warp inclusive scans
+    for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, tinc, o), b = __shfl_up_sync(0xffffffffu, ainc, o);
+        if (lane >= o) { tinc += a; ainc += b; }
+    }
+    if (lane == 31) { s_w[2][wid] = tinc; s_w[3][wid] = ainc; }
+    __syncthreads();
+    int toff = 0, aoff = 0, ttot = 0, atot = 0;
+    for (int w = 0; w < NW; w++) {
+        if (w < wid) { toff += s_w[2][w]; aoff += s_w[3][w]; }
+        ttot += s_w[2][w]; atot += s_w[3][w];
+    }
+    int tb = toff + tinc - tsum, ab = aoff + ainc - asum;
+    for (int p = p0; p < p1; p++) {
+        c.tile_base[p] = tb; c.ablock_base[p] = ab;
+        if (c.status[p] == PAIR_BIG) {
+            const int32_t *cp = cnt_ptr(c, buf, p);
+            const int nlr = __ldcg(cp), nlc = __ldcg(cp + 1);
+            tb += tiles_of(nlr, nlc, tile_rows, cpt);
+            ab += ablocks_of(nlr, nlc);
+        }
+    }
+    if (tid == 0) {
+        c.plan->total_tiles = ttot; c.plan->total_ablocks = atot;
+        c.tile_base[c.n_pairs] = ttot; c.ablock_base[c.n_pairs] = atot;
+    }
+}
+
+// Runs `plan_device(c, r)` in the last block of the calling grid to finish.
+__device__ __forceinline__ void plan_in_last_block(const Chunk &c, int r, unsigned total_blocks) {
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&c.plan->ticket, 1u) == total_blocks - 1);
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        plan_device(c, r);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// init: live lists = identity, keys = none, counts[0] = (n1, n2); the last
+// block plans round 0.  The host resets PlanInfo before the launch.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(ACCEPT_THREADS) init_kernel(Chunk c) {
     const int p = blockIdx.y;
     const PairDesc pd = c.pairs[p];
     const int n = max(pd.n1, pd.n2);
@@ -123,99 +266,10 @@ __global__ void init_kernel(Chunk c) {
         c0[0] = pd.n1; c0[1] = pd.n2;
         int32_t *c1 = cnt_ptr(c, 1, p), *c2 = cnt_ptr(c, 2, p);
         c1[0] = c1[1] = 0; c2[0] = c2[1] = 0;
-        if (p == 0) { c.plan->evals = 0ull; c.plan->accept_ticket = 0u; c.plan->done_round = -1; }
+        c.status[p] = PAIR_BIG;                      // classified by plan(0)
     }
+    plan_in_last_block(c, 0, gridDim.x * gridDim.y);
 }
-
-// ---------------------------------------------------------------------------
-// planner: one CTA.  Classifies every pair from counts[r % 3], sizes the
-// tiles so the round kernel gets ~target_tiles work items, and writes the
-// per-pair exclusive prefixes the round/accept kernels search.
-// ---------------------------------------------------------------------------
-__device__ void plan_device(const Chunk &c, int r) {
-    __shared__ unsigned long long s_evals[32];
-    __shared__ int s_cnt[2][32];
-    __shared__ int s_scan[2][ACCEPT_THREADS];
-    __shared__ int s_cpt;
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
-    const int buf = r % 3;
-
-    unsigned long long ev = 0; int nbig = 0, nsmall = 0;
-    for (int p = tid; p < c.n_pairs; p += nt) {
-        const int32_t *cp = cnt_ptr(c, buf, p);
-        const int nlr = __ldcg(cp), nlc = __ldcg(cp + 1);
-        uint8_t st = PAIR_DONE;
-        if (nlr > 0 && nlc > 0) {
-            const bool small = nlr <= FIN_MAX_DIM && nlc <= FIN_MAX_DIM && nlr * nlc <= FIN_MAX_EVALS;
-            st = small ? PAIR_SMALL : PAIR_BIG;
-            if (small) nsmall++; else { nbig++; ev += (unsigned long long)nlr * (unsigned long long)nlc; }
-        }
-        c.status[p] = st;
-        int32_t *nx = cnt_ptr(c, (r + 1) % 3, p);   // accept(r) appends here
-        nx[0] = 0; nx[1] = 0;
-    }
-    for (int o = 16; o; o >>= 1) {
-        ev += __shfl_xor_sync(0xffffffffu, ev, o);
-        nbig += __shfl_xor_sync(0xffffffffu, nbig, o);
-        nsmall += __shfl_xor_sync(0xffffffffu, nsmall, o);
-    }
-    if (lane == 0) { s_evals[wid] = ev; s_cnt[0][wid] = nbig; s_cnt[1][wid] = nsmall; }
-    __syncthreads();
-    if (tid == 0) {
-        unsigned long long e = 0; int b = 0, s = 0;
-        for (int w = 0; w < (nt + 31) / 32; w++) { e += s_evals[w]; b += s_cnt[0][w]; s += s_cnt[1][w]; }
-        unsigned long long per_tile = e / (unsigned long long)max(c.target_tiles, 1);
-        if (per_tile < (unsigned long long)c.min_tile_evals) per_tile = c.min_tile_evals;
-        unsigned long long cpt = (per_tile + c.tile_rows - 1) / c.tile_rows;
-        cpt = ((cpt + STAGE_COLS - 1) / STAGE_COLS) * STAGE_COLS;
-        if (cpt < STAGE_COLS) cpt = STAGE_COLS;
-        if (cpt > (unsigned long long)MAX_N) cpt = MAX_N;
-        s_cpt = (int)cpt;
-        c.plan->cols_per_tile = (int)cpt;
-        c.plan->n_big = b; c.plan->n_small = s; c.plan->round = r;
-        c.plan->accept_ticket = 0u;
-        c.plan->evals += e;
-        if (b == 0 && c.plan->done_round < 0) c.plan->done_round = r;
-    }
-    __syncthreads();
-    const int cpt = s_cpt;
-    // exclusive scan over pairs: each thread owns a contiguous slice
-    const int per = (c.n_pairs + nt - 1) / nt;
-    const int p0 = min(tid * per, c.n_pairs), p1 = min(p0 + per, c.n_pairs);
-    int tsum = 0, asum = 0;
-    for (int p = p0; p < p1; p++) {
-        if (c.status[p] == PAIR_BIG) {
-            const int32_t *cp = cnt_ptr(c, buf, p);
-            const int nlr = __ldcg(cp), nlc = __ldcg(cp + 1);
-            tsum += ((nlr + c.tile_rows - 1) / c.tile_rows) * ((nlc + cpt - 1) / cpt);
-            asum += (nlr + ACCEPT_THREADS - 1) / ACCEPT_THREADS + (nlc + ACCEPT_THREADS - 1) / ACCEPT_THREADS;
-        }
-    }
-    s_scan[0][tid] = tsum; s_scan[1][tid] = asum;
-    __syncthreads();
-    if (tid == 0) {
-        int a = 0, b = 0;
-        for (int k = 0; k < nt; k++) {
-            int x = s_scan[0][k], y = s_scan[1][k];
-            s_scan[0][k] = a; s_scan[1][k] = b; a += x; b += y;
-        }
-        c.plan->total_tiles = a; c.plan->total_ablocks = b;
-        c.tile_base[c.n_pairs] = a; c.ablock_base[c.n_pairs] = b;
-    }
-    __syncthreads();
-    int tb = s_scan[0][tid], ab = s_scan[1][tid];
-    for (int p = p0; p < p1; p++) {
-        c.tile_base[p] = tb; c.ablock_base[p] = ab;
-        if (c.status[p] == PAIR_BIG) {
-            const int32_t *cp = cnt_ptr(c, buf, p);
-            const int nlr = __ldcg(cp), nlc = __ldcg(cp + 1);
-            tb += ((nlr + c.tile_rows - 1) / c.tile_rows) * ((nlc + cpt - 1) / cpt);
-            ab += (nlr + ACCEPT_THREADS - 1) / ACCEPT_THREADS + (nlc + ACCEPT_THREADS - 1) / ACCEPT_THREADS;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(ACCEPT_THREADS) plan_kernel(Chunk c, int r) { plan_device(c, r); }
 
 // ---------------------------------------------------------------------------
 // distance of one query (registers) against one train descriptor (registers)
@@ -231,23 +285,18 @@ __device__ __forceinline__ uint32_t hamming_words(const uint32_t (&q)[WORDS], co
 // ---------------------------------------------------------------------------
 // round kernel: live rows x live columns of every PAIR_BIG pair.
 // One thread owns RQ query descriptors in registers; the CTA streams train
-// descriptors through shared memory in stages of STAGE_COLS (128-bit loads,
+// descriptors through shared memory in stages of STAGE (128-bit loads,
 // 128-bit broadcast LDS).  Row argmin stays in registers for the whole tile;
 // the column argmin is a warp REDUX.MIN of the packed keys followed by one
 // shared-memory atomicMin per (warp, column).
 // ---------------------------------------------------------------------------
-template <int WORDS, int RQ>
-__global__ void __launch_bounds__(ROUND_THREADS) hamming_round_kernel(Chunk c, int r) {
+template <int WORDS, int RQ, int STAGE>
+__device__ __forceinline__ void round_tiles(const Chunk &c, int r, int total, int cpt,
+                                            uint4 *s_t, uint32_t *s_jkey, uint32_t *s_col) {
     constexpr int V4 = WORDS / 4;
-    __shared__ uint4 s_t[STAGE_COLS * V4];
-    __shared__ uint32_t s_jkey[STAGE_COLS];
-    __shared__ uint32_t s_col[STAGE_COLS];
-
-    const int tid = threadIdx.x, lane = tid & 31;
+    constexpr int tile_rows = ROUND_THREADS * RQ;
+    const int tid = threadIdx.x;
     const int cur = r & 1, buf = r % 3;
-    const int total = __ldcg(&c.plan->total_tiles);
-    const int cpt = __ldcg(&c.plan->cols_per_tile);
-    const int tile_rows = ROUND_THREADS * RQ;
 
     for (int g = blockIdx.x; g < total; g += gridDim.x) {
         const int p = find_pair(c.tile_base, c.n_pairs, g);
@@ -282,9 +331,9 @@ __global__ void __launch_bounds__(ROUND_THREADS) hamming_round_kernel(Chunk c, i
         }
 
         const int c0 = ct * cpt, c1 = min(nlc, c0 + cpt);
-        for (int s0 = c0; s0 < c1; s0 += STAGE_COLS) {
+        for (int s0 = c0; s0 < c1; s0 += STAGE) {
             __syncthreads();                       // previous stage fully consumed
-            for (int k = tid; k < STAGE_COLS * V4; k += ROUND_THREADS) {
+            for (int k = tid; k < STAGE * V4; k += ROUND_THREADS) {
                 const int col = k / V4, part = k - col * V4, y = s0 + col;
                 uint4 x = make_uint4(0u, 0u, 0u, 0u);
                 uint32_t jk = KEY_INVALID;
@@ -296,10 +345,10 @@ __global__ void __launch_bounds__(ROUND_THREADS) hamming_round_kernel(Chunk c, i
                 s_t[k] = x;
                 if (part == 0) s_jkey[col] = jk;
             }
-            if (tid < STAGE_COLS) s_col[tid] = KEY_NONE;
+            if (tid < STAGE) s_col[tid] = KEY_NONE;
             __syncthreads();
 
-            const int ncs = min(STAGE_COLS, (c1 - s0 + 7) & ~7);
+            const int ncs = min(STAGE, (c1 - s0 + 7) & ~7);
             for (int jj0 = 0; jj0 < ncs; jj0 += 8) {
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
@@ -324,7 +373,7 @@ __global__ void __launch_bounds__(ROUND_THREADS) hamming_round_kernel(Chunk c, i
                 }
             }
             __syncthreads();
-            if (tid < STAGE_COLS) {
+            if (tid < STAGE) {
                 const uint32_t jk = s_jkey[tid], v = s_col[tid];
                 if (jk != KEY_INVALID && v < KEY_INVALID)
                     atomicMin(c.colbest[cur] + pd.col_base + jk, v);
@@ -337,6 +386,19 @@ __global__ void __launch_bounds__(ROUND_THREADS) hamming_round_kernel(Chunk c, i
     }
 }
 
+template <int WORDS>
+__global__ void __launch_bounds__(ROUND_THREADS) hamming_round_kernel(Chunk c, int r) {
+    __shared__ uint4 s_t[STAGE_LARGE * (WORDS / 4)];
+    __shared__ uint32_t s_jkey[STAGE_LARGE];
+    __shared__ uint32_t s_col[STAGE_LARGE];
+    const int total = __ldcg(&c.plan->total_tiles);
+    if ((int)blockIdx.x >= total) return;
+    const int cpt = __ldcg(&c.plan->cols_per_tile);
+    const int rq = __ldcg(&c.plan->rq);
+    if (rq == RQ_LARGE) round_tiles<WORDS, RQ_LARGE, STAGE_LARGE>(c, r, total, cpt, s_t, s_jkey, s_col);
+    else round_tiles<WORDS, RQ_SMALL, STAGE_SMALL>(c, r, total, cpt, s_t, s_jkey, s_col);
+}
+
 // ---------------------------------------------------------------------------
 // accept kernel: a row and a column that chose each other are the minimum of
 // every edge touching either of them, i.e. the pair the reference's next
@@ -345,7 +407,6 @@ __global__ void __launch_bounds__(ROUND_THREADS) hamming_round_kernel(Chunk c, i
 // are reset.  The last block to finish plans round r+1.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(ACCEPT_THREADS) accept_kernel(Chunk c, int r) {
-    __shared__ bool s_last;
     const int tid = threadIdx.x, lane = tid & 31;
     const int cur = r & 1, nxt = cur ^ 1, buf = r % 3, nbuf = (r + 1) % 3;
     const int total = __ldcg(&c.plan->total_ablocks);
@@ -391,33 +452,27 @@ __global__ void __launch_bounds__(ACCEPT_THREADS) accept_kernel(Chunk c, int r) 
             }
         }
     }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(&c.plan->accept_ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        plan_device(c, r + 1);
-    }
+    plan_in_last_block(c, r + 1, gridDim.x);
 }
 
 // ---------------------------------------------------------------------------
 // finisher: one CTA per PAIR_SMALL pair runs every remaining round out of a
 // u16 distance matrix in shared memory.  Live lists arrive in arbitrary order
 // (atomic append), so they are rank-sorted first: local positions then order
-// like the original indices and keys can carry positions.
+// like the original indices and keys can carry positions.  After the first
+// round a row (column) is rescanned only if the column (row) it had chosen
+// was matched to someone else -- otherwise its argmin is still valid.
 // ---------------------------------------------------------------------------
 template <int WORDS>
-__global__ void __launch_bounds__(FIN_THREADS) finisher_kernel(Chunk c, int r) {
+__global__ void __launch_bounds__(FIN_THREADS) finisher_kernel(Chunk c) {
     extern __shared__ __align__(16) unsigned char fin_smem[];
     const int p = blockIdx.x;
     if (c.status[p] != PAIR_SMALL) return;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int cur = r & 1, buf = r % 3;
+    const int tid = threadIdx.x, nt = FIN_THREADS;
     const PairDesc pd = c.pairs[p];
-    int32_t *cp = cnt_ptr(c, buf, p);
-    const int nr = cp[0], nc = cp[1];
-    int S = (nc + 1) & ~1;            // row pitch in u16; S/2 odd -> row scans hit 32 banks
+    const SmallInfo si = c.small[p];
+    const int nr = si.nlr, nc = si.nlc, cur = si.parity;
+    int S = (nc + 1) & ~1;            // row pitch in u16; S/2 odd -> row scans hit 32 distinct banks
     if (((S >> 1) & 1) == 0) S += 2;
 
     int32_t *rowid = reinterpret_cast<int32_t *>(fin_smem);
@@ -439,9 +494,10 @@ __global__ void __launch_bounds__(FIN_THREADS) finisher_kernel(Chunk c, int r) {
         const int32_t *src = is_row ? tmp : tmp + FIN_MAX_DIM;
         const int n = is_row ? nr : nc, me = src[is_row ? k : k - nr];
         int rank = 0;
+#pragma unroll 8
         for (int m = 0; m < n; m++) rank += (src[m] < me);
-        if (is_row) { rowid[rank] = me; rkoff[rank] = (uint32_t)rank; }
-        else { colid[rank] = me; ckoff[rank] = (uint32_t)rank; }
+        if (is_row) { rowid[rank] = me; rkoff[rank] = (uint32_t)rank; rbest[rank] = KEY_NONE; }
+        else { colid[rank] = me; ckoff[rank] = (uint32_t)rank; cbest[rank] = KEY_NONE; }
     }
     __syncthreads();
 
@@ -457,6 +513,7 @@ __global__ void __launch_bounds__(FIN_THREADS) finisher_kernel(Chunk c, int r) {
             const uint4 a = __ldg(qs + v);
             q[4 * v] = a.x; q[4 * v + 1] = a.y; q[4 * v + 2] = a.z; q[4 * v + 3] = a.w;
         }
+#pragma unroll 2
         for (int y = gy; y < nc; y += cg) {
             uint32_t t[WORDS];
             const uint4 *ts = reinterpret_cast<const uint4 *>(pd.t + (size_t)colid[y] * WORDS);
@@ -473,19 +530,37 @@ __global__ void __launch_bounds__(FIN_THREADS) finisher_kernel(Chunk c, int r) {
     int live_r = nr, live_c = nc;
     while (live_r > 0 && live_c > 0) {
         for (int k = tid; k < nr + nc; k += nt) {
-            uint32_t best = KEY_NONE;
             if (k < nr) {
-                if (rkoff[k] != KEY_INVALID) {
-                    const uint16_t *row = D + k * S;
-                    for (int y = 0; y < nc; y++) best = min(best, ((uint32_t)row[y] << KEY_IDX_BITS) + ckoff[y]);
+                if (rkoff[k] == KEY_INVALID) continue;
+                const uint32_t old = rbest[k];
+                if (old != KEY_NONE && ckoff[old & KEY_IDX_MASK] != KEY_INVALID) continue;   // choice still alive
+                const uint16_t *row = D + k * S;
+                uint32_t b0 = KEY_NONE, b1 = KEY_NONE, b2 = KEY_NONE, b3 = KEY_NONE;
+                int y = 0;
+                for (; y + 4 <= nc; y += 4) {
+                    b0 = min(b0, ((uint32_t)row[y] << KEY_IDX_BITS) + ckoff[y]);
+                    b1 = min(b1, ((uint32_t)row[y + 1] << KEY_IDX_BITS) + ckoff[y + 1]);
+                    b2 = min(b2, ((uint32_t)row[y + 2] << KEY_IDX_BITS) + ckoff[y + 2]);
+                    b3 = min(b3, ((uint32_t)row[y + 3] << KEY_IDX_BITS) + ckoff[y + 3]);
                 }
-                rbest[k] = best;
+                for (; y < nc; y++) b0 = min(b0, ((uint32_t)row[y] << KEY_IDX_BITS) + ckoff[y]);
+                rbest[k] = min(min(b0, b1), min(b2, b3));
             } else {
                 const int y = k - nr;
-                if (ckoff[y] != KEY_INVALID) {
-                    for (int x = 0; x < nr; x++) best = min(best, ((uint32_t)D[x * S + y] << KEY_IDX_BITS) + rkoff[x]);
+                if (ckoff[y] == KEY_INVALID) continue;
+                const uint32_t old = cbest[y];
+                if (old != KEY_NONE && rkoff[old & KEY_IDX_MASK] != KEY_INVALID) continue;
+                const uint16_t *col = D + y;
+                uint32_t b0 = KEY_NONE, b1 = KEY_NONE, b2 = KEY_NONE, b3 = KEY_NONE;
+                int x = 0;
+                for (; x + 4 <= nr; x += 4) {
+                    b0 = min(b0, ((uint32_t)col[x * S] << KEY_IDX_BITS) + rkoff[x]);
+                    b1 = min(b1, ((uint32_t)col[(x + 1) * S] << KEY_IDX_BITS) + rkoff[x + 1]);
+                    b2 = min(b2, ((uint32_t)col[(x + 2) * S] << KEY_IDX_BITS) + rkoff[x + 2]);
+                    b3 = min(b3, ((uint32_t)col[(x + 3) * S] << KEY_IDX_BITS) + rkoff[x + 3]);
                 }
-                cbest[y] = best;
+                for (; x < nr; x++) b0 = min(b0, ((uint32_t)col[x * S] << KEY_IDX_BITS) + rkoff[x]);
+                cbest[y] = min(min(b0, b1), min(b2, b3));
             }
         }
         __syncthreads();
@@ -496,15 +571,18 @@ __global__ void __launch_bounds__(FIN_THREADS) finisher_kernel(Chunk c, int r) {
             const uint32_t y = rk & KEY_IDX_MASK;
             if ((cbest[y] & KEY_IDX_MASK) == (uint32_t)tid) {
                 c.match_key[pd.row_base + rowid[tid]] = (rk & ~KEY_IDX_MASK) | (uint32_t)colid[y];
-                rkoff[tid] = KEY_INVALID;    // nobody else touches rkoff[tid] / ckoff[y] in this phase:
-                ckoff[y] = KEY_INVALID;      // column y is claimed by exactly one accepted row
                 accepted = 1;
             }
         }
-        const int n_acc = __syncthreads_count(accepted);
+        const int n_acc = __syncthreads_count(accepted);   // everyone has read rkoff/ckoff/cbest
+        if (accepted) {
+            ckoff[rbest[tid] & KEY_IDX_MASK] = KEY_INVALID;  // column claimed by exactly this row
+            rkoff[tid] = KEY_INVALID;
+        }
         live_r -= n_acc; live_c -= n_acc;
+        __syncthreads();
     }
-    if (tid == 0) { cp[0] = 0; cp[1] = 0; c.status[p] = PAIR_DONE; }
+    if (tid == 0) c.status[p] = PAIR_DONE;
 }
 
 inline size_t finisher_smem_bytes() {
@@ -516,47 +594,61 @@ inline size_t finisher_smem_bytes() {
 // order kernel: one CTA per pair.  Stable counting sort of the matched rows by
 // distance (rows are visited in ascending i, and a row has one j), which is
 // the (distance, i, j) order the reference emits; then the degenerate tail.
+// Keys of the first ORDER_KEY_CACHE rows are cached in shared memory so the
+// ranking pass does not wait on global loads.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(ORDER_THREADS) order_kernel(Chunk c, int nbins, uint32_t flags,
                                                              int32_t *out_qi, int32_t *out_tj, int32_t *out_dist) {
-    extern __shared__ int32_t s_hist[];          // [ORDER_WARPS][nbins + 1]
-    __shared__ int32_t s_tot[1024 + 8];
+    extern __shared__ int32_t s_order[];         // [ORDER_WARPS][nbins + 1] hist | key cache
+    __shared__ int32_t s_wsum[ORDER_WARPS];
     const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const PairDesc pd = c.pairs[p];
     const int hb = nbins + 1;                    // last bin: unmatched rows (never written out)
+    int32_t *s_hist = s_order;
+    uint32_t *s_keys = reinterpret_cast<uint32_t *>(s_order + ORDER_WARPS * hb);
+    const uint32_t *mk = c.match_key + pd.row_base;
     for (int k = tid; k < ORDER_WARPS * hb; k += ORDER_THREADS) s_hist[k] = 0;
-    __syncthreads();
     int seg = (pd.n1 + ORDER_WARPS - 1) / ORDER_WARPS;
     seg = (seg + 31) & ~31;
     const int x0 = min(pd.n1, wid * seg), x1 = min(pd.n1, x0 + seg);
-    for (int x = x0 + lane; x < x1; x += 32) {
-        const uint32_t key = c.match_key[pd.row_base + x];
-        if (key != KEY_NONE) atomicAdd(&s_hist[wid * hb + (key >> KEY_IDX_BITS)], 1);
+    __syncthreads();
+    for (int xb = x0; xb < x1; xb += 128) {      // 4 independent loads in flight per lane
+        uint32_t k4[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int x = xb + 32 * u + lane;
+            k4[u] = x < x1 ? __ldcg(mk + x) : KEY_NONE;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int x = xb + 32 * u + lane;
+            if (x < x1) {
+                if (x < ORDER_KEY_CACHE) s_keys[x] = k4[u];
+                if (k4[u] != KEY_NONE) atomicAdd(&s_hist[wid * hb + (k4[u] >> KEY_IDX_BITS)], 1);
+            }
+        }
     }
     __syncthreads();
-    // per-distance totals -> exclusive scan over distances
-    for (int d = tid; d < nbins; d += ORDER_THREADS) {
-        int t = 0;
-        for (int w = 0; w < ORDER_WARPS; w++) t += s_hist[w * hb + d];
-        s_tot[d] = t;
-    }
+    // thread t owns bins 2t and 2t+1 (nbins <= 513 < 2 * ORDER_THREADS): totals over the
+    // warps' histograms, block-wide exclusive scan over distances, then per-warp bases
+    const int b0 = 2 * tid, b1 = 2 * tid + 1;
+    int ta = 0, tb = 0;
+    if (b0 < nbins) for (int w = 0; w < ORDER_WARPS; w++) ta += s_hist[w * hb + b0];
+    if (b1 < nbins) for (int w = 0; w < ORDER_WARPS; w++) tb += s_hist[w * hb + b1];
+    int inc = ta + tb;
+    for (int o = 1; o < 32; o <<= 1) { const int a = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += a; }
+    if (lane == 31) s_wsum[wid] = inc;
     __syncthreads();
-    if (tid == 0) {
-        int a = 0;
-        for (int d = 0; d < nbins; d++) { int t = s_tot[d]; s_tot[d] = a; a += t; }
-        s_tot[nbins] = a;
-    }
+    int woff = 0;
+    for (int w = 0; w < wid; w++) woff += s_wsum[w];
+    int a = woff + inc - (ta + tb);
+    if (b0 < nbins) for (int w = 0; w < ORDER_WARPS; w++) { const int t = s_hist[w * hb + b0]; s_hist[w * hb + b0] = a; a += t; }
+    if (b1 < nbins) for (int w = 0; w < ORDER_WARPS; w++) { const int t = s_hist[w * hb + b1]; s_hist[w * hb + b1] = a; a += t; }
     __syncthreads();
-    for (int d = tid; d < nbins; d += ORDER_THREADS) {
-        int a = s_tot[d];
-        for (int w = 0; w < ORDER_WARPS; w++) { int t = s_hist[w * hb + d]; s_hist[w * hb + d] = a; a += t; }
-    }
-    __syncthreads();
-    const int matched = s_tot[nbins];
     for (int xb = x0; xb < x1; xb += 32) {
         const int x = xb + lane;
         uint32_t key = KEY_NONE;
-        if (x < x1) key = c.match_key[pd.row_base + x];
+        if (x < x1) key = x < ORDER_KEY_CACHE ? s_keys[x] : __ldcg(mk + x);
         const int d = key != KEY_NONE ? (int)(key >> KEY_IDX_BITS) : nbins;
         const unsigned peers = __match_any_sync(0xffffffffu, d);
         const int rank = __popc(peers & ((1u << lane) - 1u));
@@ -569,12 +661,17 @@ __global__ void __launch_bounds__(ORDER_THREADS) order_kernel(Chunk c, int nbins
             out_qi[o] = x; out_tj[o] = (int32_t)(key & KEY_IDX_MASK); out_dist[o] = d;
         }
     }
-    if (flags & 1u) {                            // PGM_FLAG_REFERENCE_COMPAT_TAIL
+    if (flags & 1u) {                            // PGM_FLAG_REFERENCE_COMPAT_TAIL (KeypointMatching.cs:38-42)
+        const int matched = min(pd.n1, pd.n2);   // every pair ends with exactly min(n1,n2) real matches
         for (int k = matched + tid; k < pd.n1; k += ORDER_THREADS) {
             const int64_t o = pd.out_base + k;
             out_qi[o] = 0; out_tj[o] = 0; out_dist[o] = 2147483647;
         }
     }
+}
+
+inline size_t order_smem_bytes(int nbins) {
+    return sizeof(int32_t) * ((size_t)ORDER_WARPS * (nbins + 1) + ORDER_KEY_CACHE);
 }
 
 // ---------------------------------------------------------------------------
@@ -698,7 +795,7 @@ __global__ void lop3_peak_kernel(uint32_t *out, int iters, uint32_t seed) {
 #pragma unroll
         for (int u = 0; u < 4; u++) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) acc[k] = (acc[k] & a[k]) ^ a[(k + 1) & 7];   // one LOP3 each
+            for (int k = 0; k < 8; k++) acc[k] = (acc[k] & a[(k + u) & 7]) ^ acc[(k + 1 + u) & 7];   // one LOP3 each
         }
     }
     uint32_t s = 0;

@@ -44,11 +44,17 @@ struct pgm_handle {
     HostBuf pin_out;  // pinned staging, device -> host
     HostBuf pin_meta; // pinned PairDesc array + PlanInfo readback
     pgm_stats stats{};
-    int rounds_hint = 6;      // grid rounds to enqueue before the first completion check
-    int round_grid = 0;       // persistent grid of the round kernel
-    int accept_grid = 0;
+    int rounds_hint = 4;      // grid rounds to enqueue before the first completion check
+    int ctas_per_sm[5] = {0, 0, 0, 0, 0};   // round-kernel occupancy per descriptor width (words / 4)
+    bool order_attr_set = false;
     bool fin_attr_set[5] = {false, false, false, false, false};
+    // profiling mode (pgm_set_profiling): events around every round-kernel launch
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;   // 2 per round
+    HostBuf pin_prof;                       // PlanInfo snapshot per round
+    int prof_rounds = 0;
 };
+constexpr int PROF_MAX_ROUNDS = 256;
 
 #define CU_CHECK(h, call)                                                                      \
     do {                                                                                       \
@@ -145,8 +151,9 @@ extern "C" int pgm_destroy(pgm_handle *h) {
     cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->state, &h->desc, &h->out, &h->misc})
         if (b->p) cudaFree(b->p);
-    for (HostBuf *b : {&h->pin_in, &h->pin_out, &h->pin_meta})
+    for (HostBuf *b : {&h->pin_in, &h->pin_out, &h->pin_meta, &h->pin_prof})
         if (b->p) cudaFreeHost(b->p);
+    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return PGM_OK;
@@ -179,11 +186,11 @@ extern "C" int pgm_get_stats(pgm_handle *h, pgm_stats *out) {
 // ---------------------------------------------------------------------------
 // kernel dispatch on descriptor width
 // ---------------------------------------------------------------------------
-constexpr int RQ_DEFAULT = 4;
+constexpr int RQ_DEFAULT = RQ_LARGE;
 
 template <int WORDS>
 static void launch_round(const Chunk &c, int r, int grid, cudaStream_t s) {
-    hamming_round_kernel<WORDS, RQ_DEFAULT><<<grid, ROUND_THREADS, 0, s>>>(c, r);
+    hamming_round_kernel<WORDS><<<grid, ROUND_THREADS, 0, s>>>(c, r);
 }
 static void dispatch_round(int words, const Chunk &c, int r, int grid, cudaStream_t s) {
     switch (words) {
@@ -194,28 +201,28 @@ static void dispatch_round(int words, const Chunk &c, int r, int grid, cudaStrea
     }
 }
 template <int WORDS>
-static cudaError_t launch_fin(pgm_handle *h, const Chunk &c, int r, cudaStream_t s) {
+static cudaError_t launch_fin(pgm_handle *h, const Chunk &c, cudaStream_t s) {
     const size_t smem = finisher_smem_bytes();
     if (!h->fin_attr_set[WORDS / 4]) {
         cudaError_t e = cudaFuncSetAttribute(finisher_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         h->fin_attr_set[WORDS / 4] = true;
     }
-    finisher_kernel<WORDS><<<c.n_pairs, FIN_THREADS, smem, s>>>(c, r);
+    finisher_kernel<WORDS><<<c.n_pairs, FIN_THREADS, smem, s>>>(c);
     return cudaSuccess;
 }
-static cudaError_t dispatch_fin(pgm_handle *h, int words, const Chunk &c, int r, cudaStream_t s) {
+static cudaError_t dispatch_fin(pgm_handle *h, int words, const Chunk &c, cudaStream_t s) {
     switch (words) {
-        case 4: return launch_fin<4>(h, c, r, s);
-        case 8: return launch_fin<8>(h, c, r, s);
-        case 12: return launch_fin<12>(h, c, r, s);
-        default: return launch_fin<16>(h, c, r, s);
+        case 4: return launch_fin<4>(h, c, s);
+        case 8: return launch_fin<8>(h, c, s);
+        case 12: return launch_fin<12>(h, c, s);
+        default: return launch_fin<16>(h, c, s);
     }
 }
 template <int WORDS>
 static int round_occupancy() {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hamming_round_kernel<WORDS, RQ_DEFAULT>, ROUND_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hamming_round_kernel<WORDS>, ROUND_THREADS, 0);
     return nb;
 }
 static int dispatch_occupancy(int words) {
@@ -286,26 +293,23 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
     const size_t o_mk = take(4 * rows);
     const size_t o_tb = take(4 * (n_pairs + 1)), o_ab = take(4 * (n_pairs + 1));
     const size_t o_st = take(n_pairs);
+    const size_t o_small = take(sizeof(SmallInfo) * n_pairs);
     const size_t o_plan = take(sizeof(PlanInfo));
     int rc = ensure_dev(h, h->state, off);
     if (rc) return rc;
-    rc = ensure_host(h, h->pin_meta, sizeof(PairDesc) * n_pairs + 256);
+    rc = ensure_host(h, h->pin_meta, sizeof(PairDesc) * n_pairs + 512);
     if (rc) return rc;
     char *base = (char *)h->state.p;
 
-    if (h->round_grid == 0) {
-        int occ = dispatch_occupancy(8);
-        if (occ < 1) occ = 1;
-        h->round_grid = h->num_sms * occ;
-        h->accept_grid = h->num_sms * 4;
-    }
+    if (h->ctas_per_sm[words / 4] == 0) h->ctas_per_sm[words / 4] = std::max(1, dispatch_occupancy(words));
+    const int ctas_per_sm = h->ctas_per_sm[words / 4];
+    const int round_grid = h->num_sms * ctas_per_sm;
 
     Chunk c{};
     c.pairs = (PairDesc *)(base + o_pairs);
     c.n_pairs = n_pairs;
-    c.tile_rows = ROUND_THREADS * RQ_DEFAULT;
-    c.target_tiles = h->round_grid * 2;
-    c.min_tile_evals = c.tile_rows * STAGE_COLS;
+    c.num_sms = h->num_sms;
+    c.ctas_per_sm = ctas_per_sm;
     c.rowbest[0] = (uint32_t *)(base + o_rb0); c.rowbest[1] = (uint32_t *)(base + o_rb1);
     c.colbest[0] = (uint32_t *)(base + o_cb0); c.colbest[1] = (uint32_t *)(base + o_cb1);
     c.live_rows[0] = (int32_t *)(base + o_lr0); c.live_rows[1] = (int32_t *)(base + o_lr1);
@@ -315,39 +319,58 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
     c.tile_base = (int32_t *)(base + o_tb);
     c.ablock_base = (int32_t *)(base + o_ab);
     c.status = (uint8_t *)(base + o_st);
+    c.small = (SmallInfo *)(base + o_small);
     c.plan = (PlanInfo *)(base + o_plan);
 
     PairDesc *hp = (PairDesc *)h->pin_meta.p;
-    PlanInfo *h_plan = (PlanInfo *)((char *)h->pin_meta.p + align_up(sizeof(PairDesc) * n_pairs, 64));
-    // (pin_meta was sized with 256 spare bytes for the PlanInfo readback)
-    int64_t rb = 0, cb = 0;
+    char *meta_tail = (char *)h->pin_meta.p + align_up(sizeof(PairDesc) * n_pairs, 64);
+    PlanInfo *h_plan = (PlanInfo *)meta_tail;             // readback slot
+    PlanInfo *h_plan0 = (PlanInfo *)(meta_tail + 128);    // initial value uploaded before init
+    int64_t rb = 0, cb = 0, ablocks = 0;
     for (int p = 0; p < n_pairs; p++) {
         hp[p].q = (const uint32_t *)pairs[p].d_q;
         hp[p].t = (const uint32_t *)pairs[p].d_t;
         hp[p].n1 = pairs[p].n1; hp[p].n2 = pairs[p].n2;
         hp[p].row_base = rb; hp[p].col_base = cb; hp[p].out_base = pairs[p].out_base;
         rb += pairs[p].n1; cb += pairs[p].n2;
+        ablocks += (pairs[p].n1 + ACCEPT_THREADS - 1) / ACCEPT_THREADS + (pairs[p].n2 + ACCEPT_THREADS - 1) / ACCEPT_THREADS;
         h->stats.distance_evals += (int64_t)pairs[p].n1 * pairs[p].n2;
         h->stats.matched += std::min(pairs[p].n1, pairs[p].n2);
     }
     h->stats.pairs += n_pairs;
+    // live sets only shrink, so the initial block count bounds every later accept launch
+    const int accept_grid = (int)std::max<int64_t>(1, std::min<int64_t>(ablocks, (int64_t)h->num_sms * 8));
+    *h_plan0 = PlanInfo{};
+    h_plan0->done_round = -1;
     CU_CHECK(h, cudaMemcpyAsync(c.pairs, hp, sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, s));
+    CU_CHECK(h, cudaMemcpyAsync(c.plan, h_plan0, sizeof(PlanInfo), cudaMemcpyHostToDevice, s));
 
-    dim3 igrid(std::min((max_n + 255) / 256, 64), n_pairs);
-    init_kernel<<<igrid, 256, 0, s>>>(c);
-    plan_kernel<<<1, ACCEPT_THREADS, 0, s>>>(c, 0);
-    CU_CHECK(h, dispatch_fin(h, words, c, 0, s));
-    h->stats.kernel_launches += 3;
+    dim3 igrid(std::max(1, std::min((max_n + ACCEPT_THREADS - 1) / ACCEPT_THREADS, 64)), n_pairs);
+    init_kernel<<<igrid, ACCEPT_THREADS, 0, s>>>(c);    // also plans round 0 in its last block
+    h->stats.kernel_launches += 1;
 
+    const bool prof = h->profiling;
+    PlanInfo *prof_plan = (PlanInfo *)h->pin_prof.p;
+    h->prof_rounds = 0;
+    if (prof) CU_CHECK(h, cudaMemcpyAsync(&prof_plan[0], c.plan, sizeof(PlanInfo), cudaMemcpyDeviceToHost, s));
     int r = 0;
-    int batch = std::max(1, h->rounds_hint);
+    int batch = std::max(0, h->rounds_hint);
     for (;;) {
         for (int k = 0; k < batch; k++, r++) {
-            dispatch_round(words, c, r, h->round_grid, s);
-            accept_kernel<<<h->accept_grid, ACCEPT_THREADS, 0, s>>>(c, r);
-            CU_CHECK(h, dispatch_fin(h, words, c, r + 1, s));
-            h->stats.kernel_launches += 3;
+            const bool pr = prof && r < PROF_MAX_ROUNDS;
+            if (pr) CU_CHECK(h, cudaEventRecord(h->prof_events[2 * r], s));
+            dispatch_round(words, c, r, round_grid, s);
+            if (pr) CU_CHECK(h, cudaEventRecord(h->prof_events[2 * r + 1], s));
+            accept_kernel<<<accept_grid, ACCEPT_THREADS, 0, s>>>(c, r);
+            if (pr) {
+                CU_CHECK(h, cudaMemcpyAsync(&prof_plan[r + 1], c.plan, sizeof(PlanInfo), cudaMemcpyDeviceToHost, s));
+                h->prof_rounds = r + 1;
+            }
+            h->stats.kernel_launches += 2;
         }
+        // pairs that became small wait in place (SmallInfo) until this launch
+        CU_CHECK(h, dispatch_fin(h, words, c, s));
+        h->stats.kernel_launches += 1;
         CU_CHECK(h, cudaMemcpyAsync(h_plan, c.plan, sizeof(PlanInfo), cudaMemcpyDeviceToHost, s));
         CU_CHECK(h, cudaStreamSynchronize(s));
         h->stats.host_syncs++;
@@ -360,10 +383,15 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
     const int needed = h_plan->done_round >= 0 ? h_plan->done_round : r;
     h->stats.rounds += needed;
     h->stats.evals_computed += (int64_t)h_plan->evals;
-    h->rounds_hint = std::max(1, std::min(needed, 64));
+    h->rounds_hint = std::max(0, std::min(needed, 64));
 
     const int nbins = desc_bits + 1;
-    const size_t osmem = sizeof(int32_t) * ORDER_WARPS * (nbins + 1);
+    const size_t osmem = order_smem_bytes(nbins);
+    if (!h->order_attr_set) {
+        CU_CHECK(h, cudaFuncSetAttribute(order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)order_smem_bytes(513)));
+        h->order_attr_set = true;
+    }
     order_kernel<<<n_pairs, ORDER_THREADS, osmem, s>>>(c, nbins, flags, d_out_qi, d_out_tj, d_out_dist);
     h->stats.kernel_launches += 1;
     CU_CHECK(h, cudaGetLastError());
@@ -700,6 +728,44 @@ extern "C" int pgm_match_ratio_crosscheck(pgm_handle *h, const uint8_t *q, int32
     }
     *out_count = cnt;
     h->stats.matched = cnt;
+    return PGM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// profiling mode
+// ---------------------------------------------------------------------------
+extern "C" int pgm_set_profiling(pgm_handle *h, int32_t enabled) {
+    if (!h) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU_CHECK(h, cudaSetDevice(h->device));
+    if (enabled && h->prof_events.empty()) {
+        h->prof_events.resize(2 * PROF_MAX_ROUNDS);
+        for (auto &e : h->prof_events) CU_CHECK(h, cudaEventCreate(&e));
+        int rc = ensure_host(h, h->pin_prof, sizeof(PlanInfo) * (PROF_MAX_ROUNDS + 2));
+        if (rc) return rc;
+    }
+    h->profiling = enabled != 0;
+    h->prof_rounds = 0;
+    return PGM_OK;
+}
+
+extern "C" int pgm_get_round_profile(pgm_handle *h, float *ms, int64_t *evals, int32_t capacity, int32_t *out_n) {
+    if (!h || !out_n) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU_CHECK(h, cudaSetDevice(h->device));
+    CU_CHECK(h, cudaStreamSynchronize(h->stream));
+    const PlanInfo *pp = (const PlanInfo *)h->pin_prof.p;
+    int n = 0;
+    for (int r = 0; r < h->prof_rounds && n < capacity; r++) {
+        const int64_t e = (int64_t)pp[r].evals - (r > 0 ? (int64_t)pp[r - 1].evals : 0);
+        if (e <= 0) continue;                       // idle round (pair already small/done)
+        float t = 0.f;
+        CU_CHECK(h, cudaEventElapsedTime(&t, h->prof_events[2 * r], h->prof_events[2 * r + 1]));
+        if (ms) ms[n] = t;
+        if (evals) evals[n] = e;
+        n++;
+    }
+    *out_n = n;
     return PGM_OK;
 }
 

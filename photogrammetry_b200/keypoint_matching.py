@@ -178,6 +178,17 @@ class Matcher:
             n1, C.byref(cnt)))
         return np.ascontiguousarray(out[:, :cnt.value].T)
 
+    def set_profiling(self, enabled: bool) -> None:
+        self._check(self._lib.pgm_set_profiling(self._h, int(bool(enabled))))
+
+    def round_profile(self):
+        """(ms float32[k], evals int64[k]) per round-kernel launch of the last greedy call."""
+        ms = np.zeros(256, dtype=np.float32)
+        ev = np.zeros(256, dtype=np.int64)
+        n = C.c_int32(0)
+        self._check(self._lib.pgm_get_round_profile(self._h, ms.ctypes.data, ev.ctypes.data, 256, C.byref(n)))
+        return ms[:n.value].copy(), ev[:n.value].copy()
+
     def measure_popc_peak(self, millis: int = 200):
         p, l = C.c_double(0), C.c_double(0)
         self._check(self._lib.pgm_measure_popc_peak(self._h, int(millis), C.byref(p), C.byref(l)))
