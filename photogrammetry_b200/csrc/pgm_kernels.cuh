@@ -44,7 +44,7 @@ constexpr int ACCEPT_THREADS = 256;
 constexpr int FIN_THREADS = 512;
 constexpr int FIN_MAX_DIM = 512;      // (== FIN_THREADS) finisher takes a pair once nlr, nlc <= this ...
 constexpr int FIN_MAX_EVALS = 49152;  // ... and nlr * nlc <= this (u16 distance matrix in smem)
-constexpr int ORDER_THREADS = 512;
+constexpr int ORDER_THREADS = 1024;
 constexpr int ORDER_WARPS = ORDER_THREADS / 32;
 constexpr int ORDER_KEY_CACHE = 16384;  // match keys cached in smem by the order kernel
 
@@ -165,18 +165,19 @@ __device__ void plan_device(const Chunk &c, int r) {
         unsigned long long e = 0; int b = 0, s = 0;
         for (int w = 0; w < NW; w++) { e += s_evals[w]; b += s_w[0][w]; s += s_w[1][w]; }
         // tile shape: large tiles while they still cover the machine ~4x over, else small ones
-        const unsigned long long slots = (unsigned long long)c.num_sms * c.ctas_per_sm;
+        const unsigned slots = (unsigned)(c.num_sms * c.ctas_per_sm);
         const unsigned long long large_tile = (unsigned long long)ROUND_THREADS * RQ_LARGE * STAGE_LARGE;
         int rq, stage;
         if (e >= 4ull * c.num_sms * large_tile) { rq = RQ_LARGE; stage = STAGE_LARGE; }
         else { rq = RQ_SMALL; stage = STAGE_SMALL; }
         const int tile_rows = ROUND_THREADS * rq;
-        unsigned long long per_tile = e / (2ull * slots);
-        const unsigned long long min_tile = (unsigned long long)tile_rows * stage;
+        // heuristic sizing in fp32 (64-bit integer division is ~100 instructions on the GPU)
+        float per_tile = (float)e / (2.0f * (float)slots);
+        const float min_tile = (float)(tile_rows * stage);
         if (per_tile < min_tile) per_tile = min_tile;
-        unsigned long long cpt = (per_tile + tile_rows - 1) / tile_rows;
+        unsigned cpt = (unsigned)(per_tile / (float)tile_rows) + 1u;
         cpt = ((cpt + stage - 1) / stage) * stage;
-        if (cpt > (unsigned long long)MAX_N) cpt = MAX_N;
+        if (cpt > (unsigned)MAX_N) cpt = MAX_N;
         s_cpt = (int)cpt; s_tile_rows = tile_rows;
         PlanInfo *pl = c.plan;
         pl->cols_per_tile = (int)cpt; pl->rq = rq;
@@ -274,12 +275,54 @@ __global__ void __launch_bounds__(ACCEPT_THREADS) init_kernel(Chunk c) {
 // ---------------------------------------------------------------------------
 // distance of one query (registers) against one train descriptor (registers)
 // ---------------------------------------------------------------------------
+// Plain form: WORDS x (LOP3 xor + POPC).  POPC.32 issues at 16 lanes/clk/SM (a
+// quarter of the LOP3/IADD3 rate), so it is the bottleneck of this form.
 template <int WORDS>
-__device__ __forceinline__ uint32_t hamming_words(const uint32_t (&q)[WORDS], const uint32_t (&t)[WORDS]) {
+__device__ __forceinline__ uint32_t hamming_words_plain(const uint32_t (&q)[WORDS], const uint32_t (&t)[WORDS]) {
     uint32_t d = 0;
 #pragma unroll
     for (int w = 0; w < WORDS; w++) d += __popc(q[w] ^ t[w]);
     return d;
+}
+
+// Carry-save form: three full adders (2 LOP3 each: xor3 = 0x96, majority = 0xE8)
+// compress 7 of every 8 xor words into one "ones" word and three "twos" words, so
+// 8 words cost 5 POPC + 14 LOP3 instead of 8 POPC + 8 LOP3.  That moves work from
+// the quarter-rate POPC pipe to the ALU pipe until the two are about balanced
+// (5 x 8 = 40 vs ~19 x 2 = 38 issue cycles per warp and distance).  Same value.
+// (inline PTX keeps the front end from re-associating the adders into longer LOP3 chains)
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+template <int WORDS>
+__device__ __forceinline__ uint32_t hamming_words(const uint32_t (&q)[WORDS], const uint32_t (&t)[WORDS]) {
+    uint32_t x[WORDS];
+#pragma unroll
+    for (int w = 0; w < WORDS; w++) x[w] = q[w] ^ t[w];
+    uint32_t ones = 0, twos = 0;
+#pragma unroll
+    for (int g = 0; g + 8 <= WORDS; g += 8) {
+        const uint32_t s1 = xor3(x[g], x[g + 1], x[g + 2]), c1 = maj3(x[g], x[g + 1], x[g + 2]);
+        const uint32_t s2 = xor3(x[g + 3], x[g + 4], x[g + 5]), c2 = maj3(x[g + 3], x[g + 4], x[g + 5]);
+        const uint32_t s3 = xor3(s1, s2, x[g + 6]), c3 = maj3(s1, s2, x[g + 6]);
+        ones += __popc(s3) + __popc(x[g + 7]);
+        twos += __popc(c1) + __popc(c2) + __popc(c3);
+    }
+    if (WORDS % 8 == 4) {
+        constexpr int g = WORDS - 4;
+        const uint32_t s1 = xor3(x[g], x[g + 1], x[g + 2]), c1 = maj3(x[g], x[g + 1], x[g + 2]);
+        ones += __popc(s1) + __popc(x[g + 3]);
+        twos += __popc(c1);
+    }
+    return ones + 2u * twos;
 }
 
 // ---------------------------------------------------------------------------
@@ -501,29 +544,27 @@ __global__ void __launch_bounds__(FIN_THREADS) finisher_kernel(Chunk c) {
     }
     __syncthreads();
 
-    // distance matrix: thread (x, column group) with the query row in registers
-    int rxt = 1;
-    while (rxt < nr && rxt < nt) rxt <<= 1;
-    const int cg = nt / rxt, gx = tid % rxt, gy = tid / rxt;
-    for (int x = gx; x < nr; x += rxt) {
-        uint32_t q[WORDS];
-        const uint4 *qs = reinterpret_cast<const uint4 *>(pd.q + (size_t)rowid[x] * WORDS);
+    // stage both descriptor sets in shared memory (coalesced 128-bit loads), then every thread
+    // computes its share of the nr x nc matrix from smem
+    constexpr int V4 = WORDS / 4;
+    uint4 *sq = reinterpret_cast<uint4 *>(D + (((size_t)nr * S + 7) & ~(size_t)7));
+    uint4 *st = sq + (size_t)nr * V4;
+    for (int k = tid; k < (nr + nc) * V4; k += nt) {
+        const int row = k / V4, part = k - row * V4;
+        sq[k] = row < nr ? __ldg(reinterpret_cast<const uint4 *>(pd.q + (size_t)rowid[row] * WORDS) + part)
+                         : __ldg(reinterpret_cast<const uint4 *>(pd.t + (size_t)colid[row - nr] * WORDS) + part);
+    }
+    __syncthreads();
+    for (int e = tid; e < nr * nc; e += nt) {
+        const int x = e / nc, y = e - x * nc;
+        uint32_t q[WORDS], t[WORDS];
 #pragma unroll
-        for (int v = 0; v < WORDS / 4; v++) {
-            const uint4 a = __ldg(qs + v);
+        for (int v = 0; v < V4; v++) {
+            const uint4 a = sq[x * V4 + v], b = st[y * V4 + v];
             q[4 * v] = a.x; q[4 * v + 1] = a.y; q[4 * v + 2] = a.z; q[4 * v + 3] = a.w;
+            t[4 * v] = b.x; t[4 * v + 1] = b.y; t[4 * v + 2] = b.z; t[4 * v + 3] = b.w;
         }
-#pragma unroll 2
-        for (int y = gy; y < nc; y += cg) {
-            uint32_t t[WORDS];
-            const uint4 *ts = reinterpret_cast<const uint4 *>(pd.t + (size_t)colid[y] * WORDS);
-#pragma unroll
-            for (int v = 0; v < WORDS / 4; v++) {
-                const uint4 a = __ldg(ts + v);
-                t[4 * v] = a.x; t[4 * v + 1] = a.y; t[4 * v + 2] = a.z; t[4 * v + 3] = a.w;
-            }
-            D[x * S + y] = (uint16_t)hamming_words<WORDS>(q, t);
-        }
+        D[x * S + y] = (uint16_t)hamming_words<WORDS>(q, t);
     }
     __syncthreads();
 
@@ -585,9 +626,11 @@ __global__ void __launch_bounds__(FIN_THREADS) finisher_kernel(Chunk c) {
     if (tid == 0) c.status[p] = PAIR_DONE;
 }
 
-inline size_t finisher_smem_bytes() {
-    // ids/keys: 8 arrays of FIN_MAX_DIM words; D: worst case rows * (pitch <= nc + 3)
-    return (size_t)8 * FIN_MAX_DIM * 4 + ((size_t)FIN_MAX_EVALS + 3 * FIN_MAX_DIM) * 2 + 64;
+inline size_t finisher_smem_bytes(int words) {
+    // ids/keys: 8 arrays of FIN_MAX_DIM words; D: worst case rows * (pitch <= nc + 3);
+    // staged descriptors: nr + nc <= FIN_MAX_DIM + FIN_MAX_EVALS / FIN_MAX_DIM rows
+    return (size_t)8 * FIN_MAX_DIM * 4 + ((size_t)FIN_MAX_EVALS + 3 * FIN_MAX_DIM) * 2 + 64 +
+           (size_t)(FIN_MAX_DIM + FIN_MAX_EVALS / FIN_MAX_DIM + 2) * words * 4;
 }
 
 // ---------------------------------------------------------------------------
@@ -629,7 +672,7 @@ __global__ void __launch_bounds__(ORDER_THREADS) order_kernel(Chunk c, int nbins
         }
     }
     __syncthreads();
-    // thread t owns bins 2t and 2t+1 (nbins <= 513 < 2 * ORDER_THREADS): totals over the
+    // thread t owns bins 2t and 2t+1 (nbins <= 513 <= 2 * ORDER_THREADS): totals over the
     // warps' histograms, block-wide exclusive scan over distances, then per-warp bases
     const int b0 = 2 * tid, b1 = 2 * tid + 1;
     int ta = 0, tb = 0;

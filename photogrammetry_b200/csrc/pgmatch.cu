@@ -202,7 +202,7 @@ static void dispatch_round(int words, const Chunk &c, int r, int grid, cudaStrea
 }
 template <int WORDS>
 static cudaError_t launch_fin(pgm_handle *h, const Chunk &c, cudaStream_t s) {
-    const size_t smem = finisher_smem_bytes();
+    const size_t smem = finisher_smem_bytes(WORDS);
     if (!h->fin_attr_set[WORDS / 4]) {
         cudaError_t e = cudaFuncSetAttribute(finisher_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -23,8 +23,10 @@ def main():
     m.set_stream(stream.cuda_stream)
     popc, lop3 = m.measure_popc_peak(300)
     print(json.dumps({"popc32_per_s": popc, "lop3_per_s": lop3, "evals256_roofline": popc / 8}))
+    dists = sys.argv[2].split(",") if len(sys.argv) > 2 else ["U", "C"]
+    ops = sys.argv[3].split(",") if len(sys.argv) > 3 else ["knn", "greedy", "host"]
     for n in sizes:
-        for dist in ("U", "C"):
+        for dist in dists:
             q, t = synthetic.config2_pair(n, dist)
             with torch.cuda.stream(stream):
                 dq = torch.from_numpy(q).cuda(non_blocking=False); dt = torch.from_numpy(t).cuda()
@@ -37,11 +39,14 @@ def main():
                 m.match_greedy_dev(dq.data_ptr(), n, dt.data_ptr(), n, 256, 32, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), n)
             def host():
                 m.match_greedy(q, t, 256)
-            med, mn = timeit(knn, stream)
-            print(json.dumps({"n": n, "dist": dist, "op": "knn2_dev", "ms_med": med, "ms_min": mn, "evals_per_s": n * n / (mn * 1e-3), "frac_popc": n * n * 8 / (mn * 1e-3) / popc}))
-            med, mn = timeit(greedy, stream)
-            st = m.stats()
-            print(json.dumps({"n": n, "dist": dist, "op": "greedy_dev", "ms_med": med, "ms_min": mn, "evals_per_s": n * n / (med * 1e-3), "stats": st}))
+            if "knn" in ops:
+              med, mn = timeit(knn, stream)
+              print(json.dumps({"n": n, "dist": dist, "op": "knn2_dev", "ms_med": med, "ms_min": mn, "evals_per_s": n * n / (mn * 1e-3), "frac_popc": n * n * 8 / (mn * 1e-3) / popc}))
+            if "greedy" in ops:
+              med, mn = timeit(greedy, stream, warm=3, reps=4)
+              st = m.stats()
+              print(json.dumps({"n": n, "dist": dist, "op": "greedy_dev", "ms_med": med, "ms_min": mn, "evals_per_s": n * n / (med * 1e-3), "stats": st}))
+            if "host" not in ops: continue
             t0 = time.perf_counter(); 
             for _ in range(5): host()
             dt_ms = (time.perf_counter() - t0) / 5 * 1e3
