@@ -257,9 +257,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         prof_ms.append(a); prof_ev.append(b)
     m.set_profiling(False)
     pm, pe = np.concatenate(prof_ms[1:]), np.concatenate(prof_ev[1:])
-    achieved = float(pe.sum() * 8 / (pm.sum() * 1e-3))                     # popc32 / s over all round launches
-    first = float(np.mean([e[0] * 8 / (t_[0] * 1e-3) for t_, e in zip(prof_ms[1:], prof_ev[1:])]))
-    round_share = float(np.sum([x.sum() for x in prof_ms[1:]]) / len(prof_ms[1:]) / np.mean(step_ms))
+    # In latency mode the dominant kernel is launched once per step (the full N1 x N2 round); the
+    # remaining short rounds run the same device code inside the persistent tail kernel.
+    achieved = float(pe.sum() * 8 / (pm.sum() * 1e-3))                     # POPC.32-equivalents / s
+    round_share = float(pm.sum() / len(prof_ms[1:]) / np.mean(step_ms))
     traffic = None
     tp = os.path.join(ROOT, "profiles", "round_kernel_traffic.json")
     if os.path.exists(tp):
@@ -269,14 +270,18 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             traffic = None
     roofline = {
         "bound": "int-pipe (POPC.32 issue rate; neither HBM nor tensor bounds this path)",
-        "kernel": "hamming_round_kernel<8,4>",
+        "kernel": "hamming_round_kernel<8> (round 0: all N1 x N2 distances + row/column argmin)",
         "achieved": achieved / 1e9, "peak": popc_peak / 1e9, "unit": "Gpopc32/s", "frac": achieved / popc_peak,
         "peak_source": "measured live: register-only POPC micro-benchmark on this GPU (pgm_measure_popc_peak); "
                        "nominal 148 SM x 16/clk x 1.965 GHz = 4654",
-        "first_launch_frac": first / popc_peak,
-        "launches_per_step": int(len(pm) / len(prof_ms[1:])),
+        "algorithmic": "8 POPC.32 per 256-bit distance (SURVEY 8d) x N1*N2 distances of the launch",
+        "note": "the kernel uses a carry-save popcount (5 POPC + 14 LOP3 per distance), which is how frac can "
+                "exceed 1.0 of the plain 8-POPC roofline; against the carry-save POPC bound (5 per distance) "
+                "the same launch sits at frac_vs_carry_save_bound",
+        "frac_vs_carry_save_bound": achieved * 5.0 / 8.0 / popc_peak,
+        "lop3_peak_gops": lop3_peak / 1e9,
+        "launch_ms": float(pm.mean()), "launches_per_step": int(len(pm) / len(prof_ms[1:])),
         "kernel_share_of_step": round_share,
-        "algorithmic": "8 POPC.32 per 256-bit distance x (live rows x live cols) of each launch",
         "hbm_gbs_for_context": float((2 * n * stride + 12 * n) / (np.mean(step_ms) * 1e-3) / 1e9),
         "traffic": traffic,
     }

@@ -21,6 +21,7 @@
 // Nothing here is translated from the reference (it has no native code).
 #pragma once
 
+#include <algorithm>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -44,8 +45,8 @@ constexpr int ACCEPT_THREADS = 256;
 constexpr int FIN_THREADS = 512;
 constexpr int FIN_MAX_DIM = 512;      // (== FIN_THREADS) finisher takes a pair once nlr, nlc <= this ...
 constexpr int FIN_MAX_EVALS = 49152;  // ... and nlr * nlc <= this (u16 distance matrix in smem)
-constexpr int ORDER_THREADS = 1024;
-constexpr int ORDER_WARPS = ORDER_THREADS / 32;
+constexpr int ORDER_THREADS_STANDALONE = 1024;
+constexpr int TAIL_THREADS = 512;     // persistent tail kernel: 1 CTA per SM, four 128-thread groups
 constexpr int ORDER_KEY_CACHE = 16384;  // match keys cached in smem by the order kernel
 
 enum PairStatus : uint8_t { PAIR_DONE = 0, PAIR_BIG = 1, PAIR_SMALL = 2 };
@@ -71,9 +72,9 @@ struct PlanInfo {                 // device resident, rewritten every round
     int32_t n_small;              // pairs waiting for the finisher
     int32_t round;
     uint32_t ticket;              // last-block-done counter (init and accept kernels)
-    int32_t done_round;           // first round whose plan found no PAIR_BIG pair (-1: not yet)
+    int32_t done_round_p1;        // 1 + first round whose plan found no PAIR_BIG pair (0: not yet)
     int32_t rq;                   // rows per thread this round (RQ_LARGE or RQ_SMALL)
-    int32_t pad;
+    uint32_t grid_bar;            // grid-barrier counter of the persistent tail kernel
     unsigned long long evals;     // XOR+popcount evaluations planned so far (grid rounds)
 };
 
@@ -94,6 +95,7 @@ struct Chunk {
     uint8_t *status;              // PairStatus per pair
     SmallInfo *small;             // per pair
     PlanInfo *plan;
+    unsigned long long *timeline; // optional (PGM_TAIL_TIMELINE=1): globaltimer stamps of the tail kernel's phases
 };
 
 __device__ __forceinline__ int32_t *cnt_ptr(const Chunk &c, int buf3, int p) {
@@ -110,8 +112,18 @@ __device__ __forceinline__ int find_pair(const int32_t *__restrict__ base, int n
     return lo;
 }
 
+// A barrier over a warp-aligned group of threads of the CTA (PTX named barrier).
+// id 0 with the whole block is __syncthreads().  Lets one 512-thread CTA of the
+// persistent tail kernel run four independent 128-thread "virtual CTAs".
+struct GroupBar {
+    int id, nthreads;
+    __device__ __forceinline__ void sync() const {
+        asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+    }
+};
+
 // ---------------------------------------------------------------------------
-// planner: one CTA of ACCEPT_THREADS threads.  Classifies every pair from
+// planner: one CTA (any multiple of 32 threads).  Classifies every pair from
 // counts[r % 3], picks the tile shape so the round kernel gets enough work
 // items to cover the machine, and writes the per-pair exclusive prefixes the
 // round/accept kernels search.
@@ -124,11 +136,11 @@ __device__ __forceinline__ int ablocks_of(int nlr, int nlc) {
 }
 
 __device__ void plan_device(const Chunk &c, int r) {
-    constexpr int NW = ACCEPT_THREADS / 32;
-    __shared__ unsigned long long s_evals[NW];
-    __shared__ int s_w[4][NW];
+    __shared__ unsigned long long s_evals[32];
+    __shared__ int s_w[4][32];
     __shared__ int s_cpt, s_tile_rows;
-    const int tid = threadIdx.x, nt = ACCEPT_THREADS, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const int NW = nt >> 5;
     const int buf = r % 3;
 
     unsigned long long ev = 0; int nbig = 0, nsmall = 0;
@@ -164,18 +176,19 @@ __device__ void plan_device(const Chunk &c, int r) {
     if (tid == 0) {
         unsigned long long e = 0; int b = 0, s = 0;
         for (int w = 0; w < NW; w++) { e += s_evals[w]; b += s_w[0][w]; s += s_w[1][w]; }
-        // tile shape: large tiles while they still cover the machine ~4x over, else small ones
+        // tile shape: large tiles while they still cover the machine ~2x over, else small ones
         const unsigned slots = (unsigned)(c.num_sms * c.ctas_per_sm);
         const unsigned long long large_tile = (unsigned long long)ROUND_THREADS * RQ_LARGE * STAGE_LARGE;
         int rq, stage;
-        if (e >= 4ull * c.num_sms * large_tile) { rq = RQ_LARGE; stage = STAGE_LARGE; }
+        if (e >= 2ull * c.num_sms * large_tile) { rq = RQ_LARGE; stage = STAGE_LARGE; }
         else { rq = RQ_SMALL; stage = STAGE_SMALL; }
         const int tile_rows = ROUND_THREADS * rq;
         // heuristic sizing in fp32 (64-bit integer division is ~100 instructions on the GPU)
         float per_tile = (float)e / (2.0f * (float)slots);
         const float min_tile = (float)(tile_rows * stage);
         if (per_tile < min_tile) per_tile = min_tile;
-        unsigned cpt = (unsigned)(per_tile / (float)tile_rows) + 1u;
+        unsigned cpt = (unsigned)(per_tile / (float)tile_rows);
+        if (cpt < 1u) cpt = 1u;
         cpt = ((cpt + stage - 1) / stage) * stage;
         if (cpt > (unsigned)MAX_N) cpt = MAX_N;
         s_cpt = (int)cpt; s_tile_rows = tile_rows;
@@ -184,7 +197,7 @@ __device__ void plan_device(const Chunk &c, int r) {
         pl->n_big = b; pl->n_small = s; pl->round = r;
         pl->ticket = 0u;
         pl->evals += e;
-        if (b == 0 && pl->done_round < 0) pl->done_round = r;
+        if (b == 0 && pl->done_round_p1 == 0) pl->done_round_p1 = r + 1;
     }
     __syncthreads();
     const int cpt = s_cpt, tile_rows = s_tile_rows;
@@ -243,11 +256,18 @@ __device__ __forceinline__ void plan_in_last_block(const Chunk &c, int r, unsign
 
 // ---------------------------------------------------------------------------
 // init: live lists = identity, keys = none, counts[0] = (n1, n2); the last
-// block plans round 0.  The host resets PlanInfo before the launch.
+// block plans round 0.  The host zeroes PlanInfo (memset) before the launch.
+// In latency mode the few pair descriptors travel as a kernel argument (no
+// pinned staging buffer to race on between back-to-back asynchronous calls).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(ACCEPT_THREADS) init_kernel(Chunk c) {
+constexpr int PACK_PAIRS = 16;
+struct PairPack { PairDesc p[PACK_PAIRS]; };
+
+template <bool PACKED>
+__global__ void __launch_bounds__(ACCEPT_THREADS) init_kernel(Chunk c, PairPack pack) {
     const int p = blockIdx.y;
-    const PairDesc pd = c.pairs[p];
+    const PairDesc pd = PACKED ? pack.p[p] : c.pairs[p];
+    if (PACKED && blockIdx.x == 0 && threadIdx.x == 0) c.pairs[p] = pd;
     const int n = max(pd.n1, pd.n2);
     for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < n; x += gridDim.x * blockDim.x) {
         if (x < pd.n1) {
@@ -333,15 +353,25 @@ __device__ __forceinline__ uint32_t hamming_words(const uint32_t (&q)[WORDS], co
 // the column argmin is a warp REDUX.MIN of the packed keys followed by one
 // shared-memory atomicMin per (warp, column).
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ void tstamp(const Chunk &c, int vb, int tid, int code) {
+    if (c.timeline && vb == 0 && tid == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        const unsigned k = atomicAdd(reinterpret_cast<unsigned *>(c.timeline + 999), 1u);
+        if (k < 480) { c.timeline[500 + k] = (t << 8) | (unsigned)code; }
+    }
+}
+
 template <int WORDS, int RQ, int STAGE>
 __device__ __forceinline__ void round_tiles(const Chunk &c, int r, int total, int cpt,
+                                            int vb, int vgrid, int tid, GroupBar bar,
                                             uint4 *s_t, uint32_t *s_jkey, uint32_t *s_col) {
     constexpr int V4 = WORDS / 4;
     constexpr int tile_rows = ROUND_THREADS * RQ;
-    const int tid = threadIdx.x;
-    const int cur = r & 1, buf = r % 3;
+    const int cur = r & 1, buf = r % 3, lane = tid & 31;
 
-    for (int g = blockIdx.x; g < total; g += gridDim.x) {
+    tstamp(c, vb, tid, 1);
+    for (int g = vb; g < total; g += vgrid) {
         const int p = find_pair(c.tile_base, c.n_pairs, g);
         const PairDesc pd = c.pairs[p];
         const int32_t *cp = cnt_ptr(c, buf, p);
@@ -373,9 +403,10 @@ __device__ __forceinline__ void round_tiles(const Chunk &c, int r, int total, in
             }
         }
 
+        tstamp(c, vb, tid, 2);
         const int c0 = ct * cpt, c1 = min(nlc, c0 + cpt);
         for (int s0 = c0; s0 < c1; s0 += STAGE) {
-            __syncthreads();                       // previous stage fully consumed
+            bar.sync();                       // previous stage fully consumed
             for (int k = tid; k < STAGE * V4; k += ROUND_THREADS) {
                 const int col = k / V4, part = k - col * V4, y = s0 + col;
                 uint4 x = make_uint4(0u, 0u, 0u, 0u);
@@ -389,33 +420,42 @@ __device__ __forceinline__ void round_tiles(const Chunk &c, int r, int total, in
                 if (part == 0) s_jkey[col] = jk;
             }
             if (tid < STAGE) s_col[tid] = KEY_NONE;
-            __syncthreads();
+            bar.sync();
+            tstamp(c, vb, tid, 3);
 
+            // 32 columns at a time: the column minimum of each (warp, column) is one CREDUX.MIN whose
+            // result lane (jj & 31) keeps; one conflict-free ATOMS.MIN per warp then publishes 32 columns.
+            // No branch or atomic sits inside the unrolled loop, so consecutive columns pipeline freely.
             const int ncs = min(STAGE, (c1 - s0 + 7) & ~7);
-            for (int jj0 = 0; jj0 < ncs; jj0 += 8) {
+            for (int jb = 0; jb < ncs; jb += 32) {
+                uint32_t mycol = KEY_NONE;
+                const int jend = min(ncs, jb + 32);
+                for (int jj0 = jb; jj0 < jend; jj0 += 8) {
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int jj = jj0 + u;
-                    uint32_t t[WORDS];
+                    for (int u = 0; u < 8; u++) {
+                        const int jj = jj0 + u;
+                        uint32_t t[WORDS];
 #pragma unroll
-                    for (int v = 0; v < V4; v++) {
-                        const uint4 x = s_t[jj * V4 + v];
-                        t[4 * v + 0] = x.x; t[4 * v + 1] = x.y; t[4 * v + 2] = x.z; t[4 * v + 3] = x.w;
+                        for (int v = 0; v < V4; v++) {
+                            const uint4 x = s_t[jj * V4 + v];
+                            t[4 * v + 0] = x.x; t[4 * v + 1] = x.y; t[4 * v + 2] = x.z; t[4 * v + 3] = x.w;
+                        }
+                        const uint32_t jk = s_jkey[jj];
+                        uint32_t cmin = KEY_NONE;
+#pragma unroll
+                        for (int k = 0; k < RQ; k++) {
+                            const uint32_t d = hamming_words<WORDS>(q[k], t) << KEY_IDX_BITS;
+                            rowkey[k] = min(rowkey[k], d + jk);
+                            cmin = min(cmin, d + ikey[k]);
+                        }
+                        const uint32_t wmin = __reduce_min_sync(0xffffffffu, cmin);
+                        if (lane == (jj & 31)) mycol = wmin;
                     }
-                    const uint32_t jk = s_jkey[jj];
-                    uint32_t cmin = KEY_NONE;
-#pragma unroll
-                    for (int k = 0; k < RQ; k++) {
-                        const uint32_t d = hamming_words<WORDS>(q[k], t) << KEY_IDX_BITS;
-                        rowkey[k] = min(rowkey[k], d + jk);
-                        cmin = min(cmin, d + ikey[k]);
-                    }
-                    // all 32 lanes hit one address: ptxas aggregates this into a single
-                    // CREDUX.MIN + one elected ATOMS.MIN per (warp, column)
-                    atomicMin(&s_col[jj], cmin);
                 }
+                atomicMin(&s_col[jb + lane], mycol);
             }
-            __syncthreads();
+            bar.sync();
+            tstamp(c, vb, tid, 4);
             if (tid < STAGE) {
                 const uint32_t jk = s_jkey[tid], v = s_col[tid];
                 if (jk != KEY_INVALID && v < KEY_INVALID)
@@ -426,6 +466,7 @@ __device__ __forceinline__ void round_tiles(const Chunk &c, int r, int total, in
         for (int k = 0; k < RQ; k++)
             if (ikey[k] != KEY_INVALID && rowkey[k] < KEY_INVALID)
                 atomicMin(c.rowbest[cur] + pd.row_base + ikey[k], rowkey[k]);
+        tstamp(c, vb, tid, 5);
     }
 }
 
@@ -438,8 +479,11 @@ __global__ void __launch_bounds__(ROUND_THREADS) hamming_round_kernel(Chunk c, i
     if ((int)blockIdx.x >= total) return;
     const int cpt = __ldcg(&c.plan->cols_per_tile);
     const int rq = __ldcg(&c.plan->rq);
-    if (rq == RQ_LARGE) round_tiles<WORDS, RQ_LARGE, STAGE_LARGE>(c, r, total, cpt, s_t, s_jkey, s_col);
-    else round_tiles<WORDS, RQ_SMALL, STAGE_SMALL>(c, r, total, cpt, s_t, s_jkey, s_col);
+    const GroupBar bar{0, ROUND_THREADS};
+    if (rq == RQ_LARGE)
+        round_tiles<WORDS, RQ_LARGE, STAGE_LARGE>(c, r, total, cpt, blockIdx.x, gridDim.x, threadIdx.x, bar, s_t, s_jkey, s_col);
+    else
+        round_tiles<WORDS, RQ_SMALL, STAGE_SMALL>(c, r, total, cpt, blockIdx.x, gridDim.x, threadIdx.x, bar, s_t, s_jkey, s_col);
 }
 
 // ---------------------------------------------------------------------------
@@ -449,12 +493,12 @@ __global__ void __launch_bounds__(ROUND_THREADS) hamming_round_kernel(Chunk c, i
 // are appended to the next live lists; their key slots in the other buffer
 // are reset.  The last block to finish plans round r+1.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(ACCEPT_THREADS) accept_kernel(Chunk c, int r) {
-    const int tid = threadIdx.x, lane = tid & 31;
+__device__ __forceinline__ void accept_blocks(const Chunk &c, int r, int vb, int vgrid, int tid) {
+    const int lane = tid & 31;
     const int cur = r & 1, nxt = cur ^ 1, buf = r % 3, nbuf = (r + 1) % 3;
     const int total = __ldcg(&c.plan->total_ablocks);
 
-    for (int b = blockIdx.x; b < total; b += gridDim.x) {
+    for (int b = vb; b < total; b += vgrid) {
         const int p = find_pair(c.ablock_base, c.n_pairs, b);
         const PairDesc pd = c.pairs[p];
         const int32_t *cp = cnt_ptr(c, buf, p);
@@ -495,6 +539,10 @@ __global__ void __launch_bounds__(ACCEPT_THREADS) accept_kernel(Chunk c, int r) 
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(ACCEPT_THREADS) accept_kernel(Chunk c, int r) {
+    accept_blocks(c, r, blockIdx.x, gridDim.x, threadIdx.x);
     plan_in_last_block(c, r + 1, gridDim.x);
 }
 
@@ -507,13 +555,11 @@ __global__ void __launch_bounds__(ACCEPT_THREADS) accept_kernel(Chunk c, int r) 
 // was matched to someone else -- otherwise its argmin is still valid.
 // ---------------------------------------------------------------------------
 template <int WORDS>
-__global__ void __launch_bounds__(FIN_THREADS) finisher_kernel(Chunk c) {
-    extern __shared__ __align__(16) unsigned char fin_smem[];
-    const int p = blockIdx.x;
-    if (c.status[p] != PAIR_SMALL) return;
+__device__ __forceinline__ void finisher_body(const Chunk &c, int p, unsigned char *fin_smem) {
     const int tid = threadIdx.x, nt = FIN_THREADS;
     const PairDesc pd = c.pairs[p];
-    const SmallInfo si = c.small[p];
+    const int4 si_raw = __ldcg(reinterpret_cast<const int4 *>(c.small + p));
+    const SmallInfo si{si_raw.x, si_raw.y, si_raw.z, si_raw.w};
     const int nr = si.nlr, nc = si.nlc, cur = si.parity;
     int S = (nc + 1) & ~1;            // row pitch in u16; S/2 odd -> row scans hit 32 distinct banks
     if (((S >> 1) & 1) == 0) S += 2;
@@ -530,7 +576,7 @@ __global__ void __launch_bounds__(FIN_THREADS) finisher_kernel(Chunk c) {
     // rank sort of the live lists (ids are distinct)
     for (int k = tid; k < nr + nc; k += nt)
         tmp[k < nr ? k : FIN_MAX_DIM + (k - nr)] =
-            k < nr ? c.live_rows[cur][pd.row_base + k] : c.live_cols[cur][pd.col_base + (k - nr)];
+            k < nr ? __ldcg(c.live_rows[cur] + pd.row_base + k) : __ldcg(c.live_cols[cur] + pd.col_base + (k - nr));
     __syncthreads();
     for (int k = tid; k < nr + nc; k += nt) {
         const bool is_row = k < nr;
@@ -626,6 +672,14 @@ __global__ void __launch_bounds__(FIN_THREADS) finisher_kernel(Chunk c) {
     if (tid == 0) c.status[p] = PAIR_DONE;
 }
 
+template <int WORDS>
+__global__ void __launch_bounds__(FIN_THREADS) finisher_kernel(Chunk c) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    const int p = blockIdx.x;
+    if (c.status[p] != PAIR_SMALL) return;
+    finisher_body<WORDS>(c, p, dyn_smem);
+}
+
 inline size_t finisher_smem_bytes(int words) {
     // ids/keys: 8 arrays of FIN_MAX_DIM words; D: worst case rows * (pitch <= nc + 3);
     // staged descriptors: nr + nc <= FIN_MAX_DIM + FIN_MAX_EVALS / FIN_MAX_DIM rows
@@ -640,11 +694,12 @@ inline size_t finisher_smem_bytes(int words) {
 // Keys of the first ORDER_KEY_CACHE rows are cached in shared memory so the
 // ranking pass does not wait on global loads.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(ORDER_THREADS) order_kernel(Chunk c, int nbins, uint32_t flags,
-                                                             int32_t *out_qi, int32_t *out_tj, int32_t *out_dist) {
-    extern __shared__ int32_t s_order[];         // [ORDER_WARPS][nbins + 1] hist | key cache
-    __shared__ int32_t s_wsum[ORDER_WARPS];
-    const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+template <int ORDER_THREADS>
+__device__ __forceinline__ void order_body(const Chunk &c, int p, int nbins, uint32_t flags,
+                                           int32_t *out_qi, int32_t *out_tj, int32_t *out_dist, int32_t *s_order) {
+    constexpr int ORDER_WARPS = ORDER_THREADS / 32;
+    __shared__ int32_t s_wsum[ORDER_WARPS];      // s_order: [ORDER_WARPS][nbins + 1] hist | key cache
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const PairDesc pd = c.pairs[p];
     const int hb = nbins + 1;                    // last bin: unmatched rows (never written out)
     int32_t *s_hist = s_order;
@@ -713,8 +768,104 @@ __global__ void __launch_bounds__(ORDER_THREADS) order_kernel(Chunk c, int nbins
     }
 }
 
-inline size_t order_smem_bytes(int nbins) {
-    return sizeof(int32_t) * ((size_t)ORDER_WARPS * (nbins + 1) + ORDER_KEY_CACHE);
+__global__ void __launch_bounds__(ORDER_THREADS_STANDALONE) order_kernel(Chunk c, int nbins, uint32_t flags,
+                                                                        int32_t *out_qi, int32_t *out_tj, int32_t *out_dist) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    order_body<ORDER_THREADS_STANDALONE>(c, blockIdx.x, nbins, flags, out_qi, out_tj, out_dist,
+                                        reinterpret_cast<int32_t *>(dyn_smem));
+}
+
+inline size_t order_smem_bytes(int nbins, int threads) {
+    return sizeof(int32_t) * ((size_t)(threads / 32) * (nbins + 1) + ORDER_KEY_CACHE);
+}
+
+// ---------------------------------------------------------------------------
+// persistent tail kernel (latency mode: one or a few pairs).  After the first
+// full round, what remains is a chain of short rounds whose cost is dominated
+// by kernel boundaries.  This kernel is launched cooperatively with one
+// 512-thread CTA per SM and runs every remaining round (round phase -> grid
+// barrier -> accept phase + planner in the last CTA -> grid barrier), then the
+// finisher and the ordering of each pair, with no host involvement.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void stamp(const Chunk &c, int &slot) {
+    if (c.timeline && blockIdx.x == 0 && threadIdx.x == 0 && slot < 1000) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        c.timeline[slot] = t;
+    }
+    slot++;
+}
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// All CTAs are co-resident (cooperative launch), so a counting barrier in global memory is safe.
+__device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned nblocks, unsigned &epoch) {
+    epoch += nblocks;                 // the counter only grows: the k-th barrier completes at k * nblocks
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (ld_acquire_u32(counter) < epoch) {}
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <int WORDS>
+inline size_t tail_smem_bytes(int nbins) {
+    const size_t round_bytes = 4 * ((size_t)STAGE_LARGE * (WORDS / 4) * 16 + (size_t)STAGE_LARGE * 8);
+    return std::max(round_bytes, std::max(finisher_smem_bytes(WORDS), order_smem_bytes(nbins, TAIL_THREADS)));
+}
+
+template <int WORDS>
+__global__ void __launch_bounds__(TAIL_THREADS, 1) tail_kernel(Chunk c, int r_start, int nbins, uint32_t flags,
+                                                              int32_t *out_qi, int32_t *out_tj, int32_t *out_dist) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    constexpr int V4 = WORDS / 4;
+    constexpr size_t GROUP_BYTES = (size_t)STAGE_LARGE * V4 * 16 + (size_t)STAGE_LARGE * 8;
+    const int tid = threadIdx.x, grp = tid >> 7, gtid = tid & 127;
+    unsigned char *gb = dyn_smem + grp * GROUP_BYTES;
+    uint4 *s_t = reinterpret_cast<uint4 *>(gb);
+    uint32_t *s_jkey = reinterpret_cast<uint32_t *>(gb + (size_t)STAGE_LARGE * V4 * 16);
+    uint32_t *s_col = s_jkey + STAGE_LARGE;
+    unsigned epoch = 0;
+    unsigned *bar_counter = &c.plan->grid_bar;
+    int slot = 0;
+    stamp(c, slot);
+
+    for (int r = r_start;; r++) {
+        // plan(r) was published before the previous barrier (or by the preceding accept kernel)
+        if (__ldcg(&c.plan->n_big) == 0) break;
+        const int total = __ldcg(&c.plan->total_tiles);
+        const int cpt = __ldcg(&c.plan->cols_per_tile);
+        const int rq = __ldcg(&c.plan->rq);
+        const GroupBar bar{1 + grp, ROUND_THREADS};
+        if (rq == RQ_LARGE)
+            round_tiles<WORDS, RQ_LARGE, STAGE_LARGE>(c, r, total, cpt, grp * gridDim.x + blockIdx.x, gridDim.x * 4, gtid, bar, s_t, s_jkey, s_col);
+        else
+            round_tiles<WORDS, RQ_SMALL, STAGE_SMALL>(c, r, total, cpt, grp * gridDim.x + blockIdx.x, gridDim.x * 4, gtid, bar, s_t, s_jkey, s_col);
+        stamp(c, slot);
+        grid_barrier(bar_counter, gridDim.x, epoch);
+        stamp(c, slot);
+        accept_blocks(c, r, (tid >> 8) * gridDim.x + blockIdx.x, gridDim.x * 2, tid & (ACCEPT_THREADS - 1));
+        plan_in_last_block(c, r + 1, gridDim.x);
+        stamp(c, slot);
+        grid_barrier(bar_counter, gridDim.x, epoch);
+        stamp(c, slot);
+    }
+    for (int p = blockIdx.x; p < c.n_pairs; p += gridDim.x) {
+        stamp(c, slot);
+        if (__ldcg(c.status + p) == PAIR_SMALL) finisher_body<WORDS>(c, p, dyn_smem);
+        __threadfence();
+        __syncthreads();
+        stamp(c, slot);
+        order_body<TAIL_THREADS>(c, p, nbins, flags, out_qi, out_tj, out_dist, reinterpret_cast<int32_t *>(dyn_smem));
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -47,6 +48,13 @@ struct pgm_handle {
     int rounds_hint = 4;      // grid rounds to enqueue before the first completion check
     int ctas_per_sm[5] = {0, 0, 0, 0, 0};   // round-kernel occupancy per descriptor width (words / 4)
     bool order_attr_set = false;
+    bool tail_attr_set[5] = {false, false, false, false, false};
+    bool force_multilaunch = false;   // PGM_FORCE_MULTILAUNCH=1: never use the persistent tail kernel
+    bool stats_pending = false;   // rounds / evals of the last latency-mode call still sit in pin_meta
+    const void *pending_plan = nullptr;
+    bool tail_plain_launch = false;  // PGM_TAIL_PLAIN_LAUNCH=1 (experiment): non-cooperative launch of the tail kernel
+    bool tail_timeline = false;      // PGM_TAIL_TIMELINE=1: dump the tail kernel's phase timeline to stderr (debug)
+    DevBuf timeline;
     bool fin_attr_set[5] = {false, false, false, false, false};
     // profiling mode (pgm_set_profiling): events around every round-kernel launch
     bool profiling = false;
@@ -55,6 +63,7 @@ struct pgm_handle {
     int prof_rounds = 0;
 };
 constexpr int PROF_MAX_ROUNDS = 256;
+constexpr int LATENCY_MODE_MAX_PAIRS = PACK_PAIRS;
 
 #define CU_CHECK(h, call)                                                                      \
     do {                                                                                       \
@@ -105,6 +114,8 @@ static int ensure_host(pgm_handle *h, HostBuf &b, size_t bytes) {
     return PGM_OK;
 }
 
+static void resolve_pending_stats(pgm_handle *h);
+
 extern "C" int pgm_version(void) { return PGM_VERSION; }
 
 extern "C" const char *pgm_status_string(int s) {
@@ -141,6 +152,12 @@ extern "C" int pgm_create(int device_ordinal, pgm_handle **out) {
         return PGM_E_CUDA;
     }
     h->stream = h->own_stream;
+    const char *fm = getenv("PGM_FORCE_MULTILAUNCH");
+    h->force_multilaunch = fm && fm[0] == '1';
+    const char *pl = getenv("PGM_TAIL_PLAIN_LAUNCH");
+    h->tail_plain_launch = pl && pl[0] == '1';
+    const char *tl = getenv("PGM_TAIL_TIMELINE");
+    h->tail_timeline = tl && tl[0] == '1';
     *out = h;
     return PGM_OK;
 }
@@ -179,6 +196,11 @@ extern "C" int pgm_synchronize(pgm_handle *h) {
 extern "C" int pgm_get_stats(pgm_handle *h, pgm_stats *out) {
     if (!h || !out) return PGM_E_INVALID_ARG;
     std::lock_guard<std::mutex> lk(h->mu);
+    if (h->stats_pending) {
+        CU_CHECK(h, cudaSetDevice(h->device));
+        CU_CHECK(h, cudaStreamSynchronize(h->stream));
+        resolve_pending_stats(h);
+    }
     *out = h->stats;
     return PGM_OK;
 }
@@ -217,6 +239,31 @@ static cudaError_t dispatch_fin(pgm_handle *h, int words, const Chunk &c, cudaSt
         case 8: return launch_fin<8>(h, c, s);
         case 12: return launch_fin<12>(h, c, s);
         default: return launch_fin<16>(h, c, s);
+    }
+}
+template <int WORDS>
+static cudaError_t launch_tail(pgm_handle *h, Chunk c, int r_start, int nbins, uint32_t flags, int32_t *oq, int32_t *ot,
+                               int32_t *od, cudaStream_t s) {
+    const size_t smem = tail_smem_bytes<WORDS>(513);
+    if (!h->tail_attr_set[WORDS / 4]) {
+        cudaError_t e = cudaFuncSetAttribute(tail_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        h->tail_attr_set[WORDS / 4] = true;
+    }
+    if (h->tail_plain_launch) {
+        tail_kernel<WORDS><<<h->num_sms, TAIL_THREADS, smem, s>>>(c, r_start, nbins, flags, oq, ot, od);
+        return cudaGetLastError();
+    }
+    void *args[] = {&c, &r_start, &nbins, &flags, &oq, &ot, &od};
+    return cudaLaunchCooperativeKernel((void *)tail_kernel<WORDS>, dim3(h->num_sms), dim3(TAIL_THREADS), args, smem, s);
+}
+static cudaError_t dispatch_tail(pgm_handle *h, int words, const Chunk &c, int r_start, int nbins, uint32_t flags,
+                                 int32_t *oq, int32_t *ot, int32_t *od, cudaStream_t s) {
+    switch (words) {
+        case 4: return launch_tail<4>(h, c, r_start, nbins, flags, oq, ot, od, s);
+        case 8: return launch_tail<8>(h, c, r_start, nbins, flags, oq, ot, od, s);
+        case 12: return launch_tail<12>(h, c, r_start, nbins, flags, oq, ot, od, s);
+        default: return launch_tail<16>(h, c, r_start, nbins, flags, oq, ot, od, s);
     }
 }
 template <int WORDS>
@@ -309,7 +356,7 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
     c.pairs = (PairDesc *)(base + o_pairs);
     c.n_pairs = n_pairs;
     c.num_sms = h->num_sms;
-    c.ctas_per_sm = ctas_per_sm;
+    c.ctas_per_sm = (n_pairs <= LATENCY_MODE_MAX_PAIRS && !h->force_multilaunch) ? TAIL_THREADS / ROUND_THREADS : ctas_per_sm;
     c.rowbest[0] = (uint32_t *)(base + o_rb0); c.rowbest[1] = (uint32_t *)(base + o_rb1);
     c.colbest[0] = (uint32_t *)(base + o_cb0); c.colbest[1] = (uint32_t *)(base + o_cb1);
     c.live_rows[0] = (int32_t *)(base + o_lr0); c.live_rows[1] = (int32_t *)(base + o_lr1);
@@ -321,11 +368,16 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
     c.status = (uint8_t *)(base + o_st);
     c.small = (SmallInfo *)(base + o_small);
     c.plan = (PlanInfo *)(base + o_plan);
+    c.timeline = nullptr;
+    if (h->tail_timeline) {
+        if ((rc = ensure_dev(h, h->timeline, 1000 * 8))) return rc;
+        CU_CHECK(h, cudaMemsetAsync(h->timeline.p, 0, 1000 * 8, s));
+        c.timeline = (unsigned long long *)h->timeline.p;
+    }
 
     PairDesc *hp = (PairDesc *)h->pin_meta.p;
     char *meta_tail = (char *)h->pin_meta.p + align_up(sizeof(PairDesc) * n_pairs, 64);
     PlanInfo *h_plan = (PlanInfo *)meta_tail;             // readback slot
-    PlanInfo *h_plan0 = (PlanInfo *)(meta_tail + 128);    // initial value uploaded before init
     int64_t rb = 0, cb = 0, ablocks = 0;
     for (int p = 0; p < n_pairs; p++) {
         hp[p].q = (const uint32_t *)pairs[p].d_q;
@@ -340,16 +392,63 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
     h->stats.pairs += n_pairs;
     // live sets only shrink, so the initial block count bounds every later accept launch
     const int accept_grid = (int)std::max<int64_t>(1, std::min<int64_t>(ablocks, (int64_t)h->num_sms * 8));
-    *h_plan0 = PlanInfo{};
-    h_plan0->done_round = -1;
-    CU_CHECK(h, cudaMemcpyAsync(c.pairs, hp, sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, s));
-    CU_CHECK(h, cudaMemcpyAsync(c.plan, h_plan0, sizeof(PlanInfo), cudaMemcpyHostToDevice, s));
-
+    const bool latency_mode = n_pairs <= LATENCY_MODE_MAX_PAIRS && !h->force_multilaunch;
+    CU_CHECK(h, cudaMemsetAsync(c.plan, 0, sizeof(PlanInfo), s));
     dim3 igrid(std::max(1, std::min((max_n + ACCEPT_THREADS - 1) / ACCEPT_THREADS, 64)), n_pairs);
-    init_kernel<<<igrid, ACCEPT_THREADS, 0, s>>>(c);    // also plans round 0 in its last block
+    if (latency_mode) {
+        PairPack pack{};
+        for (int p = 0; p < n_pairs; p++) pack.p[p] = hp[p];
+        init_kernel<true><<<igrid, ACCEPT_THREADS, 0, s>>>(c, pack);     // also plans round 0 in its last block
+    } else {
+        CU_CHECK(h, cudaMemcpyAsync(c.pairs, hp, sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, s));
+        init_kernel<false><<<igrid, ACCEPT_THREADS, 0, s>>>(c, PairPack{});
+    }
     h->stats.kernel_launches += 1;
 
+    const int nbins = desc_bits + 1;
     const bool prof = h->profiling;
+    // ---- latency mode: a few pairs.  init, one full round, then the persistent tail kernel runs
+    // every remaining round, the finisher and the ordering without coming back to the host.
+    if (latency_mode) {
+        bool any_big = false;
+        for (int p = 0; p < n_pairs; p++) {
+            const int64_t a = pairs[p].n1, b = pairs[p].n2;
+            if (a > 0 && b > 0 && !(a <= FIN_MAX_DIM && b <= FIN_MAX_DIM && a * b <= FIN_MAX_EVALS)) any_big = true;
+        }
+        int r_start = 0;
+        h->prof_rounds = 0;
+        if (any_big) {
+            PlanInfo *pp = (PlanInfo *)h->pin_prof.p;
+            if (prof) {   // events around the one standalone launch of the dominant kernel
+                CU_CHECK(h, cudaMemcpyAsync(&pp[0], c.plan, sizeof(PlanInfo), cudaMemcpyDeviceToHost, s));
+                CU_CHECK(h, cudaEventRecord(h->prof_events[0], s));
+            }
+            dispatch_round(words, c, 0, round_grid, s);
+            if (prof) CU_CHECK(h, cudaEventRecord(h->prof_events[1], s));
+            accept_kernel<<<accept_grid, ACCEPT_THREADS, 0, s>>>(c, 0);
+            if (prof) h->prof_rounds = 1;
+            h->stats.kernel_launches += 2;
+            r_start = 1;
+        }
+        CU_CHECK(h, dispatch_tail(h, words, c, r_start, nbins, flags, d_out_qi, d_out_tj, d_out_dist, s));
+        h->stats.kernel_launches += 1;
+        CU_CHECK(h, cudaMemcpyAsync(h_plan, c.plan, sizeof(PlanInfo), cudaMemcpyDeviceToHost, s));
+        h->stats_pending = true;          // resolved by pgm_get_stats / the host-buffer entry points after their sync
+        h->pending_plan = h_plan;
+        CU_CHECK(h, cudaGetLastError());
+        if (h->tail_timeline) {
+            std::vector<unsigned long long> tl(1000);
+            CU_CHECK(h, cudaMemcpyAsync(tl.data(), h->timeline.p, 1000 * 8, cudaMemcpyDeviceToHost, s));
+            CU_CHECK(h, cudaStreamSynchronize(s));
+            fprintf(stderr, "[pgm tail timeline, us since kernel start]");
+            for (int k = 1; k < 1000 && tl[k]; k++) fprintf(stderr, " %.1f", (tl[k] - tl[0]) * 1e-3);
+            fprintf(stderr, "\n[tile stamps code:us]");
+            for (int k = 500; k < 980 && tl[k]; k++) fprintf(stderr, " %d:%.1f", (int)(tl[k] & 0xFF), (double)(((tl[k] >> 8) - (tl[0] & 0x00FFFFFFFFFFFFFFull)) & 0xFFFFFFFFFFull) * 1e-3);
+            fprintf(stderr, "\n");
+        }
+        return PGM_OK;
+    }
+
     PlanInfo *prof_plan = (PlanInfo *)h->pin_prof.p;
     h->prof_rounds = 0;
     if (prof) CU_CHECK(h, cudaMemcpyAsync(&prof_plan[0], c.plan, sizeof(PlanInfo), cudaMemcpyDeviceToHost, s));
@@ -380,22 +479,30 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
     }
     // grid rounds actually needed = first round whose plan had no big pair; the next call on this
     // handle enqueues that many before its first completion check
-    const int needed = h_plan->done_round >= 0 ? h_plan->done_round : r;
+    const int needed = h_plan->done_round_p1 > 0 ? h_plan->done_round_p1 - 1 : r;
     h->stats.rounds += needed;
     h->stats.evals_computed += (int64_t)h_plan->evals;
     h->rounds_hint = std::max(0, std::min(needed, 64));
 
-    const int nbins = desc_bits + 1;
-    const size_t osmem = order_smem_bytes(nbins);
+    const size_t osmem = order_smem_bytes(nbins, ORDER_THREADS_STANDALONE);
     if (!h->order_attr_set) {
         CU_CHECK(h, cudaFuncSetAttribute(order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)order_smem_bytes(513)));
+                                         (int)order_smem_bytes(513, ORDER_THREADS_STANDALONE)));
         h->order_attr_set = true;
     }
-    order_kernel<<<n_pairs, ORDER_THREADS, osmem, s>>>(c, nbins, flags, d_out_qi, d_out_tj, d_out_dist);
+    order_kernel<<<n_pairs, ORDER_THREADS_STANDALONE, osmem, s>>>(c, nbins, flags, d_out_qi, d_out_tj, d_out_dist);
     h->stats.kernel_launches += 1;
     CU_CHECK(h, cudaGetLastError());
     return PGM_OK;
+}
+
+// Folds the PlanInfo read back by a latency-mode call into the stats (the stream must be idle).
+static void resolve_pending_stats(pgm_handle *h) {
+    if (!h->stats_pending) return;
+    const PlanInfo *pl = (const PlanInfo *)h->pending_plan;
+    h->stats.rounds += pl->done_round_p1 > 0 ? pl->done_round_p1 - 1 : pl->round;
+    h->stats.evals_computed += (int64_t)pl->evals;
+    h->stats_pending = false;
 }
 
 static int32_t out_count_for(int32_t n1, int32_t n2, uint32_t flags) {
@@ -421,6 +528,7 @@ extern "C" int pgm_match_hamming_greedy_dev(pgm_handle *h, const uint8_t *d_q, i
     rc = check_pair(h, n1, n2);
     if (rc) return rc;
     h->stats = pgm_stats{};
+    h->stats_pending = false;
     const int32_t cnt = out_count_for(n1, n2, flags);
     if (out_count) *out_count = cnt;
     if (n1 == 0) return PGM_OK;
@@ -441,6 +549,7 @@ extern "C" int pgm_match_hamming_greedy(pgm_handle *h, const uint8_t *q, int32_t
     rc = check_pair(h, n1, n2);
     if (rc) return rc;
     h->stats = pgm_stats{};
+    h->stats_pending = false;
     const int32_t cnt = out_count_for(n1, n2, flags);
     if (out_count) *out_count = cnt;
     if (n1 == 0) return PGM_OK;
@@ -465,6 +574,7 @@ extern "C" int pgm_match_hamming_greedy(pgm_handle *h, const uint8_t *q, int32_t
     CU_CHECK(h, cudaMemcpyAsync(h->pin_out.p, h->out.p, (size_t)3 * n1 * 4, cudaMemcpyDeviceToHost, s));
     CU_CHECK(h, cudaStreamSynchronize(s));
     h->stats.host_syncs++;
+    resolve_pending_stats(h);
     const int32_t *po = (const int32_t *)h->pin_out.p;
     memcpy(out_qi, po, (size_t)cnt * 4);
     memcpy(out_tj, po + n1, (size_t)cnt * 4);
@@ -539,6 +649,7 @@ static int batch_impl(pgm_handle *h, const uint8_t *d_all_desc, const int64_t *i
             CU_CHECK(h, cudaMemcpyAsync(out_dist + done_rows, d_dd, (size_t)rows * 4, cudaMemcpyDeviceToHost, s));
             CU_CHECK(h, cudaStreamSynchronize(s));
             h->stats.host_syncs++;
+            resolve_pending_stats(h);
             h->stats.d2h_bytes += (int64_t)3 * rows * 4;
         }
         done_rows += rows;
@@ -558,6 +669,7 @@ extern "C" int pgm_match_pairs_batch_dev(pgm_handle *h, const uint8_t *d_all_des
     if (n_images < 0 || n_pairs < 0 || !image_offsets || (n_pairs > 0 && !pair_list))
         return fail(h, PGM_E_INVALID_ARG, "bad image/pair arguments");
     h->stats = pgm_stats{};
+    h->stats_pending = false;
     if (n_pairs == 0) return PGM_OK;
     CU_CHECK(h, cudaSetDevice(h->device));
     return batch_impl(h, d_all_desc, image_offsets, n_images, pair_list, n_pairs, desc_bits, stride_bytes, d_out_qi,
@@ -575,6 +687,7 @@ extern "C" int pgm_match_pairs_batch(pgm_handle *h, const uint8_t *all_desc, con
     if (n_images < 0 || n_pairs < 0 || !image_offsets || (n_pairs > 0 && !pair_list))
         return fail(h, PGM_E_INVALID_ARG, "bad image/pair arguments");
     h->stats = pgm_stats{};
+    h->stats_pending = false;
     if (n_pairs == 0) return PGM_OK;
     CU_CHECK(h, cudaSetDevice(h->device));
     const size_t bytes = (size_t)image_offsets[n_images] * stride_bytes;
@@ -624,6 +737,7 @@ extern "C" int pgm_knn2_hamming_dev(pgm_handle *h, const uint8_t *d_q, int32_t n
     if (rc) return rc;
     if (n1 < 0 || n2 < 0 || n1 >= MAX_N || n2 >= MAX_N) return fail(h, PGM_E_INVALID_ARG, "bad sizes");
     h->stats = pgm_stats{};
+    h->stats_pending = false;
     if (n1 == 0) return PGM_OK;
     CU_CHECK(h, cudaSetDevice(h->device));
     if (n2 == 0) {
@@ -659,6 +773,7 @@ extern "C" int pgm_knn2_hamming(pgm_handle *h, const uint8_t *q, int32_t n1, con
     if (rc) return rc;
     if (n1 < 0 || n2 < 0 || n1 >= MAX_N || n2 >= MAX_N) return fail(h, PGM_E_INVALID_ARG, "bad sizes");
     h->stats = pgm_stats{};
+    h->stats_pending = false;
     if (n1 == 0) return PGM_OK;
     if (n2 == 0) {
         for (int32_t *o : {best_j, best_d, second_j, second_d}) std::fill(o, o + n1, -1);
@@ -694,6 +809,7 @@ extern "C" int pgm_match_ratio_crosscheck(pgm_handle *h, const uint8_t *q, int32
     if (rc) return rc;
     if (n1 < 0 || n2 < 0 || n1 >= MAX_N || n2 >= MAX_N) return fail(h, PGM_E_INVALID_ARG, "bad sizes");
     h->stats = pgm_stats{};
+    h->stats_pending = false;
     *out_count = 0;
     if (n1 == 0 || n2 == 0) return PGM_OK;
     CU_CHECK(h, cudaSetDevice(h->device));
