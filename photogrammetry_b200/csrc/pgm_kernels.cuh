@@ -423,14 +423,11 @@ __device__ __forceinline__ void round_tiles(const Chunk &c, int r, int total, in
             bar.sync();
             tstamp(c, vb, tid, 3);
 
-            // 32 columns at a time: the column minimum of each (warp, column) is one CREDUX.MIN whose
-            // result lane (jj & 31) keeps; one conflict-free ATOMS.MIN per warp then publishes 32 columns.
-            // No branch or atomic sits inside the unrolled loop, so consecutive columns pipeline freely.
             const int ncs = min(STAGE, (c1 - s0 + 7) & ~7);
-            for (int jb = 0; jb < ncs; jb += 32) {
-                uint32_t mycol = KEY_NONE;
-                const int jend = min(ncs, jb + 32);
-                for (int jj0 = jb; jj0 < jend; jj0 += 8) {
+            if (RQ >= 4) {
+                // large tiles: one warp-aggregated shared atomicMin per (warp, column); ptxas turns the
+                // 32 same-address lanes into CREDUX.MIN + one elected ATOMS.MIN
+                for (int jj0 = 0; jj0 < ncs; jj0 += 8) {
 #pragma unroll
                     for (int u = 0; u < 8; u++) {
                         const int jj = jj0 + u;
@@ -448,11 +445,41 @@ __device__ __forceinline__ void round_tiles(const Chunk &c, int r, int total, in
                             rowkey[k] = min(rowkey[k], d + jk);
                             cmin = min(cmin, d + ikey[k]);
                         }
-                        const uint32_t wmin = __reduce_min_sync(0xffffffffu, cmin);
-                        if (lane == (jj & 31)) mycol = wmin;
+                        atomicMin(&s_col[jj], cmin);
                     }
                 }
-                atomicMin(&s_col[jb + lane], mycol);
+            } else {
+                // small tiles (latency-bound late rounds): 32 columns at a time, the column minimum of
+                // each (warp, column) is one CREDUX.MIN whose result lane (jj & 31) keeps; a single
+                // conflict-free ATOMS.MIN per warp then publishes 32 columns.  No branch or atomic sits
+                // inside the unrolled loop, so consecutive columns pipeline freely.
+                for (int jb = 0; jb < ncs; jb += 32) {
+                    uint32_t mycol = KEY_NONE;
+                    const int jend = min(ncs, jb + 32);
+                    for (int jj0 = jb; jj0 < jend; jj0 += 8) {
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const int jj = jj0 + u;
+                            uint32_t t[WORDS];
+#pragma unroll
+                            for (int v = 0; v < V4; v++) {
+                                const uint4 x = s_t[jj * V4 + v];
+                                t[4 * v + 0] = x.x; t[4 * v + 1] = x.y; t[4 * v + 2] = x.z; t[4 * v + 3] = x.w;
+                            }
+                            const uint32_t jk = s_jkey[jj];
+                            uint32_t cmin = KEY_NONE;
+#pragma unroll
+                            for (int k = 0; k < RQ; k++) {
+                                const uint32_t d = hamming_words<WORDS>(q[k], t) << KEY_IDX_BITS;
+                                rowkey[k] = min(rowkey[k], d + jk);
+                                cmin = min(cmin, d + ikey[k]);
+                            }
+                            const uint32_t wmin = __reduce_min_sync(0xffffffffu, cmin);
+                            if (lane == (jj & 31)) mycol = wmin;
+                        }
+                    }
+                    atomicMin(&s_col[jb + lane], mycol);
+                }
             }
             bar.sync();
             tstamp(c, vb, tid, 4);

@@ -1,0 +1,101 @@
+"""Multi-process host logic of the pair-sharded mode on CPU (gloo, world_size 2).
+
+The CUDA matcher cannot run here, so each rank's `Matcher` is replaced by a stand-in that
+answers from the oracle -- allowed in tests/ only; the product path never does this."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from oracle import orc
+from photogrammetry_b200 import sharding, synthetic
+
+
+def test_partition_is_contiguous_and_balanced():
+    sizes = [100, 400, 50, 300, 300, 10, 250]
+    pairs = sharding.all_pairs(len(sizes))
+    assert len(pairs) == 21 and (pairs[:, 0] < pairs[:, 1]).all()
+    for world in (1, 2, 3, 4, 8, 30):
+        parts = sharding.partition_pairs(pairs, sizes, world)
+        assert len(parts) == world and parts[0][0] == 0 and parts[-1][1] == len(pairs)
+        assert all(parts[k][1] == parts[k + 1][0] for k in range(world - 1))
+        cost = sharding.pair_costs(pairs, sizes)
+        loads = [cost[a:b].sum() for a, b in parts]
+        if world <= 4:
+            assert max(loads) <= cost.sum() / world + cost.max()
+    assert sharding.partition_pairs(pairs[:0], sizes, 3) == [(0, 0)] * 3
+    assert (sharding.consecutive_pairs(4) == [[0, 1], [1, 2], [2, 3]]).all()
+    # uniform sizes -> equal counts (the 512-image config: 16352 pairs per GPU at 8 GPUs)
+    parts = sharding.partition_pairs(sharding.all_pairs(512), [4096] * 512, 8)
+    assert [b - a for a, b in parts] == [16352] * 8
+
+
+def test_merge_top2_matches_unsharded_knn():
+    q = orc.gen_uniform(1, 60, 8)
+    t = orc.gen_uniform(2, 90, 8)          # 8-bit descriptors: many ties
+    bj, bd, sj, sd = orc.knn2(q, t)
+    none = np.uint32(0xFFFFFFFF)
+    kb, ks = [], []
+    for lo, hi in [(0, 31), (31, 32), (32, 90)]:
+        a, b, c, d = orc.knn2(q, t[lo:hi])
+        kb.append(np.where(a >= 0, (b.astype(np.uint32) << 20) | (a + lo).astype(np.uint32), none))
+        ks.append(np.where(c >= 0, (d.astype(np.uint32) << 20) | (c + lo).astype(np.uint32), none))
+    best, second = sharding.merge_top2(np.stack(kb), np.stack(ks))
+    assert ((best & 0xFFFFF) == bj).all() and ((best >> 20) == bd).all()
+    assert ((second & 0xFFFFF) == sj).all() and ((second >> 20) == sd).all()
+
+
+class _OracleMatcher:
+    """Stand-in for Matcher.match_pairs_batch in the CPU test (oracle-backed)."""
+
+    def match_pairs_batch(self, all_desc, image_offsets, pair_list, desc_bits=256, reference_compat_tail=True):
+        offs = np.asarray(image_offsets, dtype=np.int64)
+        out, starts, counts, base = [], [], [], 0
+        for a, b in np.asarray(pair_list).reshape(-1, 2):
+            tr = orc.match_sweep(all_desc[offs[a]:offs[a + 1]], all_desc[offs[b]:offs[b + 1]])
+            out.append(tr); starts.append(base); counts.append(len(tr)); base += len(tr)
+        return (np.concatenate(out) if out else np.zeros((0, 3), np.int32), np.asarray(starts, np.int64),
+                np.asarray(counts, np.int32))
+
+
+def _worker(rank, world, port, sizes, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        imgs = [synthetic.uniform_descriptors(50 + k, n, 64) for k, n in enumerate(sizes)]
+        all_desc = np.concatenate(imgs)
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        pairs = sharding.all_pairs(len(sizes))
+        local = sharding.match_pairs_sharded(_OracleMatcher(), all_desc, offs, pairs, rank, world, 64)
+        res = sharding.gather_match_lists(local, rank, world, dst=0)
+        if rank == 0:
+            q.put(res)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_pair_sharded_world2_gloo_equals_single_process():
+    import torch.multiprocessing as mp
+    sizes = [40, 25, 60, 10, 33]
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, sizes, queue)) for r in range(2)]
+    for p in procs:
+        p.start()
+    triples, starts, counts = queue.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    imgs = [synthetic.uniform_descriptors(50 + k, n, 64) for k, n in enumerate(sizes)]
+    pairs = sharding.all_pairs(len(sizes))
+    assert len(counts) == len(pairs) == 10
+    for p, (a, b) in enumerate(pairs):
+        exp = orc.match_sweep(imgs[a], imgs[b])
+        assert counts[p] == len(exp) and (triples[starts[p]:starts[p] + counts[p]] == exp).all()
