@@ -174,6 +174,38 @@ int pgm_match_ratio_crosscheck(pgm_handle *h,
                                int32_t *out_qi, int32_t *out_tj, int32_t *out_dist,
                                int32_t capacity, int32_t *out_count);
 
+/* ---- train-sharded single pair (multi-GPU) ----------
+ * For ONE huge pair (BASELINE configs[3]: 200k x 200k) every rank holds all n1
+ * queries and a contiguous slice [col_offset, col_offset + n2_local) of the
+ * n2_total train descriptors.  The library runs the local steps; the two
+ * `min` all-reduces per round over n1 packed 32-bit keys are the caller's
+ * (torch.distributed / NCCL), which keeps NCCL out of the ABI:
+ *
+ *   pgm_shard_create
+ *   repeat:
+ *     pgm_shard_round(shard, xkeys)            local distances + row/column argmin
+ *     all_reduce(xkeys, MIN)   as int32        best (distance, global column) per row
+ *     pgm_shard_propose(shard, xkeys, xacc)    mutual pairs whose column this rank owns
+ *     all_reduce(xacc, MIN)    as int32
+ *     pgm_shard_commit(shard, xacc, &live_rows, &live_cols_local)
+ *   until live_rows == 0 or n2_total - (n1 - live_rows) == 0
+ *   pgm_shard_finish                            reference-ordered triples on every rank
+ *
+ * Exchange buffers hold keys (distance << 20 | global train index); "none" is
+ * 0x7F7F7F7F, so a signed 32-bit MIN orders them like the reference's
+ * (distance, i, j) tie-break.  The result is bit-identical to
+ * pgm_match_hamming_greedy on the unsharded pair.  All pointers are device
+ * memory on the handle's device. */
+typedef struct pgm_shard pgm_shard;
+int pgm_shard_create(pgm_handle *h, const uint8_t *d_q, int32_t n1, const uint8_t *d_t_local, int32_t n2_local,
+                     int32_t col_offset, int32_t n2_total, int32_t desc_bits, int32_t stride_bytes, pgm_shard **out);
+int pgm_shard_round(pgm_shard *s, uint32_t *d_xkeys);
+int pgm_shard_propose(pgm_shard *s, const uint32_t *d_xkeys, uint32_t *d_xacc);
+int pgm_shard_commit(pgm_shard *s, const uint32_t *d_xacc, int32_t *live_rows, int32_t *live_cols_local);
+int pgm_shard_finish(pgm_shard *s, int32_t *d_out_qi, int32_t *d_out_tj, int32_t *d_out_dist, uint32_t flags,
+                     int32_t *out_count, int32_t *out_rounds);
+int pgm_shard_destroy(pgm_shard *s);
+
 /* ---- measurement helpers -------------------------------------------------
  * Profiling mode brackets every launch of the dominant kernel (the round
  * kernel) with CUDA events on the handle's stream and records how many

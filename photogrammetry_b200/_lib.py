@@ -34,6 +34,8 @@ EXPORTED_SYMBOLS = (
     "pgm_match_hamming_greedy", "pgm_match_hamming_greedy_dev",
     "pgm_match_pairs_batch", "pgm_match_pairs_batch_dev",
     "pgm_knn2_hamming", "pgm_knn2_hamming_dev", "pgm_match_ratio_crosscheck",
+    "pgm_shard_create", "pgm_shard_round", "pgm_shard_propose", "pgm_shard_commit", "pgm_shard_finish",
+    "pgm_shard_destroy",
     "pgm_set_profiling", "pgm_get_round_profile", "pgm_measure_popc_peak",
 )
 
@@ -118,6 +120,14 @@ def load() -> C.CDLL:
         lib.pgm_match_ratio_crosscheck.argtypes = [C.c_void_p, u8p, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32,
                                                    C.c_float, C.c_int32, C.c_int32, i32p, i32p, i32p, C.c_int32,
                                                    C.POINTER(C.c_int32)]
+        lib.pgm_shard_create.argtypes = [C.c_void_p, u8p, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_int32, C.POINTER(C.c_void_p)]
+        lib.pgm_shard_round.argtypes = [C.c_void_p, C.c_void_p]
+        lib.pgm_shard_propose.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pgm_shard_commit.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        lib.pgm_shard_finish.argtypes = [C.c_void_p, i32p, i32p, i32p, C.c_uint32, C.POINTER(C.c_int32),
+                                         C.POINTER(C.c_int32)]
+        lib.pgm_shard_destroy.argtypes = [C.c_void_p]
         lib.pgm_set_profiling.argtypes = [C.c_void_p, C.c_int32]
         lib.pgm_get_round_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
         lib.pgm_measure_popc_peak.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]

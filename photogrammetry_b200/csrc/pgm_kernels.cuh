@@ -58,7 +58,10 @@ struct PairDesc {
     int64_t row_base;    // first slot of this pair in the per-row state arrays
     int64_t col_base;    // first slot in the per-column state arrays
     int64_t out_base;    // where this pair's triples start in the output arrays
+    int32_t col_id_offset;   // added to train indices inside keys (train-sharded mode: global column ids)
+    int32_t flags;           // PAIR_FLAG_*
 };
+constexpr int PAIR_FLAG_NO_FINISHER = 1;   // never hand this pair to the single-CTA finisher
 
 struct SmallInfo {       // written when the planner hands a pair to the finisher
     int32_t nlr, nlc, parity, pad;
@@ -152,7 +155,8 @@ __device__ void plan_device(const Chunk &c, int r) {
             const int nlr = __ldcg(cp), nlc = __ldcg(cp + 1);
             st = PAIR_DONE;
             if (nlr > 0 && nlc > 0) {
-                const bool small = nlr <= FIN_MAX_DIM && nlc <= FIN_MAX_DIM && nlr * nlc <= FIN_MAX_EVALS;
+                const bool small = nlr <= FIN_MAX_DIM && nlc <= FIN_MAX_DIM && nlr * nlc <= FIN_MAX_EVALS &&
+                                   !(__ldg(&c.pairs[p].flags) & PAIR_FLAG_NO_FINISHER);
                 if (small) {
                     st = PAIR_SMALL; nsmall++;
                     c.small[p] = SmallInfo{nlr, nlc, r & 1, 0};
@@ -414,7 +418,7 @@ __device__ __forceinline__ void round_tiles(const Chunk &c, int r, int total, in
                 if (y < c1) {
                     const int j = __ldcg(live_cols + y);
                     x = __ldg(reinterpret_cast<const uint4 *>(pd.t + (size_t)j * WORDS) + part);
-                    jk = (uint32_t)j;
+                    jk = (uint32_t)(j + pd.col_id_offset);
                 }
                 s_t[k] = x;
                 if (part == 0) s_jkey[col] = jk;
@@ -485,8 +489,8 @@ __device__ __forceinline__ void round_tiles(const Chunk &c, int r, int total, in
             tstamp(c, vb, tid, 4);
             if (tid < STAGE) {
                 const uint32_t jk = s_jkey[tid], v = s_col[tid];
-                if (jk != KEY_INVALID && v < KEY_INVALID)
-                    atomicMin(c.colbest[cur] + pd.col_base + jk, v);
+                if (jk != KEY_INVALID && v < KEY_INVALID)      // jk carries the global id; the state arrays are local
+                    atomicMin(c.colbest[cur] + pd.col_base + (jk - (uint32_t)pd.col_id_offset), v);
             }
         }
 #pragma unroll
@@ -893,6 +897,97 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_kernel(Chunk c, int r_st
         order_body<TAIL_THREADS>(c, p, nbins, flags, out_qi, out_tj, out_dist, reinterpret_cast<int32_t *>(dyn_smem));
         __syncthreads();
     }
+}
+
+// ---------------------------------------------------------------------------
+// train-sharded single pair: every rank holds all N1
+// queries and a contiguous slice of the train set.  Per round: the ordinary
+// round kernel on (live rows x live LOCAL columns) with global column ids in
+// the row keys; `min` all-reduce of the exported row keys (done by the host
+// side over NCCL); each rank proposes the mutual pairs whose winning column it
+// owns; `min` all-reduce of the proposals; every rank commits identically.
+// Exchange buffers use 0x7F7F7F7F for "none" so that a signed 32-bit min (what
+// the collective libraries offer) orders them like the unsigned keys.
+// ---------------------------------------------------------------------------
+constexpr uint32_t XKEY_NONE = 0x7F7F7F7Fu;   // memset-able, above every real key, positive as int32
+
+__global__ void shard_export_kernel(Chunk c, int r, uint32_t *xkeys) {
+    const PairDesc pd = c.pairs[0];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pd.n1; i += gridDim.x * blockDim.x) {
+        const uint32_t k = __ldcg(c.rowbest[r & 1] + i);
+        xkeys[i] = k == KEY_NONE ? XKEY_NONE : k;
+    }
+}
+
+// xkeys: globally reduced row keys.  xacc[i] = key if this rank owns the winning column and the
+// column's best row is i (mutual), else none.
+__global__ void shard_propose_kernel(Chunk c, int r, const uint32_t *xkeys, uint32_t *xacc, int n2_local) {
+    const PairDesc pd = c.pairs[0];
+    const int nlr = __ldcg(cnt_ptr(c, r % 3, 0));
+    // xacc was filled with XKEY_NONE (memset 0x7F) before the launch
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < nlr; x += gridDim.x * blockDim.x) {
+        const int i = __ldcg(c.live_rows[r & 1] + x);
+        const uint32_t rk = __ldcg(xkeys + i);
+        if (rk == XKEY_NONE) continue;
+        const int jl = (int)(rk & KEY_IDX_MASK) - pd.col_id_offset;
+        if (jl < 0 || jl >= n2_local) continue;
+        const uint32_t ck = __ldcg(c.colbest[r & 1] + jl);
+        if ((ck & KEY_IDX_MASK) == (uint32_t)i) xacc[i] = rk;
+    }
+}
+
+// xacc: globally reduced proposals.  Rows: record matches / append survivors.  Owned matched
+// columns are flagged dead in coldead[].
+__global__ void shard_commit_rows_kernel(Chunk c, int r, const uint32_t *xacc, uint8_t *coldead, int n2_local) {
+    const PairDesc pd = c.pairs[0];
+    const int cur = r & 1, nxt = cur ^ 1, lane = threadIdx.x & 31;
+    const int nlr = __ldcg(cnt_ptr(c, r % 3, 0));
+    const int nrounded = (nlr + 31) & ~31;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < nrounded; x += gridDim.x * blockDim.x) {
+        bool survive = false;
+        int i = 0;
+        if (x < nlr) {
+            i = __ldcg(c.live_rows[cur] + x);
+            const uint32_t a = __ldcg(xacc + i);
+            if (a != XKEY_NONE) {
+                c.match_key[i] = a;
+                const int jl = (int)(a & KEY_IDX_MASK) - pd.col_id_offset;
+                if (jl >= 0 && jl < n2_local) coldead[jl] = 1;
+            } else {
+                survive = true;
+                c.rowbest[nxt][i] = KEY_NONE;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, survive);
+        if (m) {
+            int base = 0;
+            if (lane == (__ffs(m) - 1)) base = atomicAdd(cnt_ptr(c, (r + 1) % 3, 0), __popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (survive) c.live_rows[nxt][base + __popc(m & ((1u << lane) - 1u))] = i;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(ACCEPT_THREADS) shard_commit_cols_kernel(Chunk c, int r, const uint8_t *coldead) {
+    const int cur = r & 1, nxt = cur ^ 1, lane = threadIdx.x & 31;
+    const int nlc = __ldcg(cnt_ptr(c, r % 3, 0) + 1);
+    const int nrounded = (nlc + 31) & ~31;
+    for (int y = blockIdx.x * blockDim.x + threadIdx.x; y < nrounded; y += gridDim.x * blockDim.x) {
+        bool survive = false;
+        int j = 0;
+        if (y < nlc) {
+            j = __ldcg(c.live_cols[cur] + y);
+            if (!coldead[j]) { survive = true; c.colbest[nxt][j] = KEY_NONE; }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, survive);
+        if (m) {
+            int base = 0;
+            if (lane == (__ffs(m) - 1)) base = atomicAdd(cnt_ptr(c, (r + 1) % 3, 0) + 1, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (survive) c.live_cols[nxt][base + __popc(m & ((1u << lane) - 1u))] = j;
+        }
+    }
+    plan_in_last_block(c, r + 1, gridDim.x);
 }
 
 // ---------------------------------------------------------------------------

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -315,6 +316,8 @@ struct HostPair {
     const uint8_t *d_q, *d_t;   // device pointers
     int32_t n1, n2;
     int64_t out_base;           // in rows, relative to the chunk's output arrays
+    int32_t col_id_offset = 0;
+    int32_t flags = 0;
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -384,6 +387,7 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
         hp[p].t = (const uint32_t *)pairs[p].d_t;
         hp[p].n1 = pairs[p].n1; hp[p].n2 = pairs[p].n2;
         hp[p].row_base = rb; hp[p].col_base = cb; hp[p].out_base = pairs[p].out_base;
+        hp[p].col_id_offset = pairs[p].col_id_offset; hp[p].flags = pairs[p].flags;
         rb += pairs[p].n1; cb += pairs[p].n2;
         ablocks += (pairs[p].n1 + ACCEPT_THREADS - 1) / ACCEPT_THREADS + (pairs[p].n2 + ACCEPT_THREADS - 1) / ACCEPT_THREADS;
         h->stats.distance_evals += (int64_t)pairs[p].n1 * pairs[p].n2;
@@ -844,6 +848,166 @@ extern "C" int pgm_match_ratio_crosscheck(pgm_handle *h, const uint8_t *q, int32
     }
     *out_count = cnt;
     h->stats.matched = cnt;
+    return PGM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// train-sharded single pair: stepwise device API; the collectives between the
+// steps belong to the caller (torch.distributed / NCCL `min` all-reduce)
+// ---------------------------------------------------------------------------
+struct pgm_shard {
+    pgm_handle *h = nullptr;
+    DevBuf state;
+    Chunk c{};
+    int words = 8, desc_bits = 256, n1 = 0, n2_local = 0, n2_total = 0, col_offset = 0;
+    int round = 0;
+    int round_grid = 0;
+    uint8_t *coldead = nullptr;
+    int32_t *h_counts = nullptr;   // pinned: live rows / live local cols after the last commit
+};
+
+extern "C" int pgm_shard_create(pgm_handle *h, const uint8_t *d_q, int32_t n1, const uint8_t *d_t_local,
+                                int32_t n2_local, int32_t col_offset, int32_t n2_total, int32_t desc_bits,
+                                int32_t stride_bytes, pgm_shard **out) {
+    if (!h || !out) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    *out = nullptr;
+    int rc = check_format(h, desc_bits, stride_bytes);
+    if (rc) return rc;
+    if (n1 <= 0 || n2_local < 0 || n2_total <= 0 || col_offset < 0 || col_offset + n2_local > n2_total ||
+        n1 >= MAX_N || n2_total >= MAX_N)
+        return fail(h, PGM_E_INVALID_ARG, "bad shard geometry");
+    CU_CHECK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    pgm_shard *sh = new pgm_shard();
+    sh->h = h; sh->words = stride_bytes / 4; sh->desc_bits = desc_bits;
+    sh->n1 = n1; sh->n2_local = n2_local; sh->n2_total = n2_total; sh->col_offset = col_offset;
+    const int64_t rows = n1, cols = std::max(n2_local, 1);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_pairs = take(sizeof(PairDesc));
+    const size_t o_rb0 = take(4 * rows), o_rb1 = take(4 * rows), o_cb0 = take(4 * cols), o_cb1 = take(4 * cols);
+    const size_t o_lr0 = take(4 * rows), o_lr1 = take(4 * rows), o_lc0 = take(4 * cols), o_lc1 = take(4 * cols);
+    const size_t o_cnt = take(sizeof(int32_t) * 6), o_mk = take(4 * rows), o_tb = take(8), o_ab = take(8);
+    const size_t o_st = take(1), o_small = take(sizeof(SmallInfo)), o_plan = take(sizeof(PlanInfo)), o_dead = take(cols);
+    if ((rc = ensure_dev(h, sh->state, off))) { delete sh; return rc; }
+    if (cudaMallocHost((void **)&sh->h_counts, 64) != cudaSuccess) { cudaFree(sh->state.p); delete sh; return PGM_E_CUDA; }
+    char *base = (char *)sh->state.p;
+    if (h->ctas_per_sm[sh->words / 4] == 0) h->ctas_per_sm[sh->words / 4] = std::max(1, dispatch_occupancy(sh->words));
+    sh->round_grid = h->num_sms * h->ctas_per_sm[sh->words / 4];
+    Chunk &c = sh->c;
+    c.pairs = (PairDesc *)(base + o_pairs); c.n_pairs = 1; c.num_sms = h->num_sms;
+    c.ctas_per_sm = h->ctas_per_sm[sh->words / 4];
+    c.rowbest[0] = (uint32_t *)(base + o_rb0); c.rowbest[1] = (uint32_t *)(base + o_rb1);
+    c.colbest[0] = (uint32_t *)(base + o_cb0); c.colbest[1] = (uint32_t *)(base + o_cb1);
+    c.live_rows[0] = (int32_t *)(base + o_lr0); c.live_rows[1] = (int32_t *)(base + o_lr1);
+    c.live_cols[0] = (int32_t *)(base + o_lc0); c.live_cols[1] = (int32_t *)(base + o_lc1);
+    c.counts = (int32_t *)(base + o_cnt); c.match_key = (uint32_t *)(base + o_mk);
+    c.tile_base = (int32_t *)(base + o_tb); c.ablock_base = (int32_t *)(base + o_ab);
+    c.status = (uint8_t *)(base + o_st); c.small = (SmallInfo *)(base + o_small); c.plan = (PlanInfo *)(base + o_plan);
+    c.timeline = nullptr;
+    sh->coldead = (uint8_t *)(base + o_dead);
+    PairPack pack{};
+    pack.p[0].q = (const uint32_t *)d_q; pack.p[0].t = (const uint32_t *)d_t_local;
+    pack.p[0].n1 = n1; pack.p[0].n2 = n2_local; pack.p[0].row_base = 0; pack.p[0].col_base = 0; pack.p[0].out_base = 0;
+    pack.p[0].col_id_offset = col_offset; pack.p[0].flags = PAIR_FLAG_NO_FINISHER;
+    CU_CHECK(h, cudaMemsetAsync(c.plan, 0, sizeof(PlanInfo), s));
+    CU_CHECK(h, cudaMemsetAsync(sh->coldead, 0, cols, s));
+    dim3 igrid(std::max(1, std::min((std::max(n1, n2_local) + ACCEPT_THREADS - 1) / ACCEPT_THREADS, 64)), 1);
+    init_kernel<true><<<igrid, ACCEPT_THREADS, 0, s>>>(c, pack);
+    CU_CHECK(h, cudaGetLastError());
+    *out = sh;
+    return PGM_OK;
+}
+
+// Step 1: local round; xkeys (device, n1 x uint32) receives this rank's row keys for the min all-reduce.
+extern "C" int pgm_shard_round(pgm_shard *sh, uint32_t *d_xkeys) {
+    if (!sh || !d_xkeys) return PGM_E_INVALID_ARG;
+    pgm_handle *h = sh->h;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU_CHECK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    dispatch_round(sh->words, sh->c, sh->round, sh->round_grid, s);
+    shard_export_kernel<<<std::min((sh->n1 + 255) / 256, h->num_sms * 8), 256, 0, s>>>(sh->c, sh->round, d_xkeys);
+    CU_CHECK(h, cudaGetLastError());
+    return PGM_OK;
+}
+
+// Step 2 (xkeys now globally min-reduced): proposals of this rank into xacc for the second min all-reduce.
+extern "C" int pgm_shard_propose(pgm_shard *sh, const uint32_t *d_xkeys, uint32_t *d_xacc) {
+    if (!sh || !d_xkeys || !d_xacc) return PGM_E_INVALID_ARG;
+    pgm_handle *h = sh->h;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU_CHECK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    CU_CHECK(h, cudaMemsetAsync(d_xacc, 0x7F, (size_t)sh->n1 * 4, s));
+    shard_propose_kernel<<<std::min((sh->n1 + 255) / 256, h->num_sms * 8), 256, 0, s>>>(sh->c, sh->round, d_xkeys, d_xacc,
+                                                                                     sh->n2_local);
+    CU_CHECK(h, cudaGetLastError());
+    return PGM_OK;
+}
+
+// Step 3 (xacc now globally min-reduced): commit; returns the live rows (identical on all ranks) and
+// this rank's live columns.  Synchronises the stream (8 bytes read back).
+extern "C" int pgm_shard_commit(pgm_shard *sh, const uint32_t *d_xacc, int32_t *live_rows, int32_t *live_cols_local) {
+    if (!sh || !d_xacc) return PGM_E_INVALID_ARG;
+    pgm_handle *h = sh->h;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU_CHECK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const int r = sh->round;
+    const int g1 = std::max(1, std::min((sh->n1 + 255) / 256, h->num_sms * 8));
+    const int g2 = std::max(1, std::min((sh->n2_local + ACCEPT_THREADS - 1) / ACCEPT_THREADS, h->num_sms * 8));
+    shard_commit_rows_kernel<<<g1, 256, 0, s>>>(sh->c, r, d_xacc, sh->coldead, sh->n2_local);
+    shard_commit_cols_kernel<<<g2, ACCEPT_THREADS, 0, s>>>(sh->c, r, sh->coldead);
+    CU_CHECK(h, cudaMemcpyAsync(sh->h_counts, sh->c.counts + 2 * ((r + 1) % 3), 8, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(h, cudaStreamSynchronize(s));
+    sh->round = r + 1;
+    if (live_rows) *live_rows = sh->h_counts[0];
+    if (live_cols_local) *live_cols_local = sh->h_counts[1];
+    return PGM_OK;
+}
+
+// Final step: every rank holds every accepted (row -> global column, distance); emit them in the
+// reference's order into device arrays of n1 triples (tail included with PGM_FLAG_REFERENCE_COMPAT_TAIL).
+extern "C" int pgm_shard_finish(pgm_shard *sh, int32_t *d_out_qi, int32_t *d_out_tj, int32_t *d_out_dist, uint32_t flags,
+                                int32_t *out_count, int32_t *out_rounds) {
+    if (!sh) return PGM_E_INVALID_ARG;
+    pgm_handle *h = sh->h;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU_CHECK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    // the order kernel derives the tail from min(n1, n2): it needs the TOTAL train size
+    CU_CHECK(h, cudaMemcpyAsync((char *)sh->c.pairs + offsetof(PairDesc, n2), &sh->n2_total, 4, cudaMemcpyHostToDevice, s));
+    const int nbins = sh->desc_bits + 1;
+    if (!h->order_attr_set) {
+        CU_CHECK(h, cudaFuncSetAttribute(order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)order_smem_bytes(513, ORDER_THREADS_STANDALONE)));
+        h->order_attr_set = true;
+    }
+    if (!(flags & PGM_FLAG_REFERENCE_COMPAT_TAIL)) {
+        CU_CHECK(h, cudaMemsetAsync(d_out_qi, 0xFF, (size_t)sh->n1 * 4, s));
+        CU_CHECK(h, cudaMemsetAsync(d_out_tj, 0xFF, (size_t)sh->n1 * 4, s));
+        CU_CHECK(h, cudaMemsetAsync(d_out_dist, 0xFF, (size_t)sh->n1 * 4, s));
+    }
+    order_kernel<<<1, ORDER_THREADS_STANDALONE, order_smem_bytes(nbins, ORDER_THREADS_STANDALONE), s>>>(
+        sh->c, nbins, flags, d_out_qi, d_out_tj, d_out_dist);
+    CU_CHECK(h, cudaGetLastError());
+    CU_CHECK(h, cudaStreamSynchronize(s));
+    if (out_count) *out_count = out_count_for(sh->n1, sh->n2_total, flags);
+    if (out_rounds) *out_rounds = sh->round;
+    return PGM_OK;
+}
+
+extern "C" int pgm_shard_destroy(pgm_shard *sh) {
+    if (!sh) return PGM_E_INVALID_ARG;
+    pgm_handle *h = sh->h;
+    std::lock_guard<std::mutex> lk(h->mu);
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (sh->state.p) cudaFree(sh->state.p);
+    if (sh->h_counts) cudaFreeHost(sh->h_counts);
+    delete sh;
     return PGM_OK;
 }
 

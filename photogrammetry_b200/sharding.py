@@ -6,6 +6,10 @@ contiguous block of the pair list balanced by estimated cost N_a * N_b, matches 
 with its own ``Matcher`` and the per-pair results are gathered to rank 0.  There is
 NO data-path collective; ``torch.distributed`` only moves the finished match lists.
 
+Mode 2, one huge pair (BASELINE configs[3], 200k x 200k): :class:`TrainShardedMatcher`.  Every rank
+holds all queries and a contiguous slice of the train set; per round the library computes the local
+row/column argmins and two ``min`` all-reduces over N1 packed keys (NCCL over NVLink) merge them.
+
 One process per GPU (``torch.distributed``; NCCL on GPUs, gloo in the CPU tests).
 """
 from __future__ import annotations
@@ -113,3 +117,149 @@ def merge_top2(keys_best: np.ndarray, keys_second: np.ndarray):
     runner = np.take_along_axis(kb, order[1:2], axis=0)[0] if kb.shape[0] > 1 else np.full_like(best, np.iinfo(kb.dtype).max)
     second_of_winner = np.take_along_axis(ks, order[:1], axis=0)[0]
     return best, np.minimum(runner, second_of_winner)
+
+
+def train_slices(n2_total: int, world_size: int) -> List[Tuple[int, int]]:
+    """Contiguous column blocks [lo, hi) of the train set, one per rank, sizes differing by at most 1."""
+    base, rem = divmod(n2_total, world_size)
+    out, lo = [], 0
+    for r in range(world_size):
+        hi = lo + base + (1 if r < rem else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+class TrainShardedMatcher:
+    """MatchKeypoints on ONE pair whose train set is sharded over the ranks.
+
+    ``d_q``: torch uint8 ``[n1, stride]`` (all queries, on this rank's GPU);
+    ``d_t_local``: torch uint8 ``[n2_local, stride]`` = train rows ``[col_offset, col_offset + n2_local)``.
+    ``reduce_min(tensor)`` performs an in-place MIN all-reduce of an int32 tensor across the ranks;
+    by default ``torch.distributed.all_reduce(op=MIN)`` on the default group.  Returns int32 ``[3, n1]``
+    (qi, tj, dist) in the reference's order -- identical on every rank and bit-identical to the
+    unsharded ``Matcher.match_greedy``.
+    """
+
+    def __init__(self, matcher, d_q, d_t_local, col_offset: int, n2_total: int, desc_bits: int = 256,
+                 reduce_min=None):
+        import ctypes as C
+
+        import torch
+        self._torch = torch
+        self._m = matcher
+        self._lib = matcher._lib
+        self.n1, self.stride = int(d_q.shape[0]), int(d_q.shape[1])
+        self.n2_local, self.n2_total = int(d_t_local.shape[0]), int(n2_total)
+        self._keep = (d_q, d_t_local)
+        self._sh = C.c_void_p()
+        matcher._check(self._lib.pgm_shard_create(
+            matcher._h, d_q.data_ptr(), self.n1, d_t_local.data_ptr() if self.n2_local else None, self.n2_local,
+            int(col_offset), self.n2_total, int(desc_bits), self.stride, C.byref(self._sh)))
+        dev = d_q.device
+        self.xkeys = torch.empty(self.n1, dtype=torch.int32, device=dev)
+        self.xacc = torch.empty(self.n1, dtype=torch.int32, device=dev)
+        self.out = torch.empty((3, self.n1), dtype=torch.int32, device=dev)
+        self._reduce = reduce_min or self._dist_reduce
+        self.rounds = 0
+
+    def _dist_reduce(self, t):
+        import torch.distributed as dist
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+
+    # the three local steps, exposed so a single process can drive several emulated ranks in lock-step
+    def step_round(self):
+        self._m._check(self._lib.pgm_shard_round(self._sh, self.xkeys.data_ptr()))
+
+    def step_propose(self):
+        self._m._check(self._lib.pgm_shard_propose(self._sh, self.xkeys.data_ptr(), self.xacc.data_ptr()))
+
+    def step_commit(self):
+        import ctypes as C
+        lr, lc = C.c_int32(0), C.c_int32(0)
+        self._m._check(self._lib.pgm_shard_commit(self._sh, self.xacc.data_ptr(), C.byref(lr), C.byref(lc)))
+        return lr.value, lc.value
+
+    def done(self, live_rows: int) -> bool:
+        return live_rows == 0 or self.n2_total - (self.n1 - live_rows) == 0
+
+    def finish(self, reference_compat_tail: bool = True):
+        import ctypes as C
+        cnt, rounds = C.c_int32(0), C.c_int32(0)
+        self._m._check(self._lib.pgm_shard_finish(
+            self._sh, self.out[0].data_ptr(), self.out[1].data_ptr(), self.out[2].data_ptr(),
+            1 if reference_compat_tail else 0, C.byref(cnt), C.byref(rounds)))
+        self.rounds = rounds.value
+        return self.out[:, :cnt.value]
+
+    def match(self, reference_compat_tail: bool = True):
+        """Runs on the matcher's stream; the collectives run on the current torch stream, so the
+        caller must make that the same stream (``with torch.cuda.stream(s)`` + ``matcher.set_stream``)."""
+        prev = self.n1 + 1
+        while True:
+            self.step_round()
+            self._reduce(self.xkeys)
+            self.step_propose()
+            self._reduce(self.xacc)
+            live_rows, _ = self.step_commit()
+            if self.done(live_rows):
+                break
+            if live_rows >= prev:          # every round accepts at least the global minimum edge
+                raise RuntimeError("train-sharded matcher made no progress (internal error)")
+            prev = live_rows
+        return self.finish(reference_compat_tail)
+
+    def close(self):
+        if self._sh and self._sh.value:
+            self._lib.pgm_shard_destroy(self._sh)
+            self._sh = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def match_train_sharded_emulated(matcher, q, t, n_shards: int, desc_bits: int = 256):
+    """All ``n_shards`` ranks of the train-sharded mode emulated in ONE process on ONE GPU, run in
+    lock-step with the all-reduces replaced by element-wise minima (SURVEY.md section 4.4 item 5:
+    no inter-dependent concurrent kernels).  For tests and single-GPU validation."""
+    import torch
+    dev = torch.device("cuda", matcher.device)
+    stream = torch.cuda.Stream(device=dev)
+    matcher.set_stream(stream.cuda_stream)
+    try:
+        with torch.cuda.stream(stream):
+            d_q = torch.from_numpy(np.ascontiguousarray(q)).to(dev)
+            d_t = torch.from_numpy(np.ascontiguousarray(t)).to(dev)
+            shards = [TrainShardedMatcher(matcher, d_q, d_t[lo:hi], lo, len(t), desc_bits, reduce_min=lambda x: None)
+                      for lo, hi in train_slices(len(t), n_shards)]
+            prev = len(q) + 1
+            while True:
+                for s in shards:
+                    s.step_round()
+                red = torch.stack([s.xkeys for s in shards]).min(dim=0).values
+                for s in shards:
+                    s.xkeys.copy_(red)
+                    s.step_propose()
+                red = torch.stack([s.xacc for s in shards]).min(dim=0).values
+                live = None
+                for s in shards:
+                    s.xacc.copy_(red)
+                    lr, _ = s.step_commit()
+                    assert live is None or live == lr, "ranks disagree on the live rows"
+                    live = lr
+                if shards[0].done(live):
+                    break
+                if live >= prev:
+                    raise RuntimeError("train-sharded matcher made no progress (internal error)")
+                prev = live
+            outs = [s.finish().T.contiguous().cpu().numpy() for s in shards]
+            rounds = shards[0].rounds
+            for s in shards:
+                s.close()
+    finally:
+        matcher.set_stream(None)
+    return outs, rounds

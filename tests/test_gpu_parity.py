@@ -162,3 +162,18 @@ def test_keypoint_matching_object_surface(lego):
     assert KeypointMatching().MatchKeypoints([], kp2) == []
     with pytest.raises(IndexError):
         KeypointMatching().MatchKeypoints(kp1, [])
+
+
+@pytest.mark.parametrize("n1,n2,shards", [(3000, 2500, 2), (2000, 3100, 3), (1500, 1500, 8), (700, 40, 4)])
+def test_train_sharded_emulated_equals_unsharded(matcher, n1, n2, shards):
+    # every emulated rank must end with the unsharded result, bit for bit
+    from photogrammetry_b200 import sharding
+    q = synthetic.uniform_descriptors(61, n1, 256)
+    t = synthetic.noisy_copy_descriptors(62, synthetic.uniform_descriptors(61, max(n1, n2), 256), 256)[:n2]
+    t[5:9] = t[5]                                      # duplicate train rows straddling ties
+    exp = orc.match_sweep(q, t)
+    outs, rounds = sharding.match_train_sharded_emulated(matcher, q, t, shards)
+    assert rounds > 0
+    for o in outs:
+        assert o.shape == exp.shape and (o == exp).all()
+    assert (matcher.match_greedy(q, t, 256) == exp).all()

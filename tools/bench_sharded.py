@@ -1,0 +1,80 @@
+#!/usr/bin/env python
+"""BASELINE configs[3]: one huge synthetic pair, train set sharded over the ranks (torchrun).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port P \
+        tools/bench_sharded.py --n 200000 [--check]
+
+Every rank holds all N queries and 1/G of the train set; two NCCL `min` all-reduces of N packed keys per
+round.  With --check rank 0 also runs the unsharded single-GPU matcher and verifies bit-identity.
+"""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+from photogrammetry_b200 import sharding, synthetic
+from photogrammetry_b200.keypoint_matching import Matcher
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=200000)
+    ap.add_argument("--dist", default="U")
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--check", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.n
+    q = synthetic.uniform_descriptors(1234, n, 256)
+    t = synthetic.uniform_descriptors(5678, n, 256) if args.dist == "U" else synthetic.noisy_copy_descriptors(42, q, 256)
+    lo, hi = sharding.train_slices(n, world)[rank]
+    m = Matcher(local)
+    stream = torch.cuda.current_stream(dev)          # NCCL collectives are enqueued on the current stream
+    m.set_stream(stream.cuda_stream)
+    d_q = torch.from_numpy(q).to(dev); d_t = torch.from_numpy(t[lo:hi].copy()).to(dev)
+    times, rounds = [], 0
+    for rep in range(args.reps + 1):
+        sm = sharding.TrainShardedMatcher(m, d_q, d_t, lo, n, 256)
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        out = sm.match()
+        e1.record(stream); e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
+        if rep > 0: times.append(ms)
+        rounds = sm.rounds
+        res = out.T.contiguous().cpu().numpy()
+        sm.close()
+    line = {"workload": f"configs[3]: single synthetic pair {n}x{n}, distribution {args.dist}, train set sharded x{world}",
+            "n_gpus": world, "ms": float(np.median(times)), "evals_per_s": float(n) * n / (np.median(times) * 1e-3),
+            "rounds": rounds, "collectives_per_round": 2 if world > 1 else 0, "bytes_per_collective": 4 * n}
+    if rank == 0:
+        # size-independent properties: permutation, strict (d,i,j) order, true distances
+        assert sorted(res[:, 0].tolist()) == list(range(n)) and sorted(res[:, 1].tolist()) == list(range(n))
+        k = res[:, 2].astype(np.int64) * (1 << 40) + res[:, 0].astype(np.int64) * (1 << 20) + res[:, 1]
+        assert (np.diff(k) > 0).all()
+        assert (np.bitwise_count(q[res[:, 0]] ^ t[res[:, 1]]).sum(axis=1) == res[:, 2]).all()
+        line["properties_ok"] = True
+        if args.check:
+            d_tf = torch.from_numpy(t).to(dev)
+            o = torch.empty((3, n), dtype=torch.int32, device=dev)
+            for _ in range(2):
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                m.match_greedy_dev(d_q.data_ptr(), n, d_tf.data_ptr(), n, 256, 32, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), n)
+                torch.cuda.synchronize(); dt = time.perf_counter() - t0
+            line["unsharded_1gpu_ms"] = dt * 1e3
+            line["bit_identical_to_unsharded"] = bool((o.T.cpu().numpy() == res).all())
+        print(json.dumps(line), flush=True)
+    m.close()
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+main()
