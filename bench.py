@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=8192, help="descriptors per image (both sides)")
+    ap.add_argument("--size", dest="n", type=int, default=8192, help="descriptors per image (both sides)")
     ap.add_argument("--dist", default="U", choices=["U", "C"])
     ap.add_argument("--cpu-sample", type=int, default=2048, help="rows/cols of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

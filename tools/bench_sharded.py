@@ -2,7 +2,7 @@
 """BASELINE configs[3]: one huge synthetic pair, train set sharded over the ranks (torchrun).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port P \
-        tools/bench_sharded.py --n 200000 [--check]
+        tools/bench_sharded.py --size 200000 [--check]
 
 Every rank holds all N queries and 1/G of the train set; two NCCL `min` all-reduces of N packed keys per
 round.  With --check rank 0 also runs the unsharded single-GPU matcher and verifies bit-identity.
@@ -18,7 +18,7 @@ from photogrammetry_b200.keypoint_matching import Matcher
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=200000)
+    ap.add_argument("--size", dest="n", type=int, default=200000)
     ap.add_argument("--dist", default="U")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--check", action="store_true")
@@ -34,7 +34,10 @@ def main():
     t = synthetic.uniform_descriptors(5678, n, 256) if args.dist == "U" else synthetic.noisy_copy_descriptors(42, q, 256)
     lo, hi = sharding.train_slices(n, world)[rank]
     m = Matcher(local)
-    stream = torch.cuda.current_stream(dev)          # NCCL collectives are enqueued on the current stream
+    # NCCL collectives are enqueued on torch's current stream: make that an explicit stream and hand
+    # the same stream to the matcher, so kernels and collectives are ordered without host syncs
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     m.set_stream(stream.cuda_stream)
     d_q = torch.from_numpy(q).to(dev); d_t = torch.from_numpy(t[lo:hi].copy()).to(dev)
     times, rounds = [], 0
