@@ -187,6 +187,22 @@ int pgm_match_ratio_crosscheck(pgm_handle *h,
                                int32_t *out_qi, int32_t *out_tj, int32_t *out_dist,
                                int32_t capacity, int32_t *out_count);
 
+/* ---- float descriptors: squared-L2 nearest / second nearest (north_star extension) --
+ * q: float[n1][dim], t: float[n2][dim], 1 <= dim <= 128.  The reference has no float
+ * descriptor; semantics are those of oracle/pgm_oracle.c orc_l2_knn2: exact squared
+ * Euclidean distance, best and second-best train index under (distance, index), -1 where
+ * absent.  Computed as ||q||^2 + ||t||^2 - 2 q.t on the tcgen05 tensor cores (split-bf16
+ * operands, fp32 accumulation in TMEM) to rank candidates, then the top candidates are
+ * re-evaluated exactly in fp32: distances are exact to fp32 rounding (<= 1e-5 relative);
+ * indices equal the oracle's except where two candidates' distances differ by less than
+ * ~1e-5 relative (near-ties).  d_debug_dist (optional, device float[n1][n2]) receives
+ * the approximate GEMM distances. */
+int pgm_knn2_l2(pgm_handle *h, const float *q, int32_t n1, const float *t, int32_t n2, int32_t dim,
+                int32_t *best_j, float *best_d, int32_t *second_j, float *second_d);
+int pgm_knn2_l2_dev(pgm_handle *h, const float *d_q, int32_t n1, const float *d_t, int32_t n2, int32_t dim,
+                    int32_t *d_best_j, float *d_best_d, int32_t *d_second_j, float *d_second_d,
+                    float *d_debug_dist);
+
 /* ---- train-sharded single pair (multi-GPU) ----------
  * For ONE huge pair (BASELINE configs[3]: 200k x 200k) every rank holds all n1
  * queries and a contiguous slice [col_offset, col_offset + n2_local) of the

@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = (
     "pgm_match_hamming_greedy", "pgm_match_hamming_greedy_dev",
     "pgm_match_pairs_batch", "pgm_match_pairs_batch_dev",
     "pgm_knn2_hamming", "pgm_knn2_hamming_dev", "pgm_match_ratio_crosscheck",
-    "pgm_match_keypoints_sorted", "pgm_match_keypoints_sorted_dev",
+    "pgm_match_keypoints_sorted", "pgm_match_keypoints_sorted_dev", "pgm_knn2_l2", "pgm_knn2_l2_dev",
     "pgm_shard_create", "pgm_shard_round", "pgm_shard_propose", "pgm_shard_commit", "pgm_shard_finish",
     "pgm_shard_destroy",
     "pgm_set_profiling", "pgm_get_round_profile", "pgm_measure_popc_peak",
@@ -120,6 +120,8 @@ def load() -> C.CDLL:
         lib.pgm_knn2_hamming_dev.argtypes = knn
         lib.pgm_match_keypoints_sorted.argtypes = [C.c_void_p, u8p, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32, i64p]
         lib.pgm_match_keypoints_sorted_dev.argtypes = lib.pgm_match_keypoints_sorted.argtypes
+        lib.pgm_knn2_l2.argtypes = [C.c_void_p, vp, C.c_int32, vp, C.c_int32, C.c_int32, i32p, vp, i32p, vp]
+        lib.pgm_knn2_l2_dev.argtypes = [C.c_void_p, vp, C.c_int32, vp, C.c_int32, C.c_int32, i32p, vp, i32p, vp, vp]
         lib.pgm_match_ratio_crosscheck.argtypes = [C.c_void_p, u8p, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32,
                                                    C.c_float, C.c_int32, C.c_int32, i32p, i32p, i32p, C.c_int32,
                                                    C.POINTER(C.c_int32)]

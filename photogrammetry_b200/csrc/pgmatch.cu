@@ -6,6 +6,7 @@
 // sm_100 device is usable every entry point fails with PGM_E_NO_DEVICE.
 #include "../../include/pgmatch.h"
 #include "pgm_kernels.cuh"
+#include "pgm_l2.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -910,6 +911,144 @@ extern "C" int pgm_match_keypoints_sorted(pgm_handle *h, const uint8_t *q, int32
     CU_CHECK(h, cudaStreamSynchronize(h->stream));
     h->stats.host_syncs++;
     h->stats.d2h_bytes += (int64_t)bytes;
+    return PGM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// float descriptors: squared-L2 nearest / second nearest on tcgen05 (pgm_l2.cuh)
+// ---------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// rows x kprime bf16, row-major; box = 64 (K, 128 bytes) x 128 rows, 128-byte swizzle
+static int make_operand_map(pgm_handle *h, CUtensorMap *map, void *base, int rows, int kprime) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return fail(h, PGM_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[2] = {(cuuint64_t)kprime, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)kprime * 2};
+    cuuint32_t box[2] = {(cuuint32_t)pgm_l2::CHUNK_K, (cuuint32_t)pgm_l2::TILE_N};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, PGM_E_CUDA, "cuTensorMapEncodeTiled failed");
+    return PGM_OK;
+}
+
+static int l2_dev_impl(pgm_handle *h, const float *d_q, int32_t n1, const float *d_t, int32_t n2, int32_t dim,
+                       int32_t *d_bj, float *d_bd, int32_t *d_sj, float *d_sd, float *d_dbg) {
+    using namespace pgm_l2;
+    cudaStream_t s = h->stream;
+    const int dp = (dim + CHUNK_K - 1) / CHUNK_K * CHUNK_K, kprime = 3 * dp, chunks = kprime / CHUNK_K;
+    const int row_tiles = (n1 + TILE_M - 1) / TILE_M, col_tiles = (n2 + TILE_N - 1) / TILE_N;
+    int splits = std::max(1, std::min(col_tiles, (2 * h->num_sms + row_tiles - 1) / row_tiles));
+    const int tps = (col_tiles + splits - 1) / splits;
+    splits = (col_tiles + tps - 1) / tps;
+    // scratch: A' | B' | qn | tn | cand_j | cand_d
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+    const size_t o_a = take((size_t)n1 * kprime * 2), o_b = take((size_t)n2 * kprime * 2);
+    const size_t o_qn = take((size_t)n1 * 4), o_tn = take((size_t)n2 * 4);
+    const size_t o_cj = take((size_t)splits * n1 * TOPK * 4), o_cd = take((size_t)splits * n1 * TOPK * 4);
+    int rc = ensure_dev(h, h->misc, off);
+    if (rc) return rc;
+    char *base = (char *)h->misc.p;
+    __nv_bfloat16 *a = (__nv_bfloat16 *)(base + o_a), *b = (__nv_bfloat16 *)(base + o_b);
+    float *qn = (float *)(base + o_qn), *tn = (float *)(base + o_tn);
+    split_kernel<<<n1, 128, 0, s>>>(d_q, n1, dim, dp, 0, a, qn);
+    split_kernel<<<n2, 128, 0, s>>>(d_t, n2, dim, dp, 1, b, tn);
+    CUtensorMap map_a, map_b;
+    if ((rc = make_operand_map(h, &map_a, a, n1, kprime))) return rc;
+    if ((rc = make_operand_map(h, &map_b, b, n2, kprime))) return rc;
+    static bool attr = false;
+    if (!attr) {
+        CU_CHECK(h, cudaFuncSetAttribute(l2_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l2_smem_bytes()));
+        attr = true;
+    }
+    L2Params p{};
+    p.n1 = n1; p.n2 = n2; p.chunks = chunks; p.tiles_per_split = tps; p.qn = qn; p.tn = tn;
+    p.cand_j = (int32_t *)(base + o_cj); p.cand_d = (float *)(base + o_cd); p.dbg_dist = d_dbg;
+    l2_topk_kernel<<<dim3(row_tiles, splits), THREADS, l2_smem_bytes(), s>>>(map_a, map_b, p);
+    l2_refine_kernel<<<(n1 * 32 + 255) / 256, 256, 0, s>>>(d_q, n1, d_t, n2, dim, p.cand_j, splits, d_bj, d_bd, d_sj, d_sd);
+    h->stats.kernel_launches += 4;
+    h->stats.distance_evals += (int64_t)n1 * n2;
+    h->stats.evals_computed += (int64_t)n1 * n2;
+    CU_CHECK(h, cudaGetLastError());
+    return PGM_OK;
+}
+
+static int l2_check(pgm_handle *h, int32_t n1, int32_t n2, int32_t dim) {
+    if (n1 < 0 || n2 < 0 || n1 >= MAX_N || n2 >= MAX_N) return fail(h, PGM_E_INVALID_ARG, "bad sizes");
+    if (dim < 1 || dim > 128) return fail(h, PGM_E_INVALID_ARG, "dim must be in 1..128");
+    return PGM_OK;
+}
+
+extern "C" int pgm_knn2_l2_dev(pgm_handle *h, const float *d_q, int32_t n1, const float *d_t, int32_t n2, int32_t dim,
+                               int32_t *d_best_j, float *d_best_d, int32_t *d_second_j, float *d_second_d,
+                               float *d_debug_dist) {
+    if (!h) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    int rc = l2_check(h, n1, n2, dim);
+    if (rc) return rc;
+    h->stats = pgm_stats{};
+    h->stats_pending = false;
+    if (n1 == 0) return PGM_OK;
+    CU_CHECK(h, cudaSetDevice(h->device));
+    if (n2 == 0) {
+        for (void *o : {(void *)d_best_j, (void *)d_second_j}) CU_CHECK(h, cudaMemsetAsync(o, 0xFF, (size_t)n1 * 4, h->stream));
+        return PGM_OK;
+    }
+    return l2_dev_impl(h, d_q, n1, d_t, n2, dim, d_best_j, d_best_d, d_second_j, d_second_d, d_debug_dist);
+}
+
+extern "C" int pgm_knn2_l2(pgm_handle *h, const float *q, int32_t n1, const float *t, int32_t n2, int32_t dim,
+                           int32_t *best_j, float *best_d, int32_t *second_j, float *second_d) {
+    if (!h) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    int rc = l2_check(h, n1, n2, dim);
+    if (rc) return rc;
+    h->stats = pgm_stats{};
+    h->stats_pending = false;
+    if (n1 == 0) return PGM_OK;
+    if (n2 == 0) {
+        std::fill(best_j, best_j + n1, -1); std::fill(second_j, second_j + n1, -1);
+        std::fill(best_d, best_d + n1, -1.f); std::fill(second_d, second_d + n1, -1.f);
+        return PGM_OK;
+    }
+    CU_CHECK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const size_t qb = (size_t)n1 * dim * 4, tb = (size_t)n2 * dim * 4, t_off = align_up(qb, 256);
+    if ((rc = ensure_dev(h, h->desc, t_off + tb))) return rc;
+    if ((rc = ensure_dev(h, h->out, (size_t)4 * n1 * 4))) return rc;
+    if ((rc = ensure_host(h, h->pin_out, (size_t)4 * n1 * 4))) return rc;
+    CU_CHECK(h, cudaMemcpyAsync(h->desc.p, q, qb, cudaMemcpyHostToDevice, s));
+    CU_CHECK(h, cudaMemcpyAsync((char *)h->desc.p + t_off, t, tb, cudaMemcpyHostToDevice, s));
+    h->stats.h2d_bytes += (int64_t)(qb + tb);
+    int32_t *o = (int32_t *)h->out.p;
+    rc = l2_dev_impl(h, (const float *)h->desc.p, n1, (const float *)((char *)h->desc.p + t_off), n2, dim, o,
+                     (float *)(o + n1), o + 2 * (size_t)n1, (float *)(o + 3 * (size_t)n1), nullptr);
+    if (rc) return rc;
+    CU_CHECK(h, cudaMemcpyAsync(h->pin_out.p, o, (size_t)4 * n1 * 4, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(h, cudaStreamSynchronize(s));
+    h->stats.host_syncs++;
+    h->stats.d2h_bytes += (int64_t)4 * n1 * 4;
+    const int32_t *po = (const int32_t *)h->pin_out.p;
+    memcpy(best_j, po, (size_t)n1 * 4);
+    memcpy(best_d, po + n1, (size_t)n1 * 4);
+    memcpy(second_j, po + 2 * (size_t)n1, (size_t)n1 * 4);
+    memcpy(second_d, po + 3 * (size_t)n1, (size_t)n1 * 4);
     return PGM_OK;
 }
 

@@ -189,6 +189,18 @@ class Matcher:
                                                          desc_bits or max(bits_q, bits_t), stride, out.ctypes.data))
         return out
 
+    def knn2_l2(self, q: np.ndarray, t: np.ndarray):
+        """Float descriptors: (best_j, best_d, second_j, second_d) under squared L2 (tcgen05 GEMM + exact refinement)."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        t = np.ascontiguousarray(t, dtype=np.float32)
+        n1, n2 = int(q.shape[0]), int(t.shape[0])
+        dim = int(q.shape[1]) if n1 else int(t.shape[1])
+        bj = np.empty(max(n1, 1), dtype=np.int32); sj = np.empty(max(n1, 1), dtype=np.int32)
+        bd = np.empty(max(n1, 1), dtype=np.float32); sd = np.empty(max(n1, 1), dtype=np.float32)
+        self._check(self._lib.pgm_knn2_l2(self._h, _addr(q), n1, _addr(t), n2, dim, bj.ctypes.data, bd.ctypes.data,
+                                          sj.ctypes.data, sd.ctypes.data))
+        return bj[:n1], bd[:n1], sj[:n1], sd[:n1]
+
     def set_profiling(self, enabled: bool) -> None:
         self._check(self._lib.pgm_set_profiling(self._h, int(bool(enabled))))
 
