@@ -22,8 +22,8 @@
 //            one of two 128-column TMEM accumulators, tcgen05.commit frees stages / publishes
 //            the accumulator
 //   warp 2   TMEM alloc / dealloc (256 columns)
-//   warps 4-7 epilogue: tcgen05.ld (32 lanes x 32 columns per instruction), d = qn + tn - 2c,
-//            per-row top-4 in registers
+//   warps 4-11 epilogue (two warpgroups, half the columns each): tcgen05.ld (32 lanes x 32
+//            columns per instruction), d = qn + tn - 2c, per-row top-4 in registers
 #pragma once
 
 #include <cstdint>
@@ -39,8 +39,10 @@ constexpr int CHUNK_K = 64;        // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K = 16;         // K of one tcgen05.mma for 16-bit inputs
 constexpr int MAX_CHUNKS = 6;      // K' = 3 * Dp <= 384  (D <= 128)
 constexpr int STAGES = 6;          // B' ring
-constexpr int THREADS = 256;
-constexpr int TOPK = 4;
+constexpr int THREADS = 384;        // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: two epilogue warpgroups
+constexpr int EPI_GROUPS = 2;       // each epilogue warpgroup reduces half of the accumulator's columns
+constexpr int TOPK = 4;             // candidates kept per (query, column split, epilogue warpgroup)
+constexpr int CAND = TOPK * EPI_GROUPS;
 constexpr uint32_t CHUNK_BYTES = TILE_N * CHUNK_K * 2;   // 16 KB (A' and B' chunks have the same shape)
 constexpr uint32_t TMEM_COLS = 256;                      // two fp32 accumulators of 128 columns
 
@@ -60,16 +62,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"     // suspend-time hint: the thread
+        "selp.u32 %0, 1, 0, p;\n\t}"                                         // sleeps in hardware, no issue slots
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
     return ok != 0;
 }
 // Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) __trap();
+        if (++spins > 2000000u) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
@@ -145,11 +147,12 @@ struct L2Params {
     int n1, n2, chunks;            // chunks = 3 * Dp / 64
     int tiles_per_split;           // column tiles handled by one blockIdx.y
     const float *qn, *tn;          // squared norms
-    int32_t *cand_j;               // [splits][n1][TOPK]
-    float *cand_d;                 // [splits][n1][TOPK] approximate distances (diagnostic)
+    int32_t *cand_j;               // [splits][n1][CAND]
+    float *cand_d;                 // [splits][n1][CAND] approximate distances (diagnostic)
     float *dbg_dist;               // optional [n1][n2] approximate distance matrix (tests)
 };
 
+template <bool DBG>
 __global__ void __launch_bounds__(THREADS, 1)
 l2_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, L2Params p) {
     extern __shared__ unsigned char smem_raw[];
@@ -173,7 +176,7 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(a_bar, 1);
-        for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4 * EPI_GROUPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -224,44 +227,75 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else if (warp >= 4) {
         // ===== epilogue: one query row per thread =====
-        const int ew = warp - 4;                                // == warp % 4: the TMEM lane quarter this warp may read
+        const int ew = warp & 3;                                // the TMEM lane quarter this warp may read (warp % 4)
+        const int eg = (warp - 4) >> 2;                         // which half of the accumulator's columns
         const int row = m0 + ew * 32 + lane;
         const float qn = row < p.n1 ? __ldg(p.qn + row) : 0.f;
         float bd[TOPK]; int bj[TOPK];
 #pragma unroll
         for (int k = 0; k < TOPK; k++) { bd[k] = 3.4e38f; bj[k] = -1; }
-        const int et = threadIdx.x - 128;                       // 0..127
+        const int et = threadIdx.x - 128;                       // 0..255
         for (int t = 0; t < ntiles; t++) {
             const int acc = t & 1;
             const int j0 = (ct0 + t) * TILE_N;
             {   // stage ||t||^2 of this tile (ordered against the previous use of the same buffer by the
                 // tempty/tfull round trip: the buffer of tile t-2 was fully consumed before tempty arrived)
                 const int j = j0 + et;
-                s_tn[acc * TILE_N + et] = j < p.n2 ? __ldg(p.tn + j) : 3.0e38f;
+                if (et < TILE_N) s_tn[acc * TILE_N + et] = j < p.n2 ? __ldg(p.tn + j) : 3.0e38f;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(&tfull[acc], (t >> 1) & 1);
             tc_fence_after();
-#pragma unroll 1
-            for (int cb = 0; cb < TILE_N; cb += 32) {
-                uint32_t v[32];
-                tc_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TILE_N + cb), v);
+            // 32 columns per tcgen05.ld, software-pipelined (the next group's load is in flight while this
+            // one is reduced).  The common case is branch-free: all 32 distances and their minimum are
+            // computed first, and only a group that can improve the row's top-4 takes the insertion path.
+            uint32_t va[32], vb[32];
+            constexpr int GROUPS = TILE_N / 32 / EPI_GROUPS;    // 32-column groups per epilogue warpgroup
+            const int cbase = eg * (TILE_N / EPI_GROUPS);
+            const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TILE_N + cbase);
+            tc_ld_32x32b_x32(trow, va);
+#pragma unroll
+            for (int g = 0; g < GROUPS; g++) {
+                uint32_t (&v)[32] = (g & 1) ? vb : va;
                 tc_wait_ld();
+                if (g + 1 < GROUPS) tc_ld_32x32b_x32(trow + (uint32_t)((g + 1) * 32), (g & 1) ? va : vb);
+                const int cb = cbase + g * 32;
+                // keys: the distance's bit pattern (non-negative floats order like unsigned integers) with
+                // the column-in-group in its 5 low mantissa bits -> one integer min yields min AND argmin.
+                // The 2^-18 relative perturbation only affects candidate ranking; distances are refined
+                // exactly afterwards.  Keeps the insertion path a short loop instead of 32 unrolled
+                // blocks (the unrolled form overflowed the instruction cache: stall_no_inst dominated).
+                uint32_t key[32];
 #pragma unroll
                 for (int c = 0; c < 32; c++) {
-                    const float tn = s_tn[acc * TILE_N + cb + c];
-                    const float d = fmaxf(fmaf(-2.f, __uint_as_float(v[c]), qn + tn), 0.f);
-                    if (p.dbg_dist && row < p.n1 && j0 + cb + c < p.n2) p.dbg_dist[(size_t)row * p.n2 + j0 + cb + c] = d;
-                    if (d < bd[TOPK - 1]) {                     // rare after the first few tiles
-                        const int j = j0 + cb + c;
-                        bd[3] = d; bj[3] = j;
+                    const float d = fmaxf(fmaf(-2.f, __uint_as_float(v[c]), qn + s_tn[acc * TILE_N + cb + c]), 0.f);
+                    key[c] = (__float_as_uint(d) & 0xFFFFFFE0u) | (uint32_t)c;
+                }
+                if (DBG && p.dbg_dist && row < p.n1) {
 #pragma unroll
-                        for (int k = 3; k > 0; k--)
-                            if (bd[k] < bd[k - 1]) {
-                                const float td = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td;
-                                const int tj = bj[k]; bj[k] = bj[k - 1]; bj[k - 1] = tj;
-                            }
-                    }
+                    for (int c = 0; c < 32; c++)
+                        if (j0 + cb + c < p.n2) p.dbg_dist[(size_t)row * p.n2 + j0 + cb + c] = __uint_as_float(key[c] & 0xFFFFFFE0u);
+                }
+                uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu, k3 = 0xFFFFFFFFu;
+#pragma unroll
+                for (int c = 0; c < 32; c += 4) {
+                    k0 = min(k0, key[c]); k1 = min(k1, key[c + 1]); k2 = min(k2, key[c + 2]); k3 = min(k3, key[c + 3]);
+                }
+                uint32_t kmin = min(min(k0, k1), min(k2, k3));
+                uint32_t thr = __float_as_uint(bd[TOPK - 1]);
+                while (kmin < thr) {                            // rarely entered, usually one iteration
+                    bd[3] = __uint_as_float(kmin & 0xFFFFFFE0u); bj[3] = j0 + cb + (int)(kmin & 31u);
+#pragma unroll
+                    for (int k = 3; k > 0; k--)
+                        if (bd[k] < bd[k - 1]) {
+                            const float td = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td;
+                            const int tj = bj[k]; bj[k] = bj[k - 1]; bj[k - 1] = tj;
+                        }
+                    thr = __float_as_uint(bd[TOPK - 1]);
+                    uint32_t nxt = 0xFFFFFFFFu;                 // next key strictly above the one just taken
+#pragma unroll
+                    for (int c = 0; c < 32; c++) nxt = min(nxt, key[c] > kmin ? key[c] : 0xFFFFFFFFu);
+                    kmin = nxt;
                 }
             }
             tc_fence_before();
@@ -269,7 +303,7 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (lane == 0) mbar_arrive(&tempty[acc]);
         }
         if (row < p.n1) {
-            const size_t o = ((size_t)blockIdx.y * p.n1 + row) * TOPK;
+            const size_t o = ((size_t)blockIdx.y * p.n1 + row) * CAND + (size_t)eg * TOPK;
 #pragma unroll
             for (int k = 0; k < TOPK; k++) { p.cand_j[o + k] = bd[k] < 3.0e38f ? bj[k] : -1; p.cand_d[o + k] = bd[k]; }
         }
@@ -294,9 +328,9 @@ __global__ void l2_refine_kernel(const float *__restrict__ q, int n1, const floa
     if (warp >= n1) return;
     const int i = warp;
     float b = 0.f, s = 0.f; int bj = -1, sj = -1;
-    for (int c = 0; c < splits * TOPK; c++) {
-        const int sp = c / TOPK, k = c - sp * TOPK;
-        const int j = cand_j[((size_t)sp * n1 + i) * TOPK + k];
+    for (int c = 0; c < splits * CAND; c++) {
+        const int sp = c / CAND, k = c - sp * CAND;
+        const int j = cand_j[((size_t)sp * n1 + i) * CAND + k];
         if (j < 0 || j >= n2) continue;
         float acc = 0.f;
         for (int d = lane; d < dim; d += 32) {

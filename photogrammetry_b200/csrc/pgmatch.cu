@@ -961,7 +961,7 @@ static int l2_dev_impl(pgm_handle *h, const float *d_q, int32_t n1, const float 
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
     const size_t o_a = take((size_t)n1 * kprime * 2), o_b = take((size_t)n2 * kprime * 2);
     const size_t o_qn = take((size_t)n1 * 4), o_tn = take((size_t)n2 * 4);
-    const size_t o_cj = take((size_t)splits * n1 * TOPK * 4), o_cd = take((size_t)splits * n1 * TOPK * 4);
+    const size_t o_cj = take((size_t)splits * n1 * CAND * 4), o_cd = take((size_t)splits * n1 * CAND * 4);
     int rc = ensure_dev(h, h->misc, off);
     if (rc) return rc;
     char *base = (char *)h->misc.p;
@@ -974,13 +974,15 @@ static int l2_dev_impl(pgm_handle *h, const float *d_q, int32_t n1, const float 
     if ((rc = make_operand_map(h, &map_b, b, n2, kprime))) return rc;
     static bool attr = false;
     if (!attr) {
-        CU_CHECK(h, cudaFuncSetAttribute(l2_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l2_smem_bytes()));
+        CU_CHECK(h, cudaFuncSetAttribute(l2_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l2_smem_bytes()));
+        CU_CHECK(h, cudaFuncSetAttribute(l2_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l2_smem_bytes()));
         attr = true;
     }
     L2Params p{};
     p.n1 = n1; p.n2 = n2; p.chunks = chunks; p.tiles_per_split = tps; p.qn = qn; p.tn = tn;
     p.cand_j = (int32_t *)(base + o_cj); p.cand_d = (float *)(base + o_cd); p.dbg_dist = d_dbg;
-    l2_topk_kernel<<<dim3(row_tiles, splits), THREADS, l2_smem_bytes(), s>>>(map_a, map_b, p);
+    if (d_dbg) l2_topk_kernel<true><<<dim3(row_tiles, splits), THREADS, l2_smem_bytes(), s>>>(map_a, map_b, p);
+    else l2_topk_kernel<false><<<dim3(row_tiles, splits), THREADS, l2_smem_bytes(), s>>>(map_a, map_b, p);
     l2_refine_kernel<<<(n1 * 32 + 255) / 256, 256, 0, s>>>(d_q, n1, d_t, n2, dim, p.cand_j, splits, d_bj, d_bd, d_sj, d_sd);
     h->stats.kernel_launches += 4;
     h->stats.distance_evals += (int64_t)n1 * n2;
