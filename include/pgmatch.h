@@ -203,6 +203,35 @@ int pgm_knn2_l2_dev(pgm_handle *h, const float *d_q, int32_t n1, const float *d_
                     int32_t *d_best_j, float *d_best_d, int32_t *d_second_j, float *d_second_d,
                     float *d_debug_dist);
 
+/* ---- the producer of the matcher's inputs ----------
+ * gray: float[height][width] = Grayscale.K (Images.Abstractions/Pixels/Grayscale.cs:19-23),
+ * pixel (x, y) at gray[y*width + x].
+ *
+ * pgm_fast_detect    KeypointDetection.Detect (KeypointDetection.cs:42-133): FAST-12 on the
+ *                    reference's ring table (typo in its last entry included); keypoints in the
+ *                    reference's row-major order, out_xy[k] = (x, y), out_score[k] = FastScore.
+ *                    *out_count always receives the number found; PGM_E_CAPACITY if > capacity.
+ * pgm_brief_describe Keypoint.GetBriefDescriptor (Keypoint.cs:29-57): pairs int32[n_pairs][4] =
+ *                    (dx1, dy1, dx2, dy2); first pair = most significant bit; descriptors in the
+ *                    matcher's row layout (desc_bits = n_pairs).
+ * pgm_nms            RedundantKeypointEliminator.EliminateRedundantKeypoints
+ *                    (RedundantKeypointEliminator.cs:16-39): out_kept = indices of the survivors in
+ *                    the reference's output order (stable by FastScore descending).
+ *
+ * flags: 0 = the C# generation.  PGM_FLAG_PYTHON_GENERATION selects the older Python generation's
+ * variants of the same two steps, which the reference tree can execute and therefore pins with golden
+ * vectors: FASTKeypointDetector (python_src/photogrammetry/image_processing/keypoint_detection.py:12-115,
+ * correct ring entry 15, same segment test) and KeyPoint._brief_descriptor
+ * (python_src/photogrammetry/models/keypoint.py:32-50: pair idx sets bit idx, LSB first). */
+#define PGM_FLAG_PYTHON_GENERATION 0x2u
+int pgm_fast_detect(pgm_handle *h, const float *gray, int32_t width, int32_t height, float threshold,
+                    uint32_t flags, int32_t *out_xy, int32_t *out_score, int32_t capacity, int32_t *out_count);
+int pgm_brief_describe(pgm_handle *h, const float *gray, int32_t width, int32_t height, const int32_t *xy,
+                       int32_t n, const int32_t *pairs, int32_t n_pairs, int32_t stride_bytes, uint32_t flags,
+                       uint8_t *out_desc);
+int pgm_nms(pgm_handle *h, const int32_t *xy, const int32_t *score, int32_t n, int32_t radius,
+            int32_t *out_kept, int32_t *out_count);
+
 /* ---- train-sharded single pair (multi-GPU) ----------
  * For ONE huge pair (BASELINE configs[3]: 200k x 200k) every rank holds all n1
  * queries and a contiguous slice [col_offset, col_offset + n2_local) of the

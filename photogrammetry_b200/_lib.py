@@ -25,6 +25,7 @@ PGM_E_EMPTY_TRAIN = -5
 PGM_E_NOMEM = -6
 PGM_E_NO_DEVICE = -7
 PGM_FLAG_REFERENCE_COMPAT_TAIL = 0x1
+PGM_FLAG_PYTHON_GENERATION = 0x2
 PGM_TAIL_DISTANCE = 2147483647
 
 # every symbol include/pgmatch.h declares (tests check the .so exports them all)
@@ -35,6 +36,7 @@ EXPORTED_SYMBOLS = (
     "pgm_match_pairs_batch", "pgm_match_pairs_batch_dev",
     "pgm_knn2_hamming", "pgm_knn2_hamming_dev", "pgm_match_ratio_crosscheck",
     "pgm_match_keypoints_sorted", "pgm_match_keypoints_sorted_dev", "pgm_knn2_l2", "pgm_knn2_l2_dev",
+    "pgm_fast_detect", "pgm_brief_describe", "pgm_nms",
     "pgm_shard_create", "pgm_shard_round", "pgm_shard_propose", "pgm_shard_commit", "pgm_shard_finish",
     "pgm_shard_destroy",
     "pgm_set_profiling", "pgm_get_round_profile", "pgm_measure_popc_peak",
@@ -125,6 +127,11 @@ def load() -> C.CDLL:
         lib.pgm_match_ratio_crosscheck.argtypes = [C.c_void_p, u8p, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32,
                                                    C.c_float, C.c_int32, C.c_int32, i32p, i32p, i32p, C.c_int32,
                                                    C.POINTER(C.c_int32)]
+        lib.pgm_fast_detect.argtypes = [C.c_void_p, vp, C.c_int32, C.c_int32, C.c_float, C.c_uint32, i32p, i32p,
+                                        C.c_int32, C.POINTER(C.c_int32)]
+        lib.pgm_brief_describe.argtypes = [C.c_void_p, vp, C.c_int32, C.c_int32, i32p, C.c_int32, i32p, C.c_int32,
+                                           C.c_int32, C.c_uint32, u8p]
+        lib.pgm_nms.argtypes = [C.c_void_p, i32p, i32p, C.c_int32, C.c_int32, i32p, C.POINTER(C.c_int32)]
         lib.pgm_shard_create.argtypes = [C.c_void_p, u8p, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_int32, C.POINTER(C.c_void_p)]
         lib.pgm_shard_round.argtypes = [C.c_void_p, C.c_void_p]

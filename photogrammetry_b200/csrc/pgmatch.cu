@@ -7,6 +7,7 @@
 #include "../../include/pgmatch.h"
 #include "pgm_kernels.cuh"
 #include "pgm_l2.cuh"
+#include "pgm_detect.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -1051,6 +1052,148 @@ extern "C" int pgm_knn2_l2(pgm_handle *h, const float *q, int32_t n1, const floa
     memcpy(best_d, po + n1, (size_t)n1 * 4);
     memcpy(second_j, po + 2 * (size_t)n1, (size_t)n1 * 4);
     memcpy(second_d, po + 3 * (size_t)n1, (size_t)n1 * 4);
+    return PGM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// keypoint producer: FAST-12, BRIEF, NMS (pgm_detect.cuh)
+// ---------------------------------------------------------------------------
+extern "C" int pgm_fast_detect(pgm_handle *h, const float *gray, int32_t width, int32_t height, float threshold,
+                               uint32_t flags, int32_t *out_xy, int32_t *out_score, int32_t capacity,
+                               int32_t *out_count) {
+    using namespace pgm_det;
+    if (!h || !out_count) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!gray || width < 1 || height < 1 || width > 65535 || height > 65535)
+        return fail(h, PGM_E_INVALID_ARG, "bad image");     // MatrixDimensions are ushort upstream
+    h->stats = pgm_stats{};
+    h->stats_pending = false;
+    CU_CHECK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const size_t npx = (size_t)width * height;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_img = take(npx * 4), o_sc = take(npx), o_cnt = take((size_t)height * 4), o_off = take((size_t)(height + 1) * 4);
+    int rc = ensure_dev(h, h->misc, off);
+    if (rc) return rc;
+    char *base = (char *)h->misc.p;
+    float *d_img = (float *)(base + o_img);
+    uint8_t *d_sc = (uint8_t *)(base + o_sc);
+    int32_t *d_cnt = (int32_t *)(base + o_cnt), *d_off = (int32_t *)(base + o_off);
+    CU_CHECK(h, cudaMemcpyAsync(d_img, gray, npx * 4, cudaMemcpyHostToDevice, s));
+    dim3 blk(32, 8), grd((width + 31) / 32, (height + 7) / 8);
+    if (flags & PGM_FLAG_PYTHON_GENERATION) fast_score_kernel<1><<<grd, blk, 0, s>>>(d_img, width, height, threshold, d_sc);
+    else fast_score_kernel<0><<<grd, blk, 0, s>>>(d_img, width, height, threshold, d_sc);
+    row_count_kernel<<<height, 128, 0, s>>>(d_sc, width, d_cnt);
+    scan_kernel<<<1, 1024, 0, s>>>(d_cnt, height, d_off);
+    if ((rc = ensure_host(h, h->pin_out, 64))) return rc;
+    CU_CHECK(h, cudaMemcpyAsync(h->pin_out.p, d_off + height, 4, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(h, cudaStreamSynchronize(s));
+    const int32_t total = *(int32_t *)h->pin_out.p;
+    *out_count = total;
+    h->stats.kernel_launches += 3; h->stats.host_syncs++; h->stats.h2d_bytes += (int64_t)npx * 4;
+    if (total > capacity) return fail(h, PGM_E_CAPACITY, "more keypoints than capacity (out_count holds the number found)");
+    if (total == 0) return PGM_OK;
+    if ((rc = ensure_dev(h, h->out, (size_t)total * 12))) return rc;
+    if ((rc = ensure_host(h, h->pin_out, (size_t)total * 12))) return rc;
+    int32_t *d_xy = (int32_t *)h->out.p, *d_s = d_xy + 2 * (size_t)total;
+    emit_kernel<<<(height + 3) / 4, 128, 0, s>>>(d_sc, width, height, d_off, total, d_xy, d_s);
+    CU_CHECK(h, cudaMemcpyAsync(h->pin_out.p, h->out.p, (size_t)total * 12, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(h, cudaStreamSynchronize(s));
+    memcpy(out_xy, h->pin_out.p, (size_t)total * 8);
+    memcpy(out_score, (char *)h->pin_out.p + (size_t)total * 8, (size_t)total * 4);
+    h->stats.kernel_launches += 1; h->stats.host_syncs++; h->stats.d2h_bytes += (int64_t)total * 12;
+    CU_CHECK(h, cudaGetLastError());
+    return PGM_OK;
+}
+
+extern "C" int pgm_brief_describe(pgm_handle *h, const float *gray, int32_t width, int32_t height, const int32_t *xy,
+                                  int32_t n, const int32_t *pairs, int32_t n_pairs, int32_t stride_bytes,
+                                  uint32_t flags, uint8_t *out_desc) {
+    using namespace pgm_det;
+    if (!h) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    int rc = check_format(h, n_pairs, stride_bytes);       // desc_bits == NumGaussianPairs
+    if (rc) return rc;
+    if (!gray || width < 1 || height < 1 || n < 0 || !pairs) return fail(h, PGM_E_INVALID_ARG, "bad arguments");
+    h->stats = pgm_stats{};
+    h->stats_pending = false;
+    if (n == 0) return PGM_OK;
+    CU_CHECK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const size_t npx = (size_t)width * height;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_img = take(npx * 4), o_xy = take((size_t)n * 8), o_pr = take((size_t)n_pairs * 16), o_d = take((size_t)n * stride_bytes);
+    if ((rc = ensure_dev(h, h->misc, off))) return rc;
+    char *base = (char *)h->misc.p;
+    CU_CHECK(h, cudaMemcpyAsync(base + o_img, gray, npx * 4, cudaMemcpyHostToDevice, s));
+    CU_CHECK(h, cudaMemcpyAsync(base + o_xy, xy, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    CU_CHECK(h, cudaMemcpyAsync(base + o_pr, pairs, (size_t)n_pairs * 16, cudaMemcpyHostToDevice, s));
+    const int warps = 4, sw = stride_bytes / 4;
+    brief_kernel<<<(n + warps - 1) / warps, warps * 32, warps * sw * 4, s>>>((const float *)(base + o_img), width, height,
+                                                                         (const int32_t *)(base + o_xy), n,
+                                                                         (const int32_t *)(base + o_pr), n_pairs, sw,
+                                                                         (flags & PGM_FLAG_PYTHON_GENERATION) ? 1 : 0,
+                                                                         (uint32_t *)(base + o_d));
+    CU_CHECK(h, cudaMemcpyAsync(out_desc, base + o_d, (size_t)n * stride_bytes, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(h, cudaStreamSynchronize(s));
+    h->stats.kernel_launches += 1; h->stats.host_syncs++;
+    h->stats.h2d_bytes += (int64_t)(npx * 4 + (size_t)n * 8); h->stats.d2h_bytes += (int64_t)n * stride_bytes;
+    CU_CHECK(h, cudaGetLastError());
+    return PGM_OK;
+}
+
+extern "C" int pgm_nms(pgm_handle *h, const int32_t *xy, const int32_t *score, int32_t n, int32_t radius,
+                       int32_t *out_kept, int32_t *out_count) {
+    using namespace pgm_det;
+    if (!h || !out_count) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (n < 0 || radius < 0 || (n > 0 && (!xy || !score || !out_kept))) return fail(h, PGM_E_INVALID_ARG, "bad arguments");
+    h->stats = pgm_stats{};
+    h->stats_pending = false;
+    *out_count = 0;
+    if (n == 0) return PGM_OK;
+    CU_CHECK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_xy = take((size_t)n * 8), o_sc = take((size_t)n * 4), o_rk = take((size_t)n * 4), o_or = take((size_t)n * 4);
+    const size_t o_s0 = take(n), o_s1 = take(n), o_kept = take((size_t)n * 4), o_cnt = take(16);
+    int rc = ensure_dev(h, h->misc, off);
+    if (rc) return rc;
+    if ((rc = ensure_host(h, h->pin_out, (size_t)n * 4 + 64))) return rc;
+    char *base = (char *)h->misc.p;
+    int32_t *d_xy = (int32_t *)(base + o_xy), *d_sc = (int32_t *)(base + o_sc), *d_rk = (int32_t *)(base + o_rk);
+    int32_t *d_or = (int32_t *)(base + o_or), *d_kept = (int32_t *)(base + o_kept), *d_cnt = (int32_t *)(base + o_cnt);
+    uint8_t *st[2] = {(uint8_t *)(base + o_s0), (uint8_t *)(base + o_s1)};
+    CU_CHECK(h, cudaMemcpyAsync(d_xy, xy, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    CU_CHECK(h, cudaMemcpyAsync(d_sc, score, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    CU_CHECK(h, cudaMemsetAsync(st[0], 0, n, s));
+    const int blocks = (n + 255) / 256;
+    nms_rank_kernel<<<blocks, 256, 0, s>>>(d_sc, n, d_rk, d_or);
+    h->stats.kernel_launches += 1;
+    int32_t *h_cnt = (int32_t *)h->pin_out.p;
+    const long long r2 = (long long)radius * radius;
+    for (int round = 0;; round++) {
+        CU_CHECK(h, cudaMemsetAsync(d_cnt, 0, 4, s));
+        nms_round_kernel<<<blocks, 256, 0, s>>>(d_xy, d_rk, n, r2, st[round & 1], st[(round + 1) & 1], d_cnt);
+        CU_CHECK(h, cudaMemcpyAsync(h_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s));
+        CU_CHECK(h, cudaStreamSynchronize(s));
+        h->stats.kernel_launches += 1; h->stats.host_syncs++; h->stats.rounds++;
+        if (*h_cnt == 0) {
+            nms_emit_kernel<<<1, 1024, 0, s>>>(d_or, st[(round + 1) & 1], n, d_kept, d_cnt);
+            break;
+        }
+        if (round > n + 2) return fail(h, PGM_E_CUDA, "NMS failed to converge (internal error)");
+    }
+    CU_CHECK(h, cudaMemcpyAsync(h_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(h, cudaMemcpyAsync(h_cnt + 16, d_kept, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(h, cudaStreamSynchronize(s));
+    *out_count = h_cnt[0];
+    memcpy(out_kept, h_cnt + 16, (size_t)h_cnt[0] * 4);
+    h->stats.kernel_launches += 1; h->stats.host_syncs++;
+    CU_CHECK(h, cudaGetLastError());
     return PGM_OK;
 }
 

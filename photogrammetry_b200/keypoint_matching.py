@@ -24,8 +24,8 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import (PGM_E_EMPTY_TRAIN, PGM_FLAG_REFERENCE_COMPAT_TAIL, PGM_OK, EmptyTrainError, PgmatchError,
-                   PgmatchLibraryError, Stats)
+from ._lib import (PGM_E_CAPACITY, PGM_E_EMPTY_TRAIN, PGM_FLAG_PYTHON_GENERATION, PGM_FLAG_REFERENCE_COMPAT_TAIL,
+                   PGM_OK, EmptyTrainError, PgmatchError, PgmatchLibraryError, Stats)
 from .descriptors import as_descriptor_rows, pack_descriptors
 from .keypoint import Keypoint, KeypointPair
 
@@ -200,6 +200,58 @@ class Matcher:
         self._check(self._lib.pgm_knn2_l2(self._h, _addr(q), n1, _addr(t), n2, dim, bj.ctypes.data, bd.ctypes.data,
                                           sj.ctypes.data, sd.ctypes.data))
         return bj[:n1], bd[:n1], sj[:n1], sd[:n1]
+
+    # -- the producer of the matcher's inputs: FAST-12, BRIEF, NMS ----------
+    def fast_detect(self, gray: np.ndarray, threshold: float, python_generation: bool = False):
+        """``KeypointDetection.Detect`` without the descriptors (KeypointDetection.cs:42-133).
+        gray: ``float32[H, W]``.  Returns (xy int32[n, 2] as (x, y) in row-major scan order, score int32[n])."""
+        gray = np.ascontiguousarray(gray, dtype=np.float32)
+        if gray.ndim != 2:
+            raise ValueError("gray must be a 2-D array [height, width]")
+        hgt, wid = gray.shape
+        flags = PGM_FLAG_PYTHON_GENERATION if python_generation else 0
+        cap = 4096
+        while True:
+            xy = np.empty((cap, 2), dtype=np.int32)
+            sc = np.empty(cap, dtype=np.int32)
+            cnt = C.c_int32(0)
+            rc = self._lib.pgm_fast_detect(self._h, gray.ctypes.data, wid, hgt, float(threshold), flags,
+                                           xy.ctypes.data, sc.ctypes.data, cap, C.byref(cnt))
+            if rc == PGM_E_CAPACITY and cnt.value > cap:
+                cap = cnt.value
+                continue
+            self._check(rc)
+            return xy[:cnt.value].copy(), sc[:cnt.value].copy()
+
+    def brief_describe(self, gray: np.ndarray, xy: np.ndarray, pairs: np.ndarray, stride: Optional[int] = None,
+                       python_generation: bool = False) -> np.ndarray:
+        """``Keypoint.GetBriefDescriptor`` (Keypoint.cs:29-57) for every (x, y) of ``xy``.
+        pairs: int32[n_pairs, 4] = (dx1, dy1, dx2, dy2).  Returns ``uint8[n, stride]`` matcher rows."""
+        gray = np.ascontiguousarray(gray, dtype=np.float32)
+        xy = np.ascontiguousarray(xy, dtype=np.int32).reshape(-1, 2)
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 4)
+        hgt, wid = gray.shape
+        n, n_pairs = len(xy), len(pairs)
+        stride = stride or ((n_pairs + 127) // 128) * 16
+        out = np.zeros((n, stride), dtype=np.uint8)
+        flags = PGM_FLAG_PYTHON_GENERATION if python_generation else 0
+        self._check(self._lib.pgm_brief_describe(self._h, gray.ctypes.data, wid, hgt, _addr(xy), n, pairs.ctypes.data,
+                                                 n_pairs, stride, flags, _addr(out)))
+        return out
+
+    def nms(self, xy: np.ndarray, score: np.ndarray, radius: int) -> np.ndarray:
+        """``RedundantKeypointEliminator.EliminateRedundantKeypoints`` (RedundantKeypointEliminator.cs:16-39):
+        indices of the surviving keypoints in the reference's output order."""
+        xy = np.ascontiguousarray(xy, dtype=np.int32).reshape(-1, 2)
+        score = np.ascontiguousarray(score, dtype=np.int32).reshape(-1)
+        n = len(xy)
+        if len(score) != n:
+            raise ValueError("xy and score differ in length")
+        kept = np.empty(max(n, 1), dtype=np.int32)
+        cnt = C.c_int32(0)
+        self._check(self._lib.pgm_nms(self._h, _addr(xy), _addr(score), n, int(radius), kept.ctypes.data,
+                                      C.byref(cnt)))
+        return kept[:cnt.value].copy()
 
     def set_profiling(self, enabled: bool) -> None:
         self._check(self._lib.pgm_set_profiling(self._h, int(bool(enabled))))
