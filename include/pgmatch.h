@@ -92,7 +92,8 @@ int pgm_create(int device_ordinal, pgm_handle **out);
 int pgm_destroy(pgm_handle *h);
 const char *pgm_last_error(pgm_handle *h);
 /* Borrow a caller-owned cudaStream_t (e.g. a torch stream) for all subsequent
- * work of this handle; NULL restores the handle's own stream. */
+ * work of this handle; NULL restores the handle's own stream.  To run on the legacy default
+ * stream pass cudaStreamLegacy ((cudaStream_t)0x1), not 0. */
 int pgm_set_stream(pgm_handle *h, void *cuda_stream);
 int pgm_synchronize(pgm_handle *h);
 int pgm_get_stats(pgm_handle *h, pgm_stats *out);

@@ -17,6 +17,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace pgm;
@@ -43,6 +44,11 @@ struct pgm_handle {
     DevBuf state;     // per-chunk matcher state (carved by carve())
     DevBuf desc;      // descriptors uploaded by the host-buffer entry points
     DevBuf out;       // device staging of outputs for the host-buffer entry points
+    DevBuf out2;      // second output buffer: the batch entry point overlaps D2H of chunk k with chunk k+1
+    HostBuf pin_out2;
+    cudaStream_t copy_stream = nullptr;            // D2H of finished chunks (batch entry point)
+    cudaEvent_t ev_done[2] = {nullptr, nullptr};   // chunk's kernels finished (main stream)
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}; // chunk's triples sit in pinned memory (copy stream)
     DevBuf misc;      // knn2 partials etc.
     HostBuf pin_in;   // pinned staging, host -> device
     HostBuf pin_out;  // pinned staging, device -> host
@@ -169,9 +175,12 @@ extern "C" int pgm_destroy(pgm_handle *h) {
     if (!h) return PGM_E_INVALID_ARG;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (DevBuf *b : {&h->state, &h->desc, &h->out, &h->misc})
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    for (cudaEvent_t e : {h->ev_done[0], h->ev_done[1], h->ev_copied[0], h->ev_copied[1]})
+        if (e) cudaEventDestroy(e);
+    for (DevBuf *b : {&h->state, &h->desc, &h->out, &h->out2, &h->misc})
         if (b->p) cudaFree(b->p);
-    for (HostBuf *b : {&h->pin_in, &h->pin_out, &h->pin_meta, &h->pin_prof})
+    for (HostBuf *b : {&h->pin_in, &h->pin_out, &h->pin_out2, &h->pin_meta, &h->pin_prof})
         if (b->p) cudaFreeHost(b->p);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -615,9 +624,22 @@ static int batch_impl(pgm_handle *h, const uint8_t *d_all_desc, const int64_t *i
     }
     if (capacity < total) return fail(h, PGM_E_CAPACITY, "capacity < sum of query sizes");
 
+    // Host outputs: chunk k's triples leave over a second stream (device buffer -> pinned staging) and a
+    // helper thread moves them into the caller's (pageable) arrays while chunk k+1 computes.
+    struct Joiner {
+        std::thread th[2];
+        ~Joiner() { for (auto &t : th) if (t.joinable()) t.join(); }
+    } jobs;
+    if (out_on_host && !h->copy_stream) {
+        CU_CHECK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; k++) {
+            CU_CHECK(h, cudaEventCreateWithFlags(&h->ev_done[k], cudaEventDisableTiming));
+            CU_CHECK(h, cudaEventCreateWithFlags(&h->ev_copied[k], cudaEventDisableTiming));
+        }
+    }
     std::vector<HostPair> chunk;
     int64_t done_rows = 0;
-    int p = 0;
+    int p = 0, chunk_no = 0;
     while (p < n_pairs) {
         chunk.clear();
         int64_t slots = 0, rows = 0;
@@ -633,11 +655,18 @@ static int batch_impl(pgm_handle *h, const uint8_t *d_all_desc, const int64_t *i
             p++;
         }
         if (rows == 0) continue;
+        const int slot = chunk_no & 1;
+        chunk_no++;
         int32_t *d_qi, *d_tj, *d_dd;
+        DevBuf &dout = slot ? h->out2 : h->out;
+        HostBuf &pin = slot ? h->pin_out2 : h->pin_out;
         if (out_on_host) {
+            // this slot's previous user (chunk k-2) must have left both the device buffer and the staging
+            if (jobs.th[slot].joinable()) jobs.th[slot].join();
             int rc;
-            if ((rc = ensure_dev(h, h->out, (size_t)3 * rows * 4))) return rc;
-            d_qi = (int32_t *)h->out.p; d_tj = d_qi + rows; d_dd = d_tj + rows;
+            if ((rc = ensure_dev(h, dout, (size_t)3 * rows * 4))) return rc;
+            if ((rc = ensure_host(h, pin, (size_t)3 * rows * 4))) return rc;
+            d_qi = (int32_t *)dout.p; d_tj = d_qi + rows; d_dd = d_tj + rows;
         } else {
             d_qi = out_qi + done_rows; d_tj = out_tj + done_rows; d_dd = out_dist + done_rows;
         }
@@ -649,16 +678,39 @@ static int batch_impl(pgm_handle *h, const uint8_t *d_all_desc, const int64_t *i
         }
         int rc = run_chunk(h, chunk.data(), (int)chunk.size(), desc_bits, stride_bytes, flags, d_qi, d_tj, d_dd);
         if (rc) return rc;
-        if (out_on_host) {
-            CU_CHECK(h, cudaMemcpyAsync(out_qi + done_rows, d_qi, (size_t)rows * 4, cudaMemcpyDeviceToHost, s));
-            CU_CHECK(h, cudaMemcpyAsync(out_tj + done_rows, d_tj, (size_t)rows * 4, cudaMemcpyDeviceToHost, s));
-            CU_CHECK(h, cudaMemcpyAsync(out_dist + done_rows, d_dd, (size_t)rows * 4, cudaMemcpyDeviceToHost, s));
+        if (h->stats_pending) {       // latency-mode chunk: its plan read-back shares pin_meta with the next chunk
             CU_CHECK(h, cudaStreamSynchronize(s));
             h->stats.host_syncs++;
             resolve_pending_stats(h);
+        }
+        if (out_on_host) {
+            CU_CHECK(h, cudaEventRecord(h->ev_done[slot], s));
+            CU_CHECK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));
+            CU_CHECK(h, cudaMemcpyAsync(pin.p, dout.p, (size_t)3 * rows * 4, cudaMemcpyDeviceToHost, h->copy_stream));
+            CU_CHECK(h, cudaEventRecord(h->ev_copied[slot], h->copy_stream));
+            const int32_t *src = (const int32_t *)pin.p;
+            int32_t *dq = out_qi + done_rows, *dt = out_tj + done_rows, *dd = out_dist + done_rows;
+            cudaEvent_t evc = h->ev_copied[slot];
+            const int dev = h->device;
+            const size_t nb = (size_t)rows * 4;
+            const int64_t nrows = rows;
+            jobs.th[slot] = std::thread([=]() {
+                cudaSetDevice(dev);
+                cudaEventSynchronize(evc);
+                memcpy(dq, src, nb);
+                memcpy(dt, src + nrows, nb);
+                memcpy(dd, src + 2 * nrows, nb);
+            });
             h->stats.d2h_bytes += (int64_t)3 * rows * 4;
         }
         done_rows += rows;
+    }
+    if (out_on_host) {
+        for (auto &t : jobs.th) if (t.joinable()) t.join();
+        CU_CHECK(h, cudaStreamSynchronize(h->copy_stream));
+        CU_CHECK(h, cudaStreamSynchronize(s));
+        h->stats.host_syncs++;
+        CU_CHECK(h, cudaGetLastError());
     }
     return PGM_OK;
 }

@@ -76,8 +76,16 @@ class Matcher:
         raise PgmatchError(rc, msg)
 
     def set_stream(self, cuda_stream: Optional[int]) -> None:
-        """Run on a caller-owned CUDA stream (e.g. ``torch.cuda.Stream().cuda_stream``)."""
-        self._check(self._lib.pgm_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        """Run on a caller-owned CUDA stream (e.g. ``torch.cuda.Stream().cuda_stream``).  ``None`` returns to the
+        handle's own stream; ``0`` (what torch reports for its default stream) selects the legacy default
+        stream explicitly (``cudaStreamLegacy``), because a NULL stream means "own stream" across the ABI."""
+        if cuda_stream is None:
+            addr = 0
+        elif int(cuda_stream) == 0:
+            addr = 1                    # cudaStreamLegacy
+        else:
+            addr = int(cuda_stream)
+        self._check(self._lib.pgm_set_stream(self._h, C.c_void_p(addr)))
 
     def synchronize(self) -> None:
         self._check(self._lib.pgm_synchronize(self._h))
@@ -118,11 +126,17 @@ class Matcher:
         return cnt.value
 
     def match_pairs_batch(self, all_desc: np.ndarray, image_offsets: Sequence[int], pair_list,
-                          desc_bits: Optional[int] = None, reference_compat_tail: bool = True):
+                          desc_bits: Optional[int] = None, reference_compat_tail: bool = True,
+                          out: Optional[np.ndarray] = None):
         """Match many image pairs in one call.
 
         Returns ``(triples int32[total, 3], starts int64[n_pairs], counts int32[n_pairs])``;
         pair ``p`` owns ``triples[starts[p]:starts[p]+counts[p]]``.
+
+        ``out``: optional caller-owned ``int32[3, >= total]`` C-contiguous array that receives the raw SoA
+        output (qi, tj, dist) and is reused across calls; the function then returns ``out[:, :total]`` itself
+        (SoA, no copy) in place of the ``[total, 3]`` array.  Gigabyte-sized result arrays are dominated by
+        the operating system's first-touch page faults when they are allocated fresh on every call.
         """
         all_desc, bits = as_descriptor_rows(all_desc, desc_bits)
         offs = np.ascontiguousarray(image_offsets, dtype=np.int64)
@@ -132,13 +146,20 @@ class Matcher:
         n1s = sizes[pairs[:, 0]] if n_pairs else np.zeros(0, dtype=np.int64)
         starts = np.concatenate([[0], np.cumsum(n1s)]).astype(np.int64)
         total = int(starts[-1])
-        out = np.empty((3, max(total, 1)), dtype=np.int32)
+        reuse = out is not None
+        if reuse:
+            if out.dtype != np.int32 or out.ndim != 2 or out.shape[0] != 3 or out.shape[1] < total or not out.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous int32[3, >= total] array")
+        else:
+            out = np.empty((3, max(total, 1)), dtype=np.int32)
         counts = np.zeros(max(n_pairs, 1), dtype=np.int32)
         flags = PGM_FLAG_REFERENCE_COMPAT_TAIL if reference_compat_tail else 0
         self._check(self._lib.pgm_match_pairs_batch(
             self._h, _addr(all_desc), offs.ctypes.data, n_images, pairs.ctypes.data, n_pairs,
             desc_bits or bits, int(all_desc.shape[1]), out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data,
             total, counts.ctypes.data, flags))
+        if reuse:
+            return out[:, :total], starts[:-1], counts[:n_pairs]
         return np.ascontiguousarray(out[:, :total].T), starts[:-1], counts[:n_pairs]
 
     def match_pairs_batch_dev(self, d_all_desc: int, image_offsets, pair_list, desc_bits: int, stride: int,

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--dist", default="U")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--stream", default="custom", choices=["custom", "default"])
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -36,8 +37,11 @@ def main():
     m = Matcher(local)
     # NCCL collectives are enqueued on torch's current stream: make that an explicit stream and hand
     # the same stream to the matcher, so kernels and collectives are ordered without host syncs
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
+    if args.stream == "custom":
+        stream = torch.cuda.Stream(device=dev)
+        torch.cuda.set_stream(stream)
+    else:
+        stream = torch.cuda.current_stream(dev)
     m.set_stream(stream.cuda_stream)
     d_q = torch.from_numpy(q).to(dev); d_t = torch.from_numpy(t[lo:hi].copy()).to(dev)
     times, rounds = [], 0
