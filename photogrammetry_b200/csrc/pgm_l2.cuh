@@ -316,6 +316,221 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
 }
 
+// ---- the same contraction on CTA pairs (cta_group::2) --------------------------------------------
+// Why: with M = 128 per CTA every byte of the streamed B' tile is written to shared memory once (TMA)
+// and read once per MMA while A' is re-read by every MMA -- 192 B/clk of shared-memory traffic per SM
+// against 128 B/clk available, so the single-CTA kernel saturates shared memory at ~0.55 of the tensor
+// peak.  A CTA pair (two SMs of one TPC, cluster 2x1x1) runs ONE tcgen05.mma.cta_group::2 of
+// M = 256 (128 query rows per CTA) x N = 256: each CTA stages only HALF of every B' tile (128 train
+// rows), the tensor cores of both SMs read both halves, and the per-SM shared-memory traffic drops to
+// ~96 B/clk.  TMEM: two accumulators of 256 fp32 columns (all 512 columns).
+//
+//   both CTAs   warp 0: TMA producer for its own A' rows and its half of each B' tile; completions are
+//               counted on the LEADER's (rank 0) full barriers
+//   leader      warp 1: issues the MMAs; tcgen05.commit.multicast arrives on both CTAs' barriers
+//   both CTAs   warps 4-11: epilogue over the CTA's own 128 rows x 256 columns (TMEM is per SM);
+//               accumulator release arrives on the leader's tempty barrier (remote arrive for rank 1)
+constexpr int TILE_N2 = 256;                  // train rows per accumulator in pair mode (128 per CTA)
+constexpr uint32_t TMEM_COLS2 = 512;
+constexpr uint32_t IDESC_BF16_M256_N256 =
+    (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE_N2 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's even CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are accounted on the leader CTA's barrier (issued by both CTAs)
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t *bar) {      // arrives on both CTAs' barrier at this offset
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+template <bool DBG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, L2Params p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *sa = smem;                                              // A' chunks of this CTA's 128 rows
+    unsigned char *sb = smem + (size_t)MAX_CHUNKS * CHUNK_BYTES;           // this CTA's half of the B' stages
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sb + (size_t)STAGES * CHUNK_BYTES);
+    uint64_t *full = bars, *empty = bars + STAGES, *a_bar = bars + 2 * STAGES;
+    uint64_t *tfull = bars + 2 * STAGES + 1, *tempty = bars + 2 * STAGES + 3;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 5);
+    float *s_tn = reinterpret_cast<float *>(bars + 2 * STAGES + 6);          // [2][TILE_N2]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int m0 = blockIdx.x * TILE_M;                                    // the pair covers 256 consecutive queries
+    const int n_col_tiles = (p.n2 + TILE_N2 - 1) / TILE_N2;
+    const int ct0 = blockIdx.y * p.tiles_per_split, ct1 = min(n_col_tiles, ct0 + p.tiles_per_split);
+    const int ntiles = max(ct1 - ct0, 0);
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(a_bar, 1);
+        for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * 4 * EPI_GROUPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS2) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();                       // barriers of both CTAs initialised before any remote arrive / TMA
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer (both CTAs): own A' rows, own half of every B' tile =====
+        if (leader) mbar_expect_tx(a_bar, 2u * (uint32_t)p.chunks * CHUNK_BYTES);
+        for (int kc = 0; kc < p.chunks; kc++) tma_load_2d_pair(sa + (size_t)kc * CHUNK_BYTES, &map_a, a_bar, kc * CHUNK_K, m0);
+        int s = 0; uint32_t ph = 0;
+        for (int t = 0; t < ntiles; t++) {
+            for (int kc = 0; kc < p.chunks; kc++) {
+                mbar_wait(&empty[s], ph ^ 1);                  // the pair's MMAs no longer read this stage (multicast commit)
+                if (leader) mbar_expect_tx(&full[s], 2u * CHUNK_BYTES);
+                tma_load_2d_pair(sb + (size_t)s * CHUNK_BYTES, &map_b, &full[s], kc * CHUNK_K,
+                                 (ct0 + t) * TILE_N2 + (int)rank * TILE_N);
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && leader) {
+        // ===== MMA issuer (leader only) =====
+        mbar_wait(a_bar, 0);
+        int s = 0; uint32_t ph = 0;
+        for (int t = 0; t < ntiles; t++) {
+            const int acc = t & 1;
+            mbar_wait(&tempty[acc], ((t >> 1) & 1) ^ 1);       // both CTAs' epilogues drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * TILE_N2;
+            for (int kc = 0; kc < p.chunks; kc++) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint64_t adesc = umma_desc_sw128(smem_u32(sa + (size_t)kc * CHUNK_BYTES));
+                const uint64_t bdesc = umma_desc_sw128(smem_u32(sb + (size_t)s * CHUNK_BYTES));
+#pragma unroll
+                for (int k = 0; k < CHUNK_K / UMMA_K; k++)
+                    tc_mma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC_BF16_M256_N256,
+                                     (uint32_t)((kc | k) != 0));
+                tc_commit_pair(&empty[s]);
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+            tc_commit_pair(&tfull[acc]);
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: one query row per thread, this CTA's 128 rows x 256 columns =====
+        const int ew = warp & 3;
+        const int eg = (warp - 4) >> 2;
+        const int row = m0 + ew * 32 + lane;
+        const float qn = row < p.n1 ? __ldg(p.qn + row) : 0.f;
+        float bd[TOPK]; int bj[TOPK];
+#pragma unroll
+        for (int k = 0; k < TOPK; k++) { bd[k] = 3.4e38f; bj[k] = -1; }
+        const int et = threadIdx.x - 128;                       // 0..255
+        for (int t = 0; t < ntiles; t++) {
+            const int acc = t & 1;
+            const int j0 = (ct0 + t) * TILE_N2;
+            {
+                const int j = j0 + et;
+                s_tn[acc * TILE_N2 + et] = j < p.n2 ? __ldg(p.tn + j) : 3.0e38f;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mbar_wait(&tfull[acc], (t >> 1) & 1);
+            tc_fence_after();
+            uint32_t va[32], vb[32];
+            constexpr int GROUPS = TILE_N2 / 32 / EPI_GROUPS;
+            const int cbase = eg * (TILE_N2 / EPI_GROUPS);
+            const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TILE_N2 + cbase);
+            tc_ld_32x32b_x32(trow, va);
+#pragma unroll
+            for (int g = 0; g < GROUPS; g++) {
+                uint32_t (&v)[32] = (g & 1) ? vb : va;
+                tc_wait_ld();
+                if (g + 1 < GROUPS) tc_ld_32x32b_x32(trow + (uint32_t)((g + 1) * 32), (g & 1) ? va : vb);
+                const int cb = cbase + g * 32;
+                uint32_t key[32];
+#pragma unroll
+                for (int c = 0; c < 32; c++) {
+                    const float d = fmaxf(fmaf(-2.f, __uint_as_float(v[c]), qn + s_tn[acc * TILE_N2 + cb + c]), 0.f);
+                    key[c] = (__float_as_uint(d) & 0xFFFFFFE0u) | (uint32_t)c;
+                }
+                if (DBG && p.dbg_dist && row < p.n1) {
+#pragma unroll
+                    for (int c = 0; c < 32; c++)
+                        if (j0 + cb + c < p.n2) p.dbg_dist[(size_t)row * p.n2 + j0 + cb + c] = __uint_as_float(key[c] & 0xFFFFFFE0u);
+                }
+                uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu, k3 = 0xFFFFFFFFu;
+#pragma unroll
+                for (int c = 0; c < 32; c += 4) {
+                    k0 = min(k0, key[c]); k1 = min(k1, key[c + 1]); k2 = min(k2, key[c + 2]); k3 = min(k3, key[c + 3]);
+                }
+                uint32_t kmin = min(min(k0, k1), min(k2, k3));
+                uint32_t thr = __float_as_uint(bd[TOPK - 1]);
+                while (kmin < thr) {
+                    bd[3] = __uint_as_float(kmin & 0xFFFFFFE0u); bj[3] = j0 + cb + (int)(kmin & 31u);
+#pragma unroll
+                    for (int k = 3; k > 0; k--)
+                        if (bd[k] < bd[k - 1]) {
+                            const float td = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td;
+                            const int tj = bj[k]; bj[k] = bj[k - 1]; bj[k - 1] = tj;
+                        }
+                    thr = __float_as_uint(bd[TOPK - 1]);
+                    uint32_t nxt = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int c = 0; c < 32; c++) nxt = min(nxt, key[c] > kmin ? key[c] : 0xFFFFFFFFu);
+                    kmin = nxt;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(&tempty[acc], 0);      // the leader's barrier counts both CTAs' warps
+        }
+        if (row < p.n1) {
+            const size_t o = ((size_t)blockIdx.y * p.n1 + row) * CAND + (size_t)eg * TOPK;
+#pragma unroll
+            for (int k = 0; k < TOPK; k++) { p.cand_j[o + k] = bd[k] < 3.0e38f ? bj[k] : -1; p.cand_d[o + k] = bd[k]; }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    cluster_sync_all();                       // neither CTA leaves (or frees TMEM) while its partner may still use it
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS2) : "memory");
+    }
+}
+
+inline size_t l2_pair_smem_bytes() {
+    return (size_t)(MAX_CHUNKS + STAGES) * CHUNK_BYTES + (2 * STAGES + 6) * 8 + 2 * TILE_N2 * 4 + 1024;
+}
+
 inline size_t l2_smem_bytes() {
     return (size_t)(MAX_CHUNKS + STAGES) * CHUNK_BYTES + (2 * STAGES + 6) * 8 + 2 * TILE_N * 4 + 1024;
 }

@@ -58,6 +58,8 @@ struct pgm_handle {
     int ctas_per_sm[5] = {0, 0, 0, 0, 0};   // round-kernel occupancy per descriptor width (words / 4)
     bool order_attr_set = false;
     bool tail_attr_set[5] = {false, false, false, false, false};
+    bool l2_attr_set = false;         // cudaFuncSetAttribute is per device, hence per handle
+    bool l2_force_single = false;     // PGM_L2_SINGLE=1: never use the CTA-pair (cta_group::2) float kernel
     bool force_multilaunch = false;   // PGM_FORCE_MULTILAUNCH=1: never use the persistent tail kernel
     bool stats_pending = false;   // rounds / evals of the last latency-mode call still sit in pin_meta
     const void *pending_plan = nullptr;
@@ -163,6 +165,8 @@ extern "C" int pgm_create(int device_ordinal, pgm_handle **out) {
     h->stream = h->own_stream;
     const char *fm = getenv("PGM_FORCE_MULTILAUNCH");
     h->force_multilaunch = fm && fm[0] == '1';
+    const char *ls = getenv("PGM_L2_SINGLE");
+    h->l2_force_single = ls && ls[0] == '1';
     const char *pl = getenv("PGM_TAIL_PLAIN_LAUNCH");
     h->tail_plain_launch = pl && pl[0] == '1';
     const char *tl = getenv("PGM_TAIL_TIMELINE");
@@ -1005,10 +1009,21 @@ static int l2_dev_impl(pgm_handle *h, const float *d_q, int32_t n1, const float 
     using namespace pgm_l2;
     cudaStream_t s = h->stream;
     const int dp = (dim + CHUNK_K - 1) / CHUNK_K * CHUNK_K, kprime = 3 * dp, chunks = kprime / CHUNK_K;
-    const int row_tiles = (n1 + TILE_M - 1) / TILE_M, col_tiles = (n2 + TILE_N - 1) / TILE_N;
-    int splits = std::max(1, std::min(col_tiles, (2 * h->num_sms + row_tiles - 1) / row_tiles));
-    const int tps = (col_tiles + splits - 1) / splits;
-    splits = (col_tiles + tps - 1) / tps;
+    const int row_tiles = (n1 + TILE_M - 1) / TILE_M;
+    // CTA pairs (cta_group::2, M = 256 x N = 256) whenever there are at least two row tiles
+    const bool pair = row_tiles >= 2 && !h->l2_force_single;
+    const int tile_n = pair ? TILE_N2 : TILE_N;
+    const int col_tiles = (n2 + tile_n - 1) / tile_n;
+    const int gx = pair ? ((row_tiles + 1) & ~1) : row_tiles;
+    // column splits: one CTA per SM is resident, so the run time is (waves) x (tiles per split); pick the
+    // split count that minimises it (half a tile of fixed cost per CTA for the resident A' load)
+    int splits = 1, tps = col_tiles;
+    double best_cost = 1e300;
+    for (int sp = 1; sp <= std::min(col_tiles, 32); sp++) {
+        const int t = (col_tiles + sp - 1) / sp, se = (col_tiles + t - 1) / t;
+        const double cost = (double)((gx * se + h->num_sms - 1) / h->num_sms) * (t + 0.5);
+        if (cost < best_cost - 1e-9) { best_cost = cost; splits = se; tps = t; }
+    }
     // scratch: A' | B' | qn | tn | cand_j | cand_d
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
@@ -1025,17 +1040,23 @@ static int l2_dev_impl(pgm_handle *h, const float *d_q, int32_t n1, const float 
     CUtensorMap map_a, map_b;
     if ((rc = make_operand_map(h, &map_a, a, n1, kprime))) return rc;
     if ((rc = make_operand_map(h, &map_b, b, n2, kprime))) return rc;
-    static bool attr = false;
-    if (!attr) {
+    if (!h->l2_attr_set) {
         CU_CHECK(h, cudaFuncSetAttribute(l2_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l2_smem_bytes()));
         CU_CHECK(h, cudaFuncSetAttribute(l2_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l2_smem_bytes()));
-        attr = true;
+        CU_CHECK(h, cudaFuncSetAttribute(l2_topk_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l2_pair_smem_bytes()));
+        CU_CHECK(h, cudaFuncSetAttribute(l2_topk_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l2_pair_smem_bytes()));
+        h->l2_attr_set = true;
     }
     L2Params p{};
     p.n1 = n1; p.n2 = n2; p.chunks = chunks; p.tiles_per_split = tps; p.qn = qn; p.tn = tn;
     p.cand_j = (int32_t *)(base + o_cj); p.cand_d = (float *)(base + o_cd); p.dbg_dist = d_dbg;
-    if (d_dbg) l2_topk_kernel<true><<<dim3(row_tiles, splits), THREADS, l2_smem_bytes(), s>>>(map_a, map_b, p);
-    else l2_topk_kernel<false><<<dim3(row_tiles, splits), THREADS, l2_smem_bytes(), s>>>(map_a, map_b, p);
+    if (pair) {
+        if (d_dbg) l2_topk_pair_kernel<true><<<dim3(gx, splits), THREADS, l2_pair_smem_bytes(), s>>>(map_a, map_b, p);
+        else l2_topk_pair_kernel<false><<<dim3(gx, splits), THREADS, l2_pair_smem_bytes(), s>>>(map_a, map_b, p);
+    } else {
+        if (d_dbg) l2_topk_kernel<true><<<dim3(gx, splits), THREADS, l2_smem_bytes(), s>>>(map_a, map_b, p);
+        else l2_topk_kernel<false><<<dim3(gx, splits), THREADS, l2_smem_bytes(), s>>>(map_a, map_b, p);
+    }
     l2_refine_kernel<<<(n1 * 32 + 255) / 256, 256, 0, s>>>(d_q, n1, d_t, n2, dim, p.cand_j, splits, d_bj, d_bd, d_sj, d_sd);
     h->stats.kernel_launches += 4;
     h->stats.distance_evals += (int64_t)n1 * n2;
