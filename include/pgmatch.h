@@ -41,6 +41,7 @@
 #ifndef PGMATCH_H
 #define PGMATCH_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -95,6 +96,12 @@ const char *pgm_last_error(pgm_handle *h);
  * work of this handle; NULL restores the handle's own stream.  To run on the legacy default
  * stream pass cudaStreamLegacy ((cudaStream_t)0x1), not 0. */
 int pgm_set_stream(pgm_handle *h, void *cuda_stream);
+/* Page-locked host memory for callers that want the host-buffer entry points to DMA straight out of /
+ * into their arrays (a C# caller pins with `fixed` only against the GC, not against paging): buffers
+ * from pgm_host_alloc (or any cudaHostAlloc / cudaHostRegister memory) are recognised and copied
+ * without the internal staging pass; pageable buffers keep working and are staged. */
+int pgm_host_alloc(size_t bytes, void **out);
+int pgm_host_free(void *p);
 int pgm_synchronize(pgm_handle *h);
 int pgm_get_stats(pgm_handle *h, pgm_stats *out);
 
@@ -232,6 +239,19 @@ int pgm_brief_describe(pgm_handle *h, const float *gray, int32_t width, int32_t 
                        uint8_t *out_desc);
 int pgm_nms(pgm_handle *h, const int32_t *xy, const int32_t *score, int32_t n, int32_t radius,
             int32_t *out_kept, int32_t *out_count);
+
+/* ---- the consumer of the match list --------------------
+ * pgm_ransac_score: the scoring loops of CameraPoseEstimation.GetFundamentalMatrix
+ * (ImageProcessing/CameraPoseEstimation.cs:41-88).  F: n_hyp row-major 3x3 float matrices (the estimates of the
+ * sampled subsets, :44); valid[k] == 0 skips hypothesis k like upstream's rank test (:46-51), NULL = all valid;
+ * xy1 / xy2: int32[n][2] = Keypoint1 / Keypoint2 coordinates of every pair.  A pair is an inlier of F when
+ * (F . (x2, y2, 1)) . (x1, y1, 1) <= threshold (:66-73, signed as upstream).  out_counts[k] = inliers of
+ * hypothesis k (-1 if skipped); *out_best = the first hypothesis with the largest positive count (:79-84), -1
+ * if none (upstream throws, :87-88); out_best_mask[p] = 1 for the winner's inliers (its bestSample).  Any
+ * output pointer may be NULL. */
+int pgm_ransac_score(pgm_handle *h, const float *F, const uint8_t *valid, int32_t n_hyp, const int32_t *xy1,
+                     const int32_t *xy2, int32_t n, float threshold, int32_t *out_counts, int32_t *out_best,
+                     uint8_t *out_best_mask);
 
 /* ---- train-sharded single pair (multi-GPU) ----------
  * For ONE huge pair (BASELINE configs[3]: 200k x 200k) every rank holds all n1

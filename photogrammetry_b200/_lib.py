@@ -31,12 +31,12 @@ PGM_TAIL_DISTANCE = 2147483647
 # every symbol include/pgmatch.h declares (tests check the .so exports them all)
 EXPORTED_SYMBOLS = (
     "pgm_version", "pgm_status_string", "pgm_create", "pgm_destroy", "pgm_last_error",
-    "pgm_set_stream", "pgm_synchronize", "pgm_get_stats",
+    "pgm_set_stream", "pgm_synchronize", "pgm_get_stats", "pgm_host_alloc", "pgm_host_free",
     "pgm_match_hamming_greedy", "pgm_match_hamming_greedy_dev",
     "pgm_match_pairs_batch", "pgm_match_pairs_batch_dev",
     "pgm_knn2_hamming", "pgm_knn2_hamming_dev", "pgm_match_ratio_crosscheck",
     "pgm_match_keypoints_sorted", "pgm_match_keypoints_sorted_dev", "pgm_knn2_l2", "pgm_knn2_l2_dev",
-    "pgm_fast_detect", "pgm_brief_describe", "pgm_nms",
+    "pgm_fast_detect", "pgm_brief_describe", "pgm_nms", "pgm_ransac_score",
     "pgm_shard_create", "pgm_shard_round", "pgm_shard_propose", "pgm_shard_commit", "pgm_shard_finish",
     "pgm_shard_destroy",
     "pgm_set_profiling", "pgm_get_round_profile", "pgm_measure_popc_peak",
@@ -108,6 +108,8 @@ def load() -> C.CDLL:
         lib.pgm_last_error.argtypes = [C.c_void_p]
         lib.pgm_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         lib.pgm_synchronize.argtypes = [C.c_void_p]
+        lib.pgm_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+        lib.pgm_host_free.argtypes = [C.c_void_p]
         lib.pgm_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         greedy = [C.c_void_p, u8p, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32, i32p, i32p, i32p,
                   C.c_int32, C.POINTER(C.c_int32), C.c_uint32]
@@ -132,6 +134,8 @@ def load() -> C.CDLL:
         lib.pgm_brief_describe.argtypes = [C.c_void_p, vp, C.c_int32, C.c_int32, i32p, C.c_int32, i32p, C.c_int32,
                                            C.c_int32, C.c_uint32, u8p]
         lib.pgm_nms.argtypes = [C.c_void_p, i32p, i32p, C.c_int32, C.c_int32, i32p, C.POINTER(C.c_int32)]
+        lib.pgm_ransac_score.argtypes = [C.c_void_p, vp, u8p, C.c_int32, i32p, i32p, C.c_int32, C.c_float, i32p,
+                                         C.POINTER(C.c_int32), u8p]
         lib.pgm_shard_create.argtypes = [C.c_void_p, u8p, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_int32, C.POINTER(C.c_void_p)]
         lib.pgm_shard_round.argtypes = [C.c_void_p, C.c_void_p]
@@ -146,6 +150,38 @@ def load() -> C.CDLL:
         _ = vp
         _lib = lib
         return _lib
+
+
+class _PinnedBlock:
+    """Owner of one pgm_host_alloc block; numpy arrays made from it keep it alive through ``.base``."""
+
+    def __init__(self, nbytes: int):
+        self._lib = load()
+        self.ptr = C.c_void_p()
+        rc = self._lib.pgm_host_alloc(max(int(nbytes), 1), C.byref(self.ptr))
+        if rc != PGM_OK or not self.ptr.value:
+            raise PgmatchLibraryError(f"pgm_host_alloc({nbytes}) failed: {self._lib.pgm_status_string(rc).decode()}")
+        self.nbytes = max(int(nbytes), 1)
+
+    def __del__(self):  # pragma: no cover
+        try:
+            if self.ptr and self.ptr.value:
+                self._lib.pgm_host_free(self.ptr)
+                self.ptr = C.c_void_p()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """A numpy array in page-locked host memory (pgm_host_alloc): the host-buffer entry points copy to and from
+    such arrays directly, without their internal staging pass."""
+    import numpy as np
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+    block = _PinnedBlock(n * dt.itemsize)
+    buf = (C.c_char * block.nbytes).from_address(block.ptr.value)
+    buf._pgm_owner = block                       # ties the allocation's lifetime to the ctypes buffer
+    return np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
 
 
 def status_string(status: int) -> str:

@@ -8,6 +8,7 @@
 #include "pgm_kernels.cuh"
 #include "pgm_l2.cuh"
 #include "pgm_detect.cuh"
+#include "pgm_ransac.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -126,6 +127,29 @@ static int ensure_host(pgm_handle *h, HostBuf &b, size_t bytes) {
 }
 
 static void resolve_pending_stats(pgm_handle *h);
+
+// Page-locked host memory (cudaHostAlloc / cudaHostRegister) can be the source or target of an asynchronous
+// copy directly; pageable memory is staged through the handle's pinned buffers.
+static bool is_pinned_host(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+extern "C" int pgm_host_alloc(size_t bytes, void **out) {
+    if (!out) return PGM_E_INVALID_ARG;
+    *out = nullptr;
+    if (bytes == 0) return PGM_OK;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); *out = nullptr; return e == cudaErrorMemoryAllocation ? PGM_E_NOMEM : PGM_E_CUDA; }
+    return PGM_OK;
+}
+
+extern "C" int pgm_host_free(void *p) {
+    if (!p) return PGM_OK;
+    return cudaFreeHost(p) == cudaSuccess ? PGM_OK : PGM_E_CUDA;
+}
 
 extern "C" int pgm_version(void) { return PGM_VERSION; }
 
@@ -579,27 +603,44 @@ extern "C" int pgm_match_hamming_greedy(pgm_handle *h, const uint8_t *q, int32_t
 
     const size_t qb = (size_t)n1 * stride_bytes, tb = (size_t)n2 * stride_bytes;
     const size_t q_off = 0, t_off = align_up(qb, 256);
-    if ((rc = ensure_host(h, h->pin_in, t_off + tb))) return rc;
+    const bool in_pinned = is_pinned_host(q) && is_pinned_host(t);
+    const bool out_pinned = is_pinned_host(out_qi) && is_pinned_host(out_tj) && is_pinned_host(out_dist);
     if ((rc = ensure_dev(h, h->desc, t_off + tb))) return rc;
     if ((rc = ensure_dev(h, h->out, (size_t)3 * n1 * 4))) return rc;
-    if ((rc = ensure_host(h, h->pin_out, (size_t)3 * n1 * 4))) return rc;
-    memcpy((char *)h->pin_in.p + q_off, q, qb);
-    memcpy((char *)h->pin_in.p + t_off, t, tb);
-    CU_CHECK(h, cudaMemcpyAsync(h->desc.p, h->pin_in.p, t_off + tb, cudaMemcpyHostToDevice, s));
+    if (in_pinned) {
+        // the caller's buffers are page-locked: DMA straight out of them
+        CU_CHECK(h, cudaMemcpyAsync((char *)h->desc.p + q_off, q, qb, cudaMemcpyHostToDevice, s));
+        CU_CHECK(h, cudaMemcpyAsync((char *)h->desc.p + t_off, t, tb, cudaMemcpyHostToDevice, s));
+    } else {
+        if ((rc = ensure_host(h, h->pin_in, t_off + tb))) return rc;
+        memcpy((char *)h->pin_in.p + q_off, q, qb);
+        memcpy((char *)h->pin_in.p + t_off, t, tb);
+        CU_CHECK(h, cudaMemcpyAsync(h->desc.p, h->pin_in.p, t_off + tb, cudaMemcpyHostToDevice, s));
+    }
     int32_t *d_qi = (int32_t *)h->out.p, *d_tj = d_qi + n1, *d_dd = d_tj + n1;
     HostPair hp{(const uint8_t *)h->desc.p + q_off, (const uint8_t *)h->desc.p + t_off, n1, n2, 0};
     rc = run_chunk(h, &hp, 1, desc_bits, stride_bytes, flags, d_qi, d_tj, d_dd);
     if (rc) return rc;
-    CU_CHECK(h, cudaMemcpyAsync(h->pin_out.p, h->out.p, (size_t)3 * n1 * 4, cudaMemcpyDeviceToHost, s));
-    CU_CHECK(h, cudaStreamSynchronize(s));
-    h->stats.host_syncs++;
-    resolve_pending_stats(h);
-    const int32_t *po = (const int32_t *)h->pin_out.p;
-    memcpy(out_qi, po, (size_t)cnt * 4);
-    memcpy(out_tj, po + n1, (size_t)cnt * 4);
-    memcpy(out_dist, po + 2 * (size_t)n1, (size_t)cnt * 4);
+    if (out_pinned) {
+        CU_CHECK(h, cudaMemcpyAsync(out_qi, d_qi, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s));
+        CU_CHECK(h, cudaMemcpyAsync(out_tj, d_tj, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s));
+        CU_CHECK(h, cudaMemcpyAsync(out_dist, d_dd, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s));
+        CU_CHECK(h, cudaStreamSynchronize(s));
+        h->stats.host_syncs++;
+        resolve_pending_stats(h);
+    } else {
+        if ((rc = ensure_host(h, h->pin_out, (size_t)3 * n1 * 4))) return rc;
+        CU_CHECK(h, cudaMemcpyAsync(h->pin_out.p, h->out.p, (size_t)3 * n1 * 4, cudaMemcpyDeviceToHost, s));
+        CU_CHECK(h, cudaStreamSynchronize(s));
+        h->stats.host_syncs++;
+        resolve_pending_stats(h);
+        const int32_t *po = (const int32_t *)h->pin_out.p;
+        memcpy(out_qi, po, (size_t)cnt * 4);
+        memcpy(out_tj, po + n1, (size_t)cnt * 4);
+        memcpy(out_dist, po + 2 * (size_t)n1, (size_t)cnt * 4);
+    }
     h->stats.h2d_bytes += (int64_t)(qb + tb);
-    h->stats.d2h_bytes += (int64_t)3 * n1 * 4;
+    h->stats.d2h_bytes += (int64_t)3 * (out_pinned ? cnt : n1) * 4;
     return PGM_OK;
 }
 
@@ -1266,6 +1307,56 @@ extern "C" int pgm_nms(pgm_handle *h, const int32_t *xy, const int32_t *score, i
     *out_count = h_cnt[0];
     memcpy(out_kept, h_cnt + 16, (size_t)h_cnt[0] * 4);
     h->stats.kernel_launches += 1; h->stats.host_syncs++;
+    CU_CHECK(h, cudaGetLastError());
+    return PGM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// the consumer of the match list: RANSAC hypothesis scoring (pgm_ransac.cuh)
+// ---------------------------------------------------------------------------
+extern "C" int pgm_ransac_score(pgm_handle *h, const float *F, const uint8_t *valid, int32_t n_hyp, const int32_t *xy1,
+                                const int32_t *xy2, int32_t n, float threshold, int32_t *out_counts, int32_t *out_best,
+                                uint8_t *out_best_mask) {
+    using namespace pgm_ransac;
+    if (!h) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (n_hyp < 0 || n < 0 || (n_hyp > 0 && !F) || (n > 0 && (!xy1 || !xy2))) return fail(h, PGM_E_INVALID_ARG, "bad arguments");
+    h->stats = pgm_stats{};
+    h->stats_pending = false;
+    if (out_best) *out_best = -1;
+    if (n_hyp == 0) return PGM_OK;
+    CU_CHECK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_f = take((size_t)n_hyp * 36), o_v = take(n_hyp), o_1 = take((size_t)std::max(n, 1) * 8), o_2 = take((size_t)std::max(n, 1) * 8);
+    const size_t o_c = take((size_t)n_hyp * 4), o_b = take(16), o_m = take(std::max(n, 1));
+    int rc = ensure_dev(h, h->misc, off);
+    if (rc) return rc;
+    if ((rc = ensure_host(h, h->pin_out, (size_t)n_hyp * 4 + 64 + (size_t)n))) return rc;
+    char *base = (char *)h->misc.p;
+    CU_CHECK(h, cudaMemcpyAsync(base + o_f, F, (size_t)n_hyp * 36, cudaMemcpyHostToDevice, s));
+    if (valid) CU_CHECK(h, cudaMemcpyAsync(base + o_v, valid, n_hyp, cudaMemcpyHostToDevice, s));
+    if (n) {
+        CU_CHECK(h, cudaMemcpyAsync(base + o_1, xy1, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+        CU_CHECK(h, cudaMemcpyAsync(base + o_2, xy2, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    }
+    score_kernel<<<n_hyp, 256, 0, s>>>((const float *)(base + o_f), valid ? (const uint8_t *)(base + o_v) : nullptr, n_hyp,
+                                       (const int32_t *)(base + o_1), (const int32_t *)(base + o_2), n, threshold,
+                                       (int32_t *)(base + o_c));
+    best_kernel<<<1, 1024, 0, s>>>((const float *)(base + o_f), (const int32_t *)(base + o_c), n_hyp, (const int32_t *)(base + o_1),
+                                   (const int32_t *)(base + o_2), n, threshold, (int32_t *)(base + o_b),
+                                   out_best_mask ? (uint8_t *)(base + o_m) : nullptr);
+    char *ph = (char *)h->pin_out.p;
+    CU_CHECK(h, cudaMemcpyAsync(ph, base + o_c, (size_t)n_hyp * 4, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(h, cudaMemcpyAsync(ph + (size_t)n_hyp * 4, base + o_b, 4, cudaMemcpyDeviceToHost, s));
+    if (out_best_mask && n) CU_CHECK(h, cudaMemcpyAsync(ph + (size_t)n_hyp * 4 + 64, base + o_m, n, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(h, cudaStreamSynchronize(s));
+    if (out_counts) memcpy(out_counts, ph, (size_t)n_hyp * 4);
+    if (out_best) *out_best = *(int32_t *)(ph + (size_t)n_hyp * 4);
+    if (out_best_mask && n) memcpy(out_best_mask, ph + (size_t)n_hyp * 4 + 64, n);
+    h->stats.kernel_launches += 2; h->stats.host_syncs++;
+    h->stats.h2d_bytes += (int64_t)n_hyp * 36 + (int64_t)n * 16; h->stats.d2h_bytes += (int64_t)n_hyp * 4 + n;
     CU_CHECK(h, cudaGetLastError());
     return PGM_OK;
 }

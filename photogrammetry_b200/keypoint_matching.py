@@ -97,8 +97,12 @@ class Matcher:
 
     # -- MatchKeypoints on packed rows ------------------------------------
     def match_greedy(self, q: np.ndarray, t: np.ndarray, desc_bits: Optional[int] = None,
-                     reference_compat_tail: bool = True) -> np.ndarray:
-        """``int32[count, 3]`` rows (query index, train index, distance) in the reference's order."""
+                     reference_compat_tail: bool = True, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """``int32[count, 3]`` rows (query index, train index, distance) in the reference's order.
+
+        ``out``: optional caller-owned C-contiguous ``int32[3, >= n1]`` array (e.g. from
+        :func:`photogrammetry_b200._lib.pinned_empty`); the call then returns the SoA view ``out[:, :count]``
+        with no further copy.  Page-locked inputs and outputs are transferred without staging."""
         q, bits_q = as_descriptor_rows(q, desc_bits)
         t, bits_t = as_descriptor_rows(t, desc_bits)
         n1, n2 = int(q.shape[0]), int(t.shape[0])
@@ -106,12 +110,19 @@ class Matcher:
         if n1 and n2 and q.shape[1] != t.shape[1]:
             raise ValueError("query and train descriptors have different strides")
         bits = desc_bits or max(bits_q, bits_t)
-        out = np.empty((3, max(n1, 1)), dtype=np.int32)
+        reuse = out is not None
+        if reuse:
+            if out.dtype != np.int32 or out.ndim != 2 or out.shape[0] != 3 or out.shape[1] < n1 or not out.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous int32[3, >= n1] array")
+        else:
+            out = np.empty((3, max(n1, 1)), dtype=np.int32)
         cnt = C.c_int32(0)
         flags = PGM_FLAG_REFERENCE_COMPAT_TAIL if reference_compat_tail else 0
         self._check(self._lib.pgm_match_hamming_greedy(
             self._h, _addr(q), n1, _addr(t), n2, bits, stride,
             out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data, n1, C.byref(cnt), flags))
+        if reuse:
+            return out[:, :cnt.value]
         return np.ascontiguousarray(out[:, :cnt.value].T)
 
     def match_greedy_dev(self, d_q: int, n1: int, d_t: int, n2: int, desc_bits: int, stride: int,
@@ -273,6 +284,26 @@ class Matcher:
         self._check(self._lib.pgm_nms(self._h, _addr(xy), _addr(score), n, int(radius), kept.ctypes.data,
                                       C.byref(cnt)))
         return kept[:cnt.value].copy()
+
+    # -- the consumer of the match list: RANSAC hypothesis scoring -----------
+    def ransac_score(self, F: np.ndarray, xy1: np.ndarray, xy2: np.ndarray, threshold: float,
+                     valid: Optional[np.ndarray] = None):
+        """Scoring loops of ``CameraPoseEstimation.GetFundamentalMatrix`` (CameraPoseEstimation.cs:41-88).
+        Returns (counts int32[n_hyp], best index or -1, inlier mask uint8[n] of the best hypothesis)."""
+        F = np.ascontiguousarray(F, dtype=np.float32).reshape(-1, 9)
+        xy1 = np.ascontiguousarray(xy1, dtype=np.int32).reshape(-1, 2)
+        xy2 = np.ascontiguousarray(xy2, dtype=np.int32).reshape(-1, 2)
+        if len(xy1) != len(xy2):
+            raise ValueError("xy1 and xy2 differ in length")
+        v = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8).reshape(-1)
+        if v is not None and len(v) != len(F):
+            raise ValueError("valid and F differ in length")
+        counts = np.empty(max(len(F), 1), dtype=np.int32)
+        mask = np.zeros(max(len(xy1), 1), dtype=np.uint8)
+        best = C.c_int32(-1)
+        self._check(self._lib.pgm_ransac_score(self._h, _addr(F), _addr(v), len(F), _addr(xy1), _addr(xy2), len(xy1),
+                                               float(threshold), counts.ctypes.data, C.byref(best), mask.ctypes.data))
+        return counts[:len(F)], int(best.value), mask[:len(xy1)]
 
     def set_profiling(self, enabled: bool) -> None:
         self._check(self._lib.pgm_set_profiling(self._h, int(bool(enabled))))
