@@ -7,9 +7,10 @@
 //     ||q - t||^2 = ||q||^2 + ||t||^2 - 2 q.t          (N1 x N2 x D GEMM)
 //
 // Precision: every fp32 component is split into bf16 hi + bf16 lo (x = hi + lo up to 2^-17
-// relative) and the dot product is evaluated as hi.hi + hi.lo + lo.hi -- ONE bf16 GEMM with
-// K' = 3*D over A' = [q_hi | q_hi | q_lo], B' = [t_hi | t_lo | t_hi], fp32 accumulation in
-// TMEM.  The GEMM ranks the candidates (top-4 per query and column split); a refinement kernel
+// relative) and the dot product is evaluated as hi.hi + lo.hi + hi.lo -- three bf16 GEMM passes
+// of K = Dp accumulated into the same fp32 TMEM accumulator.  Operand rows are stored once as
+// [x_hi | x_lo] (2*Dp bf16); the train-side hi chunks are staged once per tile and used by two of
+// the passes, so a tile costs 4 chunk loads for 6 chunk MMAs.  The GEMM ranks the candidates (top-4 per query and column split); a refinement kernel
 // recomputes those few distances exactly in fp32 (sum of squared differences) and picks
 // best/second, so reported distances are exact to fp32 rounding and only candidates whose
 // approximate distances differ by < ~1e-5 relative (near-ties) can be mis-selected.
@@ -37,8 +38,8 @@ constexpr int TILE_M = 128;        // queries per CTA (TMEM lanes)
 constexpr int TILE_N = 128;        // train rows per accumulator
 constexpr int CHUNK_K = 64;        // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K = 16;         // K of one tcgen05.mma for 16-bit inputs
-constexpr int MAX_CHUNKS = 6;      // K' = 3 * Dp <= 384  (D <= 128)
-constexpr int STAGES = 6;          // B' ring
+constexpr int MAX_CHUNKS = 4;      // resident A' chunks: [hi | lo], Dp <= 128
+constexpr int STAGES = 8;          // B' ring of chunk slots: two whole tiles deep at Dp = 128
 constexpr int THREADS = 384;        // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: two epilogue warpgroups
 constexpr int EPI_GROUPS = 2;       // each epilogue warpgroup reduces half of the accumulator's columns
 constexpr int TOPK = 4;             // candidates kept per (query, column split, epilogue warpgroup)
@@ -115,8 +116,8 @@ constexpr uint32_t IDESC_BF16_M128_N128 =
     (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 
 // ---- preprocessing: fp32 rows -> split bf16 operand rows + squared norms ------------------
-// role 0 (queries): [hi | hi | lo]; role 1 (train): [hi | lo | hi]; each block Dp wide, zero padded.
-__global__ void split_kernel(const float *__restrict__ x, int n, int dim, int dp, int role,
+// both roles: [hi | lo], each block Dp wide, zero padded.
+__global__ void split_kernel(const float *__restrict__ x, int n, int dim, int dp,
                              __nv_bfloat16 *__restrict__ out, float *__restrict__ norm2) {
     const int row = blockIdx.x;
     if (row >= n) return;
@@ -125,10 +126,9 @@ __global__ void split_kernel(const float *__restrict__ x, int n, int dim, int dp
         const float v = k < dim ? x[(size_t)row * dim + k] : 0.f;
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
         const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-        __nv_bfloat16 *o = out + (size_t)row * 3 * dp;
+        __nv_bfloat16 *o = out + (size_t)row * 2 * dp;
         o[k] = hi;
-        o[dp + k] = role == 0 ? hi : lo;
-        o[2 * dp + k] = role == 0 ? lo : hi;
+        o[dp + k] = lo;
         acc += v * v;
     }
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -144,7 +144,7 @@ __global__ void split_kernel(const float *__restrict__ x, int n, int dim, int dp
 
 // ---- the GEMM + top-4 kernel ----------------------------------------------------------------
 struct L2Params {
-    int n1, n2, chunks;            // chunks = 3 * Dp / 64
+    int n1, n2, dpc;               // dpc = Dp / 64: chunks per operand part (hi or lo)
     int tiles_per_split;           // column tiles handled by one blockIdx.y
     const float *qn, *tn;          // squared norms
     int32_t *cand_j;               // [splits][n1][CAND]
@@ -191,11 +191,12 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
-        mbar_expect_tx(a_bar, (uint32_t)p.chunks * CHUNK_BYTES);
-        for (int kc = 0; kc < p.chunks; kc++) tma_load_2d(sa + (size_t)kc * CHUNK_BYTES, &map_a, a_bar, kc * CHUNK_K, m0);
+        const int nch = 2 * p.dpc;
+        mbar_expect_tx(a_bar, (uint32_t)nch * CHUNK_BYTES);
+        for (int kc = 0; kc < nch; kc++) tma_load_2d(sa + (size_t)kc * CHUNK_BYTES, &map_a, a_bar, kc * CHUNK_K, m0);
         int s = 0; uint32_t ph = 0;
         for (int t = 0; t < ntiles; t++) {
-            for (int kc = 0; kc < p.chunks; kc++) {
+            for (int kc = 0; kc < nch; kc++) {               // t_hi chunks, then t_lo chunks
                 mbar_wait(&empty[s], ph ^ 1);
                 mbar_expect_tx(&full[s], CHUNK_BYTES);
                 tma_load_2d(sb + (size_t)s * CHUNK_BYTES, &map_b, &full[s], kc * CHUNK_K, (ct0 + t) * TILE_N);
@@ -205,24 +206,29 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
         mbar_wait(a_bar, 0);
-        int s = 0; uint32_t ph = 0;
+        const int dpc = p.dpc;
+        uint32_t g = 0;                                         // running chunk-slot counter of the B' ring
         for (int t = 0; t < ntiles; t++) {
             const int acc = t & 1;
             mbar_wait(&tempty[acc], ((t >> 1) & 1) ^ 1);       // epilogue drained this accumulator
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * TILE_N;
-            for (int kc = 0; kc < p.chunks; kc++) {
-                mbar_wait(&full[s], ph);
-                tc_fence_after();
-                const uint64_t adesc = umma_desc_sw128(smem_u32(sa + (size_t)kc * CHUNK_BYTES));
-                const uint64_t bdesc = umma_desc_sw128(smem_u32(sb + (size_t)s * CHUNK_BYTES));
+            // pass 0: q_hi . t_hi (waits for the hi slots), pass 1: q_lo . t_hi (frees them), pass 2: q_hi . t_lo
+            for (int pass = 0; pass < 3; pass++) {
+                for (int c = 0; c < dpc; c++) {
+                    const uint32_t i = g + (uint32_t)(pass == 2 ? dpc + c : c), s = i % STAGES, ph = (i / STAGES) & 1u;
+                    if (pass != 1) { mbar_wait(&full[s], ph); tc_fence_after(); }
+                    const int ac = pass == 1 ? dpc + c : c;
+                    const uint64_t adesc = umma_desc_sw128(smem_u32(sa + (size_t)ac * CHUNK_BYTES));
+                    const uint64_t bdesc = umma_desc_sw128(smem_u32(sb + (size_t)s * CHUNK_BYTES));
 #pragma unroll
-                for (int k = 0; k < CHUNK_K / UMMA_K; k++)     // +32 B per K step inside the 128-B swizzle row
-                    tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC_BF16_M128_N128,
-                                (uint32_t)((kc | k) != 0));
-                tc_commit(&empty[s]);                           // stage reusable once these MMAs retire
-                if (++s == STAGES) { s = 0; ph ^= 1; }
+                    for (int k = 0; k < CHUNK_K / UMMA_K; k++)     // +32 B per K step inside the 128-B swizzle row
+                        tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC_BF16_M128_N128,
+                                    (uint32_t)((pass | c | k) != 0));
+                    if (pass != 0) tc_commit(&empty[s]);            // slot reusable once these MMAs retire
+                }
             }
+            g += 2u * (uint32_t)dpc;
             tc_commit(&tfull[acc]);                             // accumulator complete
         }
     } else if (warp >= 4) {
@@ -409,11 +415,12 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer (both CTAs): own A' rows, own half of every B' tile =====
-        if (leader) mbar_expect_tx(a_bar, 2u * (uint32_t)p.chunks * CHUNK_BYTES);
-        for (int kc = 0; kc < p.chunks; kc++) tma_load_2d_pair(sa + (size_t)kc * CHUNK_BYTES, &map_a, a_bar, kc * CHUNK_K, m0);
+        const int nch = 2 * p.dpc;
+        if (leader) mbar_expect_tx(a_bar, 2u * (uint32_t)nch * CHUNK_BYTES);
+        for (int kc = 0; kc < nch; kc++) tma_load_2d_pair(sa + (size_t)kc * CHUNK_BYTES, &map_a, a_bar, kc * CHUNK_K, m0);
         int s = 0; uint32_t ph = 0;
         for (int t = 0; t < ntiles; t++) {
-            for (int kc = 0; kc < p.chunks; kc++) {
+            for (int kc = 0; kc < nch; kc++) {                 // t_hi chunks, then t_lo chunks
                 mbar_wait(&empty[s], ph ^ 1);                  // the pair's MMAs no longer read this stage (multicast commit)
                 if (leader) mbar_expect_tx(&full[s], 2u * CHUNK_BYTES);
                 tma_load_2d_pair(sb + (size_t)s * CHUNK_BYTES, &map_b, &full[s], kc * CHUNK_K,
@@ -424,24 +431,29 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     } else if (warp == 1 && lane == 0 && leader) {
         // ===== MMA issuer (leader only) =====
         mbar_wait(a_bar, 0);
-        int s = 0; uint32_t ph = 0;
+        const int dpc = p.dpc;
+        uint32_t g = 0;                                         // running chunk-slot counter of the B' ring
         for (int t = 0; t < ntiles; t++) {
             const int acc = t & 1;
             mbar_wait(&tempty[acc], ((t >> 1) & 1) ^ 1);       // both CTAs' epilogues drained this accumulator
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * TILE_N2;
-            for (int kc = 0; kc < p.chunks; kc++) {
-                mbar_wait(&full[s], ph);
-                tc_fence_after();
-                const uint64_t adesc = umma_desc_sw128(smem_u32(sa + (size_t)kc * CHUNK_BYTES));
-                const uint64_t bdesc = umma_desc_sw128(smem_u32(sb + (size_t)s * CHUNK_BYTES));
+            // pass 0: q_hi . t_hi (waits for the hi slots), pass 1: q_lo . t_hi (frees them), pass 2: q_hi . t_lo
+            for (int pass = 0; pass < 3; pass++) {
+                for (int c = 0; c < dpc; c++) {
+                    const uint32_t i = g + (uint32_t)(pass == 2 ? dpc + c : c), s = i % STAGES, ph = (i / STAGES) & 1u;
+                    if (pass != 1) { mbar_wait(&full[s], ph); tc_fence_after(); }
+                    const int ac = pass == 1 ? dpc + c : c;
+                    const uint64_t adesc = umma_desc_sw128(smem_u32(sa + (size_t)ac * CHUNK_BYTES));
+                    const uint64_t bdesc = umma_desc_sw128(smem_u32(sb + (size_t)s * CHUNK_BYTES));
 #pragma unroll
-                for (int k = 0; k < CHUNK_K / UMMA_K; k++)
-                    tc_mma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC_BF16_M256_N256,
-                                     (uint32_t)((kc | k) != 0));
-                tc_commit_pair(&empty[s]);
-                if (++s == STAGES) { s = 0; ph ^= 1; }
+                    for (int k = 0; k < CHUNK_K / UMMA_K; k++)
+                        tc_mma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC_BF16_M256_N256,
+                                         (uint32_t)((pass | c | k) != 0));
+                    if (pass != 0) tc_commit_pair(&empty[s]);
+                }
             }
+            g += 2u * (uint32_t)dpc;
             tc_commit_pair(&tfull[acc]);
         }
     } else if (warp >= 4) {

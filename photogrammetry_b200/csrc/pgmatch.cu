@@ -1049,7 +1049,7 @@ static int l2_dev_impl(pgm_handle *h, const float *d_q, int32_t n1, const float 
                        int32_t *d_bj, float *d_bd, int32_t *d_sj, float *d_sd, float *d_dbg) {
     using namespace pgm_l2;
     cudaStream_t s = h->stream;
-    const int dp = (dim + CHUNK_K - 1) / CHUNK_K * CHUNK_K, kprime = 3 * dp, chunks = kprime / CHUNK_K;
+    const int dp = (dim + CHUNK_K - 1) / CHUNK_K * CHUNK_K, kprime = 2 * dp, dpc = dp / CHUNK_K;   // rows = [hi | lo]
     const int row_tiles = (n1 + TILE_M - 1) / TILE_M;
     // CTA pairs (cta_group::2, M = 256 x N = 256) whenever there are at least two row tiles
     const bool pair = row_tiles >= 2 && !h->l2_force_single;
@@ -1076,8 +1076,8 @@ static int l2_dev_impl(pgm_handle *h, const float *d_q, int32_t n1, const float 
     char *base = (char *)h->misc.p;
     __nv_bfloat16 *a = (__nv_bfloat16 *)(base + o_a), *b = (__nv_bfloat16 *)(base + o_b);
     float *qn = (float *)(base + o_qn), *tn = (float *)(base + o_tn);
-    split_kernel<<<n1, 128, 0, s>>>(d_q, n1, dim, dp, 0, a, qn);
-    split_kernel<<<n2, 128, 0, s>>>(d_t, n2, dim, dp, 1, b, tn);
+    split_kernel<<<n1, 128, 0, s>>>(d_q, n1, dim, dp, a, qn);
+    split_kernel<<<n2, 128, 0, s>>>(d_t, n2, dim, dp, b, tn);
     CUtensorMap map_a, map_b;
     if ((rc = make_operand_map(h, &map_a, a, n1, kprime))) return rc;
     if ((rc = make_operand_map(h, &map_b, b, n2, kprime))) return rc;
@@ -1089,7 +1089,7 @@ static int l2_dev_impl(pgm_handle *h, const float *d_q, int32_t n1, const float 
         h->l2_attr_set = true;
     }
     L2Params p{};
-    p.n1 = n1; p.n2 = n2; p.chunks = chunks; p.tiles_per_split = tps; p.qn = qn; p.tn = tn;
+    p.n1 = n1; p.n2 = n2; p.dpc = dpc; p.tiles_per_split = tps; p.qn = qn; p.tn = tn;
     p.cand_j = (int32_t *)(base + o_cj); p.cand_d = (float *)(base + o_cd); p.dbg_dist = d_dbg;
     if (pair) {
         if (d_dbg) l2_topk_pair_kernel<true><<<dim3(gx, splits), THREADS, l2_pair_smem_bytes(), s>>>(map_a, map_b, p);
