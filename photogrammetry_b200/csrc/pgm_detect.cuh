@@ -33,35 +33,40 @@ __global__ void fast_score_kernel(const float *__restrict__ img, int w, int h, f
     if (x >= w || y >= h) return;
     uint8_t out = 0;
     if (x >= 3 && x < w - 3 && y >= 3 && y < h - 3) {                 // Detect's loop bounds, :45-47
-        const float c = __ldg(img + (size_t)y * w + x);
+        const float *p = img + (size_t)y * w + x;
+        const float c = __ldg(p);
         const float lo = c - threshold, hi = c + threshold;            // InThreshold, :135-138
         unsigned inside = 0;                                           // bit k: ring pixel k is inside the threshold
+        // IsPotentialKeypoint (:116-133): the compass points are ring entries 0, 4, 8, 12; at most one may be
+        // inside.  Most pixels of a natural image fail here and never touch the other twelve taps.
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            const float t = __ldg(img + (size_t)(y + c_ring[RING][k][1]) * w + (x + c_ring[RING][k][0]));
+        for (int k = 0; k < 16; k += 4) {
+            const float t = __ldg(p + c_ring[RING][k][1] * w + c_ring[RING][k][0]);
             inside |= (unsigned)(t > lo && t < hi) << k;
         }
-        // IsPotentialKeypoint (:116-133): compass points are ring entries 0, 4, 8, 12; at most one may be inside
-        const bool potential = __popc(inside & 0x1111u) <= 1;
-        // GetIntensityValueIfKeypoint (:65-114)
-        bool beginning = true, dead = false;
-        int n_begin = 0, longest = 0, current = 0, n_fail = 0;
+        if (__popc(inside) <= 1) {
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            if ((inside >> k) & 1u) {
-                beginning = false;
-                longest = max(longest, current);
-                current = 0;
-                if (n_fail >= 4) dead = true;
-                n_fail++;
-            } else {
-                current++;
-                if (beginning) n_begin++;
+            for (int k = 0; k < 16; k++) {
+                if ((k & 3) == 0) continue;
+                const float t = __ldg(p + c_ring[RING][k][1] * w + c_ring[RING][k][0]);
+                inside |= (unsigned)(t > lo && t < hi) << k;
+            }
+            // GetIntensityValueIfKeypoint (:65-114): longest circular run of ring pixels OUTSIDE the threshold,
+            // accepted from 12 up.  (Its early exit on a fifth inside pixel cannot change the outcome: five
+            // inside pixels leave at most eleven outside.)  On the doubled ring a circular run is a linear run;
+            // bit i of `r` survives the shifts iff bits i .. i+11 are all set.
+            const unsigned o16 = ~inside & 0xFFFFu;
+            if (o16 == 0xFFFFu) out = 16;
+            else {
+                unsigned r = o16 | (o16 << 16);
+                r &= r >> 1; r &= r >> 2; r &= r >> 4; r &= r >> 4;
+                if (r) {
+                    int len = 12;
+                    while ((r &= r >> 1) != 0u) len++;
+                    out = (uint8_t)len;
+                }
             }
         }
-        if (!beginning) current += n_begin;
-        longest = max(longest, current);
-        if (potential && !dead && longest >= 12) out = (uint8_t)longest;
     }
     score[(size_t)y * w + x] = out;
 }
@@ -199,6 +204,79 @@ __global__ void nms_round_kernel(const int32_t *__restrict__ xy, const int32_t *
         }
         state_out[i] = ns;
     }
+}
+
+// ---- spatially binned form of the same rounds -------------------------------------------------------
+// Cells of side max(radius, 1): every keypoint within `radius` of (x, y) lies in the 3 x 3 cells around it.
+// Keypoints are sorted by cell id (64-bit radix sort); a round then visits only the 9 neighbouring runs
+// instead of all n keypoints, so the cost is O(n . neighbours) per round instead of O(n^2).
+__global__ void nms_cell_kernel(const int32_t *__restrict__ xy, int n, int cs, int minx, int miny, long long ncx,
+                                unsigned long long *__restrict__ cell, int32_t *__restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long cx = ((long long)xy[2 * i] - minx) / cs, cy = ((long long)xy[2 * i + 1] - miny) / cs;
+    cell[i] = (unsigned long long)(cy * ncx + cx);
+    idx[i] = i;
+}
+
+// key[i] = (inverted score << 32) | i: an ascending sort of the keys is the stable order by score descending
+__global__ void nms_score_key_kernel(const int32_t *__restrict__ sc, int n, unsigned long long *__restrict__ key) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) key[i] = ((unsigned long long)(~((unsigned)sc[i] ^ 0x80000000u)) << 32) | (unsigned)i;
+}
+
+// order[r] = keypoint of rank r, rank[order[r]] = r
+__global__ void nms_order_from_keys_kernel(const unsigned long long *__restrict__ sorted_key, int n,
+                                           int32_t *__restrict__ order, int32_t *__restrict__ rank) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int i = (int)(unsigned)sorted_key[r];
+    order[r] = i; rank[i] = r;
+}
+
+__device__ __forceinline__ int lower_bound_u64(const unsigned long long *__restrict__ a, int n, unsigned long long key) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void nms_round_binned_kernel(const int32_t *__restrict__ xy, const int32_t *__restrict__ rank, int n,
+                                        long long radius2, int cs, int minx, int miny, long long ncx, long long ncy,
+                                        const unsigned long long *__restrict__ sorted_cell,
+                                        const int32_t *__restrict__ sorted_idx, const uint8_t *__restrict__ state_in,
+                                        uint8_t *__restrict__ state_out, int32_t *__restrict__ n_undecided) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t st = state_in[i];
+    if (st != 0) { state_out[i] = st; return; }
+    const int x = xy[2 * i], y = xy[2 * i + 1], r = rank[i];
+    const long long cx = ((long long)x - minx) / cs, cy = ((long long)y - miny) / cs;
+    bool any_kept = false, any_undecided = false;
+    for (int dy = -1; dy <= 1 && !any_kept; dy++) {
+        const long long yy = cy + dy;
+        if (yy < 0 || yy >= ncy) continue;
+        // the three cells (cx-1 .. cx+1) of one cell row are consecutive ids: one search, one run
+        const long long x0 = cx > 0 ? cx - 1 : 0, x1 = cx + 1 < ncx ? cx + 1 : ncx - 1;
+        const unsigned long long c0 = (unsigned long long)(yy * ncx + x0), c1 = (unsigned long long)(yy * ncx + x1);
+        for (int k = lower_bound_u64(sorted_cell, n, c0); k < n && sorted_cell[k] <= c1; k++) {
+            const int j = sorted_idx[k];
+            if (rank[j] >= r) continue;
+            const uint8_t sj = state_in[j];
+            if (sj == 2) continue;
+            const long long ddx = (long long)xy[2 * j] - x, ddy = (long long)xy[2 * j + 1] - y;
+            if (ddx * ddx + ddy * ddy > radius2) continue;       // IsAcceptableDistance: distance > radius survives
+            if (sj == 1) { any_kept = true; break; }
+            any_undecided = true;
+        }
+    }
+    uint8_t ns = 0;
+    if (any_kept) ns = 2;
+    else if (!any_undecided) ns = 1;
+    if (ns == 0) atomicAdd(n_undecided, 1);
+    state_out[i] = ns;
 }
 
 // kept keypoints in rank order = the reference's output order (acceptableList, :21-26)

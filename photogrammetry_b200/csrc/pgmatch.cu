@@ -10,6 +10,8 @@
 #include "pgm_detect.cuh"
 #include "pgm_ransac.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <algorithm>
 #include <chrono>
 #include <cstddef>
@@ -1274,6 +1276,7 @@ extern "C" int pgm_nms(pgm_handle *h, const int32_t *xy, const int32_t *score, i
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t o_xy = take((size_t)n * 8), o_sc = take((size_t)n * 4), o_rk = take((size_t)n * 4), o_or = take((size_t)n * 4);
     const size_t o_s0 = take(n), o_s1 = take(n), o_kept = take((size_t)n * 4), o_cnt = take(16);
+    const size_t o_k0 = take((size_t)n * 8), o_k1 = take((size_t)n * 8), o_v0 = take((size_t)n * 4), o_v1 = take((size_t)n * 4);
     int rc = ensure_dev(h, h->misc, off);
     if (rc) return rc;
     if ((rc = ensure_host(h, h->pin_out, (size_t)n * 4 + 64))) return rc;
@@ -1285,21 +1288,69 @@ extern "C" int pgm_nms(pgm_handle *h, const int32_t *xy, const int32_t *score, i
     CU_CHECK(h, cudaMemcpyAsync(d_sc, score, (size_t)n * 4, cudaMemcpyHostToDevice, s));
     CU_CHECK(h, cudaMemsetAsync(st[0], 0, n, s));
     const int blocks = (n + 255) / 256;
-    nms_rank_kernel<<<blocks, 256, 0, s>>>(d_sc, n, d_rk, d_or);
-    h->stats.kernel_launches += 1;
     int32_t *h_cnt = (int32_t *)h->pin_out.p;
     const long long r2 = (long long)radius * radius;
-    for (int round = 0;; round++) {
-        CU_CHECK(h, cudaMemsetAsync(d_cnt, 0, 4, s));
-        nms_round_kernel<<<blocks, 256, 0, s>>>(d_xy, d_rk, n, r2, st[round & 1], st[(round + 1) & 1], d_cnt);
-        CU_CHECK(h, cudaMemcpyAsync(h_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s));
-        CU_CHECK(h, cudaStreamSynchronize(s));
-        h->stats.kernel_launches += 1; h->stats.host_syncs++; h->stats.rounds++;
-        if (*h_cnt == 0) {
-            nms_emit_kernel<<<1, 1024, 0, s>>>(d_or, st[(round + 1) & 1], n, d_kept, d_cnt);
-            break;
+
+    // Spatial binning pays once the all-pairs scans (n^2 per round) outweigh two radix sorts.  PGM_NMS_MODE=dense
+    // or =binned forces one form (tests run both); the answers are identical.
+    const int cs = std::max(radius, 1);
+    long long minx = xy[0], miny = xy[1], maxx = xy[0], maxy = xy[1];
+    for (int i = 1; i < n; i++) {
+        minx = std::min<long long>(minx, xy[2 * i]); maxx = std::max<long long>(maxx, xy[2 * i]);
+        miny = std::min<long long>(miny, xy[2 * i + 1]); maxy = std::max<long long>(maxy, xy[2 * i + 1]);
+    }
+    const long long ncx = (maxx - minx) / cs + 1, ncy = (maxy - miny) / cs + 1;   // each <= 2^32
+    bool binned = n >= 1024 && (ncx >= 8 || ncy >= 8) && ncx * (double)ncy >= 64.0;  // else 3 x 3 cells hold most keypoints
+    if (const char *mode = getenv("PGM_NMS_MODE")) {
+        if (!strcmp(mode, "dense")) binned = false;
+        else if (!strcmp(mode, "binned")) binned = true;
+    }
+    if (!binned) {
+        nms_rank_kernel<<<blocks, 256, 0, s>>>(d_sc, n, d_rk, d_or);
+        h->stats.kernel_launches += 1;
+        for (int round = 0;; round++) {
+            CU_CHECK(h, cudaMemsetAsync(d_cnt, 0, 4, s));
+            nms_round_kernel<<<blocks, 256, 0, s>>>(d_xy, d_rk, n, r2, st[round & 1], st[(round + 1) & 1], d_cnt);
+            CU_CHECK(h, cudaMemcpyAsync(h_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s));
+            CU_CHECK(h, cudaStreamSynchronize(s));
+            h->stats.kernel_launches += 1; h->stats.host_syncs++; h->stats.rounds++;
+            if (*h_cnt == 0) {
+                nms_emit_kernel<<<1, 1024, 0, s>>>(d_or, st[(round + 1) & 1], n, d_kept, d_cnt);
+                break;
+            }
+            if (round > n + 2) return fail(h, PGM_E_CUDA, "NMS failed to converge (internal error)");
         }
-        if (round > n + 2) return fail(h, PGM_E_CUDA, "NMS failed to converge (internal error)");
+    } else {
+        // order: ascending sort of (inverted score << 32 | index) = stable order by score descending
+        unsigned long long *k_in = (unsigned long long *)(base + o_k0), *k_out = (unsigned long long *)(base + o_k1);
+        int32_t *v_in = (int32_t *)(base + o_v0), *d_cidx = (int32_t *)(base + o_v1);
+        size_t tmp_bytes = 0, tmp2 = 0;
+        CU_CHECK(h, cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, k_in, k_out, n, 0, 64, s));
+        CU_CHECK(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp2, k_in, k_out, v_in, d_cidx, n, 0, 64, s));
+        tmp_bytes = std::max(tmp_bytes, tmp2);
+        if ((rc = ensure_dev(h, h->out, tmp_bytes))) return rc;
+        nms_score_key_kernel<<<blocks, 256, 0, s>>>(d_sc, n, k_in);
+        CU_CHECK(h, cub::DeviceRadixSort::SortKeys(h->out.p, tmp_bytes, k_in, k_out, n, 0, 64, s));
+        nms_order_from_keys_kernel<<<blocks, 256, 0, s>>>(k_out, n, d_or, d_rk);
+        // cells: keypoints sorted by cell id
+        nms_cell_kernel<<<blocks, 256, 0, s>>>(d_xy, n, cs, (int)minx, (int)miny, ncx, k_in, v_in);
+        int cell_bits = 1;
+        while (cell_bits < 64 && ((unsigned long long)ncx * (unsigned long long)ncy - 1) >> cell_bits) cell_bits++;
+        CU_CHECK(h, cub::DeviceRadixSort::SortPairs(h->out.p, tmp_bytes, k_in, k_out, v_in, d_cidx, n, 0, cell_bits, s));
+        h->stats.kernel_launches += 3;
+        for (int round = 0;; round++) {
+            CU_CHECK(h, cudaMemsetAsync(d_cnt, 0, 4, s));
+            nms_round_binned_kernel<<<blocks, 256, 0, s>>>(d_xy, d_rk, n, r2, cs, (int)minx, (int)miny, ncx, ncy, k_out,
+                                                           d_cidx, st[round & 1], st[(round + 1) & 1], d_cnt);
+            CU_CHECK(h, cudaMemcpyAsync(h_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s));
+            CU_CHECK(h, cudaStreamSynchronize(s));
+            h->stats.kernel_launches += 1; h->stats.host_syncs++; h->stats.rounds++;
+            if (*h_cnt == 0) {
+                nms_emit_kernel<<<1, 1024, 0, s>>>(d_or, st[(round + 1) & 1], n, d_kept, d_cnt);
+                break;
+            }
+            if (round > n + 2) return fail(h, PGM_E_CUDA, "NMS failed to converge (internal error)");
+        }
     }
     CU_CHECK(h, cudaMemcpyAsync(h_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s));
     CU_CHECK(h, cudaMemcpyAsync(h_cnt + 16, d_kept, (size_t)n * 4, cudaMemcpyDeviceToHost, s));

@@ -111,13 +111,28 @@ def test_brief_upstream_sampler_pairs(matcher, star):
     assert all(k.Value == gray[k.Coordinate.Y, k.Coordinate.X] for k in kps)
 
 
+@pytest.mark.parametrize("mode", ["dense", "binned"])
 @pytest.mark.parametrize("n,radius,span", [(1, 5, 10), (2, 0, 1), (50, 3, 20), (400, 20, 200), (3000, 50, 4000),
                                            (2500, 7, 60), (700, 1000, 100)])
-def test_nms_against_oracle(matcher, n, radius, span):
+def test_nms_against_oracle(matcher, monkeypatch, mode, n, radius, span):
+    monkeypatch.setenv("PGM_NMS_MODE", mode)
     rng = np.random.default_rng(n + radius)
     xy = rng.integers(0, span, size=(n, 2)).astype(np.int32)
     sc = rng.integers(12, 17, size=n).astype(np.int32)
     exp = D.eliminate_redundant(xy, sc, radius)
+    got = matcher.nms(xy, sc, radius)
+    assert got.tolist() == exp.tolist()
+
+
+@pytest.mark.parametrize("n,radius,span,lo", [(30000, 6, 2000, 0), (20000, 1, 500, -250), (30000, 0, 100, 0),
+                                              (20000, 40, 2_000_000_000, -1_000_000_000)])
+def test_nms_large_default_mode(matcher, n, radius, span, lo):
+    """Sizes where the default picks the spatially binned rounds; negative and extreme coordinates, radius 0
+    (only exact duplicates suppress each other), many duplicates."""
+    rng = np.random.default_rng(n)
+    xy = (rng.integers(0, span, size=(n, 2)) + lo).astype(np.int32)
+    sc = rng.integers(-3, 17, size=n).astype(np.int32)
+    exp = D.eliminate_redundant_vectorised(xy, sc, radius)
     got = matcher.nms(xy, sc, radius)
     assert got.tolist() == exp.tolist()
 

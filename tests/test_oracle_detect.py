@@ -101,6 +101,11 @@ def test_nms_known_answer_and_properties():
     d2 = ((kc[:, None, :] - kc[None, :, :]) ** 2).sum(-1)
     assert (d2[~np.eye(len(kept), dtype=bool)] > 400).all()
     assert (np.diff(s[kept]) <= 0).all()
+    # the vectorised form used at large sizes is the same function
+    for n, radius, span in [(400, 20, 200), (900, 3, 60), (300, 0, 10), (500, 1000, 100)]:
+        c = rng.integers(-span, span, size=(n, 2)).astype(np.int32)
+        s = rng.integers(-2, 17, size=n).astype(np.int32)
+        assert D.eliminate_redundant_vectorised(c, s, radius).tolist() == D.eliminate_redundant(c, s, radius).tolist()
 
 
 # ---- host-side product logic (no GPU) ---------------------------------------------------------

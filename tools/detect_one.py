@@ -39,7 +39,7 @@ out.update({"keypoints": int(len(xy)), "after_nms": int(len(kept)), "after_nms_2
 if check:
     from oracle import detect_np as D, orc
     exy, esc = D.detect_vectorised(img, 0.1)
-    ek = D.eliminate_redundant(exy, esc, 10) if len(exy) < 20000 else None
+    ek = D.eliminate_redundant_vectorised(exy, esc, 10) if len(exy) < 200000 else None
     out["fast_equals_oracle"] = bool(len(exy) == len(xy) and (exy == xy).all() and (esc == sc).all())
     if ek is not None:
         out["nms_equals_oracle"] = bool(ek.tolist() == kept.tolist())
