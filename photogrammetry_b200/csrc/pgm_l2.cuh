@@ -9,8 +9,13 @@
 // Precision: every fp32 component is split into bf16 hi + bf16 lo (x = hi + lo up to 2^-17
 // relative) and the dot product is evaluated as hi.hi + lo.hi + hi.lo -- three bf16 GEMM passes
 // of K = Dp accumulated into the same fp32 TMEM accumulator.  Operand rows are stored once as
-// [x_hi | x_lo] (2*Dp bf16); the train-side hi chunks are staged once per tile and used by two of
-// the passes, so a tile costs 4 chunk loads for 6 chunk MMAs.  The GEMM ranks the candidates (top-4 per query and column split); a refinement kernel
+// [x_hi | x_lo | norm] (2*Dp + 64 bf16); the train-side hi chunks are staged once per tile and used
+// by two of the passes.  The norm chunk folds ||q||^2 and ||t||^2 into the SAME accumulator: the
+// query row carries -||q||^2/2 as three bf16 terms (24 bits, exact) against ones on the train side
+// and vice versa, so one extra K = 16 MMA per tile leaves  q.t - (||q||^2 + ||t||^2)/2 = -d/2  in
+// TMEM and the epilogue needs no arithmetic at all: a distance's rank is its bit pattern with the
+// sign masked off.  A tile costs 5 chunk loads for 6 chunk MMAs + 1 MMA instruction.
+// The GEMM ranks the candidates (top-4 per query and column split); a refinement kernel
 // recomputes those few distances exactly in fp32 (sum of squared differences) and picks
 // best/second, so reported distances are exact to fp32 rounding and only candidates whose
 // approximate distances differ by < ~1e-5 relative (near-ties) can be mis-selected.
@@ -24,7 +29,8 @@
 //            the accumulator
 //   warp 2   TMEM alloc / dealloc (256 columns)
 //   warps 4-11 epilogue (two warpgroups, half the columns each): tcgen05.ld (32 lanes x 32
-//            columns per instruction), d = qn + tn - 2c, per-row top-4 in registers
+//            columns per instruction), key = |acc| bits with the column in the 5 low bits (one
+//            LOP3), integer min tree, per-row top-4 in registers
 #pragma once
 
 #include <cstdint>
@@ -38,7 +44,7 @@ constexpr int TILE_M = 128;        // queries per CTA (TMEM lanes)
 constexpr int TILE_N = 128;        // train rows per accumulator
 constexpr int CHUNK_K = 64;        // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K = 16;         // K of one tcgen05.mma for 16-bit inputs
-constexpr int MAX_CHUNKS = 4;      // resident A' chunks: [hi | lo], Dp <= 128
+constexpr int MAX_CHUNKS = 5;      // resident A' chunks: [hi | lo | norm], Dp <= 128
 constexpr int STAGES = 8;          // B' ring of chunk slots: two whole tiles deep at Dp = 128
 constexpr int THREADS = 384;        // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: two epilogue warpgroups
 constexpr int EPI_GROUPS = 2;       // each epilogue warpgroup reduces half of the accumulator's columns
@@ -115,42 +121,116 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 constexpr uint32_t IDESC_BF16_M128_N128 =
     (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 
-// ---- preprocessing: fp32 rows -> split bf16 operand rows + squared norms ------------------
-// both roles: [hi | lo], each block Dp wide, zero padded.
-__global__ void split_kernel(const float *__restrict__ x, int n, int dim, int dp,
-                             __nv_bfloat16 *__restrict__ out, float *__restrict__ norm2) {
-    const int row = blockIdx.x;
-    if (row >= n) return;
+// ---- preprocessing: fp32 rows -> split bf16 operand rows (one launch for both operands) --------
+// Row layout: [hi (Dp) | lo (Dp) | norm chunk (64)], zero padded.  Norm chunk of a query row:
+// (h0, h1, h2, 1, 1, 1, 0...) with h0 + h1 + h2 = -||q||^2 / 2 exactly (three bf16 terms carry 24 bits);
+// of a train row: (1, 1, 1, h0, h1, h2, 0...).  Their dot product is -(||q||^2 + ||t||^2) / 2.
+// One warp per row: rows [0, n1) are queries, rows [n1, n1 + n2) train descriptors.
+__global__ void __launch_bounds__(256) split_kernel(const float *__restrict__ q, int n1, const float *__restrict__ t, int n2,
+                                                    int dim, int dp, __nv_bfloat16 *__restrict__ a,
+                                                    __nv_bfloat16 *__restrict__ b) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n1 + n2) return;
+    const bool train = w >= n1;
+    const int row = train ? w - n1 : w;
+    const float *x = (train ? t : q) + (size_t)row * dim;
+    __nv_bfloat16 *o = (train ? b : a) + (size_t)row * (2 * dp + CHUNK_K);
     float acc = 0.f;
-    for (int k = threadIdx.x; k < dp; k += blockDim.x) {
-        const float v = k < dim ? x[(size_t)row * dim + k] : 0.f;
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-        __nv_bfloat16 *o = out + (size_t)row * 2 * dp;
-        o[k] = hi;
-        o[dp + k] = lo;
-        acc += v * v;
+    for (int k = 2 * lane; k < dp; k += 64) {
+        const float v0 = k < dim ? x[k] : 0.f, v1 = k + 1 < dim ? x[k + 1] : 0.f;
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+        __nv_bfloat162 hi, lo;
+        hi.x = h0; hi.y = h1;
+        lo.x = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+        lo.y = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+        *reinterpret_cast<__nv_bfloat162 *>(o + k) = hi;
+        *reinterpret_cast<__nv_bfloat162 *>(o + dp + k) = lo;
+        acc = fmaf(v0, v0, acc);
+        acc = fmaf(v1, v1, acc);
     }
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    __shared__ float s[8];
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int w = 0; w < (int)(blockDim.x + 31) / 32; w++) t += s[w];
-        norm2[row] = t;
-    }
+    for (int sh = 16; sh; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
+    const float hn = -0.5f * acc;
+    const __nv_bfloat16 e0 = __float2bfloat16_rn(hn);
+    const float r1 = hn - __bfloat162float(e0);
+    const __nv_bfloat16 e1 = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 e2 = __float2bfloat16_rn(r1 - __bfloat162float(e1));
+    const __nv_bfloat16 one = __float2bfloat16_rn(1.f), zero = __float2bfloat16_rn(0.f);
+    // columns 0..2 and 3..5 of the norm chunk; lane l writes columns 2l and 2l + 1
+    const __nv_bfloat16 n0 = train ? one : e0, n1v = train ? one : e1, n2v = train ? one : e2;
+    const __nv_bfloat16 n3 = train ? e0 : one, n4 = train ? e1 : one, n5 = train ? e2 : one;
+    __nv_bfloat162 ext;
+    ext.x = lane == 0 ? n0 : lane == 1 ? n2v : lane == 2 ? n4 : zero;
+    ext.y = lane == 0 ? n1v : lane == 1 ? n3 : lane == 2 ? n5 : zero;
+    *reinterpret_cast<__nv_bfloat162 *>(o + 2 * dp + 2 * lane) = ext;
 }
 
 // ---- the GEMM + top-4 kernel ----------------------------------------------------------------
 struct L2Params {
     int n1, n2, dpc;               // dpc = Dp / 64: chunks per operand part (hi or lo)
     int tiles_per_split;           // column tiles handled by one blockIdx.y
-    const float *qn, *tn;          // squared norms
+    uint32_t key_mask;             // 0x7FFFFFE0, passed as data so that (acc & mask) | column is ONE LOP3
     int32_t *cand_j;               // [splits][n1][CAND]
     float *cand_d;                 // [splits][n1][CAND] approximate distances (diagnostic)
     float *dbg_dist;               // optional [n1][n2] approximate distance matrix (tests)
 };
+
+// Epilogue reducer shared by both kernels: NCOLS accumulator columns of this thread's row, starting at TMEM
+// address `taddr` = global train index `jbase`.  The accumulator holds -d/2 (see the header), so the rank
+// key of a column is |acc|'s bit pattern (non-negative floats order like unsigned integers) with the
+// column-in-group in its 5 low mantissa bits: one LOP3 per element, an integer min tree per 32 columns, and
+// only a group that can improve the row's top-4 takes the insertion loop.  The 2^-18 relative perturbation
+// only affects candidate ranking; distances are refined exactly afterwards.  bk[] = keys of the row's top-4
+// (ascending, index bits cleared), bj[] their train indices.  Rows that do not exist pass bk[] = 0 and
+// never insert; columns >= n2 (zero rows from the TMA's out-of-bounds fill, key ~ 0) are skipped on insertion.
+template <int NCOLS, bool DBG>
+__device__ __forceinline__ void epilogue_reduce(uint32_t taddr, int jbase, int n2, uint32_t mask, uint32_t (&bk)[TOPK],
+                                                int (&bj)[TOPK], float *dbg_row) {
+    uint32_t va[32], vb[32];
+    constexpr int GROUPS = NCOLS / 32;
+    tc_ld_32x32b_x32(taddr, va);
+#pragma unroll
+    for (int g = 0; g < GROUPS; g++) {
+        uint32_t (&v)[32] = (g & 1) ? vb : va;
+        tc_wait_ld();
+        if (g + 1 < GROUPS) tc_ld_32x32b_x32(taddr + (uint32_t)((g + 1) * 32), (g & 1) ? va : vb);
+        const int jg = jbase + g * 32;
+#pragma unroll
+        for (int c = 0; c < 32; c++) v[c] = (v[c] & mask) | (uint32_t)c;
+        if (DBG && dbg_row) {
+#pragma unroll
+            for (int c = 0; c < 32; c++)
+                if (jg + c < n2) dbg_row[jg + c] = 2.f * __uint_as_float(v[c] & 0xFFFFFFE0u);
+        }
+        uint32_t k0 = v[0], k1 = v[1], k2 = v[2], k3 = v[3];
+#pragma unroll
+        for (int c = 4; c < 32; c += 4) {
+            k0 = min(k0, v[c]); k1 = min(k1, v[c + 1]); k2 = min(k2, v[c + 2]); k3 = min(k3, v[c + 3]);
+        }
+        uint32_t kmin = min(min(k0, k1), min(k2, k3));
+        uint32_t thr = bk[TOPK - 1];
+        while (kmin < thr) {                            // usually zero or one iteration
+            const int j = jg + (int)(kmin & 31u);
+            if (j < n2) {
+                bk[3] = kmin & 0xFFFFFFE0u; bj[3] = j;
+#pragma unroll
+                for (int k = 3; k > 0; k--)
+                    if (bk[k] < bk[k - 1]) {
+                        const uint32_t tk = bk[k]; bk[k] = bk[k - 1]; bk[k - 1] = tk;
+                        const int tj = bj[k]; bj[k] = bj[k - 1]; bj[k - 1] = tj;
+                    }
+                thr = bk[TOPK - 1];
+            }
+            // next key strictly above the one just taken: keys at or below it wrap to >= 2^31 under the
+            // unsigned subtraction (all keys are < 2^31), so one add+min per element finds it
+            const uint32_t k1p = kmin + 1u;
+            uint32_t dlt = 0xFFFFFFFFu;
+#pragma unroll
+            for (int c = 0; c < 32; c++) dlt = min(dlt, v[c] - k1p);
+            if (dlt >= 0x80000000u) break;
+            kmin = k1p + dlt;
+        }
+    }
+}
 
 template <bool DBG>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -158,14 +238,13 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B atoms need 1024-byte alignment: align the dynamic window by hand (1 KB of slack is allocated)
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    // layout: A' chunks | B' stages | barriers | tn staging
+    // layout: A' chunks | B' stages | barriers
     unsigned char *sa = smem;
     unsigned char *sb = smem + (size_t)MAX_CHUNKS * CHUNK_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sb + (size_t)STAGES * CHUNK_BYTES);
     uint64_t *full = bars, *empty = bars + STAGES, *a_bar = bars + 2 * STAGES;
     uint64_t *tfull = bars + 2 * STAGES + 1, *tempty = bars + 2 * STAGES + 3;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 5);
-    float *s_tn = reinterpret_cast<float *>(bars + 2 * STAGES + 6);          // [2][TILE_N]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * TILE_M;
@@ -191,12 +270,12 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
-        const int nch = 2 * p.dpc;
+        const int nch = 2 * p.dpc + 1;                    // hi chunks, lo chunks, norm chunk
         mbar_expect_tx(a_bar, (uint32_t)nch * CHUNK_BYTES);
         for (int kc = 0; kc < nch; kc++) tma_load_2d(sa + (size_t)kc * CHUNK_BYTES, &map_a, a_bar, kc * CHUNK_K, m0);
         int s = 0; uint32_t ph = 0;
         for (int t = 0; t < ntiles; t++) {
-            for (int kc = 0; kc < nch; kc++) {               // t_hi chunks, then t_lo chunks
+            for (int kc = 0; kc < nch; kc++) {               // t_hi chunks, t_lo chunks, norm chunk
                 mbar_wait(&empty[s], ph ^ 1);
                 mbar_expect_tx(&full[s], CHUNK_BYTES);
                 tma_load_2d(sb + (size_t)s * CHUNK_BYTES, &map_b, &full[s], kc * CHUNK_K, (ct0 + t) * TILE_N);
@@ -228,7 +307,14 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (pass != 0) tc_commit(&empty[s]);            // slot reusable once these MMAs retire
                 }
             }
-            g += 2u * (uint32_t)dpc;
+            {   // norm chunk: one K = 16 step adds -(||q||^2 + ||t||^2) / 2
+                const uint32_t i = g + 2u * (uint32_t)dpc, s = i % STAGES, ph = (i / STAGES) & 1u;
+                mbar_wait(&full[s], ph); tc_fence_after();
+                tc_mma_bf16(d_tmem, umma_desc_sw128(smem_u32(sa + (size_t)(2 * dpc) * CHUNK_BYTES)),
+                            umma_desc_sw128(smem_u32(sb + (size_t)s * CHUNK_BYTES)), IDESC_BF16_M128_N128, 1u);
+                tc_commit(&empty[s]);
+            }
+            g += 2u * (uint32_t)dpc + 1u;
             tc_commit(&tfull[acc]);                             // accumulator complete
         }
     } else if (warp >= 4) {
@@ -236,74 +322,18 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int ew = warp & 3;                                // the TMEM lane quarter this warp may read (warp % 4)
         const int eg = (warp - 4) >> 2;                         // which half of the accumulator's columns
         const int row = m0 + ew * 32 + lane;
-        const float qn = row < p.n1 ? __ldg(p.qn + row) : 0.f;
-        float bd[TOPK]; int bj[TOPK];
+        uint32_t bk[TOPK]; int bj[TOPK];
 #pragma unroll
-        for (int k = 0; k < TOPK; k++) { bd[k] = 3.4e38f; bj[k] = -1; }
-        const int et = threadIdx.x - 128;                       // 0..255
+        for (int k = 0; k < TOPK; k++) { bk[k] = row < p.n1 ? 0xFFFFFFFFu : 0u; bj[k] = -1; }
+        constexpr int NCOLS = TILE_N / EPI_GROUPS;
         for (int t = 0; t < ntiles; t++) {
             const int acc = t & 1;
-            const int j0 = (ct0 + t) * TILE_N;
-            {   // stage ||t||^2 of this tile (ordered against the previous use of the same buffer by the
-                // tempty/tfull round trip: the buffer of tile t-2 was fully consumed before tempty arrived)
-                const int j = j0 + et;
-                if (et < TILE_N) s_tn[acc * TILE_N + et] = j < p.n2 ? __ldg(p.tn + j) : 3.0e38f;
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(&tfull[acc], (t >> 1) & 1);
             tc_fence_after();
-            // 32 columns per tcgen05.ld, software-pipelined (the next group's load is in flight while this
-            // one is reduced).  The common case is branch-free: all 32 distances and their minimum are
-            // computed first, and only a group that can improve the row's top-4 takes the insertion path.
-            uint32_t va[32], vb[32];
-            constexpr int GROUPS = TILE_N / 32 / EPI_GROUPS;    // 32-column groups per epilogue warpgroup
-            const int cbase = eg * (TILE_N / EPI_GROUPS);
-            const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TILE_N + cbase);
-            tc_ld_32x32b_x32(trow, va);
-#pragma unroll
-            for (int g = 0; g < GROUPS; g++) {
-                uint32_t (&v)[32] = (g & 1) ? vb : va;
-                tc_wait_ld();
-                if (g + 1 < GROUPS) tc_ld_32x32b_x32(trow + (uint32_t)((g + 1) * 32), (g & 1) ? va : vb);
-                const int cb = cbase + g * 32;
-                // keys: the distance's bit pattern (non-negative floats order like unsigned integers) with
-                // the column-in-group in its 5 low mantissa bits -> one integer min yields min AND argmin.
-                // The 2^-18 relative perturbation only affects candidate ranking; distances are refined
-                // exactly afterwards.  Keeps the insertion path a short loop instead of 32 unrolled
-                // blocks (the unrolled form overflowed the instruction cache: stall_no_inst dominated).
-                uint32_t key[32];
-#pragma unroll
-                for (int c = 0; c < 32; c++) {
-                    const float d = fmaxf(fmaf(-2.f, __uint_as_float(v[c]), qn + s_tn[acc * TILE_N + cb + c]), 0.f);
-                    key[c] = (__float_as_uint(d) & 0xFFFFFFE0u) | (uint32_t)c;
-                }
-                if (DBG && p.dbg_dist && row < p.n1) {
-#pragma unroll
-                    for (int c = 0; c < 32; c++)
-                        if (j0 + cb + c < p.n2) p.dbg_dist[(size_t)row * p.n2 + j0 + cb + c] = __uint_as_float(key[c] & 0xFFFFFFE0u);
-                }
-                uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu, k3 = 0xFFFFFFFFu;
-#pragma unroll
-                for (int c = 0; c < 32; c += 4) {
-                    k0 = min(k0, key[c]); k1 = min(k1, key[c + 1]); k2 = min(k2, key[c + 2]); k3 = min(k3, key[c + 3]);
-                }
-                uint32_t kmin = min(min(k0, k1), min(k2, k3));
-                uint32_t thr = __float_as_uint(bd[TOPK - 1]);
-                while (kmin < thr) {                            // rarely entered, usually one iteration
-                    bd[3] = __uint_as_float(kmin & 0xFFFFFFE0u); bj[3] = j0 + cb + (int)(kmin & 31u);
-#pragma unroll
-                    for (int k = 3; k > 0; k--)
-                        if (bd[k] < bd[k - 1]) {
-                            const float td = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td;
-                            const int tj = bj[k]; bj[k] = bj[k - 1]; bj[k - 1] = tj;
-                        }
-                    thr = __float_as_uint(bd[TOPK - 1]);
-                    uint32_t nxt = 0xFFFFFFFFu;                 // next key strictly above the one just taken
-#pragma unroll
-                    for (int c = 0; c < 32; c++) nxt = min(nxt, key[c] > kmin ? key[c] : 0xFFFFFFFFu);
-                    kmin = nxt;
-                }
-            }
+            const int jbase = (ct0 + t) * TILE_N + eg * NCOLS;
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TILE_N + eg * NCOLS);
+            epilogue_reduce<NCOLS, DBG>(taddr, jbase, p.n2, p.key_mask, bk, bj,
+                                        DBG && p.dbg_dist && row < p.n1 ? p.dbg_dist + (size_t)row * p.n2 : nullptr);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -311,7 +341,10 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (row < p.n1) {
             const size_t o = ((size_t)blockIdx.y * p.n1 + row) * CAND + (size_t)eg * TOPK;
 #pragma unroll
-            for (int k = 0; k < TOPK; k++) { p.cand_j[o + k] = bd[k] < 3.0e38f ? bj[k] : -1; p.cand_d[o + k] = bd[k]; }
+            for (int k = 0; k < TOPK; k++) {
+                p.cand_j[o + k] = bk[k] != 0xFFFFFFFFu ? bj[k] : -1;
+                p.cand_d[o + k] = 2.f * __uint_as_float(bk[k] & 0x7FFFFFFFu);
+            }
         }
     }
     tc_fence_before();
@@ -387,7 +420,6 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint64_t *full = bars, *empty = bars + STAGES, *a_bar = bars + 2 * STAGES;
     uint64_t *tfull = bars + 2 * STAGES + 1, *tempty = bars + 2 * STAGES + 3;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 5);
-    float *s_tn = reinterpret_cast<float *>(bars + 2 * STAGES + 6);          // [2][TILE_N2]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -415,12 +447,12 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer (both CTAs): own A' rows, own half of every B' tile =====
-        const int nch = 2 * p.dpc;
+        const int nch = 2 * p.dpc + 1;                    // hi chunks, lo chunks, norm chunk
         if (leader) mbar_expect_tx(a_bar, 2u * (uint32_t)nch * CHUNK_BYTES);
         for (int kc = 0; kc < nch; kc++) tma_load_2d_pair(sa + (size_t)kc * CHUNK_BYTES, &map_a, a_bar, kc * CHUNK_K, m0);
         int s = 0; uint32_t ph = 0;
         for (int t = 0; t < ntiles; t++) {
-            for (int kc = 0; kc < nch; kc++) {                 // t_hi chunks, then t_lo chunks
+            for (int kc = 0; kc < nch; kc++) {                 // t_hi chunks, t_lo chunks, norm chunk
                 mbar_wait(&empty[s], ph ^ 1);                  // the pair's MMAs no longer read this stage (multicast commit)
                 if (leader) mbar_expect_tx(&full[s], 2u * CHUNK_BYTES);
                 tma_load_2d_pair(sb + (size_t)s * CHUNK_BYTES, &map_b, &full[s], kc * CHUNK_K,
@@ -453,7 +485,14 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     if (pass != 0) tc_commit_pair(&empty[s]);
                 }
             }
-            g += 2u * (uint32_t)dpc;
+            {   // norm chunk: one K = 16 step adds -(||q||^2 + ||t||^2) / 2
+                const uint32_t i = g + 2u * (uint32_t)dpc, s = i % STAGES, ph = (i / STAGES) & 1u;
+                mbar_wait(&full[s], ph); tc_fence_after();
+                tc_mma_bf16_pair(d_tmem, umma_desc_sw128(smem_u32(sa + (size_t)(2 * dpc) * CHUNK_BYTES)),
+                                 umma_desc_sw128(smem_u32(sb + (size_t)s * CHUNK_BYTES)), IDESC_BF16_M256_N256, 1u);
+                tc_commit_pair(&empty[s]);
+            }
+            g += 2u * (uint32_t)dpc + 1u;
             tc_commit_pair(&tfull[acc]);
         }
     } else if (warp >= 4) {
@@ -461,65 +500,18 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int ew = warp & 3;
         const int eg = (warp - 4) >> 2;
         const int row = m0 + ew * 32 + lane;
-        const float qn = row < p.n1 ? __ldg(p.qn + row) : 0.f;
-        float bd[TOPK]; int bj[TOPK];
+        uint32_t bk[TOPK]; int bj[TOPK];
 #pragma unroll
-        for (int k = 0; k < TOPK; k++) { bd[k] = 3.4e38f; bj[k] = -1; }
-        const int et = threadIdx.x - 128;                       // 0..255
+        for (int k = 0; k < TOPK; k++) { bk[k] = row < p.n1 ? 0xFFFFFFFFu : 0u; bj[k] = -1; }
+        constexpr int NCOLS = TILE_N2 / EPI_GROUPS;
         for (int t = 0; t < ntiles; t++) {
             const int acc = t & 1;
-            const int j0 = (ct0 + t) * TILE_N2;
-            {
-                const int j = j0 + et;
-                s_tn[acc * TILE_N2 + et] = j < p.n2 ? __ldg(p.tn + j) : 3.0e38f;
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(&tfull[acc], (t >> 1) & 1);
             tc_fence_after();
-            uint32_t va[32], vb[32];
-            constexpr int GROUPS = TILE_N2 / 32 / EPI_GROUPS;
-            const int cbase = eg * (TILE_N2 / EPI_GROUPS);
-            const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TILE_N2 + cbase);
-            tc_ld_32x32b_x32(trow, va);
-#pragma unroll
-            for (int g = 0; g < GROUPS; g++) {
-                uint32_t (&v)[32] = (g & 1) ? vb : va;
-                tc_wait_ld();
-                if (g + 1 < GROUPS) tc_ld_32x32b_x32(trow + (uint32_t)((g + 1) * 32), (g & 1) ? va : vb);
-                const int cb = cbase + g * 32;
-                uint32_t key[32];
-#pragma unroll
-                for (int c = 0; c < 32; c++) {
-                    const float d = fmaxf(fmaf(-2.f, __uint_as_float(v[c]), qn + s_tn[acc * TILE_N2 + cb + c]), 0.f);
-                    key[c] = (__float_as_uint(d) & 0xFFFFFFE0u) | (uint32_t)c;
-                }
-                if (DBG && p.dbg_dist && row < p.n1) {
-#pragma unroll
-                    for (int c = 0; c < 32; c++)
-                        if (j0 + cb + c < p.n2) p.dbg_dist[(size_t)row * p.n2 + j0 + cb + c] = __uint_as_float(key[c] & 0xFFFFFFE0u);
-                }
-                uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu, k3 = 0xFFFFFFFFu;
-#pragma unroll
-                for (int c = 0; c < 32; c += 4) {
-                    k0 = min(k0, key[c]); k1 = min(k1, key[c + 1]); k2 = min(k2, key[c + 2]); k3 = min(k3, key[c + 3]);
-                }
-                uint32_t kmin = min(min(k0, k1), min(k2, k3));
-                uint32_t thr = __float_as_uint(bd[TOPK - 1]);
-                while (kmin < thr) {
-                    bd[3] = __uint_as_float(kmin & 0xFFFFFFE0u); bj[3] = j0 + cb + (int)(kmin & 31u);
-#pragma unroll
-                    for (int k = 3; k > 0; k--)
-                        if (bd[k] < bd[k - 1]) {
-                            const float td = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td;
-                            const int tj = bj[k]; bj[k] = bj[k - 1]; bj[k - 1] = tj;
-                        }
-                    thr = __float_as_uint(bd[TOPK - 1]);
-                    uint32_t nxt = 0xFFFFFFFFu;
-#pragma unroll
-                    for (int c = 0; c < 32; c++) nxt = min(nxt, key[c] > kmin ? key[c] : 0xFFFFFFFFu);
-                    kmin = nxt;
-                }
-            }
+            const int jbase = (ct0 + t) * TILE_N2 + eg * NCOLS;
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TILE_N2 + eg * NCOLS);
+            epilogue_reduce<NCOLS, DBG>(taddr, jbase, p.n2, p.key_mask, bk, bj,
+                                        DBG && p.dbg_dist && row < p.n1 ? p.dbg_dist + (size_t)row * p.n2 : nullptr);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(&tempty[acc], 0);      // the leader's barrier counts both CTAs' warps
@@ -527,7 +519,10 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (row < p.n1) {
             const size_t o = ((size_t)blockIdx.y * p.n1 + row) * CAND + (size_t)eg * TOPK;
 #pragma unroll
-            for (int k = 0; k < TOPK; k++) { p.cand_j[o + k] = bd[k] < 3.0e38f ? bj[k] : -1; p.cand_d[o + k] = bd[k]; }
+            for (int k = 0; k < TOPK; k++) {
+                p.cand_j[o + k] = bk[k] != 0xFFFFFFFFu ? bj[k] : -1;
+                p.cand_d[o + k] = 2.f * __uint_as_float(bk[k] & 0x7FFFFFFFu);
+            }
         }
     }
     __syncwarp();
@@ -540,35 +535,64 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 }
 
 inline size_t l2_pair_smem_bytes() {
-    return (size_t)(MAX_CHUNKS + STAGES) * CHUNK_BYTES + (2 * STAGES + 6) * 8 + 2 * TILE_N2 * 4 + 1024;
+    return (size_t)(MAX_CHUNKS + STAGES) * CHUNK_BYTES + (2 * STAGES + 6) * 8 + 1024;
 }
 
 inline size_t l2_smem_bytes() {
-    return (size_t)(MAX_CHUNKS + STAGES) * CHUNK_BYTES + (2 * STAGES + 6) * 8 + 2 * TILE_N * 4 + 1024;
+    return (size_t)(MAX_CHUNKS + STAGES) * CHUNK_BYTES + (2 * STAGES + 6) * 8 + 1024;
 }
 
 // ---- refinement: exact fp32 distances of the candidates, best / second by (distance, index) ----
-__global__ void l2_refine_kernel(const float *__restrict__ q, int n1, const float *__restrict__ t, int n2, int dim,
-                                 const int32_t *__restrict__ cand_j, int splits,
-                                 int32_t *best_j, float *best_d, int32_t *second_j, float *second_d) {
+// One warp per query.  The query's components stay in registers (dim <= 128: four per lane), the
+// candidates are taken four at a time so that sixteen independent train-row loads are in flight per lane
+// instead of a dependent chain of single candidates.  Summation order per distance: each lane's strided
+// partial sum, then a butterfly -- the same for every candidate, whatever the batch it falls into.
+__global__ void __launch_bounds__(256) l2_refine_kernel(const float *__restrict__ q, int n1, const float *__restrict__ t, int n2,
+                                                        int dim, const int32_t *__restrict__ cand_j, int splits,
+                                                        int32_t *best_j, float *best_d, int32_t *second_j, float *second_d) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n1) return;
     const int i = warp;
+    float qv[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) qv[k] = lane + 32 * k < dim ? __ldg(q + (size_t)i * dim + lane + 32 * k) : 0.f;
     float b = 0.f, s = 0.f; int bj = -1, sj = -1;
-    for (int c = 0; c < splits * CAND; c++) {
-        const int sp = c / CAND, k = c - sp * CAND;
-        const int j = cand_j[((size_t)sp * n1 + i) * CAND + k];
-        if (j < 0 || j >= n2) continue;
-        float acc = 0.f;
-        for (int d = lane; d < dim; d += 32) {
-            const float df = q[(size_t)i * dim + d] - t[(size_t)j * dim + d];
-            acc = fmaf(df, df, acc);
+    const int ncand = splits * CAND;
+    for (int c0 = 0; c0 < ncand; c0 += 4) {
+        int j[4]; float acc[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int c = c0 + u, sp = c / CAND, k = c - sp * CAND;
+            j[u] = c < ncand ? __ldg(cand_j + ((size_t)sp * n1 + i) * CAND + k) : -1;
+            if (j[u] >= n2) j[u] = -1;
         }
-        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        const bool lt_b = bj < 0 || acc < b || (acc == b && j < bj);
-        const bool lt_s = sj < 0 || acc < s || (acc == s && j < sj);
-        if (lt_b) { s = b; sj = bj; b = acc; bj = j; }
-        else if (lt_s) { s = acc; sj = j; }
+        float tv[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                tv[u][k] = (j[u] >= 0 && lane + 32 * k < dim) ? __ldg(t + (size_t)j[u] * dim + lane + 32 * k) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            acc[u] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float df = qv[k] - tv[u][k];
+                if (lane + 32 * k < dim) acc[u] = fmaf(df, df, acc[u]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < 4; u++) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (j[u] < 0) continue;
+            const bool lt_b = bj < 0 || acc[u] < b || (acc[u] == b && j[u] < bj);
+            const bool lt_s = sj < 0 || acc[u] < s || (acc[u] == s && j[u] < sj);
+            if (lt_b) { s = b; sj = bj; b = acc[u]; bj = j[u]; }
+            else if (lt_s) { s = acc[u]; sj = j[u]; }
+        }
     }
     if (lane == 0) {
         best_j[i] = bj; best_d[i] = bj < 0 ? -1.f : b;

@@ -1051,7 +1051,7 @@ static int l2_dev_impl(pgm_handle *h, const float *d_q, int32_t n1, const float 
                        int32_t *d_bj, float *d_bd, int32_t *d_sj, float *d_sd, float *d_dbg) {
     using namespace pgm_l2;
     cudaStream_t s = h->stream;
-    const int dp = (dim + CHUNK_K - 1) / CHUNK_K * CHUNK_K, kprime = 2 * dp, dpc = dp / CHUNK_K;   // rows = [hi | lo]
+    const int dp = (dim + CHUNK_K - 1) / CHUNK_K * CHUNK_K, kprime = 2 * dp + CHUNK_K, dpc = dp / CHUNK_K;   // rows = [hi | lo | norm]
     const int row_tiles = (n1 + TILE_M - 1) / TILE_M;
     // CTA pairs (cta_group::2, M = 256 x N = 256) whenever there are at least two row tiles
     const bool pair = row_tiles >= 2 && !h->l2_force_single;
@@ -1067,19 +1067,16 @@ static int l2_dev_impl(pgm_handle *h, const float *d_q, int32_t n1, const float 
         const double cost = (double)((gx * se + h->num_sms - 1) / h->num_sms) * (t + 0.5);
         if (cost < best_cost - 1e-9) { best_cost = cost; splits = se; tps = t; }
     }
-    // scratch: A' | B' | qn | tn | cand_j | cand_d
+    // scratch: A' | B' | cand_j | cand_d
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
     const size_t o_a = take((size_t)n1 * kprime * 2), o_b = take((size_t)n2 * kprime * 2);
-    const size_t o_qn = take((size_t)n1 * 4), o_tn = take((size_t)n2 * 4);
     const size_t o_cj = take((size_t)splits * n1 * CAND * 4), o_cd = take((size_t)splits * n1 * CAND * 4);
     int rc = ensure_dev(h, h->misc, off);
     if (rc) return rc;
     char *base = (char *)h->misc.p;
     __nv_bfloat16 *a = (__nv_bfloat16 *)(base + o_a), *b = (__nv_bfloat16 *)(base + o_b);
-    float *qn = (float *)(base + o_qn), *tn = (float *)(base + o_tn);
-    split_kernel<<<n1, 128, 0, s>>>(d_q, n1, dim, dp, a, qn);
-    split_kernel<<<n2, 128, 0, s>>>(d_t, n2, dim, dp, b, tn);
+    split_kernel<<<(int)(((size_t)(n1 + n2) * 32 + 255) / 256), 256, 0, s>>>(d_q, n1, d_t, n2, dim, dp, a, b);
     CUtensorMap map_a, map_b;
     if ((rc = make_operand_map(h, &map_a, a, n1, kprime))) return rc;
     if ((rc = make_operand_map(h, &map_b, b, n2, kprime))) return rc;
@@ -1091,7 +1088,7 @@ static int l2_dev_impl(pgm_handle *h, const float *d_q, int32_t n1, const float 
         h->l2_attr_set = true;
     }
     L2Params p{};
-    p.n1 = n1; p.n2 = n2; p.dpc = dpc; p.tiles_per_split = tps; p.qn = qn; p.tn = tn;
+    p.n1 = n1; p.n2 = n2; p.dpc = dpc; p.tiles_per_split = tps; p.key_mask = 0x7FFFFFE0u;
     p.cand_j = (int32_t *)(base + o_cj); p.cand_d = (float *)(base + o_cd); p.dbg_dist = d_dbg;
     if (pair) {
         if (d_dbg) l2_topk_pair_kernel<true><<<dim3(gx, splits), THREADS, l2_pair_smem_bytes(), s>>>(map_a, map_b, p);
@@ -1100,8 +1097,8 @@ static int l2_dev_impl(pgm_handle *h, const float *d_q, int32_t n1, const float 
         if (d_dbg) l2_topk_kernel<true><<<dim3(gx, splits), THREADS, l2_smem_bytes(), s>>>(map_a, map_b, p);
         else l2_topk_kernel<false><<<dim3(gx, splits), THREADS, l2_smem_bytes(), s>>>(map_a, map_b, p);
     }
-    l2_refine_kernel<<<(n1 * 32 + 255) / 256, 256, 0, s>>>(d_q, n1, d_t, n2, dim, p.cand_j, splits, d_bj, d_bd, d_sj, d_sd);
-    h->stats.kernel_launches += 4;
+    l2_refine_kernel<<<(int)(((size_t)n1 * 32 + 255) / 256), 256, 0, s>>>(d_q, n1, d_t, n2, dim, p.cand_j, splits, d_bj, d_bd, d_sj, d_sd);
+    h->stats.kernel_launches += 3;
     h->stats.distance_evals += (int64_t)n1 * n2;
     h->stats.evals_computed += (int64_t)n1 * n2;
     CU_CHECK(h, cudaGetLastError());

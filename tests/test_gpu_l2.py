@@ -52,3 +52,31 @@ def test_l2_config2_shape_8k(matcher):
     q = rng.random((8192, 128), dtype=np.float32)           # SIFT-like non-negative descriptors
     t = rng.random((8192, 128), dtype=np.float32)
     _check(matcher, q, t)
+
+
+def test_l2_heterogeneous_norms(matcher):
+    # row norms spread over four orders of magnitude on both sides: the norms are folded into the GEMM
+    # (-(|q|^2 + |t|^2)/2 rides in an extra operand chunk), so their precision must hold per pair of rows
+    rng = np.random.default_rng(21)
+    q = (rng.standard_normal((700, 96)) * 10.0 ** rng.uniform(-2, 2, size=(700, 1))).astype(np.float32)
+    t = (rng.standard_normal((1500, 96)) * 10.0 ** rng.uniform(-2, 2, size=(1500, 1))).astype(np.float32)
+    _check(matcher, q, t)
+
+
+def test_l2_exact_duplicates_and_ties(matcher):
+    # every query occurs verbatim in the train set (distance exactly 0) and every train row occurs twice
+    # (exact ties: best = smaller index, second = its copy)
+    rng = np.random.default_rng(22)
+    q = rng.standard_normal((513, 128)).astype(np.float32)
+    base = np.concatenate([q[rng.permutation(513)], rng.standard_normal((300, 128)).astype(np.float32)])
+    t = np.concatenate([base, base])
+    bj, bd, sj, sd = _check(matcher, q, t)
+    assert (bd == 0).all() and (sd == 0).all() and (sj == bj + len(base)).all()
+
+
+def test_l2_zero_rows(matcher):
+    # all-zero queries and train rows: -d/2 accumulators are exactly 0 for (0, 0) pairs
+    rng = np.random.default_rng(23)
+    q = rng.standard_normal((200, 64)).astype(np.float32); q[::7] = 0
+    t = rng.standard_normal((333, 64)).astype(np.float32); t[5] = 0; t[100] = 0
+    _check(matcher, q, t)

@@ -2,7 +2,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from photogrammetry_b200.keypoint_matching import Matcher
-m = Matcher(0); n, dim = 16384, 128
+m = Matcher(0); n, dim = int(os.environ.get("L2_N", "16384")), 128
 q = torch.rand((n, dim), device="cuda"); t = torch.rand((n, dim), device="cuda")
 oj = torch.empty((2, n), dtype=torch.int32, device="cuda"); od = torch.empty((2, n), device="cuda")
 for _ in range(3):
