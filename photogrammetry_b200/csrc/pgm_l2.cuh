@@ -109,6 +109,11 @@ __device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[3
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
 }
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may
+// start (prologue: barriers, TMEM allocation) while its predecessor drains; pdl_wait() blocks until the
+// predecessor grid has completed and its memory is visible.  pdl_trigger() lets the successor start early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
@@ -130,6 +135,7 @@ __global__ void __launch_bounds__(256) split_kernel(const float *__restrict__ q,
                                                     int dim, int dp, __nv_bfloat16 *__restrict__ a,
                                                     __nv_bfloat16 *__restrict__ b) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();                                   // the GEMM kernel's prologue may overlap this kernel
     if (w >= n1 + n2) return;
     const bool train = w >= n1;
     const int row = train ? w - n1 : w;
@@ -267,6 +273,7 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                      // operands are written by split_kernel
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
@@ -343,10 +350,11 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < TOPK; k++) {
                 p.cand_j[o + k] = bk[k] != 0xFFFFFFFFu ? bj[k] : -1;
-                p.cand_d[o + k] = 2.f * __uint_as_float(bk[k] & 0x7FFFFFFFu);
+                p.cand_d[o + k] = bk[k] != 0xFFFFFFFFu ? 2.f * __uint_as_float(bk[k]) : 3.4e38f;
             }
         }
     }
+    pdl_trigger();                                   // the refinement kernel may be scheduled
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
@@ -444,6 +452,7 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     cluster_sync_all();                       // barriers of both CTAs initialised before any remote arrive / TMA
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                      // operands are written by split_kernel
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer (both CTAs): own A' rows, own half of every B' tile =====
@@ -521,10 +530,11 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
             for (int k = 0; k < TOPK; k++) {
                 p.cand_j[o + k] = bk[k] != 0xFFFFFFFFu ? bj[k] : -1;
-                p.cand_d[o + k] = 2.f * __uint_as_float(bk[k] & 0x7FFFFFFFu);
+                p.cand_d[o + k] = bk[k] != 0xFFFFFFFFu ? 2.f * __uint_as_float(bk[k]) : 3.4e38f;
             }
         }
     }
+    pdl_trigger();                                   // the refinement kernel may be scheduled
     __syncwarp();
     tc_fence_before();
     cluster_sync_all();                       // neither CTA leaves (or frees TMEM) while its partner may still use it
@@ -543,55 +553,92 @@ inline size_t l2_smem_bytes() {
 }
 
 // ---- refinement: exact fp32 distances of the candidates, best / second by (distance, index) ----
-// One warp per query.  The query's components stay in registers (dim <= 128: four per lane), the
-// candidates are taken four at a time so that sixteen independent train-row loads are in flight per lane
-// instead of a dependent chain of single candidates.  Summation order per distance: each lane's strided
-// partial sum, then a butterfly -- the same for every candidate, whatever the batch it falls into.
+// One warp per query.  Step 1 prunes with the approximate distances the GEMM kernel left in cand_d: a
+// candidate whose approximate distance exceeds the second-smallest one by more than the error bound of
+// the two approximations cannot be among the exact top two, so its train row is never read (typically 2-4
+// of the 8 x splits candidates survive; the gather of 512-byte train rows is what this kernel costs).
+// Error bound: |approx - exact| <= 2^-14.5 (|q|^2 + |t|^2) worst case (bf16 hi/lo residuals 2^-15.7 |q||t|,
+// fp32 accumulation over K' = 272, the key's 5 dropped mantissa bits); |t|^2 <= 2|q|^2 + 2d, hence the slack
+// 2^-12 (3|q|^2 + 2 d_approx) covers both approximations with a factor 2.8 to spare.
+// Step 2: the survivors four at a time, so sixteen independent train-row loads are in flight per lane.
+// Summation order per distance: each lane's strided partial sum, then a butterfly.
 __global__ void __launch_bounds__(256) l2_refine_kernel(const float *__restrict__ q, int n1, const float *__restrict__ t, int n2,
-                                                        int dim, const int32_t *__restrict__ cand_j, int splits,
+                                                        int dim, const int32_t *__restrict__ cand_j,
+                                                        const float *__restrict__ cand_d, int splits,
                                                         int32_t *best_j, float *best_d, int32_t *second_j, float *second_d) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n1) return;
     const int i = warp;
-    float qv[4];
+    float qv[4], qn = 0.f;
 #pragma unroll
-    for (int k = 0; k < 4; k++) qv[k] = lane + 32 * k < dim ? __ldg(q + (size_t)i * dim + lane + 32 * k) : 0.f;
-    float b = 0.f, s = 0.f; int bj = -1, sj = -1;
+    for (int k = 0; k < 4; k++) {
+        qv[k] = lane + 32 * k < dim ? __ldg(q + (size_t)i * dim + lane + 32 * k) : 0.f;
+        qn = fmaf(qv[k], qv[k], qn);
+    }
+    for (int o = 16; o; o >>= 1) qn += __shfl_xor_sync(0xffffffffu, qn, o);
+    pdl_wait();                                      // candidates are written by the GEMM kernel
     const int ncand = splits * CAND;
-    for (int c0 = 0; c0 < ncand; c0 += 4) {
-        int j[4]; float acc[4];
+    // second-smallest approximate distance over all candidates (two warp minima per 32 candidates)
+    float m1 = 3.4e38f, m2 = 3.4e38f;
+    for (int c0 = 0; c0 < ncand; c0 += 32) {
+        const int c = c0 + lane, sp = c / CAND, k = c - sp * CAND;
+        const size_t o = ((size_t)sp * n1 + i) * CAND + k;
+        const int j = c < ncand ? __ldg(cand_j + o) : -1;
+        float d = (j >= 0 && j < n2) ? __ldg(cand_d + o) : 3.4e38f;
+        float a = d;
+        for (int sh = 16; sh; sh >>= 1) a = fminf(a, __shfl_xor_sync(0xffffffffu, a, sh));
+        const unsigned holders = __ballot_sync(0xffffffffu, d == a);
+        if (lane == __ffs(holders) - 1) d = 3.4e38f;                 // drop ONE instance of the minimum
+        float b2 = d;
+        for (int sh = 16; sh; sh >>= 1) b2 = fminf(b2, __shfl_xor_sync(0xffffffffu, b2, sh));
+        // merge (a <= b2) into (m1 <= m2)
+        const float n1m = fminf(m1, a), n2m = fminf(fmaxf(m1, a), fminf(m2, b2));
+        m1 = n1m; m2 = n2m;
+    }
+    float b = 0.f, s = 0.f; int bj = -1, sj = -1;
+    for (int c0 = 0; c0 < ncand; c0 += 32) {
+        const int c = c0 + lane, sp = c / CAND, k = c - sp * CAND;
+        const size_t o = ((size_t)sp * n1 + i) * CAND + k;
+        const int jc = c < ncand ? __ldg(cand_j + o) : -1;
+        const float dc = (jc >= 0 && jc < n2) ? __ldg(cand_d + o) : 3.4e38f;
+        const bool keep = jc >= 0 && jc < n2 && dc <= m2 + 0.000244140625f * (3.f * qn + 2.f * dc);
+        unsigned todo = __ballot_sync(0xffffffffu, keep);
+        while (todo) {                                               // ascending candidate order, four per batch
+            int j[4]; float acc[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int c = c0 + u, sp = c / CAND, k = c - sp * CAND;
-            j[u] = c < ncand ? __ldg(cand_j + ((size_t)sp * n1 + i) * CAND + k) : -1;
-            if (j[u] >= n2) j[u] = -1;
-        }
-        float tv[4][4];
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                tv[u][k] = (j[u] >= 0 && lane + 32 * k < dim) ? __ldg(t + (size_t)j[u] * dim + lane + 32 * k) : 0.f;
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            acc[u] = 0.f;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const float df = qv[k] - tv[u][k];
-                if (lane + 32 * k < dim) acc[u] = fmaf(df, df, acc[u]);
+            for (int u = 0; u < 4; u++) {
+                const int src = todo ? __ffs(todo) - 1 : 0;
+                const int ju = __shfl_sync(0xffffffffu, jc, src);
+                j[u] = todo ? ju : -1;
+                todo &= todo - 1;
             }
-        }
+            float tv[4][4];
 #pragma unroll
-        for (int o = 16; o; o >>= 1)
+            for (int u = 0; u < 4; u++)
 #pragma unroll
-            for (int u = 0; u < 4; u++) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+                for (int k2 = 0; k2 < 4; k2++)
+                    tv[u][k2] = (j[u] >= 0 && lane + 32 * k2 < dim) ? __ldg(t + (size_t)j[u] * dim + lane + 32 * k2) : 0.f;
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (j[u] < 0) continue;
-            const bool lt_b = bj < 0 || acc[u] < b || (acc[u] == b && j[u] < bj);
-            const bool lt_s = sj < 0 || acc[u] < s || (acc[u] == s && j[u] < sj);
-            if (lt_b) { s = b; sj = bj; b = acc[u]; bj = j[u]; }
-            else if (lt_s) { s = acc[u]; sj = j[u]; }
+            for (int u = 0; u < 4; u++) {
+                acc[u] = 0.f;
+#pragma unroll
+                for (int k2 = 0; k2 < 4; k2++) {
+                    const float df = qv[k2] - tv[u][k2];
+                    if (lane + 32 * k2 < dim) acc[u] = fmaf(df, df, acc[u]);
+                }
+            }
+#pragma unroll
+            for (int sh = 16; sh; sh >>= 1)
+#pragma unroll
+                for (int u = 0; u < 4; u++) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], sh);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (j[u] < 0) continue;
+                const bool lt_b = bj < 0 || acc[u] < b || (acc[u] == b && j[u] < bj);
+                const bool lt_s = sj < 0 || acc[u] < s || (acc[u] == s && j[u] < sj);
+                if (lt_b) { s = b; sj = bj; b = acc[u]; bj = j[u]; }
+                else if (lt_s) { s = acc[u]; sj = j[u]; }
+            }
         }
     }
     if (lane == 0) {

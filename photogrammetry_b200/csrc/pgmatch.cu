@@ -1090,14 +1090,23 @@ static int l2_dev_impl(pgm_handle *h, const float *d_q, int32_t n1, const float 
     L2Params p{};
     p.n1 = n1; p.n2 = n2; p.dpc = dpc; p.tiles_per_split = tps; p.key_mask = 0x7FFFFFE0u;
     p.cand_j = (int32_t *)(base + o_cj); p.cand_d = (float *)(base + o_cd); p.dbg_dist = d_dbg;
+    // the GEMM kernel and the refinement are programmatic dependents of their predecessors (griddepcontrol)
+    cudaLaunchAttribute pdl{};
+    pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl.val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(gx, splits); cfg.blockDim = dim3(THREADS); cfg.stream = s; cfg.attrs = &pdl; cfg.numAttrs = 1;
+    cfg.dynamicSmemBytes = pair ? l2_pair_smem_bytes() : l2_smem_bytes();
     if (pair) {
-        if (d_dbg) l2_topk_pair_kernel<true><<<dim3(gx, splits), THREADS, l2_pair_smem_bytes(), s>>>(map_a, map_b, p);
-        else l2_topk_pair_kernel<false><<<dim3(gx, splits), THREADS, l2_pair_smem_bytes(), s>>>(map_a, map_b, p);
+        if (d_dbg) CU_CHECK(h, cudaLaunchKernelEx(&cfg, l2_topk_pair_kernel<true>, map_a, map_b, p));
+        else CU_CHECK(h, cudaLaunchKernelEx(&cfg, l2_topk_pair_kernel<false>, map_a, map_b, p));
     } else {
-        if (d_dbg) l2_topk_kernel<true><<<dim3(gx, splits), THREADS, l2_smem_bytes(), s>>>(map_a, map_b, p);
-        else l2_topk_kernel<false><<<dim3(gx, splits), THREADS, l2_smem_bytes(), s>>>(map_a, map_b, p);
+        if (d_dbg) CU_CHECK(h, cudaLaunchKernelEx(&cfg, l2_topk_kernel<true>, map_a, map_b, p));
+        else CU_CHECK(h, cudaLaunchKernelEx(&cfg, l2_topk_kernel<false>, map_a, map_b, p));
     }
-    l2_refine_kernel<<<(int)(((size_t)n1 * 32 + 255) / 256), 256, 0, s>>>(d_q, n1, d_t, n2, dim, p.cand_j, splits, d_bj, d_bd, d_sj, d_sd);
+    cfg.gridDim = dim3((unsigned)(((size_t)n1 * 32 + 255) / 256)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0;
+    CU_CHECK(h, cudaLaunchKernelEx(&cfg, l2_refine_kernel, d_q, n1, d_t, n2, dim, (const int32_t *)p.cand_j,
+                                   (const float *)p.cand_d, splits, d_bj, d_bd, d_sj, d_sd));
     h->stats.kernel_launches += 3;
     h->stats.distance_evals += (int64_t)n1 * n2;
     h->stats.evals_computed += (int64_t)n1 * n2;
