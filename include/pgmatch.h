@@ -169,6 +169,30 @@ int pgm_knn2_hamming_dev(pgm_handle *h,
                          int32_t desc_bits, int32_t stride_bytes,
                          int32_t *d_best_j, int32_t *d_best_d, int32_t *d_second_j, int32_t *d_second_d);
 
+/* ---- train-sharded nearest neighbours: the "top-2 merge" (north_star) ----
+ * A single huge pair whose train set is split over G ranks: every rank runs
+ * pgm_knn2_hamming_dev on (all queries x its train slice), packs the result with
+ * pgm_pack_top2_keys_dev (key = distance << 20 | (local j + index_offset), 0x7F7F7F7F where
+ * absent: integer order == the (distance, j) order, positive as int32), exchanges the
+ * [2][n] key arrays with ONE all-gather (NCCL over NVLink, done by the caller), and
+ * pgm_merge_top2_dev picks the two smallest of the 2G keys of every query: the result is
+ * bit-identical to pgm_knn2_hamming_dev on the unsharded train set.
+ * d_keys of pgm_merge_top2_dev: int32[n_shards][2][n]. */
+int pgm_pack_top2_keys_dev(pgm_handle *h, const int32_t *d_best_j, const int32_t *d_best_d,
+                           const int32_t *d_second_j, const int32_t *d_second_d, int32_t n,
+                           int32_t index_offset, int32_t *d_keys);
+int pgm_merge_top2_dev(pgm_handle *h, const int32_t *d_keys, int32_t n_shards, int32_t n,
+                       int32_t *d_best_j, int32_t *d_best_d, int32_t *d_second_j, int32_t *d_second_d);
+
+/* The filter of pgm_match_ratio_crosscheck on device-resident knn2 results (all pointers
+ * device memory except out_count): d_col_best_i[n2] = best query of every train row under
+ * (distance, i) (ignored unless cross_check).  Writes the kept (i, j1, d1) triples in
+ * ascending i and their number. */
+int pgm_ratio_crosscheck_filter_dev(pgm_handle *h, int32_t n1, int32_t n2,
+                                    const int32_t *d_best_j, const int32_t *d_best_d, const int32_t *d_second_d,
+                                    const int32_t *d_col_best_i, float ratio, int32_t cross_check, int32_t max_dist,
+                                    int32_t *d_out_qi, int32_t *d_out_tj, int32_t *d_out_dist, int32_t *out_count);
+
 /* ---- match_keypoints of the Python generation (keypoint_matching.py:7-33) ---
  * out: int64[n1][n2][2] = (idx2, dist) with every row sorted by dist -- the array
  * `match_keypoints(keypoints1, keypoints2, hamming_threshold)` returns (the

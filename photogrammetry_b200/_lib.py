@@ -35,6 +35,7 @@ EXPORTED_SYMBOLS = (
     "pgm_match_hamming_greedy", "pgm_match_hamming_greedy_dev",
     "pgm_match_pairs_batch", "pgm_match_pairs_batch_dev",
     "pgm_knn2_hamming", "pgm_knn2_hamming_dev", "pgm_match_ratio_crosscheck",
+    "pgm_pack_top2_keys_dev", "pgm_merge_top2_dev", "pgm_ratio_crosscheck_filter_dev",
     "pgm_match_keypoints_sorted", "pgm_match_keypoints_sorted_dev", "pgm_knn2_l2", "pgm_knn2_l2_dev",
     "pgm_fast_detect", "pgm_brief_describe", "pgm_nms", "pgm_ransac_score",
     "pgm_shard_create", "pgm_shard_round", "pgm_shard_propose", "pgm_shard_commit", "pgm_shard_finish",
@@ -122,6 +123,11 @@ def load() -> C.CDLL:
         knn = [C.c_void_p, u8p, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32, i32p, i32p, i32p, i32p]
         lib.pgm_knn2_hamming.argtypes = knn
         lib.pgm_knn2_hamming_dev.argtypes = knn
+        lib.pgm_pack_top2_keys_dev.argtypes = [C.c_void_p, i32p, i32p, i32p, i32p, C.c_int32, C.c_int32, i32p]
+        lib.pgm_merge_top2_dev.argtypes = [C.c_void_p, i32p, C.c_int32, C.c_int32, i32p, i32p, i32p, i32p]
+        lib.pgm_ratio_crosscheck_filter_dev.argtypes = [C.c_void_p, C.c_int32, C.c_int32, i32p, i32p, i32p, i32p,
+                                                        C.c_float, C.c_int32, C.c_int32, i32p, i32p, i32p,
+                                                        C.POINTER(C.c_int32)]
         lib.pgm_match_keypoints_sorted.argtypes = [C.c_void_p, u8p, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32, i64p]
         lib.pgm_match_keypoints_sorted_dev.argtypes = lib.pgm_match_keypoints_sorted.argtypes
         lib.pgm_knn2_l2.argtypes = [C.c_void_p, vp, C.c_int32, vp, C.c_int32, C.c_int32, i32p, vp, i32p, vp]

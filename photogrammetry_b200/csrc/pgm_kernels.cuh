@@ -1162,6 +1162,66 @@ __global__ void ratio_crosscheck_kernel(int n1, int n2, const int32_t *best_j, c
 }
 
 // ---------------------------------------------------------------------------
+// train-sharded nearest / second-nearest neighbour ("top-2 merge"):
+// every rank searches its slice of the train set, the (best, second) pairs travel as packed keys
+// (distance << 20 | GLOBAL train index, XKEY_NONE where absent -- integer order == the (distance, j)
+// order) through one all-gather, and every rank picks the two smallest of the 2G keys of each query.
+// ---------------------------------------------------------------------------
+__global__ void pack_top2_kernel(const int32_t *__restrict__ bj, const int32_t *__restrict__ bd,
+                                 const int32_t *__restrict__ sj, const int32_t *__restrict__ sd, int n, int offset,
+                                 uint32_t *__restrict__ keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = bj[i] >= 0 ? ((uint32_t)bd[i] << KEY_IDX_BITS) | (uint32_t)(bj[i] + offset) : XKEY_NONE;
+    keys[(size_t)n + i] = sj[i] >= 0 ? ((uint32_t)sd[i] << KEY_IDX_BITS) | (uint32_t)(sj[i] + offset) : XKEY_NONE;
+}
+
+__global__ void merge_top2_kernel(const uint32_t *__restrict__ keys, int n_shards, int n, int32_t *__restrict__ bj,
+                                  int32_t *__restrict__ bd, int32_t *__restrict__ sj, int32_t *__restrict__ sd) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k1 = XKEY_NONE, k2 = XKEY_NONE;                  // the two smallest keys (train slices are disjoint: no duplicates)
+    for (int g = 0; g < 2 * n_shards; g++) {
+        const uint32_t k = keys[(size_t)g * n + i];
+        k2 = min(k2, max(k1, k));
+        k1 = min(k1, k);
+    }
+    bj[i] = k1 != XKEY_NONE ? (int32_t)(k1 & KEY_IDX_MASK) : -1;
+    bd[i] = k1 != XKEY_NONE ? (int32_t)(k1 >> KEY_IDX_BITS) : -1;
+    sj[i] = k2 != XKEY_NONE ? (int32_t)(k2 & KEY_IDX_MASK) : -1;
+    sd[i] = k2 != XKEY_NONE ? (int32_t)(k2 >> KEY_IDX_BITS) : -1;
+}
+
+// kept rows (ascending i) -> (i, best_j, best_d) triples; single block, ordered compaction
+__global__ void __launch_bounds__(1024) compact_matches_kernel(const uint8_t *__restrict__ keep, const int32_t *__restrict__ best_j,
+                                                               const int32_t *__restrict__ best_d, int n1,
+                                                               int32_t *__restrict__ qi, int32_t *__restrict__ tj,
+                                                               int32_t *__restrict__ dist, int32_t *__restrict__ count) {
+    __shared__ int s_w[32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n1; i0 += 1024) {
+        const int i = i0 + tid;
+        const bool hit = i < n1 && keep[i];
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) s_w[wid] = __popc(m);
+        __syncthreads();
+        int off = s_base;
+        for (int k = 0; k < wid; k++) off += s_w[k];
+        if (hit) {
+            const int o = off + __popc(m & ((1u << lane) - 1u));
+            qi[o] = i; tj[o] = best_j[i]; dist[o] = best_d[i];
+        }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int k = 0; k < 32; k++) t += s_w[k]; s_base += t; }
+        __syncthreads();
+    }
+    if (tid == 0) *count = s_base;
+}
+
+// ---------------------------------------------------------------------------
 // integer-pipe micro-benchmarks (roofline denominators)
 // ---------------------------------------------------------------------------
 __global__ void popc_peak_kernel(uint32_t *out, int iters, uint32_t seed) {

@@ -953,6 +953,71 @@ extern "C" int pgm_match_ratio_crosscheck(pgm_handle *h, const uint8_t *q, int32
 }
 
 // ---------------------------------------------------------------------------
+// train-sharded nearest neighbours: key exchange format, top-2 merge, device-side filter
+// ---------------------------------------------------------------------------
+extern "C" int pgm_pack_top2_keys_dev(pgm_handle *h, const int32_t *d_best_j, const int32_t *d_best_d,
+                                      const int32_t *d_second_j, const int32_t *d_second_d, int32_t n,
+                                      int32_t index_offset, int32_t *d_keys) {
+    if (!h) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (n < 0 || index_offset < 0 || index_offset >= MAX_N ||
+        (n > 0 && (!d_best_j || !d_best_d || !d_second_j || !d_second_d || !d_keys)))
+        return fail(h, PGM_E_INVALID_ARG, "bad arguments");
+    if (n == 0) return PGM_OK;
+    CU_CHECK(h, cudaSetDevice(h->device));
+    pack_top2_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(d_best_j, d_best_d, d_second_j, d_second_d, n, index_offset,
+                                                             (uint32_t *)d_keys);
+    h->stats.kernel_launches += 1;
+    CU_CHECK(h, cudaGetLastError());
+    return PGM_OK;
+}
+
+extern "C" int pgm_merge_top2_dev(pgm_handle *h, const int32_t *d_keys, int32_t n_shards, int32_t n, int32_t *d_best_j,
+                                  int32_t *d_best_d, int32_t *d_second_j, int32_t *d_second_d) {
+    if (!h) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (n < 0 || n_shards < 1 || (n > 0 && (!d_keys || !d_best_j || !d_best_d || !d_second_j || !d_second_d)))
+        return fail(h, PGM_E_INVALID_ARG, "bad arguments");
+    if (n == 0) return PGM_OK;
+    CU_CHECK(h, cudaSetDevice(h->device));
+    merge_top2_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>((const uint32_t *)d_keys, n_shards, n, d_best_j, d_best_d,
+                                                              d_second_j, d_second_d);
+    h->stats.kernel_launches += 1;
+    CU_CHECK(h, cudaGetLastError());
+    return PGM_OK;
+}
+
+extern "C" int pgm_ratio_crosscheck_filter_dev(pgm_handle *h, int32_t n1, int32_t n2, const int32_t *d_best_j,
+                                               const int32_t *d_best_d, const int32_t *d_second_d,
+                                               const int32_t *d_col_best_i, float ratio, int32_t cross_check,
+                                               int32_t max_dist, int32_t *d_out_qi, int32_t *d_out_tj,
+                                               int32_t *d_out_dist, int32_t *out_count) {
+    if (!h || !out_count) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    *out_count = 0;
+    if (n1 < 0 || n2 < 0 || n1 >= MAX_N || (cross_check && n1 > 0 && n2 > 0 && !d_col_best_i) ||
+        (n1 > 0 && (!d_best_j || !d_best_d || !d_second_d || !d_out_qi || !d_out_tj || !d_out_dist)))
+        return fail(h, PGM_E_INVALID_ARG, "bad arguments");
+    if (n1 == 0 || n2 == 0) return PGM_OK;
+    CU_CHECK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    int rc = ensure_dev(h, h->out, align_up(n1, 16) + 16);
+    if (rc) return rc;
+    if ((rc = ensure_host(h, h->pin_out, 64))) return rc;
+    uint8_t *keep = (uint8_t *)h->out.p;
+    int32_t *d_cnt = (int32_t *)((char *)h->out.p + align_up(n1, 16));
+    ratio_crosscheck_kernel<<<(n1 + 255) / 256, 256, 0, s>>>(n1, n2, d_best_j, d_best_d, d_second_d, d_col_best_i, ratio,
+                                                             cross_check, max_dist, keep);
+    compact_matches_kernel<<<1, 1024, 0, s>>>(keep, d_best_j, d_best_d, n1, d_out_qi, d_out_tj, d_out_dist, d_cnt);
+    CU_CHECK(h, cudaMemcpyAsync(h->pin_out.p, d_cnt, 4, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(h, cudaStreamSynchronize(s));
+    *out_count = *(const int32_t *)h->pin_out.p;
+    h->stats.kernel_launches += 2; h->stats.host_syncs++; h->stats.matched = *out_count;
+    CU_CHECK(h, cudaGetLastError());
+    return PGM_OK;
+}
+
+// ---------------------------------------------------------------------------
 // match_keypoints of the Python generation: every row ranked (keypoint_matching.py:7-33)
 // ---------------------------------------------------------------------------
 template <int WORDS>

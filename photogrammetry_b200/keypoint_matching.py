@@ -210,6 +210,49 @@ class Matcher:
             n1, C.byref(cnt)))
         return np.ascontiguousarray(out[:, :cnt.value].T)
 
+    # -- device-resident forms (torch tensors on this matcher's GPU; used by sharding.TrainShardedKnn) --
+    def knn2_hamming_dev(self, d_q, d_t, desc_bits: int = 256):
+        """(best_j, best_d, second_j, second_d) as int32 tensors; ``d_q``/``d_t``: uint8 ``[n, stride]`` on the GPU."""
+        import torch
+        n1, n2 = int(d_q.shape[0]), int(d_t.shape[0])
+        stride = int(d_q.shape[1]) if n1 else int(d_t.shape[1])
+        out = torch.empty((4, max(n1, 1)), dtype=torch.int32, device=d_q.device)
+        self._check(self._lib.pgm_knn2_hamming_dev(self._h, d_q.data_ptr() if n1 else None, n1,
+                                                   d_t.data_ptr() if n2 else None, n2, int(desc_bits), stride,
+                                                   *(out[k].data_ptr() for k in range(4))))
+        return tuple(out[k, :n1] for k in range(4))
+
+    def pack_top2_keys_dev(self, best_j, best_d, second_j, second_d, index_offset: int):
+        """int32 ``[2, n]`` exchange keys (distance << 20 | global train index, 0x7F7F7F7F = absent)."""
+        import torch
+        n = int(best_j.shape[0])
+        keys = torch.empty((2, max(n, 1)), dtype=torch.int32, device=best_j.device)
+        self._check(self._lib.pgm_pack_top2_keys_dev(self._h, best_j.data_ptr(), best_d.data_ptr(), second_j.data_ptr(),
+                                                     second_d.data_ptr(), n, int(index_offset), keys.data_ptr()))
+        return keys[:, :n] if n else keys[:, :0]
+
+    def merge_top2_dev(self, keys):
+        """``keys``: int32 ``[n_shards, 2, n]`` (contiguous) -> the merged (best_j, best_d, second_j, second_d)."""
+        import torch
+        g, _, n = (int(x) for x in keys.shape)
+        keys = keys.contiguous()
+        out = torch.empty((4, max(n, 1)), dtype=torch.int32, device=keys.device)
+        self._check(self._lib.pgm_merge_top2_dev(self._h, keys.data_ptr(), g, n, *(out[k].data_ptr() for k in range(4))))
+        return tuple(out[k, :n] for k in range(4))
+
+    def ratio_crosscheck_filter_dev(self, n2: int, best_j, best_d, second_d, col_best_i, ratio: float = 0.8,
+                                    cross_check: bool = True, max_dist: int = -1):
+        """The filter of ``match_ratio_crosscheck`` on device-resident knn2 results -> int32 ``[3, count]``."""
+        import torch
+        n1 = int(best_j.shape[0])
+        out = torch.empty((3, max(n1, 1)), dtype=torch.int32, device=best_j.device)
+        cnt = C.c_int32(0)
+        self._check(self._lib.pgm_ratio_crosscheck_filter_dev(
+            self._h, n1, int(n2), best_j.data_ptr(), best_d.data_ptr(), second_d.data_ptr(),
+            col_best_i.data_ptr() if col_best_i is not None and col_best_i.numel() else None, float(ratio),
+            int(bool(cross_check)), int(max_dist), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), C.byref(cnt)))
+        return out[:, :cnt.value]
+
     def match_keypoints_sorted(self, q: np.ndarray, t: np.ndarray, desc_bits: Optional[int] = None) -> np.ndarray:
         """``int64[n1, n2, 2]`` = (idx2, dist), rows sorted by (dist, idx2) (keypoint_matching.py:7-33)."""
         q, bits_q = as_descriptor_rows(q, desc_bits)

@@ -9,12 +9,14 @@ NO data-path collective; ``torch.distributed`` only moves the finished match lis
 Mode 2, one huge pair (BASELINE configs[3], 200k x 200k): :class:`TrainShardedMatcher`.  Every rank
 holds all queries and a contiguous slice of the train set; per round the library computes the local
 row/column argmins and two ``min`` all-reduces over N1 packed keys (NCCL over NVLink) merge them.
+:class:`TrainShardedKnn` is the same sharding for the nearest / second-nearest search with ratio test and
+cross-check: one all-gather of packed (best, second) keys and a device-side top-2 merge.
 
 One process per GPU (``torch.distributed``; NCCL on GPUs, gloo in the CPU tests).
 """
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -220,6 +222,95 @@ class TrainShardedMatcher:
             self.close()
         except Exception:
             pass
+
+
+class TrainShardedKnn:
+    """Nearest / second-nearest neighbour, ratio test and cross-check on ONE pair whose train set is
+    sharded over the ranks -- north_star's "train-set shard with a top-2 merge" (SURVEY.md section 8e).
+
+    Every rank holds all queries ``d_q`` and the train rows ``[col_offset, col_offset + n2_local)`` of
+    ``train_slices(n2_total, world_size)``.  ``knn2()``: local search -> packed keys -> ONE all-gather of
+    ``[2, n1]`` int32 per rank -> the two smallest of the 2G keys per query.  ``match_ratio_crosscheck()``
+    adds the column side: each rank finds the best query of its own train rows (it sees every query, so
+    the search needs no exchange) and the per-slice results are all-gathered into ``col_best_i[n2_total]``.
+    Results are identical on every rank and bit-identical to the unsharded ``Matcher.knn2`` /
+    ``Matcher.match_ratio_crosscheck``.
+
+    ``all_gather(tensor, tag) -> tensor[world, *tensor.shape]`` (tag: "keys" or "cols"); default:
+    ``torch.distributed.all_gather_into_tensor`` on the default group (NCCL over NVLink on GPUs).
+    ``matcher`` provides ``knn2_hamming_dev``, ``pack_top2_keys_dev``, ``merge_top2_dev`` and
+    ``ratio_crosscheck_filter_dev`` (keypoint_matching.Matcher)."""
+
+    def __init__(self, matcher, d_q, d_t_local, col_offset: int, n2_total: int, desc_bits: int = 256,
+                 all_gather=None, world_size: Optional[int] = None):
+        self._m = matcher
+        self.d_q, self.d_t = d_q, d_t_local
+        self.col_offset, self.n2_total, self.desc_bits = int(col_offset), int(n2_total), int(desc_bits)
+        self.n1, self.n2_local = int(d_q.shape[0]), int(d_t_local.shape[0])
+        self._gather = all_gather or self._dist_gather
+        if world_size is None:
+            import torch.distributed as dist
+            world_size = dist.get_world_size() if dist.is_initialized() else 1
+        self.world_size = int(world_size)
+        self._slices = train_slices(self.n2_total, self.world_size)
+        self._pad = max(max(hi - lo for lo, hi in self._slices), 1)
+
+    def _dist_gather(self, t, tag):
+        import torch
+        import torch.distributed as dist
+        if self.world_size == 1:
+            return t.unsqueeze(0)
+        t = t.contiguous()                          # output = the ranks' tensors concatenated along dim 0
+        out = torch.empty((self.world_size * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t)
+        return out.view((self.world_size,) + tuple(t.shape))
+
+    def local_keys(self):
+        """This rank's exchange keys, int32 ``[2, n1]``."""
+        bj, bd, sj, sd = self._m.knn2_hamming_dev(self.d_q, self.d_t, self.desc_bits)
+        return self._m.pack_top2_keys_dev(bj, bd, sj, sd, self.col_offset)
+
+    def local_col_best(self):
+        """Best query (under (distance, i)) of every LOCAL train row, padded with -1 to the largest slice."""
+        import torch
+        ci = self._m.knn2_hamming_dev(self.d_t, self.d_q, self.desc_bits)[0]
+        out = torch.full((self._pad,), -1, dtype=torch.int32, device=self.d_q.device)
+        out[:self.n2_local] = ci
+        return out
+
+    def knn2(self):
+        return self._m.merge_top2_dev(self._gather(self.local_keys(), "keys"))
+
+    def match_ratio_crosscheck(self, ratio: float = 0.8, cross_check: bool = True, max_dist: int = -1):
+        """int32 ``[3, count]`` = (i, j1, d1) of the kept queries in ascending i (global train indices)."""
+        import torch
+        bj, bd, _, sd = self.knn2()
+        col = None
+        if cross_check:
+            allc = self._gather(self.local_col_best(), "cols")
+            col = torch.cat([allc[r, :hi - lo] for r, (lo, hi) in enumerate(self._slices)]).contiguous()
+        return self._m.ratio_crosscheck_filter_dev(self.n2_total, bj, bd, sd, col, ratio, cross_check, max_dist)
+
+
+def knn_train_sharded_emulated(matcher, d_q, d_t, n_shards: int, desc_bits: int = 256, ratio: float = 0.8,
+                               cross_check: bool = True, max_dist: int = -1):
+    """All ranks of TrainShardedKnn emulated in one process on one device: every rank's contribution is
+    computed first, the all-gathers become stacks, then every rank merges.  Returns
+    ((best_j, best_d, second_j, second_d), kept_triples) after asserting that all ranks agree."""
+    import torch
+    n2 = int(d_t.shape[0])
+    ranks = [TrainShardedKnn(matcher, d_q, d_t[lo:hi], lo, n2, desc_bits, world_size=n_shards)
+             for lo, hi in train_slices(n2, n_shards)]
+    bus = {"keys": torch.stack([r.local_keys() for r in ranks])}
+    if cross_check:
+        bus["cols"] = torch.stack([r.local_col_best() for r in ranks])
+    results = []
+    for r in ranks:
+        r._gather = lambda t, tag: bus[tag]
+        results.append((r.knn2(), r.match_ratio_crosscheck(ratio, cross_check, max_dist)))
+    for knn, kept in results[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(knn, results[0][0])) and torch.equal(kept, results[0][1])
+    return results[0]
 
 
 def match_train_sharded_emulated(matcher, q, t, n_shards: int, desc_bits: int = 256):

@@ -179,6 +179,30 @@ def test_train_sharded_emulated_equals_unsharded(matcher, n1, n2, shards):
     assert (matcher.match_greedy(q, t, 256) == exp).all()
 
 
+@pytest.mark.parametrize("n1,n2,shards,bits", [(3000, 2500, 2, 256), (2000, 3101, 3, 256), (1500, 1500, 8, 256),
+                                                 (700, 40, 4, 256), (600, 900, 5, 8), (50, 3, 4, 256), (40, 1, 2, 256)])
+def test_train_sharded_knn_top2_merge_equals_unsharded(matcher, n1, n2, shards, bits):
+    # north_star's "train-set shard with a top-2 merge": packed keys -> all-gather (a stack here) -> device merge;
+    # every emulated rank must hold the unsharded knn2 and ratio / cross-check results, bit for bit
+    import torch
+    from photogrammetry_b200 import sharding
+    q = synthetic.uniform_descriptors(71, n1, bits)
+    t = synthetic.uniform_descriptors(72, n2, bits)
+    if bits == 256 and n2 > 100:
+        t[: n2 // 2] = synthetic.noisy_copy_descriptors(73, q, 256)[: n2 // 2]
+        t[7:11] = t[7]                                 # duplicate train rows: ties across slice boundaries
+    dev = torch.device("cuda", matcher.device)
+    d_q, d_t = torch.from_numpy(q).to(dev), torch.from_numpy(t).to(dev)
+    for ratio, cc, md in [(0.8, True, -1), (0.0, True, 70), (0.9, False, -1)]:
+        knn, kept = sharding.knn_train_sharded_emulated(matcher, d_q, d_t, shards, bits, ratio, cc, md)
+        for a, b in zip(knn, orc.knn2(q, t)):
+            assert (a.cpu().numpy() == b).all()
+        exp = orc.match_ratio_crosscheck(q, t, ratio, cc, md)
+        got = kept.cpu().numpy().T
+        assert got.shape == exp.shape and (got == exp).all(), (ratio, cc, md)
+        assert (got == matcher.match_ratio_crosscheck(q, t, ratio, cc, md, bits)).all()
+
+
 def test_python_twin_sorted_rows(matcher, lego):
     # match_keypoints (keypoint_matching.py:7-33): golden rows produced by the reference's own function
     got = matcher.match_keypoints_sorted(lego["left"][:48], lego["right"][:40], 256)

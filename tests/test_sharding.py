@@ -99,3 +99,90 @@ def test_pair_sharded_world2_gloo_equals_single_process():
     for p, (a, b) in enumerate(pairs):
         exp = orc.match_sweep(imgs[a], imgs[b])
         assert counts[p] == len(exp) and (triples[starts[p]:starts[p] + counts[p]] == exp).all()
+
+
+# ---- train-sharded nearest neighbours: the top-2 merge over an all-gather (gloo, world_size 2) --------
+class _OracleKnnMatcher:
+    """CPU stand-in for the four device-side Matcher methods TrainShardedKnn uses (oracle-backed, tests only)."""
+
+    def knn2_hamming_dev(self, d_q, d_t, desc_bits=256):
+        import torch
+        n1 = d_q.shape[0]
+        if n1 == 0 or d_t.shape[0] == 0:
+            return tuple(torch.full((n1,), -1, dtype=torch.int32) for _ in range(4))
+        return tuple(torch.from_numpy(np.ascontiguousarray(a)) for a in orc.knn2(d_q.numpy(), d_t.numpy()))
+
+    def pack_top2_keys_dev(self, bj, bd, sj, sd, off):
+        import torch
+        none = torch.tensor(0x7F7F7F7F, dtype=torch.int32)
+        return torch.stack([torch.where(bj >= 0, (bd << 20) | (bj + off), none),
+                            torch.where(sj >= 0, (sd << 20) | (sj + off), none)])
+
+    def merge_top2_dev(self, keys):
+        import torch
+        flat = keys.reshape(-1, keys.shape[-1]).numpy().astype(np.uint32)
+        flat = np.where(flat == 0x7F7F7F7F, np.uint32(0xFFFFFFFF), flat)
+        g = flat.shape[0] // 2
+        best, second = sharding.merge_top2(flat.reshape(g, 2, -1)[:, 0], flat.reshape(g, 2, -1)[:, 1])
+        def unpack(k):
+            ok = k != 0xFFFFFFFF
+            return (torch.from_numpy(np.where(ok, k & 0xFFFFF, -1).astype(np.int32)),
+                    torch.from_numpy(np.where(ok, k >> 20, -1).astype(np.int32)))
+        (bj, bd), (sj, sd) = unpack(best), unpack(second)
+        return bj, bd, sj, sd
+
+    def ratio_crosscheck_filter_dev(self, n2, bj, bd, sd, col, ratio=0.8, cross_check=True, max_dist=-1):
+        import torch
+        bj, bd, sd = bj.numpy(), bd.numpy(), sd.numpy()
+        keep = bj >= 0
+        if ratio > 0 and n2 >= 2:
+            keep &= bd.astype(np.float32) < np.float32(ratio) * sd.astype(np.float32)
+        if cross_check:
+            keep &= col.numpy()[np.maximum(bj, 0)] == np.arange(len(bj))
+        if max_dist >= 0:
+            keep &= bd <= max_dist
+        i = np.nonzero(keep)[0].astype(np.int32)
+        return torch.from_numpy(np.stack([i, bj[i], bd[i]]).astype(np.int32))
+
+
+def _knn_worker(rank, world, port, q_out):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        q = orc.gen_uniform(3, 150, 16)
+        t = orc.gen_uniform(4, 201, 16)                       # 16-bit descriptors: many ties; odd size: uneven slices
+        lo, hi = sharding.train_slices(len(t), world)[rank]
+        sh = sharding.TrainShardedKnn(_OracleKnnMatcher(), torch.from_numpy(q), torch.from_numpy(t[lo:hi]), lo, len(t), 16)
+        knn = [a.numpy() for a in sh.knn2()]
+        kept = sh.match_ratio_crosscheck(0.9, True, -1).numpy()
+        q_out.put((rank, knn, kept))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_train_sharded_knn_world2_gloo_equals_unsharded():
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    procs = [ctx.Process(target=_knn_worker, args=(r, 2, port, queue)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [queue.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    q = orc.gen_uniform(3, 150, 16)
+    t = orc.gen_uniform(4, 201, 16)
+    exp_knn = orc.knn2(q, t)
+    exp_kept = orc.match_ratio_crosscheck(q, t, 0.9, True, -1)
+    for _, knn, kept in got:                                   # every rank holds the full, identical answer
+        for a, b in zip(knn, exp_knn):
+            assert (a == b).all()
+        assert (kept.T == exp_kept).all()

@@ -6,6 +6,10 @@
 
 Every rank holds all N queries and 1/G of the train set; two NCCL `min` all-reduces of N packed keys per
 round.  With --check rank 0 also runs the unsharded single-GPU matcher and verifies bit-identity.
+
+--mode knn: the nearest / second-nearest search with ratio test and cross-check on the same sharding
+(sharding.TrainShardedKnn): local searches, two NCCL all-gathers (packed (best, second) keys; per-slice column
+bests) and the device-side top-2 merge.
 """
 import argparse, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -16,6 +20,41 @@ from photogrammetry_b200 import sharding, synthetic
 from photogrammetry_b200.keypoint_matching import Matcher
 
 
+def knn_mode(args, m, d_q, d_t, q, t, lo, n, world, rank, dev, stream):
+    sh = sharding.TrainShardedKnn(m, d_q, d_t, lo, n, 256, world_size=world)
+    times = []
+    for rep in range(args.reps + 1):
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        kept = sh.match_ratio_crosscheck(0.8, True, -1)
+        e1.record(stream); e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
+        if rep > 0: times.append(ms)
+    res = kept.T.contiguous().cpu().numpy()
+    # both directions are searched (rows for knn2, columns for the cross-check): 2 N^2 distances
+    line = {"workload": f"configs[3] shape, knn2 + ratio 0.8 + cross-check: {n}x{n}, distribution {args.dist}, train set sharded x{world}",
+            "n_gpus": world, "ms": float(np.median(times)), "evals_per_s": 2.0 * n * n / (np.median(times) * 1e-3),
+            "kept": int(len(res)), "collectives": 2 if world > 1 else 0, "bytes_gathered_per_rank": 8 * n + 4 * (-(-n // world))}
+    if rank == 0:
+        assert (np.diff(res[:, 0]) > 0).all()
+        assert (np.bitwise_count(q[res[:, 0]] ^ t[res[:, 1]]).sum(axis=1) == res[:, 2]).all()
+        line["properties_ok"] = True
+        if args.check:
+            d_tf = torch.from_numpy(t).to(dev)
+            one = sharding.TrainShardedKnn(m, d_q, d_tf, 0, n, 256, world_size=1)
+            for _ in range(2):
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                ref = one.match_ratio_crosscheck(0.8, True, -1)
+                torch.cuda.synchronize(); dt = time.perf_counter() - t0
+            line["unsharded_1gpu_ms"] = dt * 1e3
+            line["bit_identical_to_unsharded"] = bool(torch.equal(ref, kept))
+        print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", dest="n", type=int, default=200000)
@@ -23,6 +62,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--stream", default="custom", choices=["custom", "default"])
+    ap.add_argument("--mode", default="greedy", choices=["greedy", "knn"])
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -44,6 +84,12 @@ def main():
         stream = torch.cuda.current_stream(dev)
     m.set_stream(stream.cuda_stream)
     d_q = torch.from_numpy(q).to(dev); d_t = torch.from_numpy(t[lo:hi].copy()).to(dev)
+    if args.mode == "knn":
+        knn_mode(args, m, d_q, d_t, q, t, lo, n, world, rank, dev, stream)
+        m.close()
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
     times, rounds = [], 0
     for rep in range(args.reps + 1):
         sm = sharding.TrainShardedMatcher(m, d_q, d_t, lo, n, 256)
