@@ -368,6 +368,44 @@ def extras(m, stream, dev, popc_peak):
     ms = e0.elapsed_time(e1) / 20
     out["knn2_8k"] = {"ms": ms, "evals_per_s": n * n / (ms * 1e-3), "frac_of_popc_peak": n * n * 8 / (ms * 1e-3) / popc_peak}
 
+    # float descriptors (north_star extension): squared-L2 top-2 on tcgen05, whole call (operand split, GEMM with
+    # the norms folded in, exact refinement), device resident; roofline = tensor pipe, measured bf16 peak
+    peak_tf, peak_src = 1590.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+    try:
+        peak_tf = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+        peak_src = "MEASURED_PEAKS.json bf16_tflops (burst)"
+    except Exception:
+        pass
+    for nf in (8192, 32768):
+        dim = 128
+        with torch.cuda.stream(stream):
+            fq = torch.rand((nf, dim), device=dev)
+            ft = torch.rand((nf, dim), device=dev)
+            fj = torch.empty((2, nf), dtype=torch.int32, device=dev)
+            fd = torch.empty((2, nf), device=dev)
+        stream.synchronize()
+
+        def l2():
+            m._check(lib.pgm_knn2_l2_dev(h, fq.data_ptr(), nf, ft.data_ptr(), nf, dim, fj[0].data_ptr(), fd[0].data_ptr(),
+                                         fj[1].data_ptr(), fd[1].data_ptr(), None))
+        for _ in range(3):
+            l2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(10):
+            l2()
+        e1.record(stream)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        tf = 2.0 * 3 * dim * nf * nf / (ms * 1e-3) / 1e12           # three bf16 split terms of K = D each
+        out[f"l2_knn2_{nf // 1024}k_d{dim}"] = {
+            "ms": ms, "evals_per_s": nf * float(nf) / (ms * 1e-3), "launches": 3,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                         "peak_source": peak_src,
+                         "algorithmic": "executed bf16 flops: 2 x 3 x D per distance (hi.hi + lo.hi + hi.lo); "
+                                        "2 x D per distance in the fp32 sense is a third of this"}}
+        del fq, ft, fj, fd
+
     # all-pairs (configs[4] scaled down): 48 images x 4096 descriptors, all i<j pairs, device resident
     n_img, per = 48, 4096
     imgs = np.concatenate([synthetic.uniform_descriptors(9000 + k, per, 256) for k in range(n_img)])
