@@ -133,26 +133,40 @@ constexpr uint32_t IDESC_BF16_M128_N128 =
 // One warp per row: rows [0, n1) are queries, rows [n1, n1 + n2) train descriptors.
 __global__ void __launch_bounds__(256) split_kernel(const float *__restrict__ q, int n1, const float *__restrict__ t, int n2,
                                                     int dim, int dp, __nv_bfloat16 *__restrict__ a,
-                                                    __nv_bfloat16 *__restrict__ b) {
+                                                    __nv_bfloat16 *__restrict__ b, int32_t *__restrict__ cand_j,
+                                                    int slots) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     pdl_trigger();                                   // the GEMM kernel's prologue may overlap this kernel
     if (w >= n1 + n2) return;
     const bool train = w >= n1;
     const int row = train ? w - n1 : w;
+    if (!train)                                      // candidate slots no segment of the GEMM kernel fills stay "absent"
+        for (int e = lane; e < slots * CAND; e += 32) cand_j[((size_t)(e / CAND) * n1 + row) * CAND + (e % CAND)] = -1;
     const float *x = (train ? t : q) + (size_t)row * dim;
     __nv_bfloat16 *o = (train ? b : a) + (size_t)row * (2 * dp + CHUNK_K);
     float acc = 0.f;
-    for (int k = 2 * lane; k < dp; k += 64) {
-        const float v0 = k < dim ? x[k] : 0.f, v1 = k + 1 < dim ? x[k + 1] : 0.f;
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-        __nv_bfloat162 hi, lo;
-        hi.x = h0; hi.y = h1;
-        lo.x = __float2bfloat16_rn(v0 - __bfloat162float(h0));
-        lo.y = __float2bfloat16_rn(v1 - __bfloat162float(h1));
-        *reinterpret_cast<__nv_bfloat162 *>(o + k) = hi;
-        *reinterpret_cast<__nv_bfloat162 *>(o + dp + k) = lo;
-        acc = fmaf(v0, v0, acc);
-        acc = fmaf(v1, v1, acc);
+    const bool vec = (dim & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);   // rows are 16-byte aligned
+    for (int k = 4 * lane; k < dp; k += 128) {       // four components per lane: one 128-bit load, two 64-bit stores
+        float v[4];
+        if (vec && k + 3 < dim) {
+            const float4 f = __ldg(reinterpret_cast<const float4 *>(x + k));
+            v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++) v[e] = k + e < dim ? __ldg(x + k + e) : 0.f;
+        }
+        __nv_bfloat162 hi[2], lo[2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * e]), h1 = __float2bfloat16_rn(v[2 * e + 1]);
+            hi[e].x = h0; hi[e].y = h1;
+            lo[e].x = __float2bfloat16_rn(v[2 * e] - __bfloat162float(h0));
+            lo[e].y = __float2bfloat16_rn(v[2 * e + 1] - __bfloat162float(h1));
+        }
+        *reinterpret_cast<uint2 *>(o + k) = make_uint2(*reinterpret_cast<uint32_t *>(&hi[0]), *reinterpret_cast<uint32_t *>(&hi[1]));
+        *reinterpret_cast<uint2 *>(o + dp + k) = make_uint2(*reinterpret_cast<uint32_t *>(&lo[0]), *reinterpret_cast<uint32_t *>(&lo[1]));
+#pragma unroll
+        for (int e = 0; e < 4; e++) acc = fmaf(v[e], v[e], acc);
     }
     for (int sh = 16; sh; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
     const float hn = -0.5f * acc;
@@ -173,12 +187,22 @@ __global__ void __launch_bounds__(256) split_kernel(const float *__restrict__ q,
 // ---- the GEMM + top-4 kernel ----------------------------------------------------------------
 struct L2Params {
     int n1, n2, dpc;               // dpc = Dp / 64: chunks per operand part (hi or lo)
-    int tiles_per_split;           // column tiles handled by one blockIdx.y
+    int tiles_per_split;           // single-CTA kernel: column tiles handled by one blockIdx.y
+    int col_tiles, items, flat;    // pair kernel: column tiles per row pair, row pairs x column tiles, work distribution
     uint32_t key_mask;             // 0x7FFFFFE0, passed as data so that (acc & mask) | column is ONE LOP3
     int32_t *cand_j;               // [splits][n1][CAND]
     float *cand_d;                 // [splits][n1][CAND] approximate distances (diagnostic)
     float *dbg_dist;               // optional [n1][n2] approximate distance matrix (tests)
+    unsigned long long *timeline;  // optional (PGM_L2_TIMELINE=1): %globaltimer stamps of cluster 0's leader CTA
 };
+__device__ __forceinline__ void l2_stamp(const L2Params &p, int slot) {
+    if (p.timeline && blockIdx.x == 0 && blockIdx.y == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.timeline[slot] = t;
+        p.timeline[128 + slot] = (unsigned long long)clock64();
+    }
+}
 
 // Epilogue reducer shared by both kernels: NCOLS accumulator columns of this thread's row, starting at TMEM
 // address `taddr` = global train index `jbase`.  The accumulator holds -d/2 (see the header), so the rank
@@ -417,6 +441,20 @@ __device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// Work distribution, two forms (the host picks by a cost model): (a) cluster = (row pair, column split), grid
+// 2*row_pairs x splits, run in waves; (b) "flat": the (row pair, column tile) items are flattened row-major and
+// cut into gridDim.x / 2 contiguous, equally long segments, one per cluster (persistent: as many clusters as are
+// co-resident) -- no wave quantisation, for shapes whose row pairs x splits do not fill the machine.  A segment that crosses into the next row pair reloads A' (after the MMAs of the old rows have
+// retired) and its epilogue flushes the finished rows' candidates; a row pair's candidates therefore arrive
+// from several segments, each writing its own slot (segment index minus the index of the first segment that
+// touches the row pair).  Unused slots keep the -1 the split kernel wrote.
+__device__ __forceinline__ int l2_segment_start(int k, int items, int clusters) {
+    return (int)(((long long)k * items) / clusters);
+}
+__device__ __forceinline__ int l2_segment_of_item(int x, int items, int clusters) {      // max k with start(k) <= x
+    return (int)((((long long)x + 1) * clusters - 1) / items);
+}
+
 template <bool DBG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, L2Params p) {
@@ -427,19 +465,23 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint64_t *bars = reinterpret_cast<uint64_t *>(sb + (size_t)STAGES * CHUNK_BYTES);
     uint64_t *full = bars, *empty = bars + STAGES, *a_bar = bars + 2 * STAGES;
     uint64_t *tfull = bars + 2 * STAGES + 1, *tempty = bars + 2 * STAGES + 3;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 5);
+    uint64_t *a_empty = bars + 2 * STAGES + 5;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 6);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
-    const int m0 = blockIdx.x * TILE_M;                                    // the pair covers 256 consecutive queries
-    const int n_col_tiles = (p.n2 + TILE_N2 - 1) / TILE_N2;
-    const int ct0 = blockIdx.y * p.tiles_per_split, ct1 = min(n_col_tiles, ct0 + p.tiles_per_split);
-    const int ntiles = max(ct1 - ct0, 0);
+    const int clusters = (int)(gridDim.x >> 1), cid = (int)(blockIdx.x >> 1);
+    const int CT = p.col_tiles, items = p.items;
+    // flat: equal segments of the flattened item list; otherwise cluster = (row pair, column split blockIdx.y)
+    const int it0 = p.flat ? l2_segment_start(cid, items, clusters) : cid * CT + (int)blockIdx.y * p.tiles_per_split;
+    const int it1 = p.flat ? l2_segment_start(cid + 1, items, clusters) : min(it0 + p.tiles_per_split, (cid + 1) * CT);
+    if (threadIdx.x == 0) l2_stamp(p, 0);
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(a_bar, 1);
+        mbar_init(a_empty, 1);
         for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * 4 * EPI_GROUPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -452,32 +494,52 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     cluster_sync_all();                       // barriers of both CTAs initialised before any remote arrive / TMA
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) l2_stamp(p, 1);
     pdl_wait();                                      // operands are written by split_kernel
+    if (threadIdx.x == 0) l2_stamp(p, 2);
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer (both CTAs): own A' rows, own half of every B' tile =====
         const int nch = 2 * p.dpc + 1;                    // hi chunks, lo chunks, norm chunk
-        if (leader) mbar_expect_tx(a_bar, 2u * (uint32_t)nch * CHUNK_BYTES);
-        for (int kc = 0; kc < nch; kc++) tma_load_2d_pair(sa + (size_t)kc * CHUNK_BYTES, &map_a, a_bar, kc * CHUNK_K, m0);
         int s = 0; uint32_t ph = 0;
-        for (int t = 0; t < ntiles; t++) {
+        int cur_rp = -1; uint32_t n_a = 0;
+        for (int it = it0; it < it1; it++) {
+            const int rp = it / CT, ct = it - rp * CT;
+            if (rp != cur_rp && cur_rp < 0) {                  // first rows of the segment: A' first
+                if (leader) mbar_expect_tx(a_bar, 2u * (uint32_t)nch * CHUNK_BYTES);
+                const int m0 = (2 * rp + (int)rank) * TILE_M;
+                for (int kc = 0; kc < nch; kc++) tma_load_2d_pair(sa + (size_t)kc * CHUNK_BYTES, &map_a, a_bar, kc * CHUNK_K, m0);
+                cur_rp = rp; n_a++;
+            }
             for (int kc = 0; kc < nch; kc++) {                 // t_hi chunks, t_lo chunks, norm chunk
                 mbar_wait(&empty[s], ph ^ 1);                  // the pair's MMAs no longer read this stage (multicast commit)
                 if (leader) mbar_expect_tx(&full[s], 2u * CHUNK_BYTES);
                 tma_load_2d_pair(sb + (size_t)s * CHUNK_BYTES, &map_b, &full[s], kc * CHUNK_K,
-                                 (ct0 + t) * TILE_N2 + (int)rank * TILE_N);
+                                 ct * TILE_N2 + (int)rank * TILE_N);
                 if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+            if (rp != cur_rp) {
+                // next row pair: its first B' tile is already on its way into the ring (the slots free up while the
+                // old rows' last MMAs run); A' can only be replaced once those MMAs have retired
+                mbar_wait(a_empty, (n_a - 1u) & 1u);
+                if (leader) mbar_expect_tx(a_bar, 2u * (uint32_t)nch * CHUNK_BYTES);
+                const int m0 = (2 * rp + (int)rank) * TILE_M;
+                for (int kc = 0; kc < nch; kc++) tma_load_2d_pair(sa + (size_t)kc * CHUNK_BYTES, &map_a, a_bar, kc * CHUNK_K, m0);
+                cur_rp = rp; n_a++;
             }
         }
     } else if (warp == 1 && lane == 0 && leader) {
         // ===== MMA issuer (leader only) =====
-        mbar_wait(a_bar, 0);
         const int dpc = p.dpc;
         uint32_t g = 0;                                         // running chunk-slot counter of the B' ring
-        for (int t = 0; t < ntiles; t++) {
+        int cur_rp = -1; uint32_t n_a = 0;
+        for (int it = it0; it < it1; it++) {
+            const int t = it - it0, rp = it / CT;
+            if (rp != cur_rp) { mbar_wait(a_bar, n_a & 1u); tc_fence_after(); cur_rp = rp; n_a++; l2_stamp(p, 3); }
             const int acc = t & 1;
             mbar_wait(&tempty[acc], ((t >> 1) & 1) ^ 1);       // both CTAs' epilogues drained this accumulator
             tc_fence_after();
+            if (t < 36) l2_stamp(p, 4 + t);
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * TILE_N2;
             // pass 0: q_hi . t_hi (waits for the hi slots), pass 1: q_lo . t_hi (frees them), pass 2: q_hi . t_lo
             for (int pass = 0; pass < 3; pass++) {
@@ -503,41 +565,55 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
             g += 2u * (uint32_t)dpc + 1u;
             tc_commit_pair(&tfull[acc]);
+            if (it + 1 < it1 && (it + 1) / CT != rp) tc_commit_pair(a_empty);   // A' may be overwritten once these retire
         }
     } else if (warp >= 4) {
         // ===== epilogue: one query row per thread, this CTA's 128 rows x 256 columns =====
         const int ew = warp & 3;
         const int eg = (warp - 4) >> 2;
-        const int row = m0 + ew * 32 + lane;
         uint32_t bk[TOPK]; int bj[TOPK];
-#pragma unroll
-        for (int k = 0; k < TOPK; k++) { bk[k] = row < p.n1 ? 0xFFFFFFFFu : 0u; bj[k] = -1; }
         constexpr int NCOLS = TILE_N2 / EPI_GROUPS;
-        for (int t = 0; t < ntiles; t++) {
+        int cur_rp = -1, row = 0;
+        auto flush = [&]() {
+            if (cur_rp < 0 || row >= p.n1) return;
+            const int slot = p.flat ? cid - l2_segment_of_item(cur_rp * CT, items, clusters) : (int)blockIdx.y;
+            const size_t o = ((size_t)slot * p.n1 + row) * CAND + (size_t)eg * TOPK;
+#pragma unroll
+            for (int k = 0; k < TOPK; k++) {
+                p.cand_j[o + k] = bk[k] != 0xFFFFFFFFu ? bj[k] : -1;
+                p.cand_d[o + k] = bk[k] != 0xFFFFFFFFu ? 2.f * __uint_as_float(bk[k]) : 3.4e38f;
+            }
+        };
+        for (int it = it0; it < it1; it++) {
+            const int t = it - it0, rp = it / CT, ct = it - rp * CT;
+            if (rp != cur_rp) {
+                flush();
+                cur_rp = rp;
+                row = (2 * rp + (int)rank) * TILE_M + ew * 32 + lane;
+#pragma unroll
+                for (int k = 0; k < TOPK; k++) { bk[k] = row < p.n1 ? 0xFFFFFFFFu : 0u; bj[k] = -1; }
+            }
             const int acc = t & 1;
             mbar_wait(&tfull[acc], (t >> 1) & 1);
             tc_fence_after();
-            const int jbase = (ct0 + t) * TILE_N2 + eg * NCOLS;
+            if (warp == 4 && lane == 0 && t < 36) l2_stamp(p, 40 + t);
+            const int jbase = ct * TILE_N2 + eg * NCOLS;
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TILE_N2 + eg * NCOLS);
             epilogue_reduce<NCOLS, DBG>(taddr, jbase, p.n2, p.key_mask, bk, bj,
                                         DBG && p.dbg_dist && row < p.n1 ? p.dbg_dist + (size_t)row * p.n2 : nullptr);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(&tempty[acc], 0);      // the leader's barrier counts both CTAs' warps
+            if (warp == 4 && lane == 0 && t < 36) l2_stamp(p, 80 + t);
         }
-        if (row < p.n1) {
-            const size_t o = ((size_t)blockIdx.y * p.n1 + row) * CAND + (size_t)eg * TOPK;
-#pragma unroll
-            for (int k = 0; k < TOPK; k++) {
-                p.cand_j[o + k] = bk[k] != 0xFFFFFFFFu ? bj[k] : -1;
-                p.cand_d[o + k] = bk[k] != 0xFFFFFFFFu ? 2.f * __uint_as_float(bk[k]) : 3.4e38f;
-            }
-        }
+        flush();
+        if (warp == 4 && lane == 0) l2_stamp(p, 120);
     }
     pdl_trigger();                                   // the refinement kernel may be scheduled
     __syncwarp();
     tc_fence_before();
     cluster_sync_all();                       // neither CTA leaves (or frees TMEM) while its partner may still use it
+    if (threadIdx.x == 0) l2_stamp(p, 121);
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS2) : "memory");
@@ -545,11 +621,11 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 }
 
 inline size_t l2_pair_smem_bytes() {
-    return (size_t)(MAX_CHUNKS + STAGES) * CHUNK_BYTES + (2 * STAGES + 6) * 8 + 1024;
+    return (size_t)(MAX_CHUNKS + STAGES) * CHUNK_BYTES + (2 * STAGES + 7) * 8 + 1024;
 }
 
 inline size_t l2_smem_bytes() {
-    return (size_t)(MAX_CHUNKS + STAGES) * CHUNK_BYTES + (2 * STAGES + 6) * 8 + 1024;
+    return (size_t)(MAX_CHUNKS + STAGES) * CHUNK_BYTES + (2 * STAGES + 7) * 8 + 1024;
 }
 
 // ---- refinement: exact fp32 distances of the candidates, best / second by (distance, index) ----

@@ -62,6 +62,7 @@ struct pgm_handle {
     bool order_attr_set = false;
     bool tail_attr_set[5] = {false, false, false, false, false};
     bool l2_attr_set = false;         // cudaFuncSetAttribute is per device, hence per handle
+    int l2_max_clusters = 1;          // co-resident CTA pairs of the float pair kernel (persistent grid)
     bool l2_force_single = false;     // PGM_L2_SINGLE=1: never use the CTA-pair (cta_group::2) float kernel
     bool force_multilaunch = false;   // PGM_FORCE_MULTILAUNCH=1: never use the persistent tail kernel
     bool stats_pending = false;   // rounds / evals of the last latency-mode call still sit in pin_meta
@@ -1120,17 +1121,61 @@ static int l2_dev_impl(pgm_handle *h, const float *d_q, int32_t n1, const float 
     const int row_tiles = (n1 + TILE_M - 1) / TILE_M;
     // CTA pairs (cta_group::2, M = 256 x N = 256) whenever there are at least two row tiles
     const bool pair = row_tiles >= 2 && !h->l2_force_single;
-    const int tile_n = pair ? TILE_N2 : TILE_N;
-    const int col_tiles = (n2 + tile_n - 1) / tile_n;
-    const int gx = pair ? ((row_tiles + 1) & ~1) : row_tiles;
-    // column splits: one CTA per SM is resident, so the run time is (waves) x (tiles per split); pick the
-    // split count that minimises it (half a tile of fixed cost per CTA for the resident A' load)
-    int splits = 1, tps = col_tiles;
-    double best_cost = 1e300;
-    for (int sp = 1; sp <= std::min(col_tiles, 32); sp++) {
-        const int t = (col_tiles + sp - 1) / sp, se = (col_tiles + t - 1) / t;
-        const double cost = (double)((gx * se + h->num_sms - 1) / h->num_sms) * (t + 0.5);
-        if (cost < best_cost - 1e-9) { best_cost = cost; splits = se; tps = t; }
+    if (!h->l2_attr_set) {
+        CU_CHECK(h, cudaFuncSetAttribute(l2_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l2_smem_bytes()));
+        CU_CHECK(h, cudaFuncSetAttribute(l2_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l2_smem_bytes()));
+        CU_CHECK(h, cudaFuncSetAttribute(l2_topk_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l2_pair_smem_bytes()));
+        CU_CHECK(h, cudaFuncSetAttribute(l2_topk_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l2_pair_smem_bytes()));
+        // how many CTA pairs are co-resident: the pair kernel is persistent, one segment of the work per cluster
+        cudaLaunchAttribute ca{};
+        ca.id = cudaLaunchAttributeClusterDimension;
+        ca.val.clusterDim.x = 2; ca.val.clusterDim.y = 1; ca.val.clusterDim.z = 1;
+        cudaLaunchConfig_t qc{};
+        qc.gridDim = dim3(2 * (unsigned)h->num_sms); qc.blockDim = dim3(THREADS);
+        qc.dynamicSmemBytes = l2_pair_smem_bytes(); qc.attrs = &ca; qc.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, l2_topk_pair_kernel<false>, &qc) != cudaSuccess || nc < 1) {
+            (void)cudaGetLastError();
+            nc = std::max(1, h->num_sms / 2);
+        }
+        h->l2_max_clusters = std::min(nc, std::max(1, h->num_sms / 2));
+        h->l2_attr_set = true;
+    }
+    int splits = 1, tps = 0, gx = row_tiles, col_tiles, items = 0, clusters = 0, flat = 0;
+    const int row_pairs = (row_tiles + 1) / 2;
+    const int slots_avail = pair ? h->l2_max_clusters : h->num_sms;      // co-resident work units
+    col_tiles = (n2 + (pair ? TILE_N2 : TILE_N) - 1) / (pair ? TILE_N2 : TILE_N);
+    {
+        // column splits: the run time is (waves) x (tiles per split); pick the split count that minimises it
+        // (half a tile of fixed cost per unit for the resident A' load)
+        const int units = pair ? row_pairs : row_tiles;
+        tps = col_tiles;
+        double best_cost = 1e300;
+        for (int sp = 1; sp <= std::min(col_tiles, 32); sp++) {
+            const int t = (col_tiles + sp - 1) / sp, se = (col_tiles + t - 1) / t;
+            const double cost = (double)(((long long)units * se + slots_avail - 1) / slots_avail) * (t + 0.5);
+            if (cost < best_cost - 1e-9) { best_cost = cost; splits = se; tps = t; }
+        }
+        if (pair) {
+            // flat form (default): equal contiguous segments of the row-major (row pair, column tile) list, one per
+            // resident cluster -- no wave quantisation.  A/B on one B200 (PGM_L2_FLAT=0 forces the split form):
+            // 8k 63.3 vs 64.9 us, 32k 0.557 vs 0.618 ms, 65k 2.08 vs 2.15 ms, 32k x D=64 0.45 vs 0.53 ms.
+            const long long total = (long long)row_pairs * col_tiles;
+            if (total > 0x7FFFFFFFll) return fail(h, PGM_E_INVALID_ARG, "problem too large for the float path");
+            items = (int)total;
+            clusters = std::min(h->l2_max_clusters, items);
+            const char *force = getenv("PGM_L2_FLAT");
+            flat = force ? (force[0] == '1') : 1;
+            if (flat) {
+                // a row pair's candidates come from every segment that touches it: slots = the most any row pair sees
+                splits = 1;
+                for (int rp = 0; rp < row_pairs; rp++) {
+                    const long long x0 = (long long)rp * col_tiles, x1 = x0 + col_tiles - 1;
+                    const int k0 = (int)(((x0 + 1) * clusters - 1) / items), k1 = (int)(((x1 + 1) * clusters - 1) / items);
+                    splits = std::max(splits, k1 - k0 + 1);
+                }
+            }
+        }
     }
     // scratch: A' | B' | cand_j | cand_d
     size_t off = 0;
@@ -1141,37 +1186,57 @@ static int l2_dev_impl(pgm_handle *h, const float *d_q, int32_t n1, const float 
     if (rc) return rc;
     char *base = (char *)h->misc.p;
     __nv_bfloat16 *a = (__nv_bfloat16 *)(base + o_a), *b = (__nv_bfloat16 *)(base + o_b);
-    split_kernel<<<(int)(((size_t)(n1 + n2) * 32 + 255) / 256), 256, 0, s>>>(d_q, n1, d_t, n2, dim, dp, a, b);
+    L2Params p{};
+    p.n1 = n1; p.n2 = n2; p.dpc = dpc; p.tiles_per_split = tps; p.col_tiles = col_tiles; p.items = items; p.flat = flat;
+    p.key_mask = 0x7FFFFFE0u;
+    p.cand_j = (int32_t *)(base + o_cj); p.cand_d = (float *)(base + o_cd); p.dbg_dist = d_dbg;
+    const bool tl = getenv("PGM_L2_TIMELINE") != nullptr;
+    if (tl) {
+        if ((rc = ensure_dev(h, h->timeline, 1000 * 8))) return rc;
+        CU_CHECK(h, cudaMemsetAsync(h->timeline.p, 0, 1000 * 8, s));
+        p.timeline = (unsigned long long *)h->timeline.p;
+    }
+    split_kernel<<<(int)(((size_t)(n1 + n2) * 32 + 255) / 256), 256, 0, s>>>(d_q, n1, d_t, n2, dim, dp, a, b, p.cand_j, splits);
     CUtensorMap map_a, map_b;
     if ((rc = make_operand_map(h, &map_a, a, n1, kprime))) return rc;
     if ((rc = make_operand_map(h, &map_b, b, n2, kprime))) return rc;
-    if (!h->l2_attr_set) {
-        CU_CHECK(h, cudaFuncSetAttribute(l2_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l2_smem_bytes()));
-        CU_CHECK(h, cudaFuncSetAttribute(l2_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l2_smem_bytes()));
-        CU_CHECK(h, cudaFuncSetAttribute(l2_topk_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l2_pair_smem_bytes()));
-        CU_CHECK(h, cudaFuncSetAttribute(l2_topk_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l2_pair_smem_bytes()));
-        h->l2_attr_set = true;
-    }
-    L2Params p{};
-    p.n1 = n1; p.n2 = n2; p.dpc = dpc; p.tiles_per_split = tps; p.key_mask = 0x7FFFFFE0u;
-    p.cand_j = (int32_t *)(base + o_cj); p.cand_d = (float *)(base + o_cd); p.dbg_dist = d_dbg;
     // the GEMM kernel and the refinement are programmatic dependents of their predecessors (griddepcontrol)
     cudaLaunchAttribute pdl{};
     pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
     pdl.val.programmaticStreamSerializationAllowed = 1;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(gx, splits); cfg.blockDim = dim3(THREADS); cfg.stream = s; cfg.attrs = &pdl; cfg.numAttrs = 1;
-    cfg.dynamicSmemBytes = pair ? l2_pair_smem_bytes() : l2_smem_bytes();
+    cfg.blockDim = dim3(THREADS); cfg.stream = s; cfg.attrs = &pdl; cfg.numAttrs = 1;
     if (pair) {
+        cfg.gridDim = flat ? dim3(2 * (unsigned)clusters) : dim3(2 * (unsigned)row_pairs, (unsigned)splits);
+        cfg.dynamicSmemBytes = l2_pair_smem_bytes();
         if (d_dbg) CU_CHECK(h, cudaLaunchKernelEx(&cfg, l2_topk_pair_kernel<true>, map_a, map_b, p));
         else CU_CHECK(h, cudaLaunchKernelEx(&cfg, l2_topk_pair_kernel<false>, map_a, map_b, p));
     } else {
+        cfg.gridDim = dim3(gx, splits); cfg.dynamicSmemBytes = l2_smem_bytes();
         if (d_dbg) CU_CHECK(h, cudaLaunchKernelEx(&cfg, l2_topk_kernel<true>, map_a, map_b, p));
         else CU_CHECK(h, cudaLaunchKernelEx(&cfg, l2_topk_kernel<false>, map_a, map_b, p));
     }
     cfg.gridDim = dim3((unsigned)(((size_t)n1 * 32 + 255) / 256)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0;
     CU_CHECK(h, cudaLaunchKernelEx(&cfg, l2_refine_kernel, d_q, n1, d_t, n2, dim, (const int32_t *)p.cand_j,
                                    (const float *)p.cand_d, splits, d_bj, d_bd, d_sj, d_sd));
+    if (tl) {                                        // debug: phase timeline of cluster 0's leader CTA, us since kernel start
+        std::vector<unsigned long long> v(256);
+        CU_CHECK(h, cudaMemcpyAsync(v.data(), h->timeline.p, 256 * 8, cudaMemcpyDeviceToHost, s));
+        CU_CHECK(h, cudaStreamSynchronize(s));
+        fprintf(stderr, "[pgm l2 plan] pair %d flat %d max_clusters %d clusters %d row_pairs %d col_tiles %d splits %d tps %d\n", (int)pair,
+                flat, h->l2_max_clusters, clusters, row_pairs, col_tiles, splits, tps);
+        fprintf(stderr, "[pgm l2 timeline us] sync %.2f pdl %.2f a_ready %.2f |", (v[1] - v[0]) * 1e-3, (v[2] - v[0]) * 1e-3,
+                (v[3] - v[0]) * 1e-3);
+        for (int t = 0; t < 36 && v[4 + t]; t++)
+            fprintf(stderr, " t%d mma %.2f full %.2f epi %.2f |", t, (v[4 + t] - v[0]) * 1e-3, (v[40 + t] - v[0]) * 1e-3,
+                    (v[80 + t] - v[0]) * 1e-3);
+        fprintf(stderr, " flushed %.2f end %.2f\n", (v[120] - v[0]) * 1e-3, (v[121] - v[0]) * 1e-3);
+        // SM cycles (clock64 of the stamping warps; all on one SM): tile-to-tile MMA completion intervals
+        fprintf(stderr, "[pgm l2 timeline cycles] whole %llu (%.0f MHz) | full-to-full:", v[128 + 121] - v[128 + 0],
+                (double)(v[128 + 121] - v[128 + 0]) / ((v[121] - v[0]) * 1e-3));
+        for (int t = 1; t < 36 && v[40 + t]; t++) fprintf(stderr, " %llu", v[128 + 40 + t] - v[128 + 40 + t - 1]);
+        fprintf(stderr, "\n");
+    }
     h->stats.kernel_launches += 3;
     h->stats.distance_evals += (int64_t)n1 * n2;
     h->stats.evals_computed += (int64_t)n1 * n2;

@@ -80,3 +80,24 @@ def test_l2_zero_rows(matcher):
     q = rng.standard_normal((200, 64)).astype(np.float32); q[::7] = 0
     t = rng.standard_normal((333, 64)).astype(np.float32); t[5] = 0; t[100] = 0
     _check(matcher, q, t)
+
+
+@pytest.mark.parametrize("flat", ["0", "1"])
+@pytest.mark.parametrize("n1,n2,dim", [(300, 500, 128), (1000, 2100, 64), (2600, 1300, 128), (257, 9000, 32)])
+def test_l2_both_work_distributions(matcher, monkeypatch, flat, n1, n2, dim):
+    # the CTA-pair kernel distributes (row pair, column tile) items either as (row pair, column split) waves or as
+    # equal flat segments (a segment may cross row pairs: A' reload, candidate slots per segment); same answers
+    monkeypatch.setenv("PGM_L2_FLAT", flat)
+    rng = np.random.default_rng(n1 + n2 + dim)
+    q = rng.standard_normal((n1, dim)).astype(np.float32)
+    t = rng.standard_normal((n2, dim)).astype(np.float32)
+    t[: min(n1, n2) // 2] = q[: min(n1, n2) // 2] + 0.05 * rng.standard_normal((min(n1, n2) // 2, dim)).astype(np.float32)
+    _check(matcher, q, t)
+
+
+def test_l2_underfilled_grid_shape(matcher):
+    # 40 row pairs x 8 column tiles: segments of 4-5 items, most of them crossing a row pair
+    rng = np.random.default_rng(99)
+    q = rng.random((10240, 64), dtype=np.float32)
+    t = rng.random((2048, 64), dtype=np.float32)
+    _check(matcher, q, t)
