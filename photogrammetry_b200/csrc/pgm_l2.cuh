@@ -638,7 +638,7 @@ inline size_t l2_smem_bytes() {
 // 2^-12 (3|q|^2 + 2 d_approx) covers both approximations with a factor 2.8 to spare.
 // Step 2: the survivors four at a time, so sixteen independent train-row loads are in flight per lane.
 // Summation order per distance: each lane's strided partial sum, then a butterfly.
-__global__ void __launch_bounds__(256) l2_refine_kernel(const float *__restrict__ q, int n1, const float *__restrict__ t, int n2,
+__global__ void __launch_bounds__(256, 7) l2_refine_kernel(const float *__restrict__ q, int n1, const float *__restrict__ t, int n2,
                                                         int dim, const int32_t *__restrict__ cand_j,
                                                         const float *__restrict__ cand_d, int splits,
                                                         int32_t *best_j, float *best_d, int32_t *second_j, float *second_d) {
