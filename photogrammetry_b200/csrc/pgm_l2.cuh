@@ -46,7 +46,7 @@ constexpr int CHUNK_K = 64;        // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K = 16;         // K of one tcgen05.mma for 16-bit inputs
 constexpr int MAX_CHUNKS = 5;      // resident A' chunks: [hi | lo | norm], Dp <= 128
 constexpr int STAGES = 8;          // B' ring of chunk slots: two whole tiles deep at Dp = 128
-constexpr int THREADS = 384;        // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: two epilogue warpgroups
+constexpr int THREADS = 384;        // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: two epilogue warpgroups (four were 8 % slower)
 constexpr int EPI_GROUPS = 2;       // each epilogue warpgroup reduces half of the accumulator's columns
 constexpr int TOPK = 4;             // candidates kept per (query, column split, epilogue warpgroup)
 constexpr int CAND = TOPK * EPI_GROUPS;
