@@ -253,9 +253,12 @@ __device__ __forceinline__ void epilogue_reduce(uint32_t taddr, int jbase, int n
             // next key strictly above the one just taken: keys at or below it wrap to >= 2^31 under the
             // unsigned subtraction (all keys are < 2^31), so one add+min per element finds it
             const uint32_t k1p = kmin + 1u;
-            uint32_t dlt = 0xFFFFFFFFu;
+            uint32_t d0 = 0xFFFFFFFFu, d1 = 0xFFFFFFFFu, d2 = 0xFFFFFFFFu, d3 = 0xFFFFFFFFu;   // four independent chains
 #pragma unroll
-            for (int c = 0; c < 32; c++) dlt = min(dlt, v[c] - k1p);
+            for (int c = 0; c < 32; c += 4) {
+                d0 = min(d0, v[c] - k1p); d1 = min(d1, v[c + 1] - k1p); d2 = min(d2, v[c + 2] - k1p); d3 = min(d3, v[c + 3] - k1p);
+            }
+            const uint32_t dlt = min(min(d0, d1), min(d2, d3));
             if (dlt >= 0x80000000u) break;
             kmin = k1p + dlt;
         }
@@ -401,9 +404,17 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 //   leader      warp 1: issues the MMAs; tcgen05.commit.multicast arrives on both CTAs' barriers
 //   both CTAs   warps 4-11: epilogue over the CTA's own 128 rows x 256 columns (TMEM is per SM);
 //               accumulator release arrives on the leader's tempty barrier (remote arrive for rank 1)
-constexpr int TILE_N2 = 256;                  // train rows per accumulator in pair mode (128 per CTA)
+#ifndef PGM_L2_PAIR_N
+#define PGM_L2_PAIR_N 256
+#endif
+constexpr int TILE_N2 = PGM_L2_PAIR_N;        // train rows per accumulator in pair mode (half per CTA)
 constexpr uint32_t TMEM_COLS2 = 512;
-constexpr uint32_t IDESC_BF16_M256_N256 =
+constexpr int NACC2 = 512 / TILE_N2;          // accumulators in flight: all 512 TMEM columns
+constexpr int B_ROWS2 = TILE_N2 / 2;          // train rows each CTA stages per tile
+constexpr uint32_t B_CHUNK_BYTES2 = B_ROWS2 * CHUNK_K * 2;
+constexpr int STAGES2 = (int)((size_t)STAGES * CHUNK_BYTES / B_CHUNK_BYTES2);   // same 128 KB ring
+static_assert(TILE_N2 == 256 || TILE_N2 == 128, "pair tile width");
+constexpr uint32_t IDESC_BF16_M256_N2 =
     (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE_N2 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's even CTA
 
@@ -462,11 +473,11 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *sa = smem;                                              // A' chunks of this CTA's 128 rows
     unsigned char *sb = smem + (size_t)MAX_CHUNKS * CHUNK_BYTES;           // this CTA's half of the B' stages
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sb + (size_t)STAGES * CHUNK_BYTES);
-    uint64_t *full = bars, *empty = bars + STAGES, *a_bar = bars + 2 * STAGES;
-    uint64_t *tfull = bars + 2 * STAGES + 1, *tempty = bars + 2 * STAGES + 3;
-    uint64_t *a_empty = bars + 2 * STAGES + 5;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 6);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sb + (size_t)STAGES2 * B_CHUNK_BYTES2);
+    uint64_t *full = bars, *empty = bars + STAGES2, *a_bar = bars + 2 * STAGES2;
+    uint64_t *tfull = bars + 2 * STAGES2 + 1, *tempty = tfull + NACC2;
+    uint64_t *a_empty = tempty + NACC2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -479,10 +490,10 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (threadIdx.x == 0) l2_stamp(p, 0);
 
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES2; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(a_bar, 1);
         mbar_init(a_empty, 1);
-        for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * 4 * EPI_GROUPS); }
+        for (int a = 0; a < NACC2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * 4 * EPI_GROUPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -513,10 +524,10 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
             for (int kc = 0; kc < nch; kc++) {                 // t_hi chunks, t_lo chunks, norm chunk
                 mbar_wait(&empty[s], ph ^ 1);                  // the pair's MMAs no longer read this stage (multicast commit)
-                if (leader) mbar_expect_tx(&full[s], 2u * CHUNK_BYTES);
-                tma_load_2d_pair(sb + (size_t)s * CHUNK_BYTES, &map_b, &full[s], kc * CHUNK_K,
-                                 ct * TILE_N2 + (int)rank * TILE_N);
-                if (++s == STAGES) { s = 0; ph ^= 1; }
+                if (leader) mbar_expect_tx(&full[s], 2u * B_CHUNK_BYTES2);
+                tma_load_2d_pair(sb + (size_t)s * B_CHUNK_BYTES2, &map_b, &full[s], kc * CHUNK_K,
+                                 ct * TILE_N2 + (int)rank * B_ROWS2);
+                if (++s == STAGES2) { s = 0; ph ^= 1; }
             }
             if (rp != cur_rp) {
                 // next row pair: its first B' tile is already on its way into the ring (the slots free up while the
@@ -536,31 +547,31 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int it = it0; it < it1; it++) {
             const int t = it - it0, rp = it / CT;
             if (rp != cur_rp) { mbar_wait(a_bar, n_a & 1u); tc_fence_after(); cur_rp = rp; n_a++; l2_stamp(p, 3); }
-            const int acc = t & 1;
-            mbar_wait(&tempty[acc], ((t >> 1) & 1) ^ 1);       // both CTAs' epilogues drained this accumulator
+            const int acc = t % NACC2;
+            mbar_wait(&tempty[acc], ((t / NACC2) & 1) ^ 1);    // both CTAs' epilogues drained this accumulator
             tc_fence_after();
             if (t < 36) l2_stamp(p, 4 + t);
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * TILE_N2;
             // pass 0: q_hi . t_hi (waits for the hi slots), pass 1: q_lo . t_hi (frees them), pass 2: q_hi . t_lo
             for (int pass = 0; pass < 3; pass++) {
                 for (int c = 0; c < dpc; c++) {
-                    const uint32_t i = g + (uint32_t)(pass == 2 ? dpc + c : c), s = i % STAGES, ph = (i / STAGES) & 1u;
+                    const uint32_t i = g + (uint32_t)(pass == 2 ? dpc + c : c), s = i % STAGES2, ph = (i / STAGES2) & 1u;
                     if (pass != 1) { mbar_wait(&full[s], ph); tc_fence_after(); }
                     const int ac = pass == 1 ? dpc + c : c;
                     const uint64_t adesc = umma_desc_sw128(smem_u32(sa + (size_t)ac * CHUNK_BYTES));
-                    const uint64_t bdesc = umma_desc_sw128(smem_u32(sb + (size_t)s * CHUNK_BYTES));
+                    const uint64_t bdesc = umma_desc_sw128(smem_u32(sb + (size_t)s * B_CHUNK_BYTES2));
 #pragma unroll
                     for (int k = 0; k < CHUNK_K / UMMA_K; k++)
-                        tc_mma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC_BF16_M256_N256,
+                        tc_mma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC_BF16_M256_N2,
                                          (uint32_t)((pass | c | k) != 0));
                     if (pass != 0) tc_commit_pair(&empty[s]);
                 }
             }
             {   // norm chunk: one K = 16 step adds -(||q||^2 + ||t||^2) / 2
-                const uint32_t i = g + 2u * (uint32_t)dpc, s = i % STAGES, ph = (i / STAGES) & 1u;
+                const uint32_t i = g + 2u * (uint32_t)dpc, s = i % STAGES2, ph = (i / STAGES2) & 1u;
                 mbar_wait(&full[s], ph); tc_fence_after();
                 tc_mma_bf16_pair(d_tmem, umma_desc_sw128(smem_u32(sa + (size_t)(2 * dpc) * CHUNK_BYTES)),
-                                 umma_desc_sw128(smem_u32(sb + (size_t)s * CHUNK_BYTES)), IDESC_BF16_M256_N256, 1u);
+                                 umma_desc_sw128(smem_u32(sb + (size_t)s * B_CHUNK_BYTES2)), IDESC_BF16_M256_N2, 1u);
                 tc_commit_pair(&empty[s]);
             }
             g += 2u * (uint32_t)dpc + 1u;
@@ -593,8 +604,8 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
                 for (int k = 0; k < TOPK; k++) { bk[k] = row < p.n1 ? 0xFFFFFFFFu : 0u; bj[k] = -1; }
             }
-            const int acc = t & 1;
-            mbar_wait(&tfull[acc], (t >> 1) & 1);
+            const int acc = t % NACC2;
+            mbar_wait(&tfull[acc], (t / NACC2) & 1);
             tc_fence_after();
             if (warp == 4 && lane == 0 && t < 36) l2_stamp(p, 40 + t);
             const int jbase = ct * TILE_N2 + eg * NCOLS;
@@ -621,7 +632,7 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 }
 
 inline size_t l2_pair_smem_bytes() {
-    return (size_t)(MAX_CHUNKS + STAGES) * CHUNK_BYTES + (2 * STAGES + 7) * 8 + 1024;
+    return (size_t)MAX_CHUNKS * CHUNK_BYTES + (size_t)STAGES2 * B_CHUNK_BYTES2 + (2 * STAGES2 + 2 * NACC2 + 4) * 8 + 1024;
 }
 
 inline size_t l2_smem_bytes() {

@@ -1100,12 +1100,12 @@ static PFN_encodeTiled get_encode_tiled() {
 }
 
 // rows x kprime bf16, row-major; box = 64 (K, 128 bytes) x 128 rows, 128-byte swizzle
-static int make_operand_map(pgm_handle *h, CUtensorMap *map, void *base, int rows, int kprime) {
+static int make_operand_map(pgm_handle *h, CUtensorMap *map, void *base, int rows, int kprime, int box_rows = pgm_l2::TILE_N) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return fail(h, PGM_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t gdim[2] = {(cuuint64_t)kprime, (cuuint64_t)rows};
     cuuint64_t gstr[1] = {(cuuint64_t)kprime * 2};
-    cuuint32_t box[2] = {(cuuint32_t)pgm_l2::CHUNK_K, (cuuint32_t)pgm_l2::TILE_N};
+    cuuint32_t box[2] = {(cuuint32_t)pgm_l2::CHUNK_K, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1199,7 +1199,7 @@ static int l2_dev_impl(pgm_handle *h, const float *d_q, int32_t n1, const float 
     split_kernel<<<(int)(((size_t)(n1 + n2) * 32 + 255) / 256), 256, 0, s>>>(d_q, n1, d_t, n2, dim, dp, a, b, p.cand_j, splits);
     CUtensorMap map_a, map_b;
     if ((rc = make_operand_map(h, &map_a, a, n1, kprime))) return rc;
-    if ((rc = make_operand_map(h, &map_b, b, n2, kprime))) return rc;
+    if ((rc = make_operand_map(h, &map_b, b, n2, kprime, pair ? B_ROWS2 : TILE_N))) return rc;
     // the GEMM kernel and the refinement are programmatic dependents of their predecessors (griddepcontrol)
     cudaLaunchAttribute pdl{};
     pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
