@@ -96,3 +96,46 @@ def test_no_gpu_fails_loudly():
         Matcher(0)
     with pytest.raises(_lib.PgmatchLibraryError):
         KeypointMatching()
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/pgmatch.h must compile as C99 and a C program must link and run against
+    libpgmatch.so (what a P/Invoke / cgo / JNI shim does).  Without a GPU pgm_create has to refuse, loudly."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        pytest.skip("no C compiler")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    src = tmp_path / "consumer.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "pgmatch.h"
+int main(void) {
+    pgm_handle *h = NULL;
+    int rc;
+    if (pgm_version() != 100) return 10;
+    if (!strstr(pgm_status_string(PGM_E_NO_DEVICE), "no CPU fallback")) return 11;
+    rc = pgm_create(0, &h);
+    if (rc == PGM_OK) {                       /* a B200 is present: one tiny call through the ABI */
+        unsigned char q[32] = {0}, t[64] = {0};
+        int32_t qi[1], tj[1], dd[1], cnt = 0;
+        t[32] = 1;                            /* train row 1 differs from the query in one bit */
+        rc = pgm_match_hamming_greedy(h, q, 1, t, 2, 256, 32, qi, tj, dd, 1, &cnt, PGM_FLAG_REFERENCE_COMPAT_TAIL);
+        if (rc != PGM_OK || cnt != 1 || qi[0] != 0 || tj[0] != 0 || dd[0] != 0) return 12;
+        pgm_destroy(h);
+        puts("gpu");
+    } else {
+        if (rc != PGM_E_NO_DEVICE || h != NULL) return 13;
+        puts("no-device");
+    }
+    return 0;
+}
+''')
+    exe = tmp_path / "consumer"
+    subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-o", str(exe), "-L", libdir, "-lpgmatch", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert out.stdout.strip() in ("gpu", "no-device")
