@@ -138,6 +138,84 @@ __device__ __forceinline__ int ablocks_of(int nlr, int nlc) {
     return (nlr + ACCEPT_THREADS - 1) / ACCEPT_THREADS + (nlc + ACCEPT_THREADS - 1) / ACCEPT_THREADS;
 }
 
+// The same plan for at most 32 pairs, by ONE warp with everything in registers (no shared memory, no block
+// barriers): in latency mode the planner sits on the critical path of every round between two grid barriers, and
+// the block-wide form costs ~5 us of dependent L2 round trips and barriers there.
+__device__ __forceinline__ void plan_warp(const Chunk &c, int r) {
+    const int lane = threadIdx.x & 31, buf = r % 3, p = lane;
+    unsigned long long ev = 0; int nbig = 0, nsmall = 0, nlr = 0, nlc = 0;
+    uint8_t st = PAIR_DONE;
+    if (p < c.n_pairs) {
+        st = c.status[p];
+        if (st == PAIR_SMALL) { nsmall = 1; }
+        else {
+            const int32_t *cp = cnt_ptr(c, buf, p);
+            nlr = __ldcg(cp); nlc = __ldcg(cp + 1);
+            st = PAIR_DONE;
+            if (nlr > 0 && nlc > 0) {
+                const bool small = nlr <= FIN_MAX_DIM && nlc <= FIN_MAX_DIM && nlr * nlc <= FIN_MAX_EVALS &&
+                                   !(__ldg(&c.pairs[p].flags) & PAIR_FLAG_NO_FINISHER);
+                if (small) { st = PAIR_SMALL; nsmall = 1; c.small[p] = SmallInfo{nlr, nlc, r & 1, 0}; }
+                else { st = PAIR_BIG; nbig = 1; ev = (unsigned long long)nlr * (unsigned long long)nlc; }
+            }
+            c.status[p] = st;
+        }
+        int32_t *nx = cnt_ptr(c, (r + 1) % 3, p);   // accept(r) appends here
+        nx[0] = 0; nx[1] = 0;
+    }
+    for (int o = 16; o; o >>= 1) {
+        ev += __shfl_xor_sync(0xffffffffu, ev, o);
+        nbig += __shfl_xor_sync(0xffffffffu, nbig, o);
+        nsmall += __shfl_xor_sync(0xffffffffu, nsmall, o);
+    }
+    // tile shape: identical arithmetic to plan_device (every lane computes it)
+    const unsigned slots = (unsigned)(c.num_sms * c.ctas_per_sm);
+    const unsigned long long large_tile = (unsigned long long)ROUND_THREADS * RQ_LARGE * STAGE_LARGE;
+    int rq, stage;
+    if (ev >= 2ull * c.num_sms * large_tile) { rq = RQ_LARGE; stage = STAGE_LARGE; }
+    else { rq = RQ_SMALL; stage = STAGE_SMALL; }
+    const int tile_rows = ROUND_THREADS * rq;
+    float per_tile = (float)ev / (2.0f * (float)slots);
+    const float min_tile = (float)(tile_rows * stage);
+    if (per_tile < min_tile) per_tile = min_tile;
+    unsigned cpt = (unsigned)(per_tile / (float)tile_rows);
+    if (cpt < 1u) cpt = 1u;
+    cpt = ((cpt + stage - 1) / stage) * stage;
+    if (cpt > (unsigned)MAX_N) cpt = MAX_N;
+    // wave-aware refinement: a round takes ~ceil(tiles / slots) x cpt; a slightly wider tile often saves a whole,
+    // mostly empty, second wave (2301 x 2301 live: 648 tiles of 64 columns on 592 slots -> 432 tiles of 96)
+    {
+        unsigned best_cpt = cpt, best_cost = 0xFFFFFFFFu;
+        for (unsigned k = 0; k < 4; k++) {
+            const unsigned cand = min(cpt + k * (unsigned)stage, (unsigned)MAX_N);
+            int tsum = st == PAIR_BIG ? tiles_of(nlr, nlc, tile_rows, (int)cand) : 0;
+            for (int o = 16; o; o >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
+            const unsigned cost = (((unsigned)tsum + slots - 1) / slots) * cand;
+            if (cost < best_cost) { best_cost = cost; best_cpt = cand; }
+        }
+        cpt = best_cpt;
+    }
+    const int tiles = st == PAIR_BIG ? tiles_of(nlr, nlc, tile_rows, (int)cpt) : 0;
+    const int ablocks = st == PAIR_BIG ? ablocks_of(nlr, nlc) : 0;
+    int tinc = tiles, ainc = ablocks;                // warp inclusive scans
+    for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, tinc, o), b = __shfl_up_sync(0xffffffffu, ainc, o);
+        if (lane >= o) { tinc += a; ainc += b; }
+    }
+    const int ttot = __shfl_sync(0xffffffffu, tinc, 31), atot = __shfl_sync(0xffffffffu, ainc, 31);
+    if (p < c.n_pairs) { c.tile_base[p] = tinc - tiles; c.ablock_base[p] = ainc - ablocks; }
+    if (lane == 0) {
+        PlanInfo *pl = c.plan;
+        pl->cols_per_tile = (int)cpt; pl->rq = rq;
+        pl->n_big = nbig; pl->n_small = nsmall; pl->round = r;
+        pl->ticket = 0u;
+        pl->evals += ev;
+        if (nbig == 0 && pl->done_round_p1 == 0) pl->done_round_p1 = r + 1;
+        pl->total_tiles = ttot; pl->total_ablocks = atot;
+        c.tile_base[c.n_pairs] = ttot; c.ablock_base[c.n_pairs] = atot;
+    }
+}
+
 __device__ void plan_device(const Chunk &c, int r) {
     __shared__ unsigned long long s_evals[32];
     __shared__ int s_w[4][32];
@@ -254,7 +332,8 @@ __device__ __forceinline__ void plan_in_last_block(const Chunk &c, int r, unsign
     __syncthreads();
     if (s_last) {
         __threadfence();
-        plan_device(c, r);
+        if (c.n_pairs <= 32) { if (threadIdx.x < 32) plan_warp(c, r); }
+        else plan_device(c, r);
     }
 }
 
@@ -620,6 +699,7 @@ __device__ __forceinline__ void finisher_body(const Chunk &c, int p, unsigned ch
         else { colid[rank] = me; ckoff[rank] = (uint32_t)rank; cbest[rank] = KEY_NONE; }
     }
     __syncthreads();
+    tstamp(c, blockIdx.x, tid, 10);
 
     // stage both descriptor sets in shared memory (coalesced 128-bit loads), then every thread
     // computes its share of the nr x nc matrix from smem
@@ -632,6 +712,7 @@ __device__ __forceinline__ void finisher_body(const Chunk &c, int p, unsigned ch
                          : __ldg(reinterpret_cast<const uint4 *>(pd.t + (size_t)colid[row - nr] * WORDS) + part);
     }
     __syncthreads();
+    tstamp(c, blockIdx.x, tid, 11);
     for (int e = tid; e < nr * nc; e += nt) {
         const int x = e / nc, y = e - x * nc;
         uint32_t q[WORDS], t[WORDS];
@@ -644,42 +725,43 @@ __device__ __forceinline__ void finisher_body(const Chunk &c, int p, unsigned ch
         D[x * S + y] = (uint16_t)hamming_words<WORDS>(q, t);
     }
     __syncthreads();
+    tstamp(c, blockIdx.x, tid, 12);
 
     int live_r = nr, live_c = nc;
+    int32_t *todo = tmp;                             // the rank-sort scratch is free now: rows / columns to rescan
+    __shared__ int s_todo;
+    const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
     while (live_r > 0 && live_c > 0) {
+        // 1. which rows / columns lost their choice (or never had one)?  Usually a minority after the first round.
+        if (tid == 0) s_todo = 0;
+        __syncthreads();
         for (int k = tid; k < nr + nc; k += nt) {
+            bool need;
             if (k < nr) {
-                if (rkoff[k] == KEY_INVALID) continue;
                 const uint32_t old = rbest[k];
-                if (old != KEY_NONE && ckoff[old & KEY_IDX_MASK] != KEY_INVALID) continue;   // choice still alive
-                const uint16_t *row = D + k * S;
-                uint32_t b0 = KEY_NONE, b1 = KEY_NONE, b2 = KEY_NONE, b3 = KEY_NONE;
-                int y = 0;
-                for (; y + 4 <= nc; y += 4) {
-                    b0 = min(b0, ((uint32_t)row[y] << KEY_IDX_BITS) + ckoff[y]);
-                    b1 = min(b1, ((uint32_t)row[y + 1] << KEY_IDX_BITS) + ckoff[y + 1]);
-                    b2 = min(b2, ((uint32_t)row[y + 2] << KEY_IDX_BITS) + ckoff[y + 2]);
-                    b3 = min(b3, ((uint32_t)row[y + 3] << KEY_IDX_BITS) + ckoff[y + 3]);
-                }
-                for (; y < nc; y++) b0 = min(b0, ((uint32_t)row[y] << KEY_IDX_BITS) + ckoff[y]);
-                rbest[k] = min(min(b0, b1), min(b2, b3));
+                need = rkoff[k] != KEY_INVALID && (old == KEY_NONE || ckoff[old & KEY_IDX_MASK] == KEY_INVALID);
             } else {
-                const int y = k - nr;
-                if (ckoff[y] == KEY_INVALID) continue;
-                const uint32_t old = cbest[y];
-                if (old != KEY_NONE && rkoff[old & KEY_IDX_MASK] != KEY_INVALID) continue;
-                const uint16_t *col = D + y;
-                uint32_t b0 = KEY_NONE, b1 = KEY_NONE, b2 = KEY_NONE, b3 = KEY_NONE;
-                int x = 0;
-                for (; x + 4 <= nr; x += 4) {
-                    b0 = min(b0, ((uint32_t)col[x * S] << KEY_IDX_BITS) + rkoff[x]);
-                    b1 = min(b1, ((uint32_t)col[(x + 1) * S] << KEY_IDX_BITS) + rkoff[x + 1]);
-                    b2 = min(b2, ((uint32_t)col[(x + 2) * S] << KEY_IDX_BITS) + rkoff[x + 2]);
-                    b3 = min(b3, ((uint32_t)col[(x + 3) * S] << KEY_IDX_BITS) + rkoff[x + 3]);
-                }
-                for (; x < nr; x++) b0 = min(b0, ((uint32_t)col[x * S] << KEY_IDX_BITS) + rkoff[x]);
-                cbest[y] = min(min(b0, b1), min(b2, b3));
+                const uint32_t old = cbest[k - nr];
+                need = ckoff[k - nr] != KEY_INVALID && (old == KEY_NONE || rkoff[old & KEY_IDX_MASK] == KEY_INVALID);
             }
+            if (need) todo[atomicAdd(&s_todo, 1)] = k;
+        }
+        __syncthreads();
+        // 2. one warp per rescan: lanes stride over the row (consecutive u16) or the column (odd word pitch:
+        //    conflict-free), then a warp minimum -- the latency of a rescan is ~nc/32 steps instead of nc
+        const int n_todo = s_todo;
+        for (int w = wid; w < n_todo; w += nw) {
+            const int k = todo[w];
+            uint32_t bmin = KEY_NONE;
+            if (k < nr) {
+                const uint16_t *row = D + k * S;
+                for (int y = lane; y < nc; y += 32) bmin = min(bmin, ((uint32_t)row[y] << KEY_IDX_BITS) + ckoff[y]);
+            } else {
+                const uint16_t *col = D + (k - nr);
+                for (int x = lane; x < nr; x += 32) bmin = min(bmin, ((uint32_t)col[x * S] << KEY_IDX_BITS) + rkoff[x]);
+            }
+            bmin = __reduce_min_sync(0xffffffffu, bmin);
+            if (lane == 0) { if (k < nr) rbest[k] = bmin; else cbest[k - nr] = bmin; }
         }
         __syncthreads();
         // FIN_MAX_DIM == FIN_THREADS: a thread owns at most one row
@@ -699,6 +781,7 @@ __device__ __forceinline__ void finisher_body(const Chunk &c, int p, unsigned ch
         }
         live_r -= n_acc; live_c -= n_acc;
         __syncthreads();
+        tstamp(c, blockIdx.x, tid, 13);
     }
     if (tid == 0) c.status[p] = PAIR_DONE;
 }
