@@ -685,6 +685,10 @@ static int batch_impl(pgm_handle *h, const uint8_t *d_all_desc, const int64_t *i
             CU_CHECK(h, cudaEventCreateWithFlags(&h->ev_copied[k], cudaEventDisableTiming));
         }
     }
+    // page-locked caller arrays (pgm_host_alloc): the copy stream writes the triples straight into them -- no
+    // staging buffer, no helper thread, a third of the host-memory traffic
+    const bool out_pinned = out_on_host && is_pinned_host(out_qi) && is_pinned_host(out_tj) && is_pinned_host(out_dist);
+    bool slot_used[2] = {false, false};
     std::vector<HostPair> chunk;
     int64_t done_rows = 0;
     int p = 0, chunk_no = 0;
@@ -712,8 +716,12 @@ static int batch_impl(pgm_handle *h, const uint8_t *d_all_desc, const int64_t *i
             // this slot's previous user (chunk k-2) must have left both the device buffer and the staging
             if (jobs.th[slot].joinable()) jobs.th[slot].join();
             int rc;
+            if (out_pinned && slot_used[slot]) {
+                if (dout.cap < (size_t)3 * rows * 4) CU_CHECK(h, cudaEventSynchronize(h->ev_copied[slot]));   // about to reallocate
+                else CU_CHECK(h, cudaStreamWaitEvent(s, h->ev_copied[slot], 0));
+            }
             if ((rc = ensure_dev(h, dout, (size_t)3 * rows * 4))) return rc;
-            if ((rc = ensure_host(h, pin, (size_t)3 * rows * 4))) return rc;
+            if (!out_pinned && (rc = ensure_host(h, pin, (size_t)3 * rows * 4))) return rc;
             d_qi = (int32_t *)dout.p; d_tj = d_qi + rows; d_dd = d_tj + rows;
         } else {
             d_qi = out_qi + done_rows; d_tj = out_tj + done_rows; d_dd = out_dist + done_rows;
@@ -734,6 +742,17 @@ static int batch_impl(pgm_handle *h, const uint8_t *d_all_desc, const int64_t *i
         if (out_on_host) {
             CU_CHECK(h, cudaEventRecord(h->ev_done[slot], s));
             CU_CHECK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));
+            if (out_pinned) {
+                const size_t nb = (size_t)rows * 4;
+                CU_CHECK(h, cudaMemcpyAsync(out_qi + done_rows, d_qi, nb, cudaMemcpyDeviceToHost, h->copy_stream));
+                CU_CHECK(h, cudaMemcpyAsync(out_tj + done_rows, d_tj, nb, cudaMemcpyDeviceToHost, h->copy_stream));
+                CU_CHECK(h, cudaMemcpyAsync(out_dist + done_rows, d_dd, nb, cudaMemcpyDeviceToHost, h->copy_stream));
+                CU_CHECK(h, cudaEventRecord(h->ev_copied[slot], h->copy_stream));
+                slot_used[slot] = true;
+                h->stats.d2h_bytes += (int64_t)3 * rows * 4;
+                done_rows += rows;
+                continue;
+            }
             CU_CHECK(h, cudaMemcpyAsync(pin.p, dout.p, (size_t)3 * rows * 4, cudaMemcpyDeviceToHost, h->copy_stream));
             CU_CHECK(h, cudaEventRecord(h->ev_copied[slot], h->copy_stream));
             const int32_t *src = (const int32_t *)pin.p;

@@ -130,6 +130,30 @@ def test_batch_equals_single(matcher):
         matcher.match_pairs_batch(all_desc, offs, [(0, 1)], 256)
 
 
+@pytest.mark.parametrize("pinned", [False, True])
+def test_batch_many_chunks_pageable_and_pinned_outputs(matcher, pinned):
+    # > 2 chunks of 4096 pairs: the double-buffered output path (device buffer -> pinned staging -> helper thread
+    # for pageable arrays; straight into the caller's arrays when they are page-locked) reuses each slot
+    from photogrammetry_b200._lib import pinned_empty
+    n_img, per = 150, 24
+    imgs = [synthetic.uniform_descriptors(500 + k, per, 256) for k in range(n_img)]
+    all_desc = np.concatenate(imgs)
+    offs = np.arange(n_img + 1, dtype=np.int64) * per
+    pairs = np.array([(a, b) for a in range(n_img) for b in range(a + 1, n_img)], dtype=np.int32)   # 11 175 pairs
+    total = len(pairs) * per
+    out = pinned_empty((3, total), np.int32) if pinned else np.empty((3, total), np.int32)
+    out[:] = -7
+    got, starts, counts = matcher.match_pairs_batch(all_desc, offs, pairs, 256, out=out)
+    assert got.shape == (3, total) and (counts == per).all()
+    single = {}
+    for p in list(range(0, len(pairs), 997)) + [4095, 4096, 8191, 8192, len(pairs) - 1]:
+        a, b = pairs[p]
+        exp = orc.match_sweep(imgs[a], imgs[b])
+        assert (got[:, starts[p]:starts[p] + per].T == exp).all(), p
+    # every row of every pair is a permutation of its query indices
+    assert (np.sort(got[0].reshape(len(pairs), per), axis=1) == np.arange(per)).all()
+
+
 def test_knn2_and_ratio_crosscheck(matcher):
     q = synthetic.uniform_descriptors(31, 3000, 256)
     t = synthetic.noisy_copy_descriptors(32, q, 256)[:2500]

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--per", type=int, default=4096)
     ap.add_argument("--reps", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--pinned-out", action="store_true", help="e2e result arrays in page-locked memory (pgm_host_alloc)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -71,13 +72,24 @@ def main():
     if not args.no_e2e:
         # caller-owned result arrays, allocated and touched once and reused by every call (a pipeline pools its
         # buffers; a fresh 6.4 GB array per call costs more in first-touch page faults than the matching)
-        host_out = np.zeros((3, len(mine) * per), dtype=np.int32)
-        sync_all(); t0 = time.perf_counter()
-        soa, starts, counts = m.match_pairs_batch(imgs, offs, mine, 256, out=host_out)
-        dt = maxr(time.perf_counter() - t0)
+        if args.pinned_out:
+            from photogrammetry_b200._lib import pinned_empty
+            host_out = pinned_empty((3, len(mine) * per), np.int32)
+            host_out[:] = 0
+        else:
+            host_out = np.zeros((3, len(mine) * per), dtype=np.int32)
+        # twice: the first call also allocates the library's double-buffered device / staging buffers (pooled in
+        # the handle afterwards); both times are reported, the steady-state one is the headline
+        e2e_times = []
+        for _ in range(2):
+            sync_all(); t0 = time.perf_counter()
+            soa, starts, counts = m.match_pairs_batch(imgs, offs, mine, 256, out=host_out)
+            e2e_times.append(maxr(time.perf_counter() - t0))
+        dt = e2e_times[-1]
         line["e2e"] = {"seconds": dt, "evals_per_s": evals / dt, "matched_pairs_per_s": len(pairs) * per / dt,
-                       "h2d_bytes_rank0": int(imgs.nbytes), "d2h_bytes_rank0": int(soa.nbytes),
-                       "output": "caller-owned int32[3, total] arrays reused across calls"}
+                       "first_call_seconds": e2e_times[0], "h2d_bytes_rank0": int(imgs.nbytes), "d2h_bytes_rank0": int(soa.nbytes),
+                       "output": "caller-owned int32[3, total] arrays reused across calls" +
+                                 (", page-locked (written by the copy stream directly)" if args.pinned_out else ", pageable (pinned staging + helper thread)")}
         if world == 1 and len(mine) * per <= (64 << 20):      # (single process only: no collective in a rank-0 branch)
             torch.cuda.synchronize(); t0 = time.perf_counter()
             m.match_pairs_batch(imgs, offs, mine, 256)
