@@ -45,6 +45,12 @@ constexpr int ACCEPT_THREADS = 256;
 constexpr int FIN_THREADS = 512;
 constexpr int FIN_MAX_DIM = 512;      // (== FIN_THREADS) finisher takes a pair once nlr, nlc <= this ...
 constexpr int FIN_MAX_EVALS = 49152;  // ... and nlr * nlc <= this (u16 distance matrix in smem)
+// Latency mode (persistent tail kernel): the matrix and the first round's minima of a small pair are computed by
+// ALL CTAs into global memory, so the single-CTA finisher can afford to start earlier (one grid round less).
+constexpr int FIN_MAX_EVALS_TAIL = 65536;
+constexpr int FIN_D_STRIDE = FIN_MAX_EVALS_TAIL + 4 * FIN_MAX_DIM;   // u16 cells per pair incl. row-pitch padding
+constexpr int FIN_SEG = 128;                                        // entries of a row / column one warp handles
+constexpr int FIN_PARTS = FIN_MAX_DIM / FIN_SEG;                    // partial minima per row / column
 constexpr int ORDER_THREADS_STANDALONE = 1024;
 constexpr int TAIL_THREADS = 512;     // persistent tail kernel: 1 CTA per SM, four 128-thread groups
 constexpr int ORDER_KEY_CACHE = 16384;  // match keys cached in smem by the order kernel
@@ -86,7 +92,7 @@ struct Chunk {
     int32_t n_pairs;
     int32_t num_sms;
     int32_t ctas_per_sm;          // resident round-kernel CTAs per SM
-    int32_t pad;
+    int32_t fin_max_evals;        // a pair goes to the finisher once nlr * nlc <= this (FIN_MAX_EVALS or _TAIL)
     uint32_t *rowbest[2];
     uint32_t *colbest[2];
     int32_t *live_rows[2];
@@ -99,6 +105,9 @@ struct Chunk {
     SmallInfo *small;             // per pair
     PlanInfo *plan;
     unsigned long long *timeline; // optional (PGM_TAIL_TIMELINE=1): globaltimer stamps of the tail kernel's phases
+    uint16_t *fin_d;              // latency mode: [n_pairs][FIN_D_STRIDE] distance matrices written by finisher_prepare
+    uint32_t *fin_rb, *fin_cb;    // latency mode: [n_pairs][FIN_PARTS][FIN_MAX_DIM] first-round row / column minima (partial)
+    int32_t *fin_ids;             // latency mode: [n_pairs][2][FIN_MAX_DIM] rank-sorted row / column ids
 };
 
 __device__ __forceinline__ int32_t *cnt_ptr(const Chunk &c, int buf3, int p) {
@@ -153,7 +162,7 @@ __device__ __forceinline__ void plan_warp(const Chunk &c, int r) {
             nlr = __ldcg(cp); nlc = __ldcg(cp + 1);
             st = PAIR_DONE;
             if (nlr > 0 && nlc > 0) {
-                const bool small = nlr <= FIN_MAX_DIM && nlc <= FIN_MAX_DIM && nlr * nlc <= FIN_MAX_EVALS &&
+                const bool small = nlr <= FIN_MAX_DIM && nlc <= FIN_MAX_DIM && nlr * nlc <= c.fin_max_evals &&
                                    !(__ldg(&c.pairs[p].flags) & PAIR_FLAG_NO_FINISHER);
                 if (small) { st = PAIR_SMALL; nsmall = 1; c.small[p] = SmallInfo{nlr, nlc, r & 1, 0}; }
                 else { st = PAIR_BIG; nbig = 1; ev = (unsigned long long)nlr * (unsigned long long)nlc; }
@@ -233,7 +242,7 @@ __device__ void plan_device(const Chunk &c, int r) {
             const int nlr = __ldcg(cp), nlc = __ldcg(cp + 1);
             st = PAIR_DONE;
             if (nlr > 0 && nlc > 0) {
-                const bool small = nlr <= FIN_MAX_DIM && nlc <= FIN_MAX_DIM && nlr * nlc <= FIN_MAX_EVALS &&
+                const bool small = nlr <= FIN_MAX_DIM && nlc <= FIN_MAX_DIM && nlr * nlc <= c.fin_max_evals &&
                                    !(__ldg(&c.pairs[p].flags) & PAIR_FLAG_NO_FINISHER);
                 if (small) {
                     st = PAIR_SMALL; nsmall++;
@@ -664,26 +673,10 @@ __global__ void __launch_bounds__(ACCEPT_THREADS) accept_kernel(Chunk c, int r) 
 // round a row (column) is rescanned only if the column (row) it had chosen
 // was matched to someone else -- otherwise its argmin is still valid.
 // ---------------------------------------------------------------------------
-template <int WORDS>
-__device__ __forceinline__ void finisher_body(const Chunk &c, int p, unsigned char *fin_smem) {
+// live lists of pair p -> rank-sorted original ids (ids are distinct) in rowid[] / colid[]
+__device__ __forceinline__ void finisher_sorted_ids(const Chunk &c, const PairDesc &pd, int nr, int nc, int cur, int32_t *rowid,
+                                                    int32_t *colid, int32_t *tmp) {
     const int tid = threadIdx.x, nt = FIN_THREADS;
-    const PairDesc pd = c.pairs[p];
-    const int4 si_raw = __ldcg(reinterpret_cast<const int4 *>(c.small + p));
-    const SmallInfo si{si_raw.x, si_raw.y, si_raw.z, si_raw.w};
-    const int nr = si.nlr, nc = si.nlc, cur = si.parity;
-    int S = (nc + 1) & ~1;            // row pitch in u16; S/2 odd -> row scans hit 32 distinct banks
-    if (((S >> 1) & 1) == 0) S += 2;
-
-    int32_t *rowid = reinterpret_cast<int32_t *>(fin_smem);
-    int32_t *colid = rowid + FIN_MAX_DIM;
-    uint32_t *rkoff = reinterpret_cast<uint32_t *>(colid + FIN_MAX_DIM);
-    uint32_t *ckoff = rkoff + FIN_MAX_DIM;
-    uint32_t *rbest = ckoff + FIN_MAX_DIM;
-    uint32_t *cbest = rbest + FIN_MAX_DIM;
-    int32_t *tmp = reinterpret_cast<int32_t *>(cbest + FIN_MAX_DIM);     // 2 * FIN_MAX_DIM
-    uint16_t *D = reinterpret_cast<uint16_t *>(tmp + 2 * FIN_MAX_DIM);
-
-    // rank sort of the live lists (ids are distinct)
     for (int k = tid; k < nr + nc; k += nt)
         tmp[k < nr ? k : FIN_MAX_DIM + (k - nr)] =
             k < nr ? __ldcg(c.live_rows[cur] + pd.row_base + k) : __ldcg(c.live_cols[cur] + pd.col_base + (k - nr));
@@ -695,12 +688,125 @@ __device__ __forceinline__ void finisher_body(const Chunk &c, int p, unsigned ch
         int rank = 0;
 #pragma unroll 8
         for (int m = 0; m < n; m++) rank += (src[m] < me);
-        if (is_row) { rowid[rank] = me; rkoff[rank] = (uint32_t)rank; rbest[rank] = KEY_NONE; }
-        else { colid[rank] = me; ckoff[rank] = (uint32_t)rank; cbest[rank] = KEY_NONE; }
+        if (is_row) rowid[rank] = me; else colid[rank] = me;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ int finisher_pitch(int nc) {
+    int S = (nc + 1) & ~1;            // row pitch in u16; S/2 odd -> row scans hit 32 distinct banks
+    if (((S >> 1) & 1) == 0) S += 2;
+    return S;
+}
+
+// Latency mode, run by EVERY CTA of the tail kernel for every small pair: one warp per row (then per column) of
+// the live x live matrix computes its distances straight from global memory, writes the row's cells and the
+// row's (column's) first-round minimum to global memory.  A single SM would need ~8 us for a 145 x 145 matrix and
+// ~6 us for the first round of scans; spread over the machine both cost one grid barrier.
+template <int WORDS>
+__device__ __forceinline__ void finisher_prepare(const Chunk &c, int p, unsigned char *fin_smem) {
+    const int tid = threadIdx.x, lane = tid & 31, nw = FIN_THREADS >> 5;
+    const PairDesc pd = c.pairs[p];
+    const int4 si_raw = __ldcg(reinterpret_cast<const int4 *>(c.small + p));
+    const int nr = si_raw.x, nc = si_raw.y, cur = si_raw.z;
+    const int S = finisher_pitch(nc);
+    int32_t *rowid = reinterpret_cast<int32_t *>(fin_smem);
+    int32_t *colid = rowid + FIN_MAX_DIM;
+    int32_t *tmp = colid + FIN_MAX_DIM;                                   // 2 * FIN_MAX_DIM
+    finisher_sorted_ids(c, pd, nr, nc, cur, rowid, colid, tmp);
+    uint16_t *Dg = c.fin_d + (size_t)p * FIN_D_STRIDE;
+    uint32_t *rb = c.fin_rb + (size_t)p * FIN_PARTS * FIN_MAX_DIM, *cb = c.fin_cb + (size_t)p * FIN_PARTS * FIN_MAX_DIM;
+    if (blockIdx.x == 0) {                                               // the finisher CTA does not sort again
+        int32_t *gi = c.fin_ids + (size_t)p * 2 * FIN_MAX_DIM;
+        for (int k = tid; k < nr + nc; k += FIN_THREADS) gi[k < nr ? k : FIN_MAX_DIM + (k - nr)] = k < nr ? rowid[k] : colid[k - nr];
+    }
+    constexpr int V4 = WORDS / 4;
+    // work item = (row or column, segment of FIN_SEG entries of the other side): four entries per lane, whose
+    // descriptor gathers are all in flight together; one item per warp at the sizes the finisher takes
+    const int segs_r = (nc + FIN_SEG - 1) / FIN_SEG, segs_c = (nr + FIN_SEG - 1) / FIN_SEG;
+    const int n_items = nr * segs_r + nc * segs_c;
+    const int gw = (int)blockIdx.x * nw + (tid >> 5), GW = (int)gridDim.x * nw;
+    for (int item = gw; item < n_items; item += GW) {
+        const bool is_row = item < nr * segs_r;
+        const int it = is_row ? item : item - nr * segs_r, segs = is_row ? segs_r : segs_c;
+        const int me = it / segs, seg = it - me * segs, n_other = is_row ? nc : nr;
+        const uint32_t *mine = (is_row ? pd.q + (size_t)rowid[me] * WORDS : pd.t + (size_t)colid[me] * WORDS);
+        uint32_t a[WORDS];
+#pragma unroll
+        for (int v = 0; v < V4; v++) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4 *>(mine) + v);
+            a[4 * v] = u.x; a[4 * v + 1] = u.y; a[4 * v + 2] = u.z; a[4 * v + 3] = u.w;
+        }
+        uint4 bv[FIN_SEG / 32][V4];
+#pragma unroll
+        for (int e = 0; e < FIN_SEG / 32; e++) {
+            const int o = seg * FIN_SEG + e * 32 + lane;
+            const int oid = o < n_other ? (is_row ? colid[o] : rowid[o]) : 0;
+            const uint32_t *oth = (is_row ? pd.t : pd.q) + (size_t)oid * WORDS;
+#pragma unroll
+            for (int v = 0; v < V4; v++) bv[e][v] = __ldg(reinterpret_cast<const uint4 *>(oth) + v);
+        }
+        uint32_t best = KEY_NONE;
+#pragma unroll
+        for (int e = 0; e < FIN_SEG / 32; e++) {
+            const int o = seg * FIN_SEG + e * 32 + lane;
+            uint32_t b[WORDS];
+#pragma unroll
+            for (int v = 0; v < V4; v++) { b[4 * v] = bv[e][v].x; b[4 * v + 1] = bv[e][v].y; b[4 * v + 2] = bv[e][v].z; b[4 * v + 3] = bv[e][v].w; }
+            const uint32_t d = hamming_words<WORDS>(a, b);
+            if (o < n_other) {
+                if (is_row) Dg[me * S + o] = (uint16_t)d;
+                best = min(best, (d << KEY_IDX_BITS) + (uint32_t)o);
+            }
+        }
+        best = __reduce_min_sync(0xffffffffu, best);
+        if (lane == 0) (is_row ? rb : cb)[seg * FIN_MAX_DIM + me] = best;
+    }
+}
+
+// PRE: the matrix and the first-round minima were left in global memory by finisher_prepare (latency mode).
+template <int WORDS, bool PRE>
+__device__ __forceinline__ void finisher_body(const Chunk &c, int p, unsigned char *fin_smem) {
+    const int tid = threadIdx.x, nt = FIN_THREADS;
+    const PairDesc pd = c.pairs[p];
+    const int4 si_raw = __ldcg(reinterpret_cast<const int4 *>(c.small + p));
+    const SmallInfo si{si_raw.x, si_raw.y, si_raw.z, si_raw.w};
+    const int nr = si.nlr, nc = si.nlc, cur = si.parity;
+    const int S = finisher_pitch(nc);
+
+    int32_t *rowid = reinterpret_cast<int32_t *>(fin_smem);
+    int32_t *colid = rowid + FIN_MAX_DIM;
+    int32_t *tmp = colid + FIN_MAX_DIM;                                   // 2 * FIN_MAX_DIM
+    uint32_t *rkoff = reinterpret_cast<uint32_t *>(tmp + 2 * FIN_MAX_DIM);
+    uint32_t *ckoff = rkoff + FIN_MAX_DIM;
+    uint32_t *rbest = ckoff + FIN_MAX_DIM;
+    uint32_t *cbest = rbest + FIN_MAX_DIM;
+    uint16_t *D = reinterpret_cast<uint16_t *>(cbest + FIN_MAX_DIM);
+
+    if (!PRE) finisher_sorted_ids(c, pd, nr, nc, cur, rowid, colid, tmp);
+    for (int k = tid; k < nr + nc; k += nt) {
+        const bool is_row = k < nr;
+        const int me = is_row ? k : k - nr;
+        uint32_t first = KEY_NONE;
+        if (PRE) {
+            const int32_t *gi = c.fin_ids + (size_t)p * 2 * FIN_MAX_DIM;
+            (is_row ? rowid : colid)[me] = __ldcg(gi + (is_row ? me : FIN_MAX_DIM + me));
+            const uint32_t *part = (is_row ? c.fin_rb : c.fin_cb) + (size_t)p * FIN_PARTS * FIN_MAX_DIM + me;
+            const int segs = ((is_row ? nc : nr) + FIN_SEG - 1) / FIN_SEG;
+            for (int sg = 0; sg < segs; sg++) first = min(first, __ldcg(part + sg * FIN_MAX_DIM));
+        }
+        if (is_row) { rkoff[me] = (uint32_t)me; rbest[me] = first; }
+        else { ckoff[me] = (uint32_t)me; cbest[me] = first; }
+    }
+    if (PRE) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(c.fin_d + (size_t)p * FIN_D_STRIDE);
+        uint4 *dst = reinterpret_cast<uint4 *>(D);
+        for (int k = tid; k < (nr * S * 2 + 15) / 16; k += nt) dst[k] = __ldcg(src + k);
     }
     __syncthreads();
     tstamp(c, blockIdx.x, tid, 10);
 
+  if (!PRE) {
     // stage both descriptor sets in shared memory (coalesced 128-bit loads), then every thread
     // computes its share of the nr x nc matrix from smem
     constexpr int V4 = WORDS / 4;
@@ -725,6 +831,7 @@ __device__ __forceinline__ void finisher_body(const Chunk &c, int p, unsigned ch
         D[x * S + y] = (uint16_t)hamming_words<WORDS>(q, t);
     }
     __syncthreads();
+  }
     tstamp(c, blockIdx.x, tid, 12);
 
     int live_r = nr, live_c = nc;
@@ -791,14 +898,14 @@ __global__ void __launch_bounds__(FIN_THREADS) finisher_kernel(Chunk c) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     const int p = blockIdx.x;
     if (c.status[p] != PAIR_SMALL) return;
-    finisher_body<WORDS>(c, p, dyn_smem);
+    finisher_body<WORDS, false>(c, p, dyn_smem);
 }
 
-inline size_t finisher_smem_bytes(int words) {
+inline size_t finisher_smem_bytes(int words, int max_evals = FIN_MAX_EVALS) {
     // ids/keys: 8 arrays of FIN_MAX_DIM words; D: worst case rows * (pitch <= nc + 3);
-    // staged descriptors: nr + nc <= FIN_MAX_DIM + FIN_MAX_EVALS / FIN_MAX_DIM rows
-    return (size_t)8 * FIN_MAX_DIM * 4 + ((size_t)FIN_MAX_EVALS + 3 * FIN_MAX_DIM) * 2 + 64 +
-           (size_t)(FIN_MAX_DIM + FIN_MAX_EVALS / FIN_MAX_DIM + 2) * words * 4;
+    // staged descriptors: nr + nc <= FIN_MAX_DIM + max_evals / FIN_MAX_DIM rows
+    return (size_t)8 * FIN_MAX_DIM * 4 + ((size_t)max_evals + 3 * FIN_MAX_DIM) * 2 + 64 +
+           (size_t)(FIN_MAX_DIM + max_evals / FIN_MAX_DIM + 2) * words * 4;
 }
 
 // ---------------------------------------------------------------------------
@@ -932,7 +1039,7 @@ __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned nblocks
 template <int WORDS>
 inline size_t tail_smem_bytes(int nbins) {
     const size_t round_bytes = 4 * ((size_t)STAGE_LARGE * (WORDS / 4) * 16 + (size_t)STAGE_LARGE * 8);
-    return std::max(round_bytes, std::max(finisher_smem_bytes(WORDS), order_smem_bytes(nbins, TAIL_THREADS)));
+    return std::max(round_bytes, std::max(finisher_smem_bytes(WORDS, FIN_MAX_EVALS_TAIL), order_smem_bytes(nbins, TAIL_THREADS)));
 }
 
 template <int WORDS>
@@ -971,9 +1078,21 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_kernel(Chunk c, int r_st
         grid_barrier(bar_counter, gridDim.x, epoch);
         stamp(c, slot);
     }
+    // every small pair's distance matrix and first-round minima, computed by all CTAs (finisher_prepare)
+    bool any_small = false;
+    for (int p = 0; p < c.n_pairs; p++)
+        if (__ldcg(c.status + p) == PAIR_SMALL) {
+            finisher_prepare<WORDS>(c, p, dyn_smem);
+            any_small = true;
+            __syncthreads();
+        }
+    if (any_small) {                                  // uniform: every CTA reads the same statuses
+        __threadfence();
+        grid_barrier(bar_counter, gridDim.x, epoch);
+    }
     for (int p = blockIdx.x; p < c.n_pairs; p += gridDim.x) {
         stamp(c, slot);
-        if (__ldcg(c.status + p) == PAIR_SMALL) finisher_body<WORDS>(c, p, dyn_smem);
+        if (__ldcg(c.status + p) == PAIR_SMALL) finisher_body<WORDS, true>(c, p, dyn_smem);
         __threadfence();
         __syncthreads();
         stamp(c, slot);

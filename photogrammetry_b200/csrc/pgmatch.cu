@@ -387,6 +387,12 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
     const size_t o_st = take(n_pairs);
     const size_t o_small = take(sizeof(SmallInfo) * n_pairs);
     const size_t o_plan = take(sizeof(PlanInfo));
+    const bool latency_mode = n_pairs <= LATENCY_MODE_MAX_PAIRS && !h->force_multilaunch;
+    // latency mode: global scratch for the finisher's matrices / first-round minima (finisher_prepare)
+    const size_t o_find = latency_mode ? take((size_t)n_pairs * FIN_D_STRIDE * 2) : 0;
+    const size_t o_finr = latency_mode ? take((size_t)n_pairs * FIN_PARTS * FIN_MAX_DIM * 4) : 0;
+    const size_t o_finc = latency_mode ? take((size_t)n_pairs * FIN_PARTS * FIN_MAX_DIM * 4) : 0;
+    const size_t o_fini = latency_mode ? take((size_t)n_pairs * 2 * FIN_MAX_DIM * 4) : 0;
     int rc = ensure_dev(h, h->state, off);
     if (rc) return rc;
     rc = ensure_host(h, h->pin_meta, sizeof(PairDesc) * n_pairs + 512);
@@ -401,7 +407,14 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
     c.pairs = (PairDesc *)(base + o_pairs);
     c.n_pairs = n_pairs;
     c.num_sms = h->num_sms;
-    c.ctas_per_sm = (n_pairs <= LATENCY_MODE_MAX_PAIRS && !h->force_multilaunch) ? TAIL_THREADS / ROUND_THREADS : ctas_per_sm;
+    c.ctas_per_sm = latency_mode ? TAIL_THREADS / ROUND_THREADS : ctas_per_sm;
+    c.fin_max_evals = latency_mode ? FIN_MAX_EVALS_TAIL : FIN_MAX_EVALS;
+    if (latency_mode) {
+        c.fin_d = (uint16_t *)(base + o_find);
+        c.fin_rb = (uint32_t *)(base + o_finr);
+        c.fin_cb = (uint32_t *)(base + o_finc);
+        c.fin_ids = (int32_t *)(base + o_fini);
+    }
     c.rowbest[0] = (uint32_t *)(base + o_rb0); c.rowbest[1] = (uint32_t *)(base + o_rb1);
     c.colbest[0] = (uint32_t *)(base + o_cb0); c.colbest[1] = (uint32_t *)(base + o_cb1);
     c.live_rows[0] = (int32_t *)(base + o_lr0); c.live_rows[1] = (int32_t *)(base + o_lr1);
@@ -438,7 +451,6 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
     h->stats.pairs += n_pairs;
     // live sets only shrink, so the initial block count bounds every later accept launch
     const int accept_grid = (int)std::max<int64_t>(1, std::min<int64_t>(ablocks, (int64_t)h->num_sms * 8));
-    const bool latency_mode = n_pairs <= LATENCY_MODE_MAX_PAIRS && !h->force_multilaunch;
     CU_CHECK(h, cudaMemsetAsync(c.plan, 0, sizeof(PlanInfo), s));
     dim3 igrid(std::max(1, std::min((max_n + ACCEPT_THREADS - 1) / ACCEPT_THREADS, 64)), n_pairs);
     if (latency_mode) {
@@ -459,7 +471,7 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
         bool any_big = false;
         for (int p = 0; p < n_pairs; p++) {
             const int64_t a = pairs[p].n1, b = pairs[p].n2;
-            if (a > 0 && b > 0 && !(a <= FIN_MAX_DIM && b <= FIN_MAX_DIM && a * b <= FIN_MAX_EVALS)) any_big = true;
+            if (a > 0 && b > 0 && !(a <= FIN_MAX_DIM && b <= FIN_MAX_DIM && a * b <= FIN_MAX_EVALS_TAIL)) any_big = true;
         }
         int r_start = 0;
         h->prof_rounds = 0;
@@ -1614,6 +1626,7 @@ extern "C" int pgm_shard_create(pgm_handle *h, const uint8_t *d_q, int32_t n1, c
     Chunk &c = sh->c;
     c.pairs = (PairDesc *)(base + o_pairs); c.n_pairs = 1; c.num_sms = h->num_sms;
     c.ctas_per_sm = h->ctas_per_sm[sh->words / 4];
+    c.fin_max_evals = FIN_MAX_EVALS;
     c.rowbest[0] = (uint32_t *)(base + o_rb0); c.rowbest[1] = (uint32_t *)(base + o_rb1);
     c.colbest[0] = (uint32_t *)(base + o_cb0); c.colbest[1] = (uint32_t *)(base + o_cb1);
     c.live_rows[0] = (int32_t *)(base + o_lr0); c.live_rows[1] = (int32_t *)(base + o_lr1);
