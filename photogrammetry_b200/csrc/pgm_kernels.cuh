@@ -49,6 +49,7 @@ constexpr int FIN_MAX_EVALS = 49152;  // ... and nlr * nlc <= this (u16 distance
 // ALL CTAs into global memory, so the single-CTA finisher can afford to start earlier (one grid round less).
 constexpr int FIN_MAX_EVALS_TAIL = 65536;
 constexpr int FIN_D_STRIDE = FIN_MAX_EVALS_TAIL + 4 * FIN_MAX_DIM;   // u16 cells per pair incl. row-pitch padding
+constexpr uint32_t TAIL_FLAG_ACCEPT_FIRST = 0x80000000u;            // tail_kernel flags bit: run accept(r_start - 1) first
 constexpr int FIN_SEG = 128;                                        // entries of a row / column one warp handles
 constexpr int FIN_PARTS = FIN_MAX_DIM / FIN_SEG;                    // partial minima per row / column
 constexpr int ORDER_THREADS_STANDALONE = 1024;
@@ -1058,6 +1059,12 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_kernel(Chunk c, int r_st
     int slot = 0;
     stamp(c, slot);
 
+    if (flags & TAIL_FLAG_ACCEPT_FIRST) {
+        // the accept phase of the standalone round r_start - 1 (one launch and its drain less than accept_kernel)
+        accept_blocks(c, r_start - 1, (tid >> 8) * gridDim.x + blockIdx.x, gridDim.x * 2, tid & (ACCEPT_THREADS - 1));
+        plan_in_last_block(c, r_start, gridDim.x);
+        grid_barrier(bar_counter, gridDim.x, epoch);
+    }
     for (int r = r_start;; r++) {
         // plan(r) was published before the previous barrier (or by the preceding accept kernel)
         if (__ldcg(&c.plan->n_big) == 0) break;

@@ -483,12 +483,12 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
             }
             dispatch_round(words, c, 0, round_grid, s);
             if (prof) CU_CHECK(h, cudaEventRecord(h->prof_events[1], s));
-            accept_kernel<<<accept_grid, ACCEPT_THREADS, 0, s>>>(c, 0);
             if (prof) h->prof_rounds = 1;
-            h->stats.kernel_launches += 2;
-            r_start = 1;
+            h->stats.kernel_launches += 1;
+            r_start = 1;                  // the tail kernel begins with round 0's accept phase
         }
-        CU_CHECK(h, dispatch_tail(h, words, c, r_start, nbins, flags, d_out_qi, d_out_tj, d_out_dist, s));
+        CU_CHECK(h, dispatch_tail(h, words, c, r_start, nbins, flags | (any_big ? TAIL_FLAG_ACCEPT_FIRST : 0u), d_out_qi,
+                                  d_out_tj, d_out_dist, s));
         h->stats.kernel_launches += 1;
         CU_CHECK(h, cudaMemcpyAsync(h_plan, c.plan, sizeof(PlanInfo), cudaMemcpyDeviceToHost, s));
         h->stats_pending = true;          // resolved by pgm_get_stats / the host-buffer entry points after their sync
