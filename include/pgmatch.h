@@ -264,6 +264,17 @@ int pgm_brief_describe(pgm_handle *h, const float *gray, int32_t width, int32_t 
 int pgm_nms(pgm_handle *h, const int32_t *xy, const int32_t *score, int32_t n, int32_t radius,
             int32_t *out_kept, int32_t *out_count);
 
+/* The same chain on a DEVICE-resident image, descriptors never leaving the GPU: FAST-12
+ * (KeypointDetection.Detect) -> optionally RedundantKeypointEliminator (nms_radius >= 0; < 0 skips it) -> BRIEF
+ * of the survivors, in the reference's output order.  d_gray, d_out_xy[capacity][2], d_out_score[capacity],
+ * d_out_desc[capacity][stride_bytes] are device memory (d_out_desc is directly a matcher operand for
+ * pgm_match_hamming_greedy_dev / pgm_match_pairs_batch_dev); `pairs` (int32[n_pairs][4]) and out_count are host
+ * memory.  PGM_E_CAPACITY with *out_count = the number of keypoints when they do not fit. */
+int pgm_detect_describe_dev(pgm_handle *h, const float *d_gray, int32_t width, int32_t height, float threshold,
+                            int32_t nms_radius, const int32_t *pairs, int32_t n_pairs, int32_t stride_bytes,
+                            uint32_t flags, int32_t *d_out_xy, int32_t *d_out_score, uint8_t *d_out_desc,
+                            int32_t capacity, int32_t *out_count);
+
 /* ---- the consumer of the match list --------------------
  * pgm_ransac_score: the scoring loops of CameraPoseEstimation.GetFundamentalMatrix
  * (ImageProcessing/CameraPoseEstimation.cs:41-88).  F: n_hyp row-major 3x3 float matrices (the estimates of the

@@ -279,6 +279,16 @@ __global__ void nms_round_binned_kernel(const int32_t *__restrict__ xy, const in
     state_out[i] = ns;
 }
 
+// gathers (xy, score) of the kept keypoints, in output order
+__global__ void gather_kept_kernel(const int32_t *__restrict__ xy, const int32_t *__restrict__ sc,
+                                   const int32_t *__restrict__ kept, int n_kept, int32_t *__restrict__ oxy,
+                                   int32_t *__restrict__ osc) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_kept) return;
+    const int i = kept[k];
+    oxy[2 * k] = xy[2 * i]; oxy[2 * k + 1] = xy[2 * i + 1]; osc[k] = sc[i];
+}
+
 // kept keypoints in rank order = the reference's output order (acceptableList, :21-26)
 __global__ void nms_emit_kernel(const int32_t *__restrict__ order, const uint8_t *__restrict__ state, int n,
                                 int32_t *__restrict__ kept, int32_t *__restrict__ n_kept) {

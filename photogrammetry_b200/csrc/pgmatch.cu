@@ -1427,44 +1427,37 @@ extern "C" int pgm_brief_describe(pgm_handle *h, const float *gray, int32_t widt
     return PGM_OK;
 }
 
-extern "C" int pgm_nms(pgm_handle *h, const int32_t *xy, const int32_t *score, int32_t n, int32_t radius,
-                       int32_t *out_kept, int32_t *out_count) {
+// NMS on device-resident keypoints (d_xy int32[n][2], d_sc int32[n]); `hxy` = the same coordinates on the host
+// (bounding box for the cell grid).  Scratch comes from h->misc (and h->out2 for the radix sorts), so the inputs
+// must live elsewhere.  On return *d_kept_out points into h->misc (valid until its next use) and *count is set.
+static int nms_core(pgm_handle *h, const int32_t *d_xy, const int32_t *d_sc, const int32_t *hxy, int32_t n, int32_t radius,
+                    int32_t **d_kept_out, int32_t *count) {
     using namespace pgm_det;
-    if (!h || !out_count) return PGM_E_INVALID_ARG;
-    std::lock_guard<std::mutex> lk(h->mu);
-    if (n < 0 || radius < 0 || (n > 0 && (!xy || !score || !out_kept))) return fail(h, PGM_E_INVALID_ARG, "bad arguments");
-    h->stats = pgm_stats{};
-    h->stats_pending = false;
-    *out_count = 0;
-    if (n == 0) return PGM_OK;
-    CU_CHECK(h, cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    const size_t o_xy = take((size_t)n * 8), o_sc = take((size_t)n * 4), o_rk = take((size_t)n * 4), o_or = take((size_t)n * 4);
+    const size_t o_rk = take((size_t)n * 4), o_or = take((size_t)n * 4);
     const size_t o_s0 = take(n), o_s1 = take(n), o_kept = take((size_t)n * 4), o_cnt = take(16);
     const size_t o_k0 = take((size_t)n * 8), o_k1 = take((size_t)n * 8), o_v0 = take((size_t)n * 4), o_v1 = take((size_t)n * 4);
     int rc = ensure_dev(h, h->misc, off);
     if (rc) return rc;
-    if ((rc = ensure_host(h, h->pin_out, (size_t)n * 4 + 64))) return rc;
+    if ((rc = ensure_host(h, h->pin_meta, 64))) return rc;
     char *base = (char *)h->misc.p;
-    int32_t *d_xy = (int32_t *)(base + o_xy), *d_sc = (int32_t *)(base + o_sc), *d_rk = (int32_t *)(base + o_rk);
+    int32_t *d_rk = (int32_t *)(base + o_rk);
     int32_t *d_or = (int32_t *)(base + o_or), *d_kept = (int32_t *)(base + o_kept), *d_cnt = (int32_t *)(base + o_cnt);
     uint8_t *st[2] = {(uint8_t *)(base + o_s0), (uint8_t *)(base + o_s1)};
-    CU_CHECK(h, cudaMemcpyAsync(d_xy, xy, (size_t)n * 8, cudaMemcpyHostToDevice, s));
-    CU_CHECK(h, cudaMemcpyAsync(d_sc, score, (size_t)n * 4, cudaMemcpyHostToDevice, s));
     CU_CHECK(h, cudaMemsetAsync(st[0], 0, n, s));
     const int blocks = (n + 255) / 256;
-    int32_t *h_cnt = (int32_t *)h->pin_out.p;
+    int32_t *h_cnt = (int32_t *)h->pin_meta.p;
     const long long r2 = (long long)radius * radius;
 
     // Spatial binning pays once the all-pairs scans (n^2 per round) outweigh two radix sorts.  PGM_NMS_MODE=dense
     // or =binned forces one form (tests run both); the answers are identical.
     const int cs = std::max(radius, 1);
-    long long minx = xy[0], miny = xy[1], maxx = xy[0], maxy = xy[1];
+    long long minx = hxy[0], miny = hxy[1], maxx = hxy[0], maxy = hxy[1];
     for (int i = 1; i < n; i++) {
-        minx = std::min<long long>(minx, xy[2 * i]); maxx = std::max<long long>(maxx, xy[2 * i]);
-        miny = std::min<long long>(miny, xy[2 * i + 1]); maxy = std::max<long long>(maxy, xy[2 * i + 1]);
+        minx = std::min<long long>(minx, hxy[2 * i]); maxx = std::max<long long>(maxx, hxy[2 * i]);
+        miny = std::min<long long>(miny, hxy[2 * i + 1]); maxy = std::max<long long>(maxy, hxy[2 * i + 1]);
     }
     const long long ncx = (maxx - minx) / cs + 1, ncy = (maxy - miny) / cs + 1;   // each <= 2^32
     bool binned = n >= 1024 && (ncx >= 8 || ncy >= 8) && ncx * (double)ncy >= 64.0;  // else 3 x 3 cells hold most keypoints
@@ -1495,15 +1488,15 @@ extern "C" int pgm_nms(pgm_handle *h, const int32_t *xy, const int32_t *score, i
         CU_CHECK(h, cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, k_in, k_out, n, 0, 64, s));
         CU_CHECK(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp2, k_in, k_out, v_in, d_cidx, n, 0, 64, s));
         tmp_bytes = std::max(tmp_bytes, tmp2);
-        if ((rc = ensure_dev(h, h->out, tmp_bytes))) return rc;
+        if ((rc = ensure_dev(h, h->out2, tmp_bytes))) return rc;
         nms_score_key_kernel<<<blocks, 256, 0, s>>>(d_sc, n, k_in);
-        CU_CHECK(h, cub::DeviceRadixSort::SortKeys(h->out.p, tmp_bytes, k_in, k_out, n, 0, 64, s));
+        CU_CHECK(h, cub::DeviceRadixSort::SortKeys(h->out2.p, tmp_bytes, k_in, k_out, n, 0, 64, s));
         nms_order_from_keys_kernel<<<blocks, 256, 0, s>>>(k_out, n, d_or, d_rk);
         // cells: keypoints sorted by cell id
         nms_cell_kernel<<<blocks, 256, 0, s>>>(d_xy, n, cs, (int)minx, (int)miny, ncx, k_in, v_in);
         int cell_bits = 1;
         while (cell_bits < 64 && ((unsigned long long)ncx * (unsigned long long)ncy - 1) >> cell_bits) cell_bits++;
-        CU_CHECK(h, cub::DeviceRadixSort::SortPairs(h->out.p, tmp_bytes, k_in, k_out, v_in, d_cidx, n, 0, cell_bits, s));
+        CU_CHECK(h, cub::DeviceRadixSort::SortPairs(h->out2.p, tmp_bytes, k_in, k_out, v_in, d_cidx, n, 0, cell_bits, s));
         h->stats.kernel_launches += 3;
         for (int round = 0;; round++) {
             CU_CHECK(h, cudaMemsetAsync(d_cnt, 0, 4, s));
@@ -1520,10 +1513,113 @@ extern "C" int pgm_nms(pgm_handle *h, const int32_t *xy, const int32_t *score, i
         }
     }
     CU_CHECK(h, cudaMemcpyAsync(h_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s));
-    CU_CHECK(h, cudaMemcpyAsync(h_cnt + 16, d_kept, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
     CU_CHECK(h, cudaStreamSynchronize(s));
-    *out_count = h_cnt[0];
-    memcpy(out_kept, h_cnt + 16, (size_t)h_cnt[0] * 4);
+    *count = h_cnt[0];
+    *d_kept_out = d_kept;
+    h->stats.kernel_launches += 1; h->stats.host_syncs++;
+    CU_CHECK(h, cudaGetLastError());
+    return PGM_OK;
+}
+
+extern "C" int pgm_nms(pgm_handle *h, const int32_t *xy, const int32_t *score, int32_t n, int32_t radius,
+                       int32_t *out_kept, int32_t *out_count) {
+    if (!h || !out_count) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (n < 0 || radius < 0 || (n > 0 && (!xy || !score || !out_kept))) return fail(h, PGM_E_INVALID_ARG, "bad arguments");
+    h->stats = pgm_stats{};
+    h->stats_pending = false;
+    *out_count = 0;
+    if (n == 0) return PGM_OK;
+    CU_CHECK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    int rc = ensure_dev(h, h->desc, (size_t)n * 12);
+    if (rc) return rc;
+    int32_t *d_xy = (int32_t *)h->desc.p, *d_sc = d_xy + 2 * (size_t)n;
+    CU_CHECK(h, cudaMemcpyAsync(d_xy, xy, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    CU_CHECK(h, cudaMemcpyAsync(d_sc, score, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    int32_t *d_kept = nullptr, cnt = 0;
+    if ((rc = nms_core(h, d_xy, d_sc, xy, n, radius, &d_kept, &cnt))) return rc;
+    if ((rc = ensure_host(h, h->pin_out, (size_t)n * 4 + 64))) return rc;
+    CU_CHECK(h, cudaMemcpyAsync(h->pin_out.p, d_kept, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(h, cudaStreamSynchronize(s));
+    memcpy(out_kept, h->pin_out.p, (size_t)cnt * 4);
+    *out_count = cnt;
+    h->stats.host_syncs++;
+    return PGM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// the producer chain on a device-resident image: FAST-12 -> (NMS) -> BRIEF, descriptors never leave the GPU
+// ---------------------------------------------------------------------------
+extern "C" int pgm_detect_describe_dev(pgm_handle *h, const float *d_gray, int32_t width, int32_t height, float threshold,
+                                       int32_t nms_radius, const int32_t *pairs, int32_t n_pairs, int32_t stride_bytes,
+                                       uint32_t flags, int32_t *d_out_xy, int32_t *d_out_score, uint8_t *d_out_desc,
+                                       int32_t capacity, int32_t *out_count) {
+    using namespace pgm_det;
+    if (!h || !out_count) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    int rc = check_format(h, n_pairs, stride_bytes);       // desc_bits == NumGaussianPairs
+    if (rc) return rc;
+    if (!d_gray || width < 1 || height < 1 || width > 65535 || height > 65535 || !pairs || capacity < 0 ||
+        (capacity > 0 && (!d_out_xy || !d_out_score || !d_out_desc)))
+        return fail(h, PGM_E_INVALID_ARG, "bad arguments");
+    h->stats = pgm_stats{};
+    h->stats_pending = false;
+    *out_count = 0;
+    CU_CHECK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    // 1. FAST-12: score map, ordered compaction into (xy | score) in h->out
+    const size_t npx = (size_t)width * height;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_sc = take(npx), o_cnt = take((size_t)height * 4), o_off = take((size_t)(height + 1) * 4);
+    if ((rc = ensure_dev(h, h->misc, off))) return rc;
+    if ((rc = ensure_host(h, h->pin_meta, 64))) return rc;
+    char *base = (char *)h->misc.p;
+    uint8_t *d_sc = (uint8_t *)(base + o_sc);
+    int32_t *d_cnt = (int32_t *)(base + o_cnt), *d_off = (int32_t *)(base + o_off);
+    dim3 blk(32, 8), grd((width + 31) / 32, (height + 7) / 8);
+    if (flags & PGM_FLAG_PYTHON_GENERATION) fast_score_kernel<1><<<grd, blk, 0, s>>>(d_gray, width, height, threshold, d_sc);
+    else fast_score_kernel<0><<<grd, blk, 0, s>>>(d_gray, width, height, threshold, d_sc);
+    row_count_kernel<<<height, 128, 0, s>>>(d_sc, width, d_cnt);
+    scan_kernel<<<1, 1024, 0, s>>>(d_cnt, height, d_off);
+    CU_CHECK(h, cudaMemcpyAsync(h->pin_meta.p, d_off + height, 4, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(h, cudaStreamSynchronize(s));
+    const int32_t total = *(int32_t *)h->pin_meta.p;
+    h->stats.kernel_launches += 3; h->stats.host_syncs++;
+    *out_count = total;
+    if (total == 0) return PGM_OK;
+    if (nms_radius < 0 && total > capacity) return fail(h, PGM_E_CAPACITY, "more keypoints than capacity (out_count holds the number found)");
+    if ((rc = ensure_dev(h, h->out, (size_t)total * 12))) return rc;
+    int32_t *d_xy = (int32_t *)h->out.p, *d_s = d_xy + 2 * (size_t)total;
+    emit_kernel<<<(height + 3) / 4, 128, 0, s>>>(d_sc, width, height, d_off, total, d_xy, d_s);
+    h->stats.kernel_launches += 1;
+    // 2. NMS (optional): survivors in the reference's output order, gathered into the caller's arrays
+    int32_t n = total;
+    if (nms_radius >= 0) {
+        if ((rc = ensure_host(h, h->pin_out, (size_t)total * 8))) return rc;
+        CU_CHECK(h, cudaMemcpyAsync(h->pin_out.p, d_xy, (size_t)total * 8, cudaMemcpyDeviceToHost, s));   // bounding box
+        CU_CHECK(h, cudaStreamSynchronize(s));
+        h->stats.host_syncs++; h->stats.d2h_bytes += (int64_t)total * 8;
+        int32_t *d_kept = nullptr;
+        if ((rc = nms_core(h, d_xy, d_s, (const int32_t *)h->pin_out.p, total, nms_radius, &d_kept, &n))) return rc;
+        *out_count = n;
+        if (n > capacity) return fail(h, PGM_E_CAPACITY, "more keypoints than capacity (out_count holds the number found)");
+        gather_kept_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_xy, d_s, d_kept, n, d_out_xy, d_out_score);
+        h->stats.kernel_launches += 1;
+    } else {
+        CU_CHECK(h, cudaMemcpyAsync(d_out_xy, d_xy, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+        CU_CHECK(h, cudaMemcpyAsync(d_out_score, d_s, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    // 3. BRIEF on the survivors, straight into the matcher's row layout
+    if ((rc = ensure_dev(h, h->out2, (size_t)n_pairs * 16))) return rc;     // (h->misc still holds d_kept for the gather)
+    CU_CHECK(h, cudaMemcpyAsync(h->out2.p, pairs, (size_t)n_pairs * 16, cudaMemcpyHostToDevice, s));
+    const int warps = 4, sw = stride_bytes / 4;
+    brief_kernel<<<(n + warps - 1) / warps, warps * 32, warps * sw * 4, s>>>(d_gray, width, height, d_out_xy, n,
+                                                                         (const int32_t *)h->out2.p, n_pairs, sw,
+                                                                         (flags & PGM_FLAG_PYTHON_GENERATION) ? 1 : 0,
+                                                                         (uint32_t *)d_out_desc);
+    CU_CHECK(h, cudaStreamSynchronize(s));        // `pairs` is a pageable host buffer: do not return before it is consumed
     h->stats.kernel_launches += 1; h->stats.host_syncs++;
     CU_CHECK(h, cudaGetLastError());
     return PGM_OK;

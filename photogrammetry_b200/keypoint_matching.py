@@ -314,6 +314,34 @@ class Matcher:
                                                  n_pairs, stride, flags, _addr(out)))
         return out
 
+    def detect_describe_dev(self, d_gray, threshold: float, pairs: np.ndarray, nms_radius: int = -1,
+                            stride: Optional[int] = None, python_generation: bool = False, capacity: int = 8192):
+        """FAST-12 -> (NMS when ``nms_radius >= 0``) -> BRIEF on a device-resident image (torch float32 ``[H, W]``
+        on this matcher's GPU).  Returns torch tensors ``(xy int32[n, 2], score int32[n], desc uint8[n, stride])``
+        on the device, in the reference's output order; ``desc`` is directly a matcher operand."""
+        import torch
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 4)
+        hgt, wid = (int(x) for x in d_gray.shape)
+        n_pairs = len(pairs)
+        stride = stride or ((n_pairs + 127) // 128) * 16
+        flags = PGM_FLAG_PYTHON_GENERATION if python_generation else 0
+        d_gray = d_gray.contiguous()
+        cap = int(capacity)
+        while True:
+            xy = torch.empty((max(cap, 1), 2), dtype=torch.int32, device=d_gray.device)
+            sc = torch.empty(max(cap, 1), dtype=torch.int32, device=d_gray.device)
+            desc = torch.zeros((max(cap, 1), stride), dtype=torch.uint8, device=d_gray.device)
+            cnt = C.c_int32(0)
+            rc = self._lib.pgm_detect_describe_dev(self._h, d_gray.data_ptr(), wid, hgt, float(threshold), int(nms_radius),
+                                                   pairs.ctypes.data, n_pairs, stride, flags, xy.data_ptr(), sc.data_ptr(),
+                                                   desc.data_ptr(), cap, C.byref(cnt))
+            if rc == PGM_E_CAPACITY and cnt.value > cap:
+                cap = cnt.value
+                continue
+            self._check(rc)
+            n = cnt.value
+            return xy[:n], sc[:n], desc[:n]
+
     def nms(self, xy: np.ndarray, score: np.ndarray, radius: int) -> np.ndarray:
         """``RedundantKeypointEliminator.EliminateRedundantKeypoints`` (RedundantKeypointEliminator.cs:16-39):
         indices of the surviving keypoints in the reference's output order."""

@@ -166,3 +166,48 @@ def test_image_pair_pipeline_against_oracle_chain(matcher, star):
     idx0 = {id(p): i for i, p in enumerate(lists[0])}
     idx1 = {id(p): i for i, p in enumerate(lists[1])}
     assert [[idx0[id(p.Keypoint1)], idx1[id(p.Keypoint2)], p.Distance] for p in got] == exp.tolist()
+
+
+# ---- the same chain with the image and every intermediate on the device ---------------------------------------
+@pytest.mark.parametrize("radius", [-1, 0, 10])
+@pytest.mark.parametrize("python_generation", [False, True])
+def test_device_resident_chain_equals_host_calls(matcher, star, radius, python_generation):
+    import torch
+    gray = kd.grayscale_from_rgb8(np.repeat(star["gray0"][:, :, None], 3, axis=2))
+    pairs = D.gaussian_pairs(5, 256, 50).reshape(-1, 4)
+    xy, sc = matcher.fast_detect(gray, 0.1, python_generation)
+    if radius >= 0:
+        kept = matcher.nms(xy, sc, radius)
+        xy, sc = xy[kept], sc[kept]
+    desc = matcher.brief_describe(gray, xy, pairs, python_generation=python_generation)
+    dev = torch.device("cuda", matcher.device)
+    d_gray = torch.from_numpy(np.ascontiguousarray(gray, dtype=np.float32)).to(dev)
+    for cap in (8192, 7):                                     # the second forces the capacity regrowth path
+        gxy, gsc, gdesc = matcher.detect_describe_dev(d_gray, 0.1, pairs, radius, python_generation=python_generation,
+                                                      capacity=cap)
+        assert (gxy.cpu().numpy() == xy).all() and (gsc.cpu().numpy() == sc).all()
+        assert gdesc.shape == desc.shape and (gdesc.cpu().numpy() == desc).all()
+    assert len(xy) > 5
+
+
+def test_device_resident_chain_into_the_matcher(matcher, star):
+    # image pair -> device chain -> pgm_match_hamming_greedy_dev on the device descriptors == oracle chain
+    import torch
+    pairs = D.gaussian_pairs(9, 256, 50).reshape(-1, 4)
+    dev = torch.device("cuda", matcher.device)
+    outs, exp_desc = [], []
+    for key in ("gray0", "gray1"):
+        gray = kd.grayscale_from_rgb8(np.repeat(star[key][:, :, None], 3, axis=2))
+        d_gray = torch.from_numpy(np.ascontiguousarray(gray, dtype=np.float32)).to(dev)
+        outs.append(matcher.detect_describe_dev(d_gray, 0.1, pairs, 10))
+        exy, esc = D.detect_vectorised(gray, 0.1)
+        ek = D.eliminate_redundant(exy, esc, 10)
+        assert (outs[-1][0].cpu().numpy() == exy[ek]).all()
+        exp_desc.append(pack_descriptors(D.brief_descriptors(gray, exy[ek], pairs.reshape(-1, 2, 2)), 256))
+        assert (outs[-1][2].cpu().numpy() == exp_desc[-1]).all()
+    d1, d2 = outs[0][2].contiguous(), outs[1][2].contiguous()
+    n1, n2 = int(d1.shape[0]), int(d2.shape[0])
+    o = torch.empty((3, n1), dtype=torch.int32, device=dev)
+    matcher.match_greedy_dev(d1.data_ptr(), n1, d2.data_ptr(), n2, 256, 32, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), n1)
+    torch.cuda.synchronize()
+    assert (o.T.cpu().numpy() == orc.match_sweep(exp_desc[0], exp_desc[1])).all()

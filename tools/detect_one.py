@@ -36,6 +36,20 @@ out.update({"keypoints": int(len(xy)), "after_nms": int(len(kept)), "after_nms_2
             "mpix_per_s_fast": W * H / (t["fast_detect_ms"] * 1e-3) / 1e6,
             "matches_with_dx150": int(((xy2[kept2][tr[:, 1], 0] - xy[kept][tr[:, 0], 0] == 150) & (tr[:, 2] < 2**31 - 1)).sum()),
             "matched": int((tr[:, 2] < 2**31 - 1).sum())})
+# the same chain with the image resident on the device and no intermediate leaving it
+import torch
+d_img = torch.from_numpy(img).cuda(); d_img2 = torch.from_numpy(img2).cuda()
+for rep in range(3):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    gxy, gsc, gdesc = m.detect_describe_dev(d_img, 0.1, det._pair_table, 10, capacity=65536)
+    gxy2, gsc2, gdesc2 = m.detect_describe_dev(d_img2, 0.1, det._pair_table, 10, capacity=65536)
+    n1d, n2d = int(gdesc.shape[0]), int(gdesc2.shape[0])
+    o = torch.empty((3, n1d), dtype=torch.int32, device="cuda")
+    m.match_greedy_dev(gdesc.data_ptr(), n1d, gdesc2.data_ptr(), n2d, 256, 32, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), n1d)
+    torch.cuda.synchronize(); dev_ms = (time.perf_counter() - t0) * 1e3
+out["device_chain_two_images_plus_match_ms"] = dev_ms
+out["device_chain_equals_host_calls"] = bool((gxy.cpu().numpy() == xy[kept]).all() and (gdesc.cpu().numpy() == desc).all()
+                                             and (o.T.cpu().numpy() == tr).all())
 if check:
     from oracle import detect_np as D, orc
     exy, esc = D.detect_vectorised(img, 0.1)
