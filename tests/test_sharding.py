@@ -186,3 +186,19 @@ def test_train_sharded_knn_world2_gloo_equals_unsharded():
         for a, b in zip(knn, exp_knn):
             assert (a == b).all()
         assert (kept.T == exp_kept).all()
+
+
+@pytest.mark.parametrize("n1,n2,shards,bits", [(150, 201, 3, 16), (90, 64, 5, 8), (40, 4, 7, 256), (33, 1, 2, 256), (60, 77, 1, 12)])
+def test_train_sharded_knn_emulated_ranks_cpu(n1, n2, shards, bits):
+    """The host logic of TrainShardedKnn (slicing, key packing, padded column gather, merge) with every rank
+    emulated in one process; slices smaller than the shard count and empty slices included."""
+    import torch
+    q = orc.gen_uniform(11, n1, bits)
+    t = orc.gen_uniform(12, n2, bits)
+    for ratio, cc, md in [(0.8, True, -1), (0.0, True, 3), (0.95, False, -1)]:
+        knn, kept = sharding.knn_train_sharded_emulated(_OracleKnnMatcher(), torch.from_numpy(q), torch.from_numpy(t), shards,
+                                                        bits, ratio, cc, md)
+        for a, b in zip(knn, orc.knn2(q, t)):
+            assert (a.numpy() == b).all()
+        exp = orc.match_ratio_crosscheck(q, t, ratio, cc, md)
+        assert kept.numpy().T.shape == exp.shape and (kept.numpy().T == exp).all()
