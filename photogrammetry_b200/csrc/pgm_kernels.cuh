@@ -704,8 +704,10 @@ __device__ __forceinline__ int finisher_pitch(int nc) {
 // the live x live matrix computes its distances straight from global memory, writes the row's cells and the
 // row's (column's) first-round minimum to global memory.  A single SM would need ~8 us for a 145 x 145 matrix and
 // ~6 us for the first round of scans; spread over the machine both cost one grid barrier.
+// The CTAs working on pair p are numbered sub_rank = 0 .. sub_count - 1 (the tail kernel splits its grid among
+// the small pairs).
 template <int WORDS>
-__device__ __forceinline__ void finisher_prepare(const Chunk &c, int p, unsigned char *fin_smem) {
+__device__ __forceinline__ void finisher_prepare(const Chunk &c, int p, unsigned char *fin_smem, int sub_rank, int sub_count) {
     const int tid = threadIdx.x, lane = tid & 31, nw = FIN_THREADS >> 5;
     const PairDesc pd = c.pairs[p];
     const int4 si_raw = __ldcg(reinterpret_cast<const int4 *>(c.small + p));
@@ -717,7 +719,7 @@ __device__ __forceinline__ void finisher_prepare(const Chunk &c, int p, unsigned
     finisher_sorted_ids(c, pd, nr, nc, cur, rowid, colid, tmp);
     uint16_t *Dg = c.fin_d + (size_t)p * FIN_D_STRIDE;
     uint32_t *rb = c.fin_rb + (size_t)p * FIN_PARTS * FIN_MAX_DIM, *cb = c.fin_cb + (size_t)p * FIN_PARTS * FIN_MAX_DIM;
-    if (blockIdx.x == 0) {                                               // the finisher CTA does not sort again
+    if (sub_rank == 0) {                                                 // the finisher CTA does not sort again
         int32_t *gi = c.fin_ids + (size_t)p * 2 * FIN_MAX_DIM;
         for (int k = tid; k < nr + nc; k += FIN_THREADS) gi[k < nr ? k : FIN_MAX_DIM + (k - nr)] = k < nr ? rowid[k] : colid[k - nr];
     }
@@ -726,7 +728,7 @@ __device__ __forceinline__ void finisher_prepare(const Chunk &c, int p, unsigned
     // descriptor gathers are all in flight together; one item per warp at the sizes the finisher takes
     const int segs_r = (nc + FIN_SEG - 1) / FIN_SEG, segs_c = (nr + FIN_SEG - 1) / FIN_SEG;
     const int n_items = nr * segs_r + nc * segs_c;
-    const int gw = (int)blockIdx.x * nw + (tid >> 5), GW = (int)gridDim.x * nw;
+    const int gw = sub_rank * nw + (tid >> 5), GW = sub_count * nw;
     for (int item = gw; item < n_items; item += GW) {
         const bool is_row = item < nr * segs_r;
         const int it = is_row ? item : item - nr * segs_r, segs = is_row ? segs_r : segs_c;
@@ -1086,14 +1088,16 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_kernel(Chunk c, int r_st
         stamp(c, slot);
     }
     // every small pair's distance matrix and first-round minima, computed by all CTAs (finisher_prepare)
-    bool any_small = false;
+    // (the grid is split among the small pairs: CTA b works on the (b mod n_small)-th of them)
+    int n_small = 0, my_pair = -1;
     for (int p = 0; p < c.n_pairs; p++)
-        if (__ldcg(c.status + p) == PAIR_SMALL) {
-            finisher_prepare<WORDS>(c, p, dyn_smem);
-            any_small = true;
-            __syncthreads();
-        }
-    if (any_small) {                                  // uniform: every CTA reads the same statuses
+        if (__ldcg(c.status + p) == PAIR_SMALL) n_small++;
+    if (n_small) {                                    // uniform: every CTA reads the same statuses
+        const int mine = (int)blockIdx.x % n_small;
+        for (int p = 0, k = 0; p < c.n_pairs; p++)
+            if (__ldcg(c.status + p) == PAIR_SMALL && k++ == mine) my_pair = p;
+        finisher_prepare<WORDS>(c, my_pair, dyn_smem, (int)blockIdx.x / n_small,
+                                ((int)gridDim.x - mine + n_small - 1) / n_small);
         __threadfence();
         grid_barrier(bar_counter, gridDim.x, epoch);
     }
