@@ -280,7 +280,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         except Exception:
             traffic = None
     roofline = {
-        "bound": "int-pipe (POPC.32 issue rate; neither HBM nor tensor bounds this path)",
+        "bound": "int-pipe",
+        "bound_note": "POPC.32 issue rate (SURVEY 8d); neither HBM nor the tensor pipe bounds this path",
         "kernel": "hamming_round_kernel<8> (round 0: all N1 x N2 distances + row/column argmin)",
         "achieved": achieved / 1e9, "peak": popc_peak / 1e9, "unit": "Gpopc32/s", "frac": achieved / popc_peak,
         "peak_source": "measured live: register-only POPC micro-benchmark on this GPU (pgm_measure_popc_peak); "
