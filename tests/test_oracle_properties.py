@@ -81,3 +81,22 @@ def test_l2_knn2_small():
     o = np.argsort(d, axis=1, kind="stable")
     assert (bj == o[:, 0]).all() and (sj == o[:, 1]).all()
     np.testing.assert_allclose(bd, d[np.arange(20), bj], rtol=1e-6)
+
+
+@pytest.mark.parametrize("K", [1, 2, 4])
+def test_topk_subround_formulation_equals_reference(K):
+    """The design study behind DESIGN.md section 9 (tools/sim_topk_rounds.py): resolving mutual pairs on per-row /
+    per-column top-K lists between distance passes yields exactly the reference's greedy assignment."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "sim_topk_rounds", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "sim_topk_rounds.py"))
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    for seed, n1, n2, bits in [(1, 300, 300, 256), (2, 200, 350, 256), (3, 260, 120, 16), (4, 150, 150, 8)]:
+        q = orc.gen_uniform(seed, n1, bits)
+        t = orc.gen_uniform(seed + 100, n2, bits)
+        got, passes = sim.match_topk_rounds(q, t, K)
+        exp = orc.match_sweep(q, t)[:min(n1, n2)]
+        assert got.shape == exp.shape and (got == exp).all(), (seed, K)
+        assert len(passes) >= 1
