@@ -109,6 +109,7 @@ struct Chunk {
     uint16_t *fin_d;              // latency mode: [n_pairs][FIN_D_STRIDE] distance matrices written by finisher_prepare
     uint32_t *fin_rb, *fin_cb;    // latency mode: [n_pairs][FIN_PARTS][FIN_MAX_DIM] first-round row / column minima (partial)
     int32_t *fin_ids;             // latency mode: [n_pairs][2][FIN_MAX_DIM] rank-sorted row / column ids
+    long long large_min_evals;    // a round with at least this many live cells uses the large (RQ = 4) tiles
 };
 
 __device__ __forceinline__ int32_t *cnt_ptr(const Chunk &c, int buf3, int p) {
@@ -180,9 +181,8 @@ __device__ __forceinline__ void plan_warp(const Chunk &c, int r) {
     }
     // tile shape: identical arithmetic to plan_device (every lane computes it)
     const unsigned slots = (unsigned)(c.num_sms * c.ctas_per_sm);
-    const unsigned long long large_tile = (unsigned long long)ROUND_THREADS * RQ_LARGE * STAGE_LARGE;
     int rq, stage;
-    if (ev >= 2ull * c.num_sms * large_tile) { rq = RQ_LARGE; stage = STAGE_LARGE; }
+    if (ev >= (unsigned long long)c.large_min_evals) { rq = RQ_LARGE; stage = STAGE_LARGE; }
     else { rq = RQ_SMALL; stage = STAGE_SMALL; }
     const int tile_rows = ROUND_THREADS * rq;
     float per_tile = (float)ev / (2.0f * (float)slots);
@@ -270,9 +270,8 @@ __device__ void plan_device(const Chunk &c, int r) {
         for (int w = 0; w < NW; w++) { e += s_evals[w]; b += s_w[0][w]; s += s_w[1][w]; }
         // tile shape: large tiles while they still cover the machine ~2x over, else small ones
         const unsigned slots = (unsigned)(c.num_sms * c.ctas_per_sm);
-        const unsigned long long large_tile = (unsigned long long)ROUND_THREADS * RQ_LARGE * STAGE_LARGE;
         int rq, stage;
-        if (e >= 2ull * c.num_sms * large_tile) { rq = RQ_LARGE; stage = STAGE_LARGE; }
+        if (e >= (unsigned long long)c.large_min_evals) { rq = RQ_LARGE; stage = STAGE_LARGE; }
         else { rq = RQ_SMALL; stage = STAGE_SMALL; }
         const int tile_rows = ROUND_THREADS * rq;
         // heuristic sizing in fp32 (64-bit integer division is ~100 instructions on the GPU)

@@ -364,6 +364,13 @@ struct HostPair {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Rounds with at least this many live cells use the large (512-row, RQ = 4) tiles: two such tiles per SM.
+// PGM_LARGE_TILE_MIN_EVALS overrides it (tuning experiments).
+static long long large_tile_min_evals(const pgm_handle *h) {
+    if (const char *e = getenv("PGM_LARGE_TILE_MIN_EVALS")) return atoll(e);
+    return 2ll * h->num_sms * ROUND_THREADS * RQ_LARGE * STAGE_LARGE;
+}
+
 static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc_bits, int stride_bytes,
                      uint32_t flags, int32_t *d_out_qi, int32_t *d_out_tj, int32_t *d_out_dist) {
     const int words = stride_bytes / 4;
@@ -409,6 +416,7 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
     c.num_sms = h->num_sms;
     c.ctas_per_sm = latency_mode ? TAIL_THREADS / ROUND_THREADS : ctas_per_sm;
     c.fin_max_evals = latency_mode ? FIN_MAX_EVALS_TAIL : FIN_MAX_EVALS;
+    c.large_min_evals = large_tile_min_evals(h);
     if (latency_mode) {
         c.fin_d = (uint16_t *)(base + o_find);
         c.fin_rb = (uint32_t *)(base + o_finr);
@@ -1723,6 +1731,7 @@ extern "C" int pgm_shard_create(pgm_handle *h, const uint8_t *d_q, int32_t n1, c
     c.pairs = (PairDesc *)(base + o_pairs); c.n_pairs = 1; c.num_sms = h->num_sms;
     c.ctas_per_sm = h->ctas_per_sm[sh->words / 4];
     c.fin_max_evals = FIN_MAX_EVALS;
+    c.large_min_evals = large_tile_min_evals(h);
     c.rowbest[0] = (uint32_t *)(base + o_rb0); c.rowbest[1] = (uint32_t *)(base + o_rb1);
     c.colbest[0] = (uint32_t *)(base + o_cb0); c.colbest[1] = (uint32_t *)(base + o_cb1);
     c.live_rows[0] = (int32_t *)(base + o_lr0); c.live_rows[1] = (int32_t *)(base + o_lr1);
