@@ -495,7 +495,7 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
             h->stats.kernel_launches += 1;
             r_start = 1;                  // the tail kernel begins with round 0's accept phase
         }
-        CU_CHECK(h, dispatch_tail(h, words, c, r_start, nbins, flags | (any_big ? TAIL_FLAG_ACCEPT_FIRST : 0u), d_out_qi,
+        CU_CHECK(h, dispatch_tail(h, words, c, r_start, nbins, (flags & ~TAIL_FLAG_ACCEPT_FIRST) | (any_big ? TAIL_FLAG_ACCEPT_FIRST : 0u), d_out_qi,
                                   d_out_tj, d_out_dist, s));
         h->stats.kernel_launches += 1;
         CU_CHECK(h, cudaMemcpyAsync(h_plan, c.plan, sizeof(PlanInfo), cudaMemcpyDeviceToHost, s));
