@@ -42,6 +42,19 @@ def test_python_generation_detect_then_match_golden(matcher, star):
     assert (rows[:, 0, 1] == star["twin_nearest_dist"]).all()
 
 
+@pytest.mark.parametrize("k", [0, 1])
+def test_python_generation_golden_natural_image(matcher, k):
+    # the second golden: the reference's own detector + BRIEF on a crop of its lego photographs (2101 / 2141 keypoints)
+    g = np.load(os.path.join(GOLDEN, "lego_crop_detect.npz"))
+    det = kd.FASTKeypointDetector(int(g["threshold"]), g[f"gray{k}"].astype(np.int16), gaussian_pairs=g["pairs"], matcher=matcher)
+    uv, desc = det.detect_arrays()
+    assert uv.shape == g[f"uv{k}"].shape and (uv == g[f"uv{k}"]).all()
+    assert (desc == g[f"desc{k}"]).all()
+    if k == 0:
+        rows = matcher.match_keypoints_sorted(g["desc0"], g["desc1"], 256)
+        assert (rows[:, :, 1] == g["twin_sorted_dists"]).all()
+
+
 # ---- C# generation vs the oracle -----------------------------------------------------------------
 def _images(star):
     rng = np.random.default_rng(2024)

@@ -47,6 +47,32 @@ def test_python_generation_detector_matches_reference_output(star, k):
     assert (pack_descriptors(ints, 256) == star[f"desc{k}"]).all()
 
 
+@pytest.fixture(scope="module")
+def lego_crop():
+    return np.load(os.path.join(GOLDEN, "lego_crop_detect.npz"))
+
+
+@pytest.mark.parametrize("k", [0, 1])
+def test_python_generation_detector_matches_reference_output_on_a_natural_image(lego_crop, k):
+    # tests/golden/make_golden_detect_lego.py: the reference's own detector and BRIEF on a 720 x 960 crop of the
+    # lego photographs it ships (2101 / 2141 keypoints at threshold 25)
+    g = lego_crop
+    gray = g[f"gray{k}"].astype(np.float32)
+    xy, _ = D.detect_vectorised(gray, float(g["threshold"]), python_generation=True)
+    assert len(xy) == len(g[f"uv{k}"]) and (xy[:, ::-1] == g[f"uv{k}"]).all()
+    pairs = D.py_pairs_to_xy(g["pairs"])
+    ints = D.brief_descriptors(gray, xy, pairs, lsb_first=True)
+    assert (pack_descriptors(ints, 256) == g[f"desc{k}"]).all()
+
+
+def test_python_twin_distances_match_reference_output_on_a_natural_image(lego_crop):
+    # match_keypoints of the reference (keypoint_matching.py:7-33) on those descriptors: every row's sorted distances
+    from oracle import orc
+    rows = orc.python_twin(lego_crop["desc0"], lego_crop["desc1"])
+    assert (rows[:, :, 1] == lego_crop["twin_sorted_dists"]).all()
+    assert (rows[:, 0, 1] == lego_crop["twin_nearest_dist"]).all()
+
+
 def test_python_pixel_test_equals_the_shared_segment_test(star):
     gray = star["gray0"].astype(np.float32)
     rng = np.random.default_rng(3)
