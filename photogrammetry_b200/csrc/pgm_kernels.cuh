@@ -12,7 +12,15 @@
 //                  keys, so an integer min IS the reference tie-break
 //                  (KeypointMatching.cs:44-54: ascending i, ascending j, strict <)
 //   accept kernel  rows/columns that chose each other are matched and retired,
-//                  survivors are compacted; the last block plans the next round
+//                  survivors are compacted
+//   candidate edges  every distance pass also keeps EVERY edge with distance <= T (T from a
+//                  Gaussian fit of sampled distances, so a row sees a handful).  That edge set is
+//                  complete up to T on both sides, hence the greedy matching restricted to it is a
+//                  prefix of the reference's matching: one CTA per pair runs mutual-best
+//                  "sub-rounds" on the sparse list out of shared memory (no distance is
+//                  recomputed), then re-compacts the survivors and plans the next pass.  Uniform
+//                  8192 x 8192: live rows per distance pass 8192 -> 1236 -> 172 instead of
+//                  8192 -> 4155 -> 2352 -> 1362 -> 782 -> 454 -> 255 (tools/sim_threshold_rounds.py)
 //   finisher       once a pair is small, one CTA runs all remaining rounds out
 //                  of a distance matrix held in shared memory
 //   order kernel   stable counting sort of the matches by distance -> the
@@ -55,6 +63,20 @@ constexpr int FIN_PARTS = FIN_MAX_DIM / FIN_SEG;                    // partial m
 constexpr int ORDER_THREADS_STANDALONE = 1024;
 constexpr int TAIL_THREADS = 512;     // persistent tail kernel: 1 CTA per SM, four 128-thread groups
 constexpr int ORDER_KEY_CACHE = 16384;  // match keys cached in smem by the order kernel
+static_assert(TAIL_THREADS == 512, "the sparse phase and the ordering slices assume 512-thread CTAs");
+// candidate edges / sparse sub-rounds
+constexpr int SCAND = 256;              // candidate edges a tile stages in shared memory before one global append
+constexpr int SP_THREADS = 512;         // threads of the CTA that runs a pair's sparse sub-rounds
+constexpr int SP_EPT = 32;              // live edges a thread of the sparse phase holds (two registers + one private smem word each)
+constexpr int SP_EPC = 4;               // ... and in the compact form, once at most SP_EPC x threads edges are left
+constexpr int SP_B = 4;                 // edges are processed in batches of SP_B: loads of a batch first, then its stores
+constexpr int SP_IPT = 8;               // ids a thread re-compacts at a time
+constexpr int SP_SMEM_BYTES = 184 * 1024;   // shared memory of a sparse phase: the edges' column-side keys (SP_EPT x threads words)
+                                            // and one min slot per live row and live column
+constexpr int SP_LCAP_MAX = SP_THREADS * SP_EPT;   // live edges per pair the global list is sized for
+constexpr int SP_MAX_SUB = 64;          // sub-rounds per sparse phase (each accepts >= 1 pair; the rest waits for the next pass)
+constexpr float CAND_TARGET = 4.0f;     // expected candidate edges per row of the smaller side
+constexpr uint32_t KEY_DEAD = 0xFFFFFFFEu;  // sparse phase: row / column matched in an earlier sub-round
 
 enum PairStatus : uint8_t { PAIR_DONE = 0, PAIR_BIG = 1, PAIR_SMALL = 2 };
 
@@ -67,8 +89,18 @@ struct PairDesc {
     int64_t out_base;    // where this pair's triples start in the output arrays
     int32_t col_id_offset;   // added to train indices inside keys (train-sharded mode: global column ids)
     int32_t flags;           // PAIR_FLAG_*
+    int64_t cand_off;        // this pair's region of Chunk::cand (raw candidate edges of the current pass)
+    int64_t ledge_off;       // this pair's region of Chunk::ledge (candidate edges whose endpoints survived the accept)
+    int32_t cand_cap, ledge_cap;
 };
 constexpr int PAIR_FLAG_NO_FINISHER = 1;   // never hand this pair to the single-CTA finisher
+constexpr int PAIR_FLAG_NO_EMIT = 2;       // no candidate edges for this pair (train-sharded mode: keys carry global ids)
+
+struct PairStat {            // per pair, written by the init kernel
+    float mu, sd;            // mean / standard deviation of a sample of this pair's distances
+    float cscale;            // multiplies CAND_TARGET; quartered whenever a pass overflowed the candidate list
+    int32_t pad;
+};
 
 struct SmallInfo {       // written when the planner hands a pair to the finisher
     int32_t nlr, nlc, parity, pad;
@@ -93,6 +125,7 @@ struct Chunk {
     int32_t n_pairs;
     int32_t num_sms;
     int32_t ctas_per_sm;          // resident round-kernel CTAs per SM
+    int32_t ctas_per_sm0;         // the same for round 0 when it runs as a standalone launch before the tail kernel (0: n/a)
     int32_t fin_max_evals;        // a pair goes to the finisher once nlr * nlc <= this (FIN_MAX_EVALS or _TAIL)
     uint32_t *rowbest[2];
     uint32_t *colbest[2];
@@ -110,6 +143,18 @@ struct Chunk {
     uint32_t *fin_rb, *fin_cb;    // latency mode: [n_pairs][FIN_PARTS][FIN_MAX_DIM] first-round row / column minima (partial)
     int32_t *fin_ids;             // latency mode: [n_pairs][2][FIN_MAX_DIM] rank-sorted row / column ids
     long long large_min_evals;    // a round with at least this many live cells uses the large (RQ = 4) tiles
+    // candidate edges (nullptr: the classic one-accept-per-pass rounds only)
+    unsigned long long *cand;     // raw candidate records of the current pass, per pair region, two words each:
+                                  // (d << 40 | i << 20 | j) with d <= T, and (RQ << 20 | first live-list slot of the emitting thread)
+    unsigned long long *ledge;    // the raw edges whose row and column both survived the pass's accept
+    int32_t *cand_cnt;            // [n_pairs] raw edges appended this pass (> cand_cap: overflow, list unusable)
+    int32_t *ledge_cnt;           // [n_pairs]
+    uint32_t *thr;                // [n_pairs] emission bound of the current pass as a key: (T + 1) << 20; 0 = none
+    PairStat *pstat;              // [n_pairs]
+    int32_t *row_pos, *col_pos;   // position of a surviving row / column in the next live list (written by accept)
+    int32_t words;                // descriptor words (runtime copy of the kernels' template parameter)
+    int32_t *order_cnt;           // latency mode: [n_pairs][ORDER_MAX_SLICES][ORDER_BIN_PITCH] per-slice distance histograms
+    float cand_target;            // expected candidate edges per row of the smaller side (CAND_TARGET; PGM_CAND_TARGET overrides)
 };
 
 __device__ __forceinline__ int32_t *cnt_ptr(const Chunk &c, int buf3, int p) {
@@ -149,6 +194,69 @@ __device__ __forceinline__ int ablocks_of(int nlr, int nlc) {
     return (nlr + ACCEPT_THREADS - 1) / ACCEPT_THREADS + (nlc + ACCEPT_THREADS - 1) / ACCEPT_THREADS;
 }
 
+// z with P(N(0,1) < -z) = p (Abramowitz-Stegun 26.2.23, |error| < 4.5e-4; any value is CORRECT, it only sizes lists)
+__device__ __forceinline__ float inv_norm_tail(float p) {
+    p = fminf(fmaxf(p, 1e-12f), 0.5f);
+    const float t = sqrtf(-2.0f * __logf(p));
+    return t - (2.515517f + t * (0.802853f + t * 0.010328f)) / (1.0f + t * (1.432788f + t * (0.189269f + t * 0.001308f)));
+}
+
+// Per pair and pass: the candidate-edge bound T such that the pass emits about CAND_TARGET x max(nlr, nlc)
+// edges (distances taken as N(mu, sd) from the init kernel's sample).  Also resets the pair's edge counters and
+// reacts to an overflow of the previous pass.  Called by the planner thread that owns pair p.
+__device__ __forceinline__ void plan_pair_emit(const Chunk &c, int p, uint8_t st, int nlr, int nlc) {
+    if (!c.cand) return;
+    uint32_t thr = 0u;
+    const PairDesc &pd = c.pairs[p];
+    if (__ldcg(c.cand_cnt + p) > pd.cand_cap) c.pstat[p].cscale *= 0.25f;       // the last pass overflowed
+    if (st == PAIR_BIG && pd.cand_cap > 0 && !(pd.flags & PAIR_FLAG_NO_EMIT)) {
+        const PairStat ps = c.pstat[p];
+        // about cand_target x max(n1, n2) raw edges in EVERY pass: later passes have fewer live rows, so each row may
+        // list more candidates for the same list size (8192 x 8192: 6 per row in pass 0, ~36 per row of the 1236 left
+        // in pass 1, after which ~30 rows remain -- tools/sim_threshold_rounds.py)
+        const float target = c.cand_target * ps.cscale * (float)max(pd.n1, pd.n2) / (float)max(nlr, nlc);
+        if (target >= 0.09f) {
+            const float z = inv_norm_tail(fminf(target / (float)min(nlr, nlc), 0.25f));
+            const float T = floorf(ps.mu - z * ps.sd - 0.5f);                  // P(d <= T) ~ Phi((T + 0.5 - mu) / sd)
+            if (T >= 0.0f) thr = ((uint32_t)fminf(T, 1022.0f) + 1u) << KEY_IDX_BITS;
+        }
+    }
+    c.thr[p] = thr;
+    c.cand_cnt[p] = 0;
+    c.ledge_cnt[p] = 0;
+}
+
+// Mean and standard deviation of 1024 sampled distances of pair p (32 rows x 32 columns spread over the pair), by one
+// warp.  Only the SIZE of the candidate lists depends on them, never a result.
+__device__ __forceinline__ void sample_pair_stats(const Chunk &c, int p, const PairDesc &pd) {
+    const int lane = threadIdx.x & 31;
+    if (!c.cand) return;
+    float mu = 0.0f, sd = 1.0f;
+    if (pd.n1 > 0 && pd.n2 > 0) {
+        const int i = (int)(((long long)lane * pd.n1) >> 5);
+        uint32_t q[16];
+#pragma unroll
+        for (int w = 0; w < 16; w++) q[w] = w < c.words ? __ldg(pd.q + (size_t)i * c.words + w) : 0u;
+        uint32_t sum = 0, sum2 = 0;
+        for (int k = 0; k < 32; k++) {
+            const int j = (int)(((long long)(k * 32 + ((lane * 7 + k) & 31)) * pd.n2) >> 10);
+            const uint32_t *t = pd.t + (size_t)j * c.words;
+            uint32_t d = 0;
+#pragma unroll
+            for (int w = 0; w < 16; w++) if (w < c.words) d += __popc(q[w] ^ __ldg(t + w));
+            sum += d; sum2 += d * d;
+        }
+        for (int o = 16; o; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            sum2 += __shfl_xor_sync(0xffffffffu, sum2, o);
+        }
+        mu = (float)sum * (1.0f / 1024.0f);
+        const float var = (float)sum2 * (1.0f / 1024.0f) - mu * mu;
+        sd = sqrtf(fmaxf(var, 1.0f));
+    }
+    if (lane == 0) c.pstat[p] = PairStat{mu, sd, 1.0f, 0};
+}
+
 // The same plan for at most 32 pairs, by ONE warp with everything in registers (no shared memory, no block
 // barriers): in latency mode the planner sits on the critical path of every round between two grid barriers, and
 // the block-wide form costs ~5 us of dependent L2 round trips and barriers there.
@@ -173,6 +281,7 @@ __device__ __forceinline__ void plan_warp(const Chunk &c, int r) {
         }
         int32_t *nx = cnt_ptr(c, (r + 1) % 3, p);   // accept(r) appends here
         nx[0] = 0; nx[1] = 0;
+        plan_pair_emit(c, p, st, nlr, nlc);
     }
     for (int o = 16; o; o >>= 1) {
         ev += __shfl_xor_sync(0xffffffffu, ev, o);
@@ -180,7 +289,7 @@ __device__ __forceinline__ void plan_warp(const Chunk &c, int r) {
         nsmall += __shfl_xor_sync(0xffffffffu, nsmall, o);
     }
     // tile shape: identical arithmetic to plan_device (every lane computes it)
-    const unsigned slots = (unsigned)(c.num_sms * c.ctas_per_sm);
+    const unsigned slots = (unsigned)(c.num_sms * (r == 0 && c.ctas_per_sm0 ? c.ctas_per_sm0 : c.ctas_per_sm));
     int rq, stage;
     if (ev >= (unsigned long long)c.large_min_evals) { rq = RQ_LARGE; stage = STAGE_LARGE; }
     else { rq = RQ_SMALL; stage = STAGE_SMALL; }
@@ -194,7 +303,20 @@ __device__ __forceinline__ void plan_warp(const Chunk &c, int r) {
     if (cpt > (unsigned)MAX_N) cpt = MAX_N;
     // wave-aware refinement: a round takes ~ceil(tiles / slots) x cpt; a slightly wider tile often saves a whole,
     // mostly empty, second wave (2301 x 2301 live: 648 tiles of 64 columns on 592 slots -> 432 tiles of 96)
-    {
+    if (c.n_pairs == 1) {
+        // one pair: 32 candidate widths at once, one per lane (a tile's column extent only has to be a multiple of 8);
+        // 8192 x 8192 on 592 slots: 224 columns -> 16 x 37 = 592 tiles, exactly one wave
+        const unsigned cand = min(cpt + 8u * (unsigned)lane, (unsigned)MAX_N);
+        const int nlr0 = __shfl_sync(0xffffffffu, nlr, 0), nlc0 = __shfl_sync(0xffffffffu, nlc, 0);
+        const int big0 = __shfl_sync(0xffffffffu, (int)(st == PAIR_BIG), 0);
+        const unsigned t = big0 ? (unsigned)tiles_of(nlr0, nlc0, tile_rows, (int)cand) : 0u;
+        unsigned long long key = ((unsigned long long)(((t + slots - 1) / slots)) * (cand + 16u) << 8) | (unsigned)lane;
+        for (int o = 16; o; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other < key ? other : key;
+        }
+        cpt = min(cpt + 8u * (unsigned)(key & 0xFFu), (unsigned)MAX_N);
+    } else {
         unsigned best_cpt = cpt, best_cost = 0xFFFFFFFFu;
         for (unsigned k = 0; k < 4; k++) {
             const unsigned cand = min(cpt + k * (unsigned)stage, (unsigned)MAX_N);
@@ -237,10 +359,11 @@ __device__ void plan_device(const Chunk &c, int r) {
     unsigned long long ev = 0; int nbig = 0, nsmall = 0;
     for (int p = tid; p < c.n_pairs; p += nt) {
         uint8_t st = c.status[p];
+        int nlr = 0, nlc = 0;
         if (st == PAIR_SMALL) { nsmall++; }
         else {
             const int32_t *cp = cnt_ptr(c, buf, p);
-            const int nlr = __ldcg(cp), nlc = __ldcg(cp + 1);
+            nlr = __ldcg(cp); nlc = __ldcg(cp + 1);
             st = PAIR_DONE;
             if (nlr > 0 && nlc > 0) {
                 const bool small = nlr <= FIN_MAX_DIM && nlc <= FIN_MAX_DIM && nlr * nlc <= c.fin_max_evals &&
@@ -257,6 +380,7 @@ __device__ void plan_device(const Chunk &c, int r) {
         }
         int32_t *nx = cnt_ptr(c, (r + 1) % 3, p);   // accept(r) appends here
         nx[0] = 0; nx[1] = 0;
+        plan_pair_emit(c, p, st, nlr, nlc);
     }
     for (int o = 16; o; o >>= 1) {
         ev += __shfl_xor_sync(0xffffffffu, ev, o);
@@ -380,7 +504,9 @@ __global__ void __launch_bounds__(ACCEPT_THREADS) init_kernel(Chunk c, PairPack 
         int32_t *c1 = cnt_ptr(c, 1, p), *c2 = cnt_ptr(c, 2, p);
         c1[0] = c1[1] = 0; c2[0] = c2[1] = 0;
         c.status[p] = PAIR_BIG;                      // classified by plan(0)
+        if (c.cand) { c.cand_cnt[p] = 0; c.ledge_cnt[p] = 0; c.thr[p] = 0u; }
     }
+    if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 64) sample_pair_stats(c, p, pd);
     plan_in_last_block(c, 0, gridDim.x * gridDim.y);
 }
 
@@ -454,10 +580,27 @@ __device__ __forceinline__ void tstamp(const Chunk &c, int vb, int tid, int code
     }
 }
 
+// Slow path of the distance loop (~0.1 % of the cells): a column minimum of this thread's RQ rows lies below the
+// candidate bound.  cm = (distance << 20 | row id) of the best of the thread's rows IS a candidate edge; the
+// thread's other rows in that column might be candidates too (rarely), which the edge filter verifies later from
+// `aux` = (RQ << 20 | live-list slot of the thread's first row) -- so the hot loop recomputes nothing.
+__device__ __forceinline__ void emit_record(uint32_t cm, uint32_t jk, uint32_t aux, uint32_t &thr,
+                                            unsigned long long *s_cand, int *s_cctl) {
+    if (cm >= thr || jk == KEY_INVALID) return;
+    const int slot = atomicAdd(&s_cctl[0], 1);
+    if (slot < SCAND) {
+        s_cand[2 * slot] = ((unsigned long long)(cm >> KEY_IDX_BITS) << 40) | ((unsigned long long)(cm & KEY_IDX_MASK) << 20) | jk;
+        s_cand[2 * slot + 1] = aux;
+    } else {
+        thr = 0u;                            // staging full: the flush marks the list unusable; stop trying
+    }
+}
+
 template <int WORDS, int RQ, int STAGE>
 __device__ __forceinline__ void round_tiles(const Chunk &c, int r, int total, int cpt,
                                             int vb, int vgrid, int tid, GroupBar bar,
-                                            uint4 *s_t, uint32_t *s_jkey, uint32_t *s_col) {
+                                            uint4 *s_t, uint32_t *s_jkey, uint32_t *s_col,
+                                            unsigned long long *s_cand, int *s_cctl) {
     constexpr int V4 = WORDS / 4;
     constexpr int tile_rows = ROUND_THREADS * RQ;
     const int cur = r & 1, buf = r % 3, lane = tid & 31;
@@ -473,6 +616,29 @@ __device__ __forceinline__ void round_tiles(const Chunk &c, int r, int total, in
         const int rt = local / nct, ct = local - rt * nct;
         const int32_t *live_rows = c.live_rows[cur] + pd.row_base;
         const int32_t *live_cols = c.live_cols[cur] + pd.col_base;
+        // candidate edges: every (i, j) of this tile with distance <= T goes to the pair's list (staged in shared
+        // memory, one global append per tile).  thr = (T + 1) << 20 as a key bound; 0 = this pass emits nothing.
+        uint32_t thr = c.cand ? __ldcg(c.thr + p) : 0u;
+        if (thr && __ldcg(c.cand_cnt + p) > pd.cand_cap) thr = 0u;     // the list already overflowed: stop feeding it
+        if (c.cand && tid == 0) s_cctl[0] = 0;                         // (ordered by the stage loop's first barrier)
+        const uint32_t aux = ((uint32_t)RQ << KEY_IDX_BITS) | (uint32_t)(rt * tile_rows + tid);
+        // Append the staged records to the pair's list once at least `at_least` (+1) are waiting.  Called by every thread
+        // of the group right after a group barrier (the count is uniform); leaves the staging buffer empty.
+        auto flush_cands = [&](int at_least) {
+            const int n = s_cctl[0];
+            if (n <= at_least) return;
+            if (n > SCAND) {                 // the staging buffer overflowed: the pair's list is incomplete, mark it unusable
+                if (tid == 0) atomicMax(c.cand_cnt + p, 0x40000000);
+            } else {
+                if (tid == 0) s_cctl[1] = atomicAdd(c.cand_cnt + p, n);
+                bar.sync();
+                const int base = s_cctl[1];
+                for (int k = tid; k < 2 * n; k += ROUND_THREADS)
+                    if (base + (k >> 1) < pd.cand_cap) c.cand[2 * (pd.cand_off + base) + k] = s_cand[k];
+            }
+            bar.sync();                      // every record is out before the counter restarts
+            if (tid == 0) s_cctl[0] = 0;     // (ordered before the next records by the next stage's / tile's barriers)
+        };
 
         uint32_t q[RQ][WORDS], ikey[RQ], rowkey[RQ];
 #pragma unroll
@@ -516,12 +682,16 @@ __device__ __forceinline__ void round_tiles(const Chunk &c, int r, int total, in
             tstamp(c, vb, tid, 3);
 
             const int ncs = min(STAGE, (c1 - s0 + 7) & ~7);
+            // No store, atomic or branch sits between the columns of a block, so their shared-memory loads and
+            // popcount chains overlap (with the column atomics inline, ptxas serialised column after column behind
+            // each ATOMS).  Candidate edges are rare (~0.1 % of the cells): a block that saw one recomputes it.
             if (RQ >= 4) {
                 // large tiles: one warp-aggregated shared atomicMin per (warp, column); ptxas turns the
                 // 32 same-address lanes into CREDUX.MIN + one elected ATOMS.MIN
-                for (int jj0 = 0; jj0 < ncs; jj0 += 8) {
+                for (int jj0 = 0; jj0 < ncs; jj0 += 4) {
+                    uint32_t cm[4];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) {
+                    for (int u = 0; u < 4; u++) {
                         const int jj = jj0 + u;
                         uint32_t t[WORDS];
 #pragma unroll
@@ -537,18 +707,24 @@ __device__ __forceinline__ void round_tiles(const Chunk &c, int r, int total, in
                             rowkey[k] = min(rowkey[k], d + jk);
                             cmin = min(cmin, d + ikey[k]);
                         }
-                        atomicMin(&s_col[jj], cmin);
+                        cm[u] = cmin;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) atomicMin(&s_col[jj0 + u], cm[u]);
+                    if (__builtin_expect(min(min(cm[0], cm[1]), min(cm[2], cm[3])) < thr, 0)) {
+#pragma unroll
+                        for (int u = 0; u < 4; u++) emit_record(cm[u], s_jkey[jj0 + u], aux, thr, s_cand, s_cctl);
                     }
                 }
             } else {
                 // small tiles (latency-bound late rounds): 32 columns at a time, the column minimum of
                 // each (warp, column) is one CREDUX.MIN whose result lane (jj & 31) keeps; a single
-                // conflict-free ATOMS.MIN per warp then publishes 32 columns.  No branch or atomic sits
-                // inside the unrolled loop, so consecutive columns pipeline freely.
+                // conflict-free ATOMS.MIN per warp then publishes 32 columns.
                 for (int jb = 0; jb < ncs; jb += 32) {
                     uint32_t mycol = KEY_NONE;
                     const int jend = min(ncs, jb + 32);
                     for (int jj0 = jb; jj0 < jend; jj0 += 8) {
+                        uint32_t bmin = KEY_NONE, cm[8];
 #pragma unroll
                         for (int u = 0; u < 8; u++) {
                             const int jj = jj0 + u;
@@ -568,6 +744,12 @@ __device__ __forceinline__ void round_tiles(const Chunk &c, int r, int total, in
                             }
                             const uint32_t wmin = __reduce_min_sync(0xffffffffu, cmin);
                             if (lane == (jj & 31)) mycol = wmin;
+                            bmin = min(bmin, cmin);
+                            cm[u] = cmin;
+                        }
+                        if (__builtin_expect(bmin < thr, 0)) {
+#pragma unroll
+                            for (int u = 0; u < 8; u++) emit_record(cm[u], s_jkey[jj0 + u], aux, thr, s_cand, s_cctl);
                         }
                     }
                     atomicMin(&s_col[jb + lane], mycol);
@@ -580,29 +762,33 @@ __device__ __forceinline__ void round_tiles(const Chunk &c, int r, int total, in
                 if (jk != KEY_INVALID && v < KEY_INVALID)      // jk carries the global id; the state arrays are local
                     atomicMin(c.colbest[cur] + pd.col_base + (jk - (uint32_t)pd.col_id_offset), v);
             }
+            if (c.cand) flush_cands(SCAND / 2);              // wide tiles (batches of pairs) see more records than one staging buffer holds
         }
 #pragma unroll
         for (int k = 0; k < RQ; k++)
             if (ikey[k] != KEY_INVALID && rowkey[k] < KEY_INVALID)
                 atomicMin(c.rowbest[cur] + pd.row_base + ikey[k], rowkey[k]);
+        if (c.cand) { bar.sync(); flush_cands(0); }     // the tile's remaining staged candidate records
         tstamp(c, vb, tid, 5);
     }
 }
 
 template <int WORDS>
-__global__ void __launch_bounds__(ROUND_THREADS) hamming_round_kernel(Chunk c, int r) {
+__global__ void __launch_bounds__(ROUND_THREADS, WORDS <= 8 ? 6 : (WORDS == 12 ? 5 : 4)) hamming_round_kernel(Chunk c, int r) {
     __shared__ uint4 s_t[STAGE_LARGE * (WORDS / 4)];
     __shared__ uint32_t s_jkey[STAGE_LARGE];
     __shared__ uint32_t s_col[STAGE_LARGE];
+    __shared__ unsigned long long s_cand[2 * SCAND];
+    __shared__ int s_cctl[2];
     const int total = __ldcg(&c.plan->total_tiles);
     if ((int)blockIdx.x >= total) return;
     const int cpt = __ldcg(&c.plan->cols_per_tile);
     const int rq = __ldcg(&c.plan->rq);
     const GroupBar bar{0, ROUND_THREADS};
     if (rq == RQ_LARGE)
-        round_tiles<WORDS, RQ_LARGE, STAGE_LARGE>(c, r, total, cpt, blockIdx.x, gridDim.x, threadIdx.x, bar, s_t, s_jkey, s_col);
+        round_tiles<WORDS, RQ_LARGE, STAGE_LARGE>(c, r, total, cpt, blockIdx.x, gridDim.x, threadIdx.x, bar, s_t, s_jkey, s_col, s_cand, s_cctl);
     else
-        round_tiles<WORDS, RQ_SMALL, STAGE_SMALL>(c, r, total, cpt, blockIdx.x, gridDim.x, threadIdx.x, bar, s_t, s_jkey, s_col);
+        round_tiles<WORDS, RQ_SMALL, STAGE_SMALL>(c, r, total, cpt, blockIdx.x, gridDim.x, threadIdx.x, bar, s_t, s_jkey, s_col, s_cand, s_cctl);
 }
 
 // ---------------------------------------------------------------------------
@@ -653,15 +839,302 @@ __device__ __forceinline__ void accept_blocks(const Chunk &c, int r, int vb, int
             base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
             if (survive) {
                 const int pos = base + __popc(m & ((1u << lane) - 1u));
-                if (is_row) c.live_rows[nxt][pd.row_base + pos] = id;
-                else c.live_cols[nxt][pd.col_base + pos] = id;
+                if (is_row) { c.live_rows[nxt][pd.row_base + pos] = id; if (c.cand) c.row_pos[pd.row_base + id] = pos; }
+                else { c.live_cols[nxt][pd.col_base + pos] = id; if (c.cand) c.col_pos[pd.col_base + id] = pos; }
             }
         }
     }
 }
 
+// ---------------------------------------------------------------------------
+// candidate edges, step 2 (same phase as the accept: both only READ the pass's row / column minima): keep the raw
+// edges of pair p whose row and column both survive the accept of round r -- a row is matched by that accept iff
+// the column it chose chose it back, which any thread can evaluate from rowbest / colbest without waiting for the
+// accept to finish.  Warps walk the list from edge `start` in steps of `step` (both multiples of 32).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void filter_edges(const Chunk &c, int r, int p, int start, int step) {
+    const int n = __ldcg(c.cand_cnt + p);
+    if (n <= 0) return;
+    const PairDesc &pd = c.pairs[p];
+    const int cap = __ldg(&pd.cand_cap), lcap = __ldg(&pd.ledge_cap);
+    if (n > cap) return;                                   // overflowed: no sparse phase for this pair this pass
+    const int lane = threadIdx.x & 31, cur = r & 1, words = c.words;
+    const int64_t row_base = __ldg(&pd.row_base), col_base = __ldg(&pd.col_base);
+    const uint32_t *rowbest = c.rowbest[cur] + row_base, *colbest = c.colbest[cur] + col_base;
+    const int32_t *live_rows = c.live_rows[cur] + row_base;
+    const int nlr = __ldcg(cnt_ptr(c, r % 3, p));
+    const uint32_t thr = __ldcg(c.thr + p);
+    const uint32_t *qd = pd.q, *td = pd.t;
+    const unsigned long long *raw = c.cand + 2 * __ldg(&pd.cand_off);
+    unsigned long long *out = c.ledge + __ldg(&pd.ledge_off);
+    for (int e0 = start; e0 < n; e0 += step) {
+        const int e = e0 + lane;
+        unsigned long long ed[RQ_LARGE];                   // the record's edge and its verified siblings (~0: none)
+#pragma unroll
+        for (int k = 0; k < RQ_LARGE; k++) ed[k] = ~0ull;
+        if (e < n) {
+            const unsigned long long key = __ldcg(raw + 2 * e);
+            const uint32_t aux = (uint32_t)__ldcg(raw + 2 * e + 1);
+            ed[0] = key;
+            const int rqn = (int)(aux >> KEY_IDX_BITS), slot0 = (int)(aux & KEY_IDX_MASK);
+            if (rqn > 1) {
+                // the emitting thread held rqn rows (live-list slots slot0 + k * ROUND_THREADS) and reported the best
+                // of them in this column: check the others against the bound
+                const uint32_t i0 = (uint32_t)(key >> KEY_IDX_BITS) & KEY_IDX_MASK, j = (uint32_t)key & KEY_IDX_MASK;
+                uint32_t tw[16];
+#pragma unroll
+                for (int w = 0; w < 16; w++) tw[w] = w < words ? __ldg(td + (size_t)j * words + w) : 0u;
+                int used = 1;
+                for (int k = 0; k < rqn && k < RQ_LARGE; k++) {
+                    const int slot = slot0 + k * ROUND_THREADS;
+                    if (slot >= nlr) break;
+                    const uint32_t i2 = (uint32_t)__ldcg(live_rows + slot);
+                    if (i2 == i0) continue;
+                    uint32_t d = 0;
+#pragma unroll
+                    for (int w = 0; w < 16; w++) if (w < words) d += __popc(__ldg(qd + (size_t)i2 * words + w) ^ tw[w]);
+                    if ((d << KEY_IDX_BITS) < thr) {
+                        const unsigned long long k2 = ((unsigned long long)d << 40) | ((unsigned long long)i2 << 20) | j;
+                        if (used == 1) ed[1] = k2; else if (used == 2) ed[2] = k2; else ed[3] = k2;
+                        used++;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int x = 0; x < RQ_LARGE; x++) {
+            bool keep = false;
+            if (ed[x] != ~0ull) {
+                const uint32_t i = (uint32_t)(ed[x] >> KEY_IDX_BITS) & KEY_IDX_MASK, j = (uint32_t)ed[x] & KEY_IDX_MASK;
+                const uint32_t rk = __ldcg(rowbest + i), ck = __ldcg(colbest + j);
+                const uint32_t ck_of_rk = __ldcg(colbest + (rk & KEY_IDX_MASK)), rk_of_ck = __ldcg(rowbest + (ck & KEY_IDX_MASK));
+                keep = (ck_of_rk & KEY_IDX_MASK) != i && (rk_of_ck & KEY_IDX_MASK) != j;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (m) {
+                int base = 0;
+                if (lane == (__ffs(m) - 1)) base = atomicAdd(c.ledge_cnt + p, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                const int pos = base + __popc(m & ((1u << lane) - 1u));
+                if (keep && pos < lcap) out[pos] = ed[x];   // (ledge_cnt > ledge_cap: the sparse phase skips the pair)
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// candidate edges, step 3: the sparse sub-rounds of pair p, by ONE CTA.
+// The pass computed every distance of live rows x live columns and listed every edge with distance <= T, so for a
+// row (column) that still has a live listed edge, its smallest live listed edge IS its best live column (row) under
+// the reference's (distance, j) / (distance, i) order; an edge that is the minimum of both its row and its column is
+// locally dominant, i.e. the pair the reference's argmin scan (KeypointMatching.cs:44-65) emits before any other
+// edge touching either endpoint.  Sub-round: atomicMin the live edges into per-row / per-column slots, accept the
+// mutual ones, drop the edges that lost an endpoint; repeat until no edge is left.  Rows whose listed edges all died
+// simply stay live for the next distance pass.  Afterwards the pair's live lists (already compacted by the accept)
+// are re-compacted in place and its counts updated.
+// Edges live in REGISTERS (SP_EPT per thread, every loop fully unrolled so the loads / atomics of a phase are all in
+// flight together -- a single CTA is latency-bound, not throughput-bound); shared memory holds one min slot per live
+// row and column, addressed by the position the accept gave the row / column in the next live list.
+// ---------------------------------------------------------------------------
+// The sub-round loop over EPT edges per thread.  ek = (d << 20 | j) or KEY_NONE (dead / absent), ep = (row slot << 16 |
+// column slot); the column-side key (d << 20 | i) sits in registers (ec) or, in the wide form, in the thread's private
+// shared-memory column ecs[k * NT].  Returns the number of live edges left; stops early once it is <= stop_at.
+template <int NT, int EPT, bool EC_SMEM>
+__device__ __forceinline__ int sparse_sub_rounds(uint32_t (&ek)[EPT], uint32_t (&ec)[EC_SMEM ? 1 : EPT], const uint32_t *ecs,
+                                                 const uint32_t (&ep)[EPT], uint32_t *rbest, uint32_t *cbest,
+                                                 uint32_t *match_key, int *s_alive, int &sub, int stop_at,
+                                                 const Chunk &c, int p) {
+    constexpr int B = EPT < SP_B ? EPT : SP_B;
+    const int tid = threadIdx.x;
+    int total = 0;
+    for (; sub < SP_MAX_SUB; sub++) {
+        if (tid == 0) s_alive[(sub + 1) & 1] = 0;
+#pragma unroll
+        for (int k = 0; k < EPT; k++)
+            if (ek[k] != KEY_NONE) {
+                atomicMin(&rbest[ep[k] >> 16], ek[k]);
+                atomicMin(&cbest[ep[k] & 0xFFFFu], EC_SMEM ? ecs[k * NT] : ec[EC_SMEM ? 0 : k]);
+            }
+        __syncthreads();
+        // loads first, stores after, in batches of B edges: a shared-memory store between two loads makes ptxas order
+        // them (possible alias), and the phase would pay one memory round trip per edge instead of one per batch
+#pragma unroll
+        for (int k0 = 0; k0 < EPT; k0 += B) {
+            uint32_t rv[B], cv[B], kc[B];
+#pragma unroll
+            for (int u = 0; u < B; u++) {
+                rv[u] = rbest[ep[k0 + u] >> 16]; cv[u] = cbest[ep[k0 + u] & 0xFFFFu];
+                kc[u] = EC_SMEM ? ecs[(k0 + u) * NT] : ec[EC_SMEM ? 0 : k0 + u];
+            }
+#pragma unroll
+            for (int u = 0; u < B; u++) {
+                const int k = k0 + u;
+                // (a concurrent KEY_DEAD store by the accepting thread of another edge of this row / column can only
+                //  turn a mismatch into a mismatch: keys within a row, and within a column, are distinct)
+                if (ek[k] != KEY_NONE && rv[u] == ek[k] && cv[u] == kc[u]) {
+                    match_key[kc[u] & KEY_IDX_MASK] = ek[k];
+                    rbest[ep[k] >> 16] = KEY_DEAD; cbest[ep[k] & 0xFFFFu] = KEY_DEAD;
+                }
+            }
+        }
+        __syncthreads();
+        int alive = 0;
+#pragma unroll
+        for (int k0 = 0; k0 < EPT; k0 += B) {
+            uint32_t rv[B], cv[B];
+#pragma unroll
+            for (int u = 0; u < B; u++) { rv[u] = rbest[ep[k0 + u] >> 16]; cv[u] = cbest[ep[k0 + u] & 0xFFFFu]; }
+#pragma unroll
+            for (int u = 0; u < B; u++) {
+                const int k = k0 + u;
+                if (ek[k] != KEY_NONE) {
+                    if (rv[u] == KEY_DEAD || cv[u] == KEY_DEAD) ek[k] = KEY_NONE;
+                    else { rbest[ep[k] >> 16] = KEY_NONE; cbest[ep[k] & 0xFFFFu] = KEY_NONE; alive++; }   // (never overwrites KEY_DEAD)
+                }
+            }
+        }
+        alive = __reduce_add_sync(0xffffffffu, alive);
+        if ((tid & 31) == 0 && alive) atomicAdd(&s_alive[sub & 1], alive);
+        tstamp(c, p, tid, 22);
+        __syncthreads();
+        total = s_alive[sub & 1];
+        if (total <= stop_at) { sub++; break; }
+    }
+    return total;
+}
+
+template <int NT>
+__device__ __forceinline__ void sparse_body(const Chunk &c, int r, int p, unsigned char *smem) {
+    if (!c.cand || __ldcg(c.status + p) != PAIR_BIG) return;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const PairDesc &pdr = c.pairs[p];
+    const int nL = __ldcg(c.ledge_cnt + p);
+    const int nxt = (r & 1) ^ 1, nbuf = (r + 1) % 3;
+    int32_t *cnt = cnt_ptr(c, nbuf, p);
+    const int nlr = __ldcg(cnt), nlc = __ldcg(cnt + 1);
+    const int n1 = __ldg(&pdr.n1), n2 = __ldg(&pdr.n2);
+    if (nL <= 0 || nL > __ldg(&pdr.ledge_cap) || nL > NT * SP_EPT || nlr <= 0 || nlc <= 0) return;
+    // min slots addressed by the ORIGINAL row / column id when the pair is small enough (no position look-ups: they
+    // are 2 random 32-byte sectors per edge, and one SM's L2 bandwidth is what bounds the loading of the edges),
+    // else by the position the accept gave the survivor in the next live list
+    constexpr size_t FIXED = 4 * (size_t)SP_EPT * NT + 12 * (size_t)SP_EPC * NT;
+    const bool by_id = FIXED + 4 * (size_t)(n1 + n2) <= (size_t)SP_SMEM_BYTES && n1 <= 65535 && n2 <= 65535;
+    const int nr = by_id ? n1 : nlr, nc = by_id ? n2 : nlc;
+    if (FIXED + 4 * (size_t)(nr + nc) > (size_t)SP_SMEM_BYTES || nr > 65535 || nc > 65535) return;
+    const int64_t row_base = __ldg(&pdr.row_base), col_base = __ldg(&pdr.col_base);
+    uint32_t *ecs = reinterpret_cast<uint32_t *>(smem) + tid;     // this thread's column-side keys: ecs[k * NT], conflict-free
+    uint32_t *cbuf = reinterpret_cast<uint32_t *>(smem) + SP_EPT * NT;   // [3][SP_EPC * NT] staging of the compact form
+    uint32_t *rbest = cbuf + 3 * SP_EPC * NT;
+    uint32_t *cbest = rbest + nr;
+    __shared__ int s_cnt[2], s_alive[2], s_nc;
+
+    tstamp(c, p, tid, 20);
+    for (int k = tid; k < nr + nc; k += NT) rbest[k] = KEY_NONE;        // (rbest and cbest are contiguous)
+    if (tid == 0) { s_alive[0] = 0; s_alive[1] = 0; s_nc = 0; }
+    uint32_t ek[SP_EPT], ep[SP_EPT], ec_none[1] = {0u};
+    {
+        const unsigned long long *edges = c.ledge + __ldg(&pdr.ledge_off);
+        const int32_t *row_pos = c.row_pos + row_base, *col_pos = c.col_pos + col_base;
+#pragma unroll
+        for (int k0 = 0; k0 < SP_EPT; k0 += SP_B) {
+            unsigned long long key[SP_B];
+#pragma unroll
+            for (int u = 0; u < SP_B; u++) { const int e = tid + (k0 + u) * NT; key[u] = e < nL ? __ldcg(edges + e) : ~0ull; }
+            uint32_t pr[SP_B], pc[SP_B];
+#pragma unroll
+            for (int u = 0; u < SP_B; u++) {
+                const bool ok = key[u] != ~0ull;
+                const uint32_t i = ok ? (uint32_t)(key[u] >> KEY_IDX_BITS) & KEY_IDX_MASK : 0u, j = ok ? (uint32_t)key[u] & KEY_IDX_MASK : 0u;
+                pr[u] = by_id ? i : (uint32_t)__ldcg(row_pos + i); pc[u] = by_id ? j : (uint32_t)__ldcg(col_pos + j);
+                const uint32_t d = (uint32_t)(key[u] >> 40);
+                ek[k0 + u] = ok ? (d << KEY_IDX_BITS) | j : KEY_NONE;
+                ecs[(k0 + u) * NT] = (d << KEY_IDX_BITS) | i;
+            }
+#pragma unroll
+            for (int u = 0; u < SP_B; u++) ep[k0 + u] = ek[k0 + u] != KEY_NONE ? (pr[u] << 16) | pc[u] : 0u;
+        }
+    }
+    __syncthreads();
+    tstamp(c, p, tid, 21);
+    uint32_t *match_key = c.match_key + row_base;
+    int sub = 0;
+    // wide form until few enough edges are left, then the survivors are dealt out again SP_EPC per thread: the cost of
+    // a sub-round is the unrolled per-slot code every thread runs, not the number of live edges
+    int left = nL;
+    if (nL > SP_EPC * NT)
+        left = sparse_sub_rounds<NT, SP_EPT, true>(ek, ec_none, ecs, ep, rbest, cbest, match_key, s_alive, sub, SP_EPC * NT, c, p);
+    if (left > 0 && sub < SP_MAX_SUB) {
+#pragma unroll
+        for (int k = 0; k < SP_EPT; k++)
+            if (ek[k] != KEY_NONE) {
+                const int at = atomicAdd(&s_nc, 1);
+                cbuf[at] = ek[k]; cbuf[SP_EPC * NT + at] = ecs[k * NT]; cbuf[2 * SP_EPC * NT + at] = ep[k];
+            }
+        __syncthreads();
+        const int ncomp = s_nc;
+        uint32_t ck[SP_EPC], cc[SP_EPC], cp[SP_EPC];
+#pragma unroll
+        for (int k = 0; k < SP_EPC; k++) {
+            const int e = tid + k * NT;
+            ck[k] = e < ncomp ? cbuf[e] : KEY_NONE;
+            cc[k] = e < ncomp ? cbuf[SP_EPC * NT + e] : KEY_NONE;
+            cp[k] = e < ncomp ? cbuf[2 * SP_EPC * NT + e] : 0u;
+        }
+        sparse_sub_rounds<NT, SP_EPC, false>(ck, cc, nullptr, cp, rbest, cbest, match_key, s_alive, sub, 0, c, p);
+    }
+    // re-compact the live lists in place, SP_IPT ids per thread at a time (order is arbitrary).  A chunk's ids are all
+    // read before any of them is written back, and the kept ones land below the chunk's end: no unread slot is hit.
+#pragma unroll 1
+    for (int side = 0; side < 2; side++) {
+        const int n = side ? nlc : nlr;
+        int32_t *live = side ? c.live_cols[nxt] + col_base : c.live_rows[nxt] + row_base;
+        const uint32_t *best = side ? cbest : rbest;
+        if (tid == 0) s_cnt[side] = 0;
+        for (int k0 = 0; k0 < n; k0 += NT * SP_IPT) {
+            int32_t id[SP_IPT];
+            bool keep[SP_IPT];
+#pragma unroll
+            for (int u = 0; u < SP_IPT; u++) {
+                const int k = k0 + u * NT + tid;
+                id[u] = k < n ? __ldcg(live + k) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < SP_IPT; u++) {
+                const int k = k0 + u * NT + tid;
+                keep[u] = k < n && best[by_id ? id[u] : k] != KEY_DEAD;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < SP_IPT; u++) {
+                const unsigned m = __ballot_sync(0xffffffffu, keep[u]);
+                if (m) {
+                    int base = 0;
+                    if (lane == (__ffs(m) - 1)) base = atomicAdd(&s_cnt[side], __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                    if (keep[u]) live[base + __popc(m & ((1u << lane) - 1u))] = id[u];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) { cnt[0] = s_cnt[0]; cnt[1] = s_cnt[1]; }
+    tstamp(c, p, tid, 23);
+}
+
+// standalone forms (throughput mode): accept + edge filter, then one sparse CTA per pair whose last block plans
 __global__ void __launch_bounds__(ACCEPT_THREADS) accept_kernel(Chunk c, int r) {
     accept_blocks(c, r, blockIdx.x, gridDim.x, threadIdx.x);
+    if (c.cand) {
+        for (int p = blockIdx.x; p < c.n_pairs; p += gridDim.x)
+            filter_edges(c, r, p, (int)(threadIdx.x & ~31u), ACCEPT_THREADS);
+    } else {
+        plan_in_last_block(c, r + 1, gridDim.x);
+    }
+}
+
+__global__ void __launch_bounds__(SP_THREADS) sparse_kernel(Chunk c, int r) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    for (int p = blockIdx.x; p < c.n_pairs; p += gridDim.x) { sparse_body<SP_THREADS>(c, r, p, dyn_smem); __syncthreads(); }
     plan_in_last_block(c, r + 1, gridDim.x);
 }
 
@@ -917,21 +1390,37 @@ inline size_t finisher_smem_bytes(int words, int max_evals = FIN_MAX_EVALS) {
 // Keys of the first ORDER_KEY_CACHE rows are cached in shared memory so the
 // ranking pass does not wait on global loads.
 // ---------------------------------------------------------------------------
+// Sliced form: the rows of pair p are cut into n_slices contiguous slices, one CTA each.  order_count histograms a
+// slice (per warp, kept in shared memory) and publishes the slice's per-distance totals; after a grid-wide barrier
+// order_emit turns them into output offsets -- rows with a smaller distance first, then the same distance in earlier
+// slices, earlier warps, earlier lanes -- and writes the triples.  n_slices == 1 needs no global scratch / barrier.
+constexpr int ORDER_MAX_SLICES = 32;
+constexpr int ORDER_BIN_PITCH = 520;            // >= 513 + 1 bins
+struct OrderSlice { int x_begin, x_end, seg; };
+
 template <int ORDER_THREADS>
-__device__ __forceinline__ void order_body(const Chunk &c, int p, int nbins, uint32_t flags,
-                                           int32_t *out_qi, int32_t *out_tj, int32_t *out_dist, int32_t *s_order) {
+__device__ __forceinline__ OrderSlice order_slice_of(int n1, int slice, int n_slices) {
     constexpr int ORDER_WARPS = ORDER_THREADS / 32;
-    __shared__ int32_t s_wsum[ORDER_WARPS];      // s_order: [ORDER_WARPS][nbins + 1] hist | key cache
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const PairDesc pd = c.pairs[p];
-    const int hb = nbins + 1;                    // last bin: unmatched rows (never written out)
-    int32_t *s_hist = s_order;
-    uint32_t *s_keys = reinterpret_cast<uint32_t *>(s_order + ORDER_WARPS * hb);
-    const uint32_t *mk = c.match_key + pd.row_base;
-    for (int k = tid; k < ORDER_WARPS * hb; k += ORDER_THREADS) s_hist[k] = 0;
-    int seg = (pd.n1 + ORDER_WARPS - 1) / ORDER_WARPS;
+    int seg = (n1 + n_slices * ORDER_WARPS - 1) / (n_slices * ORDER_WARPS);   // rows per warp, a multiple of 32
     seg = (seg + 31) & ~31;
-    const int x0 = min(pd.n1, wid * seg), x1 = min(pd.n1, x0 + seg);
+    const int b = min(n1, slice * seg * ORDER_WARPS);
+    return OrderSlice{b, min(n1, b + seg * ORDER_WARPS), seg};
+}
+
+template <int ORDER_THREADS>
+__device__ __forceinline__ void order_count(const Chunk &c, int p, int slice, int n_slices, int nbins, int32_t *s_order,
+                                            int32_t *g_cnt /* [pairs][ORDER_MAX_SLICES][ORDER_BIN_PITCH] or nullptr */) {
+    constexpr int ORDER_WARPS = ORDER_THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const PairDesc &pd = c.pairs[p];
+    const int n1 = __ldg(&pd.n1);
+    const int hb = nbins + 1;                    // last bin: unmatched rows (never written out)
+    int32_t *s_hist = s_order;                   // s_order: [ORDER_WARPS][nbins + 1] hist | key cache
+    uint32_t *s_keys = reinterpret_cast<uint32_t *>(s_order + ORDER_WARPS * hb);
+    const uint32_t *mk = c.match_key + __ldg(&pd.row_base);
+    const OrderSlice sl = order_slice_of<ORDER_THREADS>(n1, slice, n_slices);
+    for (int k = tid; k < ORDER_WARPS * hb; k += ORDER_THREADS) s_hist[k] = 0;
+    const int x0 = min(sl.x_end, sl.x_begin + wid * sl.seg), x1 = min(sl.x_end, x0 + sl.seg);
     __syncthreads();
     for (int xb = x0; xb < x1; xb += 128) {      // 4 independent loads in flight per lane
         uint32_t k4[4];
@@ -944,32 +1433,70 @@ __device__ __forceinline__ void order_body(const Chunk &c, int p, int nbins, uin
         for (int u = 0; u < 4; u++) {
             const int x = xb + 32 * u + lane;
             if (x < x1) {
-                if (x < ORDER_KEY_CACHE) s_keys[x] = k4[u];
+                if (x - sl.x_begin < ORDER_KEY_CACHE) s_keys[x - sl.x_begin] = k4[u];
                 if (k4[u] != KEY_NONE) atomicAdd(&s_hist[wid * hb + (k4[u] >> KEY_IDX_BITS)], 1);
             }
         }
     }
     __syncthreads();
-    // thread t owns bins 2t and 2t+1 (nbins <= 513 <= 2 * ORDER_THREADS): totals over the
-    // warps' histograms, block-wide exclusive scan over distances, then per-warp bases
+    if (g_cnt && n_slices > 1) {
+        int32_t *mine = g_cnt + ((size_t)p * ORDER_MAX_SLICES + slice) * ORDER_BIN_PITCH;
+        for (int b = tid; b < nbins; b += ORDER_THREADS) {
+            int t = 0;
+            for (int w = 0; w < ORDER_WARPS; w++) t += s_hist[w * hb + b];
+            mine[b] = t;
+        }
+    }
+}
+
+template <int ORDER_THREADS>
+__device__ __forceinline__ void order_emit(const Chunk &c, int p, int slice, int n_slices, int nbins, uint32_t flags,
+                                           int32_t *out_qi, int32_t *out_tj, int32_t *out_dist, int32_t *s_order,
+                                           const int32_t *g_cnt) {
+    constexpr int ORDER_WARPS = ORDER_THREADS / 32;
+    __shared__ int32_t s_wsum[ORDER_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const PairDesc &pd = c.pairs[p];
+    const int n1 = __ldg(&pd.n1), n2 = __ldg(&pd.n2);
+    const int64_t out_base = __ldg(&pd.out_base);
+    const int hb = nbins + 1;
+    int32_t *s_hist = s_order;
+    const uint32_t *s_keys = reinterpret_cast<const uint32_t *>(s_order + ORDER_WARPS * hb);
+    const uint32_t *mk = c.match_key + __ldg(&pd.row_base);
+    const OrderSlice sl = order_slice_of<ORDER_THREADS>(n1, slice, n_slices);
+    const int x0 = min(sl.x_end, sl.x_begin + wid * sl.seg), x1 = min(sl.x_end, x0 + sl.seg);
+    // thread t owns bins 2t and 2t+1 (nbins <= 513 <= 2 * ORDER_THREADS): totals over all slices and over the earlier
+    // slices, block-wide exclusive scan over distances, then per-warp bases
     const int b0 = 2 * tid, b1 = 2 * tid + 1;
-    int ta = 0, tb = 0;
-    if (b0 < nbins) for (int w = 0; w < ORDER_WARPS; w++) ta += s_hist[w * hb + b0];
-    if (b1 < nbins) for (int w = 0; w < ORDER_WARPS; w++) tb += s_hist[w * hb + b1];
+    int ta = 0, tb = 0, pa = 0, pb = 0;          // totals of the bin over every slice; over the slices before this one
+    if (n_slices > 1) {
+        const int32_t *pc = g_cnt + (size_t)p * ORDER_MAX_SLICES * ORDER_BIN_PITCH;
+        for (int sidx = 0; sidx < n_slices; sidx++) {
+            const int va = b0 < nbins ? __ldcg(pc + (size_t)sidx * ORDER_BIN_PITCH + b0) : 0;
+            const int vb = b1 < nbins ? __ldcg(pc + (size_t)sidx * ORDER_BIN_PITCH + b1) : 0;
+            ta += va; tb += vb;
+            if (sidx < slice) { pa += va; pb += vb; }
+        }
+    } else {
+        if (b0 < nbins) for (int w = 0; w < ORDER_WARPS; w++) ta += s_hist[w * hb + b0];
+        if (b1 < nbins) for (int w = 0; w < ORDER_WARPS; w++) tb += s_hist[w * hb + b1];
+    }
     int inc = ta + tb;
     for (int o = 1; o < 32; o <<= 1) { const int a = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += a; }
     if (lane == 31) s_wsum[wid] = inc;
     __syncthreads();
     int woff = 0;
     for (int w = 0; w < wid; w++) woff += s_wsum[w];
-    int a = woff + inc - (ta + tb);
+    const int start = woff + inc - (ta + tb);    // first output slot of distance b0
+    int a = start + pa;
     if (b0 < nbins) for (int w = 0; w < ORDER_WARPS; w++) { const int t = s_hist[w * hb + b0]; s_hist[w * hb + b0] = a; a += t; }
+    a = start + ta + pb;
     if (b1 < nbins) for (int w = 0; w < ORDER_WARPS; w++) { const int t = s_hist[w * hb + b1]; s_hist[w * hb + b1] = a; a += t; }
     __syncthreads();
     for (int xb = x0; xb < x1; xb += 32) {
         const int x = xb + lane;
         uint32_t key = KEY_NONE;
-        if (x < x1) key = x < ORDER_KEY_CACHE ? s_keys[x] : __ldcg(mk + x);
+        if (x < x1) key = x - sl.x_begin < ORDER_KEY_CACHE ? s_keys[x - sl.x_begin] : __ldcg(mk + x);
         const int d = key != KEY_NONE ? (int)(key >> KEY_IDX_BITS) : nbins;
         const unsigned peers = __match_any_sync(0xffffffffu, d);
         const int rank = __popc(peers & ((1u << lane) - 1u));
@@ -978,17 +1505,24 @@ __device__ __forceinline__ void order_body(const Chunk &c, int p, int nbins, uin
         if (rank == 0) s_hist[wid * hb + d] = base + __popc(peers);
         __syncwarp();
         if (key != KEY_NONE) {
-            const int64_t o = pd.out_base + base + rank;
+            const int64_t o = out_base + base + rank;
             out_qi[o] = x; out_tj[o] = (int32_t)(key & KEY_IDX_MASK); out_dist[o] = d;
         }
     }
     if (flags & 1u) {                            // PGM_FLAG_REFERENCE_COMPAT_TAIL (KeypointMatching.cs:38-42)
-        const int matched = min(pd.n1, pd.n2);   // every pair ends with exactly min(n1,n2) real matches
-        for (int k = matched + tid; k < pd.n1; k += ORDER_THREADS) {
-            const int64_t o = pd.out_base + k;
+        const int matched = min(n1, n2);         // every pair ends with exactly min(n1,n2) real matches
+        for (int k = matched + slice * ORDER_THREADS + tid; k < n1; k += n_slices * ORDER_THREADS) {
+            const int64_t o = out_base + k;
             out_qi[o] = 0; out_tj[o] = 0; out_dist[o] = 2147483647;
         }
     }
+}
+
+template <int ORDER_THREADS>
+__device__ __forceinline__ void order_body(const Chunk &c, int p, int nbins, uint32_t flags,
+                                           int32_t *out_qi, int32_t *out_tj, int32_t *out_dist, int32_t *s_order) {
+    order_count<ORDER_THREADS>(c, p, 0, 1, nbins, s_order, nullptr);
+    order_emit<ORDER_THREADS>(c, p, 0, 1, nbins, flags, out_qi, out_tj, out_dist, s_order, nullptr);
 }
 
 __global__ void __launch_bounds__(ORDER_THREADS_STANDALONE) order_kernel(Chunk c, int nbins, uint32_t flags,
@@ -1039,9 +1573,14 @@ __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned nblocks
 }
 
 template <int WORDS>
+__host__ __device__ constexpr size_t tail_group_bytes() {   // one 128-thread group of the round phase: staged train tile, keys, column minima, edges
+    return (size_t)STAGE_LARGE * (WORDS / 4) * 16 + (size_t)STAGE_LARGE * 8 + (size_t)SCAND * 16 + 16;
+}
+template <int WORDS>
 inline size_t tail_smem_bytes(int nbins) {
-    const size_t round_bytes = 4 * ((size_t)STAGE_LARGE * (WORDS / 4) * 16 + (size_t)STAGE_LARGE * 8);
-    return std::max(round_bytes, std::max(finisher_smem_bytes(WORDS, FIN_MAX_EVALS_TAIL), order_smem_bytes(nbins, TAIL_THREADS)));
+    const size_t round_bytes = 4 * tail_group_bytes<WORDS>();
+    return std::max(std::max(round_bytes, (size_t)SP_SMEM_BYTES),
+                    std::max(finisher_smem_bytes(WORDS, FIN_MAX_EVALS_TAIL), order_smem_bytes(nbins, TAIL_THREADS)));
 }
 
 template <int WORDS>
@@ -1049,42 +1588,63 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_kernel(Chunk c, int r_st
                                                               int32_t *out_qi, int32_t *out_tj, int32_t *out_dist) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     constexpr int V4 = WORDS / 4;
-    constexpr size_t GROUP_BYTES = (size_t)STAGE_LARGE * V4 * 16 + (size_t)STAGE_LARGE * 8;
+    constexpr size_t GROUP_BYTES = tail_group_bytes<WORDS>();
     const int tid = threadIdx.x, grp = tid >> 7, gtid = tid & 127;
     unsigned char *gb = dyn_smem + grp * GROUP_BYTES;
     uint4 *s_t = reinterpret_cast<uint4 *>(gb);
     uint32_t *s_jkey = reinterpret_cast<uint32_t *>(gb + (size_t)STAGE_LARGE * V4 * 16);
     uint32_t *s_col = s_jkey + STAGE_LARGE;
+    unsigned long long *s_cand = reinterpret_cast<unsigned long long *>(s_col + STAGE_LARGE);
+    int *s_cctl = reinterpret_cast<int *>(s_cand + 2 * SCAND);
     unsigned epoch = 0;
     unsigned *bar_counter = &c.plan->grid_bar;
     int slot = 0;
     stamp(c, slot);
 
-    if (flags & TAIL_FLAG_ACCEPT_FIRST) {
-        // the accept phase of the standalone round r_start - 1 (one launch and its drain less than accept_kernel)
-        accept_blocks(c, r_start - 1, (tid >> 8) * gridDim.x + blockIdx.x, gridDim.x * 2, tid & (ACCEPT_THREADS - 1));
-        plan_in_last_block(c, r_start, gridDim.x);
-        grid_barrier(bar_counter, gridDim.x, epoch);
-    }
-    for (int r = r_start;; r++) {
-        // plan(r) was published before the previous barrier (or by the preceding accept kernel)
-        if (__ldcg(&c.plan->n_big) == 0) break;
-        const int total = __ldcg(&c.plan->total_tiles);
-        const int cpt = __ldcg(&c.plan->cols_per_tile);
-        const int rq = __ldcg(&c.plan->rq);
-        const GroupBar bar{1 + grp, ROUND_THREADS};
-        if (rq == RQ_LARGE)
-            round_tiles<WORDS, RQ_LARGE, STAGE_LARGE>(c, r, total, cpt, grp * gridDim.x + blockIdx.x, gridDim.x * 4, gtid, bar, s_t, s_jkey, s_col);
-        else
-            round_tiles<WORDS, RQ_SMALL, STAGE_SMALL>(c, r, total, cpt, grp * gridDim.x + blockIdx.x, gridDim.x * 4, gtid, bar, s_t, s_jkey, s_col);
-        stamp(c, slot);
-        grid_barrier(bar_counter, gridDim.x, epoch);
-        stamp(c, slot);
+    // what follows every distance pass r: accept + candidate-edge filter (all CTAs) | barrier | sparse sub-rounds of
+    // pair p in CTA p, the last of them plans pass r + 1 | barrier
+    auto after_pass = [&](int r) {
         accept_blocks(c, r, (tid >> 8) * gridDim.x + blockIdx.x, gridDim.x * 2, tid & (ACCEPT_THREADS - 1));
-        plan_in_last_block(c, r + 1, gridDim.x);
+        if (c.cand) {
+            const int gw32 = (int)((blockIdx.x * TAIL_THREADS + tid) & ~31u);
+            for (int p = 0; p < c.n_pairs; p++) filter_edges(c, r, p, gw32, (int)gridDim.x * TAIL_THREADS);
+        } else {
+            plan_in_last_block(c, r + 1, gridDim.x);
+        }
         stamp(c, slot);
         grid_barrier(bar_counter, gridDim.x, epoch);
         stamp(c, slot);
+        if (c.cand) {
+            if ((int)blockIdx.x < c.n_pairs) {
+                sparse_body<TAIL_THREADS>(c, r, blockIdx.x, dyn_smem);
+                if (c.n_pairs == 1) { __syncthreads(); if (tid < 32) plan_warp(c, r + 1); }   // (no ticket to take)
+                else plan_in_last_block(c, r + 1, (unsigned)c.n_pairs);
+            }
+            stamp(c, slot);
+            grid_barrier(bar_counter, gridDim.x, epoch);
+            stamp(c, slot);
+        }
+    };
+    // (one copy of the pass body: the kernel's code size is what its short phases pay for in instruction-cache misses)
+    bool have_pass = (flags & TAIL_FLAG_ACCEPT_FIRST) != 0;         // round r_start - 1 ran as a standalone launch
+    for (int r = have_pass ? r_start - 1 : r_start;; r++) {
+        if (!have_pass) {
+            // plan(r) was published before the previous barrier (or by the preceding kernel)
+            if (__ldcg(&c.plan->n_big) == 0) break;
+            const int total = __ldcg(&c.plan->total_tiles);
+            const int cpt = __ldcg(&c.plan->cols_per_tile);
+            const int rq = __ldcg(&c.plan->rq);
+            const GroupBar bar{1 + grp, ROUND_THREADS};
+            if (rq == RQ_LARGE)
+                round_tiles<WORDS, RQ_LARGE, STAGE_LARGE>(c, r, total, cpt, grp * gridDim.x + blockIdx.x, gridDim.x * 4, gtid, bar, s_t, s_jkey, s_col, s_cand, s_cctl);
+            else
+                round_tiles<WORDS, RQ_SMALL, STAGE_SMALL>(c, r, total, cpt, grp * gridDim.x + blockIdx.x, gridDim.x * 4, gtid, bar, s_t, s_jkey, s_col, s_cand, s_cctl);
+            stamp(c, slot);
+            grid_barrier(bar_counter, gridDim.x, epoch);
+            stamp(c, slot);
+        }
+        have_pass = false;
+        after_pass(r);
     }
     // every small pair's distance matrix and first-round minima, computed by all CTAs (finisher_prepare)
     // (the grid is split among the small pairs: CTA b works on the (b mod n_small)-th of them)
@@ -1103,12 +1663,23 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_kernel(Chunk c, int r_st
     for (int p = blockIdx.x; p < c.n_pairs; p += gridDim.x) {
         stamp(c, slot);
         if (__ldcg(c.status + p) == PAIR_SMALL) finisher_body<WORDS, true>(c, p, dyn_smem);
-        __threadfence();
-        __syncthreads();
-        stamp(c, slot);
-        order_body<TAIL_THREADS>(c, p, nbins, flags, out_qi, out_tj, out_dist, reinterpret_cast<int32_t *>(dyn_smem));
-        __syncthreads();
     }
+    if (n_small) {                                    // the finishers' matches must be visible to every ordering CTA
+        __threadfence();
+        grid_barrier(bar_counter, gridDim.x, epoch);
+    }
+    stamp(c, slot);
+    // ordering, sliced over the grid: S CTAs per pair (count | barrier | emit)
+    const int S = max(1, min(ORDER_MAX_SLICES, (int)gridDim.x / c.n_pairs));
+    const bool ordering = (int)blockIdx.x < c.n_pairs * S;
+    const int op = (int)blockIdx.x / S, oslice = (int)blockIdx.x - op * S;
+    __syncthreads();                                  // the finisher's shared memory is reused
+    if (ordering) order_count<TAIL_THREADS>(c, op, oslice, S, nbins, reinterpret_cast<int32_t *>(dyn_smem), c.order_cnt);
+    if (S > 1) grid_barrier(bar_counter, gridDim.x, epoch);
+    stamp(c, slot);
+    if (ordering) order_emit<TAIL_THREADS>(c, op, oslice, S, nbins, flags, out_qi, out_tj, out_dist,
+                                           reinterpret_cast<int32_t *>(dyn_smem), c.order_cnt);
+    stamp(c, slot);
 }
 
 // ---------------------------------------------------------------------------

@@ -71,6 +71,8 @@ struct pgm_handle {
     bool tail_timeline = false;      // PGM_TAIL_TIMELINE=1: dump the tail kernel's phase timeline to stderr (debug)
     DevBuf timeline;
     bool fin_attr_set[5] = {false, false, false, false, false};
+    bool sparse_attr_set = false;
+    bool no_cand = false;            // PGM_NO_CAND=1: classic rounds only, no candidate edges / sparse sub-rounds (A/B)
     // profiling mode (pgm_set_profiling): events around every round-kernel launch
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;   // 2 per round
@@ -196,6 +198,8 @@ extern "C" int pgm_create(int device_ordinal, pgm_handle **out) {
     h->l2_force_single = ls && ls[0] == '1';
     const char *pl = getenv("PGM_TAIL_PLAIN_LAUNCH");
     h->tail_plain_launch = pl && pl[0] == '1';
+    const char *nc = getenv("PGM_NO_CAND");
+    h->no_cand = nc && nc[0] == '1';
     const char *tl = getenv("PGM_TAIL_TIMELINE");
     h->tail_timeline = tl && tl[0] == '1';
     *out = h;
@@ -400,6 +404,27 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
     const size_t o_finr = latency_mode ? take((size_t)n_pairs * FIN_PARTS * FIN_MAX_DIM * 4) : 0;
     const size_t o_finc = latency_mode ? take((size_t)n_pairs * FIN_PARTS * FIN_MAX_DIM * 4) : 0;
     const size_t o_fini = latency_mode ? take((size_t)n_pairs * 2 * FIN_MAX_DIM * 4) : 0;
+    const size_t o_ocnt = latency_mode ? take((size_t)n_pairs * ORDER_MAX_SLICES * ORDER_BIN_PITCH * 4) : 0;
+    // candidate edges (pgm_kernels.cuh): per pair a raw list of about 2 x CAND_TARGET entries per row and a list of the
+    // edges that survive the accept, sized for the sparse phase's shared memory
+    const bool use_cand = !h->no_cand;
+    float cand_target = CAND_TARGET;
+    if (const char *e = getenv("PGM_CAND_TARGET")) cand_target = std::max(0.1f, (float)atof(e));   // tuning experiments
+    std::vector<int64_t> cand_off(n_pairs + 1, 0), ledge_off(n_pairs + 1, 0);
+    if (use_cand) {
+        for (int p = 0; p < n_pairs; p++) {
+            const int64_t cells = (int64_t)pairs[p].n1 * pairs[p].n2;
+            const int64_t cap = pairs[p].flags & PAIR_FLAG_NO_EMIT ? 0
+                                : std::min<int64_t>(cells, (int64_t)(2.0f * cand_target + 1.0f) * std::max(pairs[p].n1, pairs[p].n2) + 1024);
+            cand_off[p + 1] = cand_off[p] + cap;
+            ledge_off[p + 1] = ledge_off[p] + std::min<int64_t>(cap, SP_LCAP_MAX);
+        }
+    }
+    const size_t o_cand = use_cand ? take(16 * (size_t)cand_off[n_pairs]) : 0;   // two words per record
+    const size_t o_ledge = use_cand ? take(8 * (size_t)ledge_off[n_pairs]) : 0;
+    const size_t o_ccnt = use_cand ? take(4 * (size_t)n_pairs) : 0, o_lcnt = use_cand ? take(4 * (size_t)n_pairs) : 0;
+    const size_t o_thr = use_cand ? take(4 * (size_t)n_pairs) : 0, o_pstat = use_cand ? take(sizeof(PairStat) * (size_t)n_pairs) : 0;
+    const size_t o_rpos = use_cand ? take(4 * rows) : 0, o_cpos = use_cand ? take(4 * cols) : 0;
     int rc = ensure_dev(h, h->state, off);
     if (rc) return rc;
     rc = ensure_host(h, h->pin_meta, sizeof(PairDesc) * n_pairs + 512);
@@ -415,6 +440,8 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
     c.n_pairs = n_pairs;
     c.num_sms = h->num_sms;
     c.ctas_per_sm = latency_mode ? TAIL_THREADS / ROUND_THREADS : ctas_per_sm;
+    c.ctas_per_sm0 = latency_mode ? ctas_per_sm : 0;    // round 0 of latency mode is a standalone launch at full occupancy
+    if (const char *e = getenv("PGM_SLOTS_PER_SM")) c.ctas_per_sm = c.ctas_per_sm0 = std::max(1, atoi(e));   // tuning experiments
     c.fin_max_evals = latency_mode ? FIN_MAX_EVALS_TAIL : FIN_MAX_EVALS;
     c.large_min_evals = large_tile_min_evals(h);
     if (latency_mode) {
@@ -422,6 +449,7 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
         c.fin_rb = (uint32_t *)(base + o_finr);
         c.fin_cb = (uint32_t *)(base + o_finc);
         c.fin_ids = (int32_t *)(base + o_fini);
+        c.order_cnt = (int32_t *)(base + o_ocnt);
     }
     c.rowbest[0] = (uint32_t *)(base + o_rb0); c.rowbest[1] = (uint32_t *)(base + o_rb1);
     c.colbest[0] = (uint32_t *)(base + o_cb0); c.colbest[1] = (uint32_t *)(base + o_cb1);
@@ -434,6 +462,14 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
     c.status = (uint8_t *)(base + o_st);
     c.small = (SmallInfo *)(base + o_small);
     c.plan = (PlanInfo *)(base + o_plan);
+    c.words = words;
+    c.cand_target = cand_target;
+    if (use_cand) {
+        c.cand = (unsigned long long *)(base + o_cand); c.ledge = (unsigned long long *)(base + o_ledge);
+        c.cand_cnt = (int32_t *)(base + o_ccnt); c.ledge_cnt = (int32_t *)(base + o_lcnt);
+        c.thr = (uint32_t *)(base + o_thr); c.pstat = (PairStat *)(base + o_pstat);
+        c.row_pos = (int32_t *)(base + o_rpos); c.col_pos = (int32_t *)(base + o_cpos);
+    }
     c.timeline = nullptr;
     if (h->tail_timeline) {
         if ((rc = ensure_dev(h, h->timeline, 1000 * 8))) return rc;
@@ -451,6 +487,8 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
         hp[p].n1 = pairs[p].n1; hp[p].n2 = pairs[p].n2;
         hp[p].row_base = rb; hp[p].col_base = cb; hp[p].out_base = pairs[p].out_base;
         hp[p].col_id_offset = pairs[p].col_id_offset; hp[p].flags = pairs[p].flags;
+        hp[p].cand_off = cand_off[p]; hp[p].ledge_off = ledge_off[p];
+        hp[p].cand_cap = (int32_t)(cand_off[p + 1] - cand_off[p]); hp[p].ledge_cap = (int32_t)(ledge_off[p + 1] - ledge_off[p]);
         rb += pairs[p].n1; cb += pairs[p].n2;
         ablocks += (pairs[p].n1 + ACCEPT_THREADS - 1) / ACCEPT_THREADS + (pairs[p].n2 + ACCEPT_THREADS - 1) / ACCEPT_THREADS;
         h->stats.distance_evals += (int64_t)pairs[p].n1 * pairs[p].n2;
@@ -471,7 +509,10 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
     }
     h->stats.kernel_launches += 1;
 
-    const int nbins = desc_bits + 1;
+    // Histogram bins of the ordering pass.  Sized by the padded row width, not by desc_bits: nothing checks that the
+    // caller zeroed the bits at positions >= desc_bits, and a distance above desc_bits must not leave its histogram.
+    (void)desc_bits;
+    const int nbins = 8 * stride_bytes + 1;
     const bool prof = h->profiling;
     // ---- latency mode: a few pairs.  init, one full round, then the persistent tail kernel runs
     // every remaining round, the finisher and the ordering without coming back to the host.
@@ -526,7 +567,15 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
             if (pr) CU_CHECK(h, cudaEventRecord(h->prof_events[2 * r], s));
             dispatch_round(words, c, r, round_grid, s);
             if (pr) CU_CHECK(h, cudaEventRecord(h->prof_events[2 * r + 1], s));
-            accept_kernel<<<accept_grid, ACCEPT_THREADS, 0, s>>>(c, r);
+            accept_kernel<<<accept_grid, ACCEPT_THREADS, 0, s>>>(c, r);        // + candidate-edge filter
+            if (use_cand) {                                                     // sparse sub-rounds, then the plan of r + 1
+                if (!h->sparse_attr_set) {
+                    CU_CHECK(h, cudaFuncSetAttribute(sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM_BYTES));
+                    h->sparse_attr_set = true;
+                }
+                sparse_kernel<<<std::min(n_pairs, h->num_sms * 4), SP_THREADS, SP_SMEM_BYTES, s>>>(c, r);
+                h->stats.kernel_launches += 1;
+            }
             if (pr) {
                 CU_CHECK(h, cudaMemcpyAsync(&prof_plan[r + 1], c.plan, sizeof(PlanInfo), cudaMemcpyDeviceToHost, s));
                 h->prof_rounds = r + 1;
@@ -1067,7 +1116,8 @@ static void launch_sorted_rows(const uint32_t *q, int n1, const uint32_t *t, int
 }
 static int sorted_rows_dev_impl(pgm_handle *h, const uint8_t *d_q, int32_t n1, const uint8_t *d_t, int32_t n2,
                                 int32_t desc_bits, int32_t stride_bytes, int64_t *d_out) {
-    const int nbins = desc_bits + 1;
+    (void)desc_bits;
+    const int nbins = 8 * stride_bytes + 1;   // by padded width: set padding bits must not index outside the histogram
     const uint32_t *q = (const uint32_t *)d_q, *t = (const uint32_t *)d_t;
     switch (stride_bytes / 4) {
         case 4: launch_sorted_rows<4>(q, n1, t, n2, nbins, (long long *)d_out, h->stream); break;
@@ -1283,6 +1333,11 @@ static int l2_dev_impl(pgm_handle *h, const float *d_q, int32_t n1, const float 
     return PGM_OK;
 }
 
+__global__ void fill_f32_kernel(float *p, int n, float v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
 static int l2_check(pgm_handle *h, int32_t n1, int32_t n2, int32_t dim) {
     if (n1 < 0 || n2 < 0 || n1 >= MAX_N || n2 >= MAX_N) return fail(h, PGM_E_INVALID_ARG, "bad sizes");
     if (dim < 1 || dim > 128) return fail(h, PGM_E_INVALID_ARG, "dim must be in 1..128");
@@ -1300,8 +1355,13 @@ extern "C" int pgm_knn2_l2_dev(pgm_handle *h, const float *d_q, int32_t n1, cons
     h->stats_pending = false;
     if (n1 == 0) return PGM_OK;
     CU_CHECK(h, cudaSetDevice(h->device));
-    if (n2 == 0) {
+    if (n2 == 0) {    // "-1 where absent" for all four arrays, like the host-buffer variant
+        if (!d_best_j || !d_best_d || !d_second_j || !d_second_d) return fail(h, PGM_E_INVALID_ARG, "null pointer");
         for (void *o : {(void *)d_best_j, (void *)d_second_j}) CU_CHECK(h, cudaMemsetAsync(o, 0xFF, (size_t)n1 * 4, h->stream));
+        const int fg = (n1 + 255) / 256;
+        fill_f32_kernel<<<fg, 256, 0, h->stream>>>(d_best_d, n1, -1.0f);
+        fill_f32_kernel<<<fg, 256, 0, h->stream>>>(d_second_d, n1, -1.0f);
+        CU_CHECK(h, cudaGetLastError());
         return PGM_OK;
     }
     return l2_dev_impl(h, d_q, n1, d_t, n2, dim, d_best_j, d_best_d, d_second_j, d_second_d, d_debug_dist);
@@ -1813,7 +1873,7 @@ extern "C" int pgm_shard_finish(pgm_shard *sh, int32_t *d_out_qi, int32_t *d_out
     cudaStream_t s = h->stream;
     // the order kernel derives the tail from min(n1, n2): it needs the TOTAL train size
     CU_CHECK(h, cudaMemcpyAsync((char *)sh->c.pairs + offsetof(PairDesc, n2), &sh->n2_total, 4, cudaMemcpyHostToDevice, s));
-    const int nbins = sh->desc_bits + 1;
+    const int nbins = 32 * sh->words + 1;     // padded width (see run_chunk)
     if (!h->order_attr_set) {
         CU_CHECK(h, cudaFuncSetAttribute(order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)order_smem_bytes(513, ORDER_THREADS_STANDALONE)));

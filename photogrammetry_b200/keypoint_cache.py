@@ -22,11 +22,25 @@ class _Bag:
     pass
 
 
+# The only globals a keypoint cache file legitimately names (the frozen fixtures use numpy.dtype and
+# numpy.core.multiarray.scalar for the ``moment`` field; arrays and plain containers are allowed for caches written by
+# newer layouts).  Everything else -- builtins.eval, os.system, numpy helpers that call back into Python -- is refused:
+# whitelisting whole modules would let a crafted file reach them through REDUCE.
+_ALLOWED_GLOBALS = frozenset({
+    ("numpy", "dtype"), ("numpy", "ndarray"),
+    ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+    ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+    ("builtins", "list"), ("builtins", "dict"), ("builtins", "tuple"), ("builtins", "set"),
+    ("builtins", "int"), ("builtins", "float"), ("builtins", "bytes"), ("builtins", "bytearray"),
+    ("_codecs", "encode"),            # how protocol <= 2 pickles spell bytes
+})
+
+
 class _CacheUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if module.split(".")[0] == "photogrammetry":
             return type(name, (_Bag,), {})
-        if module.split(".")[0] not in ("numpy", "builtins", "collections", "copyreg", "_codecs"):
+        if (module, name) not in _ALLOWED_GLOBALS:
             raise pickle.UnpicklingError(f"refusing to load {module}.{name} from a keypoint cache file")
         return super().find_class(module, name)
 

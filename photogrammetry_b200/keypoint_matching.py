@@ -18,6 +18,7 @@ All compute happens in CUDA kernels behind ``pgm_*``; nothing here touches
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from typing import List, Optional, Sequence
 
@@ -47,6 +48,7 @@ class Matcher:
                 f"pgm_create(device={device}) failed: {self._lib.pgm_status_string(rc).decode()} "
                 "(libpgmatch has no CPU fallback)")
         self.device = int(device)
+        self._user_stream: Optional[int] = None     # what set_stream() bound (None: the handle's own stream)
 
     # -- lifetime ---------------------------------------------------------
     def close(self) -> None:
@@ -86,6 +88,24 @@ class Matcher:
         else:
             addr = int(cuda_stream)
         self._check(self._lib.pgm_set_stream(self._h, C.c_void_p(addr)))
+        self._user_stream = None if cuda_stream is None else int(cuda_stream)
+
+    @contextlib.contextmanager
+    def torch_ordered(self, device=None):
+        """Entry points that take or return torch tensors must be ordered against torch's work.  If the caller
+        bound a stream with :meth:`set_stream` that is their contract; otherwise the handle is bound to torch's
+        CURRENT stream for the duration of the call, so inputs written by torch kernels are visible and the
+        returned tensors can be consumed by torch (or NCCL) without an extra synchronisation."""
+        if self._user_stream is not None:
+            yield
+            return
+        import torch
+        cur = torch.cuda.current_stream(torch.device("cuda", self.device) if device is None else device).cuda_stream
+        self._check(self._lib.pgm_set_stream(self._h, C.c_void_p(1 if int(cur) == 0 else int(cur))))
+        try:
+            yield
+        finally:
+            self._check(self._lib.pgm_set_stream(self._h, C.c_void_p(0)))
 
     def synchronize(self) -> None:
         self._check(self._lib.pgm_synchronize(self._h))
@@ -217,9 +237,10 @@ class Matcher:
         n1, n2 = int(d_q.shape[0]), int(d_t.shape[0])
         stride = int(d_q.shape[1]) if n1 else int(d_t.shape[1])
         out = torch.empty((4, max(n1, 1)), dtype=torch.int32, device=d_q.device)
-        self._check(self._lib.pgm_knn2_hamming_dev(self._h, d_q.data_ptr() if n1 else None, n1,
-                                                   d_t.data_ptr() if n2 else None, n2, int(desc_bits), stride,
-                                                   *(out[k].data_ptr() for k in range(4))))
+        with self.torch_ordered(d_q.device):
+            self._check(self._lib.pgm_knn2_hamming_dev(self._h, d_q.data_ptr() if n1 else None, n1,
+                                                       d_t.data_ptr() if n2 else None, n2, int(desc_bits), stride,
+                                                       *(out[k].data_ptr() for k in range(4))))
         return tuple(out[k, :n1] for k in range(4))
 
     def pack_top2_keys_dev(self, best_j, best_d, second_j, second_d, index_offset: int):
@@ -227,8 +248,10 @@ class Matcher:
         import torch
         n = int(best_j.shape[0])
         keys = torch.empty((2, max(n, 1)), dtype=torch.int32, device=best_j.device)
-        self._check(self._lib.pgm_pack_top2_keys_dev(self._h, best_j.data_ptr(), best_d.data_ptr(), second_j.data_ptr(),
-                                                     second_d.data_ptr(), n, int(index_offset), keys.data_ptr()))
+        with self.torch_ordered(best_j.device):
+            self._check(self._lib.pgm_pack_top2_keys_dev(self._h, best_j.data_ptr(), best_d.data_ptr(),
+                                                         second_j.data_ptr(), second_d.data_ptr(), n, int(index_offset),
+                                                         keys.data_ptr()))
         return keys[:, :n] if n else keys[:, :0]
 
     def merge_top2_dev(self, keys):
@@ -237,7 +260,8 @@ class Matcher:
         g, _, n = (int(x) for x in keys.shape)
         keys = keys.contiguous()
         out = torch.empty((4, max(n, 1)), dtype=torch.int32, device=keys.device)
-        self._check(self._lib.pgm_merge_top2_dev(self._h, keys.data_ptr(), g, n, *(out[k].data_ptr() for k in range(4))))
+        with self.torch_ordered(keys.device):
+            self._check(self._lib.pgm_merge_top2_dev(self._h, keys.data_ptr(), g, n, *(out[k].data_ptr() for k in range(4))))
         return tuple(out[k, :n] for k in range(4))
 
     def ratio_crosscheck_filter_dev(self, n2: int, best_j, best_d, second_d, col_best_i, ratio: float = 0.8,
@@ -247,10 +271,12 @@ class Matcher:
         n1 = int(best_j.shape[0])
         out = torch.empty((3, max(n1, 1)), dtype=torch.int32, device=best_j.device)
         cnt = C.c_int32(0)
-        self._check(self._lib.pgm_ratio_crosscheck_filter_dev(
-            self._h, n1, int(n2), best_j.data_ptr(), best_d.data_ptr(), second_d.data_ptr(),
-            col_best_i.data_ptr() if col_best_i is not None and col_best_i.numel() else None, float(ratio),
-            int(bool(cross_check)), int(max_dist), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), C.byref(cnt)))
+        with self.torch_ordered(best_j.device):
+            self._check(self._lib.pgm_ratio_crosscheck_filter_dev(
+                self._h, n1, int(n2), best_j.data_ptr(), best_d.data_ptr(), second_d.data_ptr(),
+                col_best_i.data_ptr() if col_best_i is not None and col_best_i.numel() else None, float(ratio),
+                int(bool(cross_check)), int(max_dist), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                C.byref(cnt)))
         return out[:, :cnt.value]
 
     def match_keypoints_sorted(self, q: np.ndarray, t: np.ndarray, desc_bits: Optional[int] = None) -> np.ndarray:
@@ -332,9 +358,10 @@ class Matcher:
             sc = torch.empty(max(cap, 1), dtype=torch.int32, device=d_gray.device)
             desc = torch.zeros((max(cap, 1), stride), dtype=torch.uint8, device=d_gray.device)
             cnt = C.c_int32(0)
-            rc = self._lib.pgm_detect_describe_dev(self._h, d_gray.data_ptr(), wid, hgt, float(threshold), int(nms_radius),
-                                                   pairs.ctypes.data, n_pairs, stride, flags, xy.data_ptr(), sc.data_ptr(),
-                                                   desc.data_ptr(), cap, C.byref(cnt))
+            with self.torch_ordered(d_gray.device):
+                rc = self._lib.pgm_detect_describe_dev(self._h, d_gray.data_ptr(), wid, hgt, float(threshold),
+                                                       int(nms_radius), pairs.ctypes.data, n_pairs, stride, flags,
+                                                       xy.data_ptr(), sc.data_ptr(), desc.data_ptr(), cap, C.byref(cnt))
             if rc == PGM_E_CAPACITY and cnt.value > cap:
                 cap = cnt.value
                 continue

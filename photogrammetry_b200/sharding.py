@@ -155,9 +155,10 @@ class TrainShardedMatcher:
         self.n2_local, self.n2_total = int(d_t_local.shape[0]), int(n2_total)
         self._keep = (d_q, d_t_local)
         self._sh = C.c_void_p()
-        matcher._check(self._lib.pgm_shard_create(
-            matcher._h, d_q.data_ptr(), self.n1, d_t_local.data_ptr() if self.n2_local else None, self.n2_local,
-            int(col_offset), self.n2_total, int(desc_bits), self.stride, C.byref(self._sh)))
+        with matcher.torch_ordered(d_q.device):
+            matcher._check(self._lib.pgm_shard_create(
+                matcher._h, d_q.data_ptr(), self.n1, d_t_local.data_ptr() if self.n2_local else None, self.n2_local,
+                int(col_offset), self.n2_total, int(desc_bits), self.stride, C.byref(self._sh)))
         dev = d_q.device
         self.xkeys = torch.empty(self.n1, dtype=torch.int32, device=dev)
         self.xacc = torch.empty(self.n1, dtype=torch.int32, device=dev)
@@ -171,16 +172,21 @@ class TrainShardedMatcher:
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
 
     # the three local steps, exposed so a single process can drive several emulated ranks in lock-step
+    # (every step runs on torch's current stream -- Matcher.torch_ordered -- unless the caller bound a stream, so
+    # the collectives torch enqueues between the steps are ordered against the library's kernels)
     def step_round(self):
-        self._m._check(self._lib.pgm_shard_round(self._sh, self.xkeys.data_ptr()))
+        with self._m.torch_ordered(self.xkeys.device):
+            self._m._check(self._lib.pgm_shard_round(self._sh, self.xkeys.data_ptr()))
 
     def step_propose(self):
-        self._m._check(self._lib.pgm_shard_propose(self._sh, self.xkeys.data_ptr(), self.xacc.data_ptr()))
+        with self._m.torch_ordered(self.xkeys.device):
+            self._m._check(self._lib.pgm_shard_propose(self._sh, self.xkeys.data_ptr(), self.xacc.data_ptr()))
 
     def step_commit(self):
         import ctypes as C
         lr, lc = C.c_int32(0), C.c_int32(0)
-        self._m._check(self._lib.pgm_shard_commit(self._sh, self.xacc.data_ptr(), C.byref(lr), C.byref(lc)))
+        with self._m.torch_ordered(self.xkeys.device):
+            self._m._check(self._lib.pgm_shard_commit(self._sh, self.xacc.data_ptr(), C.byref(lr), C.byref(lc)))
         return lr.value, lc.value
 
     def done(self, live_rows: int) -> bool:
@@ -189,15 +195,16 @@ class TrainShardedMatcher:
     def finish(self, reference_compat_tail: bool = True):
         import ctypes as C
         cnt, rounds = C.c_int32(0), C.c_int32(0)
-        self._m._check(self._lib.pgm_shard_finish(
-            self._sh, self.out[0].data_ptr(), self.out[1].data_ptr(), self.out[2].data_ptr(),
-            1 if reference_compat_tail else 0, C.byref(cnt), C.byref(rounds)))
+        with self._m.torch_ordered(self.xkeys.device):
+            self._m._check(self._lib.pgm_shard_finish(
+                self._sh, self.out[0].data_ptr(), self.out[1].data_ptr(), self.out[2].data_ptr(),
+                1 if reference_compat_tail else 0, C.byref(cnt), C.byref(rounds)))
         self.rounds = rounds.value
         return self.out[:, :cnt.value]
 
     def match(self, reference_compat_tail: bool = True):
-        """Runs on the matcher's stream; the collectives run on the current torch stream, so the
-        caller must make that the same stream (``with torch.cuda.stream(s)`` + ``matcher.set_stream``)."""
+        """Library steps and collectives alternate on torch's current stream (or on the stream the caller bound
+        with ``matcher.set_stream``, which must then also be torch's current stream)."""
         prev = self.n1 + 1
         while True:
             self.step_round()

@@ -57,6 +57,16 @@ def test_keypoint_cache_roundtrip(tmp_path):
     assert [k.coord for k in back] == [(3, 4), (0, 9)]
 
 
+def test_keypoint_cache_refuses_code_execution(tmp_path):
+    """A crafted cache file must not reach builtins.eval / os.system through REDUCE (exact-name whitelist)."""
+    import pickle
+    for payload in (b"cbuiltins\neval\n(V1+1\ntR.", b"cos\nsystem\n(Vtrue\ntR.", b"cnumpy\nload\n(Vx\ntR."):
+        path = tmp_path / "evil.dat"
+        path.write_bytes(payload)
+        with pytest.raises(pickle.UnpicklingError):
+            load_keypoint_dat(str(path))
+
+
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "pgmatch.h")).read()
     declared = sorted(set(re.findall(r"\b(pgm_[a-z0-9_]+)\s*\(", header)))
