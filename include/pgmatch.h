@@ -55,7 +55,7 @@ typedef enum pgm_status {
     PGM_E_INVALID_ARG = -1,
     PGM_E_CAPACITY = -2,    /* output buffer too small */
     PGM_E_CUDA = -3,        /* a CUDA runtime call failed; see pgm_last_error */
-    PGM_E_NCCL = -4,        /* reserved for the train-sharded multi-GPU mode */
+    PGM_E_NCCL = -4,        /* pgm_multi_*: NCCL could not be loaded, or a collective / communicator call failed */
     PGM_E_EMPTY_TRAIN = -5, /* n1 > 0 and n2 == 0: the reference throws
                                ArgumentOutOfRangeException at KeypointMatching.cs:61 */
     PGM_E_NOMEM = -6,
@@ -275,6 +275,18 @@ int pgm_detect_describe_dev(pgm_handle *h, const float *d_gray, int32_t width, i
                             uint32_t flags, int32_t *d_out_xy, int32_t *d_out_score, uint8_t *d_out_desc,
                             int32_t capacity, int32_t *out_count);
 
+/* The batched form for a frame sequence (BASELINE configs[2]; the step the reference runs per frame,
+ * TestService.cs:85-91, KeypointDetection.Detect KeypointDetection.cs:42-63): n_images device-resident images of one
+ * size, d_gray[n_images][height][width].  Image k's keypoints go to its own `capacity` slots --
+ * d_out_xy[n_images][capacity][2], d_out_score[n_images][capacity], d_out_desc[n_images][capacity][stride_bytes] --
+ * and its keypoint count to d_out_counts[k] (device); a count above `capacity` means the list was truncated.
+ * Nothing is read back between the images: the call enqueues six kernels for the whole batch.  out_counts
+ * (host, int32[n_images]) may be NULL, in which case the call does not synchronise at all.  No NMS in this form. */
+int pgm_detect_describe_batch_dev(pgm_handle *h, const float *d_gray, int32_t n_images, int32_t width, int32_t height,
+                                  float threshold, const int32_t *pairs, int32_t n_pairs, int32_t stride_bytes,
+                                  uint32_t flags, int32_t *d_out_xy, int32_t *d_out_score, uint8_t *d_out_desc,
+                                  int32_t capacity, int32_t *d_out_counts, int32_t *out_counts);
+
 /* ---- the consumer of the match list --------------------
  * pgm_ransac_score: the scoring loops of CameraPoseEstimation.GetFundamentalMatrix
  * (ImageProcessing/CameraPoseEstimation.cs:41-88).  F: n_hyp row-major 3x3 float matrices (the estimates of the
@@ -289,36 +301,57 @@ int pgm_ransac_score(pgm_handle *h, const float *F, const uint8_t *valid, int32_
                      uint8_t *out_best_mask);
 
 /* ---- train-sharded single pair (multi-GPU) ----------
- * For ONE huge pair (BASELINE configs[3]: 200k x 200k) every rank holds all n1
- * queries and a contiguous slice [col_offset, col_offset + n2_local) of the
- * n2_total train descriptors.  The library runs the local steps; the two
- * `min` all-reduces per round over n1 packed 32-bit keys are the caller's
- * (torch.distributed / NCCL), which keeps NCCL out of the ABI:
+ * For ONE huge pair (BASELINE configs[3]: 200k x 200k; the call it shards is MatchKeypoints,
+ * KeypointMatching.cs:14-69) every rank holds all n1 queries and a contiguous slice
+ * [col_offset, col_offset + n2_local) of the n2_total train descriptors.  Two surfaces:
  *
- *   pgm_shard_create
- *   repeat:
- *     pgm_shard_round(shard, xkeys)            local distances + row/column argmin
- *     all_reduce(xkeys, MIN)   as int32        best (distance, global column) per row
- *     pgm_shard_propose(shard, xkeys, xacc)    mutual pairs whose column this rank owns
- *     all_reduce(xacc, MIN)    as int32
- *     pgm_shard_commit(shard, xacc, &live_rows, &live_cols_local)
- *   until live_rows == 0 or n2_total - (n1 - live_rows) == 0
- *   pgm_shard_finish                            reference-ordered triples on every rank
+ * (1) pgm_multi_*: the library owns the communicator -- one pgm_multi per rank (= per handle = per GPU; one process
+ *     per GPU, or one thread per GPU inside a process), NCCL over NVLink.  The host distributes the 128-byte id of
+ *     pgm_multi_unique_id (made on rank 0) by whatever channel it has; nothing else crosses the ABI.  NCCL is loaded
+ *     at run time (dlopen "libnccl.so.2"), so single-GPU users need no NCCL; failures return PGM_E_NCCL.
+ *       pgm_multi_match_train_sharded_dev   the greedy matcher; per round ONE min all-reduce of 2 x bound 32-bit keys
+ *                                           (bound = live rows, rounded up), no host synchronisation per round
+ *       pgm_multi_knn2_train_sharded_dev    nearest / second nearest with the top-2 merge: one all-gather of [2][n1]
+ *     Both are collective calls: every rank calls them with the same sizes / format / flags.
  *
- * Exchange buffers hold keys (distance << 20 | global train index); "none" is
- * 0x7F7F7F7F, so a signed 32-bit MIN orders them like the reference's
- * (distance, i, j) tie-break.  The result is bit-identical to
- * pgm_match_hamming_greedy on the unsharded pair.  All pointers are device
- * memory on the handle's device. */
+ * (2) pgm_shard_*: the same steps with the exchange left to the caller (another transport, or several emulated ranks
+ *     on one GPU in the tests):
+ *       pgm_shard_create
+ *       repeat:
+ *         pgm_shard_round(shard, x, bound)         local distances + row/column argmin; x[2 * bound] = [R | P]:
+ *                                                  R[pos] best key of live row pos over this rank's columns,
+ *                                                  P[pos] best key among this rank's columns that chose row pos
+ *         x = element-wise MIN of x over the ranks (as int32 or uint32)
+ *         pgm_shard_commit(shard, x, bound, &live_rows, &done)    row pos is matched iff R[pos] == P[pos]
+ *       until done
+ *       pgm_shard_finish                           reference-ordered triples on every rank
+ *     bound >= the number of live rows (n1 always works; the value pgm_shard_commit returned is the tight one).
+ *
+ * Exchange keys are (distance << 20 | global train index); "none" is 0x7F7F7F7F, so a signed 32-bit MIN orders them
+ * like the reference's (distance, i, j) tie-break.  The result is bit-identical to pgm_match_hamming_greedy on the
+ * unsharded pair.  All data pointers are device memory on the handle's device. */
 typedef struct pgm_shard pgm_shard;
 int pgm_shard_create(pgm_handle *h, const uint8_t *d_q, int32_t n1, const uint8_t *d_t_local, int32_t n2_local,
                      int32_t col_offset, int32_t n2_total, int32_t desc_bits, int32_t stride_bytes, pgm_shard **out);
-int pgm_shard_round(pgm_shard *s, uint32_t *d_xkeys);
-int pgm_shard_propose(pgm_shard *s, const uint32_t *d_xkeys, uint32_t *d_xacc);
-int pgm_shard_commit(pgm_shard *s, const uint32_t *d_xacc, int32_t *live_rows, int32_t *live_cols_local);
+int pgm_shard_round(pgm_shard *s, uint32_t *d_x, int32_t bound);
+int pgm_shard_commit(pgm_shard *s, const uint32_t *d_x, int32_t bound, int32_t *live_rows, int32_t *done);
 int pgm_shard_finish(pgm_shard *s, int32_t *d_out_qi, int32_t *d_out_tj, int32_t *d_out_dist, uint32_t flags,
                      int32_t *out_count, int32_t *out_rounds);
 int pgm_shard_destroy(pgm_shard *s);
+
+typedef struct pgm_multi pgm_multi;
+int pgm_multi_unique_id(uint8_t *out_id128);
+int pgm_multi_create(pgm_handle *h, const uint8_t *id128, int32_t rank, int32_t world, pgm_multi **out);
+int pgm_multi_destroy(pgm_multi *m);
+int pgm_multi_match_train_sharded_dev(pgm_multi *m, const uint8_t *d_q, int32_t n1, const uint8_t *d_t_local,
+                                      int32_t n2_local, int32_t col_offset, int32_t n2_total, int32_t desc_bits,
+                                      int32_t stride_bytes, int32_t *d_out_qi, int32_t *d_out_tj, int32_t *d_out_dist,
+                                      int32_t capacity, int32_t *out_count, uint32_t flags, int32_t *out_rounds);
+int pgm_multi_knn2_train_sharded_dev(pgm_multi *m, const uint8_t *d_q, int32_t n1, const uint8_t *d_t_local,
+                                     int32_t n2_local, int32_t col_offset, int32_t desc_bits, int32_t stride_bytes,
+                                     int32_t *d_best_j, int32_t *d_best_d, int32_t *d_second_j, int32_t *d_second_d);
+/* bytes this rank contributed to collectives, and their number, in the last pgm_multi_* call */
+int pgm_multi_get_exchange(pgm_multi *m, int64_t *bytes, int32_t *collectives);
 
 /* ---- measurement helpers -------------------------------------------------
  * Profiling mode brackets every launch of the dominant kernel (the round

@@ -37,9 +37,11 @@ EXPORTED_SYMBOLS = (
     "pgm_knn2_hamming", "pgm_knn2_hamming_dev", "pgm_match_ratio_crosscheck",
     "pgm_pack_top2_keys_dev", "pgm_merge_top2_dev", "pgm_ratio_crosscheck_filter_dev",
     "pgm_match_keypoints_sorted", "pgm_match_keypoints_sorted_dev", "pgm_knn2_l2", "pgm_knn2_l2_dev",
-    "pgm_fast_detect", "pgm_brief_describe", "pgm_nms", "pgm_detect_describe_dev", "pgm_ransac_score",
-    "pgm_shard_create", "pgm_shard_round", "pgm_shard_propose", "pgm_shard_commit", "pgm_shard_finish",
-    "pgm_shard_destroy",
+    "pgm_fast_detect", "pgm_brief_describe", "pgm_nms", "pgm_detect_describe_dev", "pgm_detect_describe_batch_dev",
+    "pgm_ransac_score",
+    "pgm_shard_create", "pgm_shard_round", "pgm_shard_commit", "pgm_shard_finish", "pgm_shard_destroy",
+    "pgm_multi_unique_id", "pgm_multi_create", "pgm_multi_destroy", "pgm_multi_match_train_sharded_dev",
+    "pgm_multi_knn2_train_sharded_dev", "pgm_multi_get_exchange",
     "pgm_set_profiling", "pgm_get_round_profile", "pgm_measure_popc_peak",
 )
 
@@ -142,13 +144,24 @@ def load() -> C.CDLL:
         lib.pgm_nms.argtypes = [C.c_void_p, i32p, i32p, C.c_int32, C.c_int32, i32p, C.POINTER(C.c_int32)]
         lib.pgm_detect_describe_dev.argtypes = [C.c_void_p, vp, C.c_int32, C.c_int32, C.c_float, C.c_int32, i32p, C.c_int32,
                                                 C.c_int32, C.c_uint32, i32p, i32p, u8p, C.c_int32, C.POINTER(C.c_int32)]
+        lib.pgm_detect_describe_batch_dev.argtypes = [C.c_void_p, vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, i32p,
+                                                      C.c_int32, C.c_int32, C.c_uint32, i32p, i32p, u8p, C.c_int32, i32p,
+                                                      i32p]
         lib.pgm_ransac_score.argtypes = [C.c_void_p, vp, u8p, C.c_int32, i32p, i32p, C.c_int32, C.c_float, i32p,
                                          C.POINTER(C.c_int32), u8p]
         lib.pgm_shard_create.argtypes = [C.c_void_p, u8p, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_int32, C.POINTER(C.c_void_p)]
-        lib.pgm_shard_round.argtypes = [C.c_void_p, C.c_void_p]
-        lib.pgm_shard_propose.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-        lib.pgm_shard_commit.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        lib.pgm_shard_round.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        lib.pgm_shard_commit.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        lib.pgm_multi_unique_id.argtypes = [C.c_void_p]
+        lib.pgm_multi_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        lib.pgm_multi_destroy.argtypes = [C.c_void_p]
+        lib.pgm_multi_match_train_sharded_dev.argtypes = [C.c_void_p, u8p, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32,
+                                                          C.c_int32, C.c_int32, i32p, i32p, i32p, C.c_int32,
+                                                          C.POINTER(C.c_int32), C.c_uint32, C.POINTER(C.c_int32)]
+        lib.pgm_multi_knn2_train_sharded_dev.argtypes = [C.c_void_p, u8p, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32,
+                                                         C.c_int32, i32p, i32p, i32p, i32p]
+        lib.pgm_multi_get_exchange.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
         lib.pgm_shard_finish.argtypes = [C.c_void_p, i32p, i32p, i32p, C.c_uint32, C.POINTER(C.c_int32),
                                          C.POINTER(C.c_int32)]
         lib.pgm_shard_destroy.argtypes = [C.c_void_p]

@@ -31,6 +31,7 @@ __global__ void fast_score_kernel(const float *__restrict__ img, int w, int h, f
                                   uint8_t *__restrict__ score) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= w || y >= h) return;
+    img += (size_t)blockIdx.z * w * h; score += (size_t)blockIdx.z * w * h;      // batched form: blockIdx.z = image
     uint8_t out = 0;
     if (x >= 3 && x < w - 3 && y >= 3 && y < h - 3) {                 // Detect's loop bounds, :45-47
         const float *p = img + (size_t)y * w + x;
@@ -74,6 +75,7 @@ __global__ void fast_score_kernel(const float *__restrict__ img, int w, int h, f
 // per-row keypoint counts (one block per row)
 __global__ void row_count_kernel(const uint8_t *__restrict__ score, int w, int32_t *__restrict__ rowcnt) {
     const int y = blockIdx.x;
+    score += (size_t)blockIdx.y * w * gridDim.x; rowcnt += (size_t)blockIdx.y * gridDim.x;   // batched form: blockIdx.y = image
     int c = 0;
     for (int x = threadIdx.x; x < w; x += blockDim.x) c += score[(size_t)y * w + x] != 0;
     __shared__ int s;
@@ -88,6 +90,7 @@ __global__ void row_count_kernel(const uint8_t *__restrict__ score, int w, int32
 // exclusive scan of n <= 65536 ints by one block of 1024 threads; total written to out[n]
 __global__ void scan_kernel(const int32_t *__restrict__ in, int n, int32_t *__restrict__ out) {
     __shared__ int s_w[32];
+    in += (size_t)blockIdx.x * n; out += (size_t)blockIdx.x * (n + 1);          // batched form: blockIdx.x = image
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int per = (n + 1023) / 1024, p0 = min(tid * per, n), p1 = min(p0 + per, n);
     int sum = 0;
@@ -107,6 +110,9 @@ __global__ void emit_kernel(const uint8_t *__restrict__ score, int w, int h, con
                             int capacity, int32_t *__restrict__ xy, int32_t *__restrict__ sc) {
     const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (y >= h) return;
+    // batched form: blockIdx.y = image; every image owns `capacity` output slots
+    score += (size_t)blockIdx.y * w * h; rowoff += (size_t)blockIdx.y * (h + 1);
+    xy += (size_t)blockIdx.y * capacity * 2; sc += (size_t)blockIdx.y * capacity;
     int base = rowoff[y];
     for (int x0 = 0; x0 < w; x0 += 32) {
         const int x = x0 + lane;
@@ -124,10 +130,16 @@ __global__ void emit_kernel(const uint8_t *__restrict__ score, int w, int h, con
 // (`descriptor <<= 1` per pair, first pair = MSB), stored little-endian in `stride` bytes.
 __global__ void brief_kernel(const float *__restrict__ img, int w, int h, const int32_t *__restrict__ xy, int n,
                              const int32_t *__restrict__ pairs /*[n_pairs][4]*/, int n_pairs, int stride_words,
-                             int lsb_first, uint32_t *__restrict__ desc) {
+                             int lsb_first, uint32_t *__restrict__ desc, const int32_t *__restrict__ rowoff = nullptr) {
     extern __shared__ uint32_t s_desc[];           // [warps][stride_words]
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + wid;
+    if (rowoff) {                                  // batched form: blockIdx.y = image, n = capacity per image, and the
+        const int z = blockIdx.y;                  // image's keypoint count sits behind its row offsets on the device
+        const int found = __ldg(rowoff + (size_t)z * (h + 1) + h);
+        img += (size_t)z * w * h; xy += (size_t)z * n * 2; desc += (size_t)z * n * stride_words;
+        n = min(n, found);
+    }
     uint32_t *mine = s_desc + wid * stride_words;
     for (int k = lane; k < stride_words; k += 32) mine[k] = 0u;
     __syncwarp();

@@ -1683,75 +1683,132 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_kernel(Chunk c, int r_st
 }
 
 // ---------------------------------------------------------------------------
-// train-sharded single pair: every rank holds all N1
-// queries and a contiguous slice of the train set.  Per round: the ordinary
-// round kernel on (live rows x live LOCAL columns) with global column ids in
-// the row keys; `min` all-reduce of the exported row keys (done by the host
-// side over NCCL); each rank proposes the mutual pairs whose winning column it
-// owns; `min` all-reduce of the proposals; every rank commits identically.
-// Exchange buffers use 0x7F7F7F7F for "none" so that a signed 32-bit min (what
-// the collective libraries offer) orders them like the unsigned keys.
+// train-sharded single pair: every rank holds all N1 queries and a contiguous slice of the
+// train set.  Per round each rank runs the ordinary round kernel on (live rows x live LOCAL columns) with global column
+// ids in the row keys, then ONE exchange decides the round: X = [R | P], both indexed by the row's position in the live
+// list (identical on every rank: the row compaction below is stable),
+//     R[pos] = the row's best key over the rank's columns          (d << 20 | global j)
+//     P[pos] = the best key among the rank's columns that CHOSE this row as their best row (each rank sees every
+//              row, so a local column's choice is final without any exchange)
+// and after an element-wise `min` over the ranks (NCCL all-reduce, or any other transport) row `pos` is matched iff
+// R[pos] == P[pos]: P >= R always (P ranges over a subset of the row's columns), with equality exactly when the row's
+// best column chose it back -- the locally dominant edge the reference's argmin scan emits next
+// (KeypointMatching.cs:44-65).  Every rank commits identically.  Exchange buffers use 0x7F7F7F7F for "none" so that a
+// signed 32-bit min (what some transports offer) orders them like the unsigned keys.
 // ---------------------------------------------------------------------------
 constexpr uint32_t XKEY_NONE = 0x7F7F7F7Fu;   // memset-able, above every real key, positive as int32
+constexpr int SHARD_BLOCK = 1024;             // rows per block of the stable row compaction
 
-__global__ void shard_export_kernel(Chunk c, int r, uint32_t *xkeys) {
-    const PairDesc pd = c.pairs[0];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pd.n1; i += gridDim.x * blockDim.x) {
-        const uint32_t k = __ldcg(c.rowbest[r & 1] + i);
-        xkeys[i] = k == KEY_NONE ? XKEY_NONE : k;
-    }
-}
+struct ShardCtl {                 // device resident, one per sharded pair
+    int32_t done;                 // sticky: no live row or no live column is left anywhere
+    int32_t live_rows;            // after the last commit (identical on every rank)
+    int32_t live_cols_local;
+    int32_t rounds;               // commits that found the pair not yet done
+};
 
-// xkeys: globally reduced row keys.  xacc[i] = key if this rank owns the winning column and the
-// column's best row is i (mutual), else none.
-__global__ void shard_propose_kernel(Chunk c, int r, const uint32_t *xkeys, uint32_t *xacc, int n2_local) {
-    const PairDesc pd = c.pairs[0];
+// X[0, bound) = R (padded with none), X[bound, 2 bound) = none (the proposals are min-ed in by the next kernel)
+__global__ void shard_export_rows_kernel(Chunk c, int r, uint32_t *__restrict__ X, int bound) {
     const int nlr = __ldcg(cnt_ptr(c, r % 3, 0));
-    // xacc was filled with XKEY_NONE (memset 0x7F) before the launch
-    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < nlr; x += gridDim.x * blockDim.x) {
-        const int i = __ldcg(c.live_rows[r & 1] + x);
-        const uint32_t rk = __ldcg(xkeys + i);
-        if (rk == XKEY_NONE) continue;
-        const int jl = (int)(rk & KEY_IDX_MASK) - pd.col_id_offset;
-        if (jl < 0 || jl >= n2_local) continue;
-        const uint32_t ck = __ldcg(c.colbest[r & 1] + jl);
-        if ((ck & KEY_IDX_MASK) == (uint32_t)i) xacc[i] = rk;
+    const int32_t *live = c.live_rows[r & 1];
+    const uint32_t *rowbest = c.rowbest[r & 1];
+    for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < bound; pos += gridDim.x * blockDim.x) {
+        uint32_t k = XKEY_NONE;
+        if (pos < nlr) { const uint32_t v = __ldcg(rowbest + __ldcg(live + pos)); if (v != KEY_NONE) k = v; }
+        X[pos] = k;
+        X[bound + pos] = XKEY_NONE;
     }
 }
 
-// xacc: globally reduced proposals.  Rows: record matches / append survivors.  Owned matched
-// columns are flagged dead in coldead[].
-__global__ void shard_commit_rows_kernel(Chunk c, int r, const uint32_t *xacc, uint8_t *coldead, int n2_local) {
-    const PairDesc pd = c.pairs[0];
-    const int cur = r & 1, nxt = cur ^ 1, lane = threadIdx.x & 31;
+// every live local column proposes (distance, its GLOBAL id) to the row it chose
+__global__ void shard_propose_cols_kernel(Chunk c, int r, uint32_t *__restrict__ X, int bound) {
+    const PairDesc &pd = c.pairs[0];
+    const int nlc = __ldcg(cnt_ptr(c, r % 3, 0) + 1);
+    const int32_t *live = c.live_cols[r & 1];
+    const uint32_t *colbest = c.colbest[r & 1];
+    const int off = __ldg(&pd.col_id_offset);
+    for (int y = blockIdx.x * blockDim.x + threadIdx.x; y < nlc; y += gridDim.x * blockDim.x) {
+        const int j = __ldcg(live + y);
+        const uint32_t ck = __ldcg(colbest + j);
+        if (ck == KEY_NONE) continue;
+        const int pos = r == 0 ? (int)(ck & KEY_IDX_MASK) : __ldcg(c.row_pos + (ck & KEY_IDX_MASK));   // round 0: identity list
+        if (pos < bound) atomicMin(X + bound + pos, (ck & ~KEY_IDX_MASK) | (uint32_t)(j + off));
+    }
+}
+
+// X: reduced over the ranks.  Pass 1 of the commit: record the matches, flag the owned matched columns dead, count the
+// surviving rows of each block of SHARD_BLOCK live-list positions.
+__global__ void __launch_bounds__(SHARD_BLOCK) shard_commit_mark_kernel(Chunk c, int r, const uint32_t *__restrict__ X, int bound,
+                                                                        uint8_t *__restrict__ coldead, int n2_local,
+                                                                        int32_t *__restrict__ blockcnt) {
+    const PairDesc &pd = c.pairs[0];
     const int nlr = __ldcg(cnt_ptr(c, r % 3, 0));
-    const int nrounded = (nlr + 31) & ~31;
-    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < nrounded; x += gridDim.x * blockDim.x) {
-        bool survive = false;
-        int i = 0;
-        if (x < nlr) {
-            i = __ldcg(c.live_rows[cur] + x);
-            const uint32_t a = __ldcg(xacc + i);
-            if (a != XKEY_NONE) {
-                c.match_key[i] = a;
-                const int jl = (int)(a & KEY_IDX_MASK) - pd.col_id_offset;
-                if (jl >= 0 && jl < n2_local) coldead[jl] = 1;
-            } else {
-                survive = true;
-                c.rowbest[nxt][i] = KEY_NONE;
-            }
+    const int pos = blockIdx.x * SHARD_BLOCK + threadIdx.x;
+    bool survive = false;
+    if (pos < nlr && pos < bound) {
+        const uint32_t R = __ldcg(X + pos), P = __ldcg(X + bound + pos);
+        if (R != XKEY_NONE && R == P) {
+            const int i = __ldcg(c.live_rows[r & 1] + pos);
+            c.match_key[i] = R;
+            const int jl = (int)(R & KEY_IDX_MASK) - __ldg(&pd.col_id_offset);
+            if (jl >= 0 && jl < n2_local) coldead[jl] = 1;
+        } else {
+            survive = true;
         }
-        const unsigned m = __ballot_sync(0xffffffffu, survive);
-        if (m) {
-            int base = 0;
-            if (lane == (__ffs(m) - 1)) base = atomicAdd(cnt_ptr(c, (r + 1) % 3, 0), __popc(m));
-            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-            if (survive) c.live_rows[nxt][base + __popc(m & ((1u << lane) - 1u))] = i;
-        }
+    }
+    const int n = __syncthreads_count(survive);
+    if (threadIdx.x == 0) blockcnt[blockIdx.x] = n;
+}
+
+// Pass 2: stable compaction of the surviving rows (block b starts behind the survivors of blocks 0 .. b-1), so every
+// rank ends up with the same list in the same order.  Also keeps row_pos and resets the survivors' keys.
+__global__ void __launch_bounds__(SHARD_BLOCK) shard_commit_scatter_kernel(Chunk c, int r, const uint32_t *__restrict__ X, int bound,
+                                                                           const int32_t *__restrict__ blockcnt, int n_blocks,
+                                                                           ShardCtl *__restrict__ ctl, int n1, int n2_total) {
+    __shared__ int s_w[SHARD_BLOCK / 32], s_base, s_total;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int cur = r & 1, nxt = cur ^ 1;
+    const int nlr = __ldcg(cnt_ptr(c, r % 3, 0));
+    int before = 0, total = 0;
+    for (int b = tid; b < n_blocks; b += SHARD_BLOCK) {
+        const int v = (b * SHARD_BLOCK < nlr) ? __ldcg(blockcnt + b) : 0;
+        total += v;
+        if (b < (int)blockIdx.x) before += v;
+    }
+    before = __reduce_add_sync(0xffffffffu, before); total = __reduce_add_sync(0xffffffffu, total);
+    if (tid == 0) { s_base = 0; s_total = 0; }
+    __syncthreads();
+    if (lane == 0) { atomicAdd(&s_base, before); atomicAdd(&s_total, total); }
+    __syncthreads();
+    const int pos = blockIdx.x * SHARD_BLOCK + tid;
+    bool survive = false;
+    int i = 0;
+    if (pos < nlr && pos < bound) {
+        const uint32_t R = __ldcg(X + pos), P = __ldcg(X + bound + pos);
+        survive = !(R != XKEY_NONE && R == P);
+        i = __ldcg(c.live_rows[cur] + pos);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, survive);
+    if (lane == 0) s_w[wid] = __popc(m);
+    __syncthreads();
+    int woff = s_base;
+    for (int w = 0; w < wid; w++) woff += s_w[w];
+    if (survive) {
+        const int np = woff + __popc(m & ((1u << lane) - 1u));
+        c.live_rows[nxt][np] = i;
+        c.row_pos[i] = np;
+        c.rowbest[nxt][i] = KEY_NONE;
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        const int left = s_total;
+        cnt_ptr(c, (r + 1) % 3, 0)[0] = left;
+        const bool was_done = ctl->done != 0;
+        ctl->live_rows = left;
+        if (!was_done) ctl->rounds = r + 1;
+        if (left == 0 || n2_total - (n1 - left) <= 0) ctl->done = 1;
     }
 }
 
-__global__ void __launch_bounds__(ACCEPT_THREADS) shard_commit_cols_kernel(Chunk c, int r, const uint8_t *coldead) {
+__global__ void __launch_bounds__(ACCEPT_THREADS) shard_commit_cols_kernel(Chunk c, int r, const uint8_t *coldead, ShardCtl *ctl) {
     const int cur = r & 1, nxt = cur ^ 1, lane = threadIdx.x & 31;
     const int nlc = __ldcg(cnt_ptr(c, r % 3, 0) + 1);
     const int nrounded = (nlc + 31) & ~31;
@@ -1771,6 +1828,7 @@ __global__ void __launch_bounds__(ACCEPT_THREADS) shard_commit_cols_kernel(Chunk
         }
     }
     plan_in_last_block(c, r + 1, gridDim.x);
+    (void)ctl;
 }
 
 // ---------------------------------------------------------------------------

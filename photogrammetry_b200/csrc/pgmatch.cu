@@ -1693,6 +1693,69 @@ extern "C" int pgm_detect_describe_dev(pgm_handle *h, const float *d_gray, int32
     return PGM_OK;
 }
 
+// Many equally sized images in one call, nothing read back in between: FAST-12 -> ordered keypoint list -> BRIEF for
+// image k into its own `capacity` output slots; the counts stay on the device (d_out_counts) and are copied to
+// `out_counts` at the end if the caller wants them (one synchronisation for the whole batch, none if NULL).  A count
+// above `capacity` means the image's list was truncated.  No NMS in this form.
+__global__ void batch_counts_kernel(const int32_t *__restrict__ rowoff, int h, int n_images, int32_t *__restrict__ counts) {
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    if (z < n_images) counts[z] = rowoff[(size_t)z * (h + 1) + h];
+}
+
+extern "C" int pgm_detect_describe_batch_dev(pgm_handle *h, const float *d_gray, int32_t n_images, int32_t width,
+                                             int32_t height, float threshold, const int32_t *pairs, int32_t n_pairs,
+                                             int32_t stride_bytes, uint32_t flags, int32_t *d_out_xy,
+                                             int32_t *d_out_score, uint8_t *d_out_desc, int32_t capacity,
+                                             int32_t *d_out_counts, int32_t *out_counts) {
+    using namespace pgm_det;
+    if (!h) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    int rc = check_format(h, n_pairs, stride_bytes);       // desc_bits == NumGaussianPairs
+    if (rc) return rc;
+    if (!d_gray || n_images < 0 || n_images > 65535 || width < 1 || height < 1 || width > 65535 || height > 65535 ||
+        !pairs || capacity < 1 || !d_out_xy || !d_out_score || !d_out_desc || !d_out_counts)
+        return fail(h, PGM_E_INVALID_ARG, "bad arguments");
+    h->stats = pgm_stats{};
+    h->stats_pending = false;
+    if (n_images == 0) return PGM_OK;
+    CU_CHECK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const size_t npx = (size_t)width * height;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_sc = take(npx * n_images), o_cnt = take((size_t)height * n_images * 4);
+    const size_t o_off = take((size_t)(height + 1) * n_images * 4), o_pairs = take((size_t)n_pairs * 16);
+    if ((rc = ensure_dev(h, h->misc, off))) return rc;
+    if ((rc = ensure_host(h, h->pin_in, (size_t)n_pairs * 16))) return rc;
+    char *base = (char *)h->misc.p;
+    uint8_t *d_sc = (uint8_t *)(base + o_sc);
+    int32_t *d_cnt = (int32_t *)(base + o_cnt), *d_off = (int32_t *)(base + o_off), *d_pairs = (int32_t *)(base + o_pairs);
+    CU_CHECK(h, cudaStreamSynchronize(s));                 // the staging buffer may still feed an earlier call's copy
+    memcpy(h->pin_in.p, pairs, (size_t)n_pairs * 16);
+    CU_CHECK(h, cudaMemcpyAsync(d_pairs, h->pin_in.p, (size_t)n_pairs * 16, cudaMemcpyHostToDevice, s));
+    dim3 blk(32, 8), grd((width + 31) / 32, (height + 7) / 8, n_images);
+    if (flags & PGM_FLAG_PYTHON_GENERATION) fast_score_kernel<1><<<grd, blk, 0, s>>>(d_gray, width, height, threshold, d_sc);
+    else fast_score_kernel<0><<<grd, blk, 0, s>>>(d_gray, width, height, threshold, d_sc);
+    row_count_kernel<<<dim3(height, n_images), 128, 0, s>>>(d_sc, width, d_cnt);
+    scan_kernel<<<n_images, 1024, 0, s>>>(d_cnt, height, d_off);
+    emit_kernel<<<dim3((height + 3) / 4, n_images), 128, 0, s>>>(d_sc, width, height, d_off, capacity, d_out_xy, d_out_score);
+    const int warps = 4, sw = stride_bytes / 4;
+    brief_kernel<<<dim3((capacity + warps - 1) / warps, n_images), warps * 32, warps * sw * 4, s>>>(
+        d_gray, width, height, d_out_xy, capacity, d_pairs, n_pairs, sw, (flags & PGM_FLAG_PYTHON_GENERATION) ? 1 : 0,
+        (uint32_t *)d_out_desc, d_off);
+    batch_counts_kernel<<<(n_images + 255) / 256, 256, 0, s>>>(d_off, height, n_images, d_out_counts);
+    h->stats.kernel_launches += 6;
+    CU_CHECK(h, cudaGetLastError());
+    if (out_counts) {
+        if ((rc = ensure_host(h, h->pin_out, (size_t)n_images * 4))) return rc;
+        CU_CHECK(h, cudaMemcpyAsync(h->pin_out.p, d_out_counts, (size_t)n_images * 4, cudaMemcpyDeviceToHost, s));
+        CU_CHECK(h, cudaStreamSynchronize(s));
+        memcpy(out_counts, h->pin_out.p, (size_t)n_images * 4);
+        h->stats.host_syncs++; h->stats.d2h_bytes += (int64_t)n_images * 4;
+    }
+    return PGM_OK;
+}
+
 // ---------------------------------------------------------------------------
 // the consumer of the match list: RANSAC hypothesis scoring (pgm_ransac.cuh)
 // ---------------------------------------------------------------------------
@@ -1744,8 +1807,12 @@ extern "C" int pgm_ransac_score(pgm_handle *h, const float *F, const uint8_t *va
 }
 
 // ---------------------------------------------------------------------------
-// train-sharded single pair: stepwise device API; the collectives between the
-// steps belong to the caller (torch.distributed / NCCL `min` all-reduce)
+// train-sharded single pair (BASELINE configs[3]).  Two surfaces over the same kernels:
+//   pgm_shard_*   stepwise: the ONE exchange per round (element-wise min of X over the ranks) belongs to the caller
+//                 (torch.distributed, MPI, or -- in the tests -- several emulated ranks on one GPU)
+//   pgm_multi_*   the library owns an NCCL communicator (one rank per handle) and runs the whole match with no host
+//                 synchronisation per round: rounds are enqueued in batches and an 8-byte status read-back per batch,
+//                 checked two batches late, stops the loop and shrinks the exchange
 // ---------------------------------------------------------------------------
 struct pgm_shard {
     pgm_handle *h = nullptr;
@@ -1755,7 +1822,9 @@ struct pgm_shard {
     int round = 0;
     int round_grid = 0;
     uint8_t *coldead = nullptr;
-    int32_t *h_counts = nullptr;   // pinned: live rows / live local cols after the last commit
+    int32_t *blockcnt = nullptr;
+    ShardCtl *ctl = nullptr;       // device
+    ShardCtl *h_ctl = nullptr;     // pinned: [8] status read-backs (ring)
 };
 
 extern "C" int pgm_shard_create(pgm_handle *h, const uint8_t *d_q, int32_t n1, const uint8_t *d_t_local,
@@ -1767,7 +1836,7 @@ extern "C" int pgm_shard_create(pgm_handle *h, const uint8_t *d_q, int32_t n1, c
     int rc = check_format(h, desc_bits, stride_bytes);
     if (rc) return rc;
     if (n1 <= 0 || n2_local < 0 || n2_total <= 0 || col_offset < 0 || col_offset + n2_local > n2_total ||
-        n1 >= MAX_N || n2_total >= MAX_N)
+        n1 >= MAX_N || n2_total >= MAX_N || !d_q || (n2_local > 0 && !d_t_local))
         return fail(h, PGM_E_INVALID_ARG, "bad shard geometry");
     CU_CHECK(h, cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
@@ -1775,6 +1844,7 @@ extern "C" int pgm_shard_create(pgm_handle *h, const uint8_t *d_q, int32_t n1, c
     sh->h = h; sh->words = stride_bytes / 4; sh->desc_bits = desc_bits;
     sh->n1 = n1; sh->n2_local = n2_local; sh->n2_total = n2_total; sh->col_offset = col_offset;
     const int64_t rows = n1, cols = std::max(n2_local, 1);
+    const int n_blocks = (n1 + SHARD_BLOCK - 1) / SHARD_BLOCK;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t o_pairs = take(sizeof(PairDesc));
@@ -1782,8 +1852,9 @@ extern "C" int pgm_shard_create(pgm_handle *h, const uint8_t *d_q, int32_t n1, c
     const size_t o_lr0 = take(4 * rows), o_lr1 = take(4 * rows), o_lc0 = take(4 * cols), o_lc1 = take(4 * cols);
     const size_t o_cnt = take(sizeof(int32_t) * 6), o_mk = take(4 * rows), o_tb = take(8), o_ab = take(8);
     const size_t o_st = take(1), o_small = take(sizeof(SmallInfo)), o_plan = take(sizeof(PlanInfo)), o_dead = take(cols);
+    const size_t o_rpos = take(4 * rows), o_bcnt = take(4 * (size_t)n_blocks), o_ctl = take(sizeof(ShardCtl));
     if ((rc = ensure_dev(h, sh->state, off))) { delete sh; return rc; }
-    if (cudaMallocHost((void **)&sh->h_counts, 64) != cudaSuccess) { cudaFree(sh->state.p); delete sh; return PGM_E_CUDA; }
+    if (cudaMallocHost((void **)&sh->h_ctl, sizeof(ShardCtl) * 8) != cudaSuccess) { cudaFree(sh->state.p); delete sh; return PGM_E_CUDA; }
     char *base = (char *)sh->state.p;
     if (h->ctas_per_sm[sh->words / 4] == 0) h->ctas_per_sm[sh->words / 4] = std::max(1, dispatch_occupancy(sh->words));
     sh->round_grid = h->num_sms * h->ctas_per_sm[sh->words / 4];
@@ -1792,6 +1863,7 @@ extern "C" int pgm_shard_create(pgm_handle *h, const uint8_t *d_q, int32_t n1, c
     c.ctas_per_sm = h->ctas_per_sm[sh->words / 4];
     c.fin_max_evals = FIN_MAX_EVALS;
     c.large_min_evals = large_tile_min_evals(h);
+    c.words = sh->words;
     c.rowbest[0] = (uint32_t *)(base + o_rb0); c.rowbest[1] = (uint32_t *)(base + o_rb1);
     c.colbest[0] = (uint32_t *)(base + o_cb0); c.colbest[1] = (uint32_t *)(base + o_cb1);
     c.live_rows[0] = (int32_t *)(base + o_lr0); c.live_rows[1] = (int32_t *)(base + o_lr1);
@@ -1799,14 +1871,18 @@ extern "C" int pgm_shard_create(pgm_handle *h, const uint8_t *d_q, int32_t n1, c
     c.counts = (int32_t *)(base + o_cnt); c.match_key = (uint32_t *)(base + o_mk);
     c.tile_base = (int32_t *)(base + o_tb); c.ablock_base = (int32_t *)(base + o_ab);
     c.status = (uint8_t *)(base + o_st); c.small = (SmallInfo *)(base + o_small); c.plan = (PlanInfo *)(base + o_plan);
+    c.row_pos = (int32_t *)(base + o_rpos);      // (c.cand stays null: no candidate edges in this mode)
     c.timeline = nullptr;
     sh->coldead = (uint8_t *)(base + o_dead);
+    sh->blockcnt = (int32_t *)(base + o_bcnt);
+    sh->ctl = (ShardCtl *)(base + o_ctl);
     PairPack pack{};
     pack.p[0].q = (const uint32_t *)d_q; pack.p[0].t = (const uint32_t *)d_t_local;
     pack.p[0].n1 = n1; pack.p[0].n2 = n2_local; pack.p[0].row_base = 0; pack.p[0].col_base = 0; pack.p[0].out_base = 0;
-    pack.p[0].col_id_offset = col_offset; pack.p[0].flags = PAIR_FLAG_NO_FINISHER;
+    pack.p[0].col_id_offset = col_offset; pack.p[0].flags = PAIR_FLAG_NO_FINISHER | PAIR_FLAG_NO_EMIT;
     CU_CHECK(h, cudaMemsetAsync(c.plan, 0, sizeof(PlanInfo), s));
     CU_CHECK(h, cudaMemsetAsync(sh->coldead, 0, cols, s));
+    CU_CHECK(h, cudaMemsetAsync(sh->ctl, 0, sizeof(ShardCtl), s));
     dim3 igrid(std::max(1, std::min((std::max(n1, n2_local) + ACCEPT_THREADS - 1) / ACCEPT_THREADS, 64)), 1);
     init_kernel<true><<<igrid, ACCEPT_THREADS, 0, s>>>(c, pack);
     CU_CHECK(h, cudaGetLastError());
@@ -1814,63 +1890,62 @@ extern "C" int pgm_shard_create(pgm_handle *h, const uint8_t *d_q, int32_t n1, c
     return PGM_OK;
 }
 
-// Step 1: local round; xkeys (device, n1 x uint32) receives this rank's row keys for the min all-reduce.
-extern "C" int pgm_shard_round(pgm_shard *sh, uint32_t *d_xkeys) {
-    if (!sh || !d_xkeys) return PGM_E_INVALID_ARG;
+// enqueue: local round r, then this rank's contribution to the exchange into d_x[2 * bound] (bound >= live rows)
+static int shard_enqueue_round(pgm_shard *sh, uint32_t *d_x, int bound, cudaStream_t s) {
     pgm_handle *h = sh->h;
-    std::lock_guard<std::mutex> lk(h->mu);
-    CU_CHECK(h, cudaSetDevice(h->device));
-    cudaStream_t s = h->stream;
     dispatch_round(sh->words, sh->c, sh->round, sh->round_grid, s);
-    shard_export_kernel<<<std::min((sh->n1 + 255) / 256, h->num_sms * 8), 256, 0, s>>>(sh->c, sh->round, d_xkeys);
-    CU_CHECK(h, cudaGetLastError());
+    const int g = std::max(1, std::min((bound + 255) / 256, h->num_sms * 8));
+    shard_export_rows_kernel<<<g, 256, 0, s>>>(sh->c, sh->round, d_x, bound);
+    const int gc = std::max(1, std::min((sh->n2_local + 255) / 256, h->num_sms * 8));
+    shard_propose_cols_kernel<<<gc, 256, 0, s>>>(sh->c, sh->round, d_x, bound);
+    h->stats.kernel_launches += 3;
     return PGM_OK;
 }
 
-// Step 2 (xkeys now globally min-reduced): proposals of this rank into xacc for the second min all-reduce.
-extern "C" int pgm_shard_propose(pgm_shard *sh, const uint32_t *d_xkeys, uint32_t *d_xacc) {
-    if (!sh || !d_xkeys || !d_xacc) return PGM_E_INVALID_ARG;
+// enqueue: commit of round r from the reduced exchange buffer; advances the round counter
+static int shard_enqueue_commit(pgm_shard *sh, const uint32_t *d_x, int bound, cudaStream_t s) {
     pgm_handle *h = sh->h;
-    std::lock_guard<std::mutex> lk(h->mu);
-    CU_CHECK(h, cudaSetDevice(h->device));
-    cudaStream_t s = h->stream;
-    CU_CHECK(h, cudaMemsetAsync(d_xacc, 0x7F, (size_t)sh->n1 * 4, s));
-    shard_propose_kernel<<<std::min((sh->n1 + 255) / 256, h->num_sms * 8), 256, 0, s>>>(sh->c, sh->round, d_xkeys, d_xacc,
-                                                                                     sh->n2_local);
-    CU_CHECK(h, cudaGetLastError());
-    return PGM_OK;
-}
-
-// Step 3 (xacc now globally min-reduced): commit; returns the live rows (identical on all ranks) and
-// this rank's live columns.  Synchronises the stream (8 bytes read back).
-extern "C" int pgm_shard_commit(pgm_shard *sh, const uint32_t *d_xacc, int32_t *live_rows, int32_t *live_cols_local) {
-    if (!sh || !d_xacc) return PGM_E_INVALID_ARG;
-    pgm_handle *h = sh->h;
-    std::lock_guard<std::mutex> lk(h->mu);
-    CU_CHECK(h, cudaSetDevice(h->device));
-    cudaStream_t s = h->stream;
     const int r = sh->round;
-    const int g1 = std::max(1, std::min((sh->n1 + 255) / 256, h->num_sms * 8));
+    const int nb = std::max(1, (std::min(bound, sh->n1) + SHARD_BLOCK - 1) / SHARD_BLOCK);
+    shard_commit_mark_kernel<<<nb, SHARD_BLOCK, 0, s>>>(sh->c, r, d_x, bound, sh->coldead, sh->n2_local, sh->blockcnt);
+    shard_commit_scatter_kernel<<<nb, SHARD_BLOCK, 0, s>>>(sh->c, r, d_x, bound, sh->blockcnt, nb, sh->ctl, sh->n1, sh->n2_total);
     const int g2 = std::max(1, std::min((sh->n2_local + ACCEPT_THREADS - 1) / ACCEPT_THREADS, h->num_sms * 8));
-    shard_commit_rows_kernel<<<g1, 256, 0, s>>>(sh->c, r, d_xacc, sh->coldead, sh->n2_local);
-    shard_commit_cols_kernel<<<g2, ACCEPT_THREADS, 0, s>>>(sh->c, r, sh->coldead);
-    CU_CHECK(h, cudaMemcpyAsync(sh->h_counts, sh->c.counts + 2 * ((r + 1) % 3), 8, cudaMemcpyDeviceToHost, s));
-    CU_CHECK(h, cudaStreamSynchronize(s));
+    shard_commit_cols_kernel<<<g2, ACCEPT_THREADS, 0, s>>>(sh->c, r, sh->coldead, sh->ctl);
+    h->stats.kernel_launches += 3;
     sh->round = r + 1;
-    if (live_rows) *live_rows = sh->h_counts[0];
-    if (live_cols_local) *live_cols_local = sh->h_counts[1];
     return PGM_OK;
 }
 
-// Final step: every rank holds every accepted (row -> global column, distance); emit them in the
-// reference's order into device arrays of n1 triples (tail included with PGM_FLAG_REFERENCE_COMPAT_TAIL).
-extern "C" int pgm_shard_finish(pgm_shard *sh, int32_t *d_out_qi, int32_t *d_out_tj, int32_t *d_out_dist, uint32_t flags,
-                                int32_t *out_count, int32_t *out_rounds) {
-    if (!sh) return PGM_E_INVALID_ARG;
+// Step 1: local round; d_x (device, uint32[2 * bound], bound >= the live rows, e.g. n1) receives this rank's [R | P].
+extern "C" int pgm_shard_round(pgm_shard *sh, uint32_t *d_x, int32_t bound) {
+    if (!sh || !d_x || bound < 1) return PGM_E_INVALID_ARG;
+    pgm_handle *h = sh->h;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU_CHECK(h, cudaSetDevice(h->device));
+    shard_enqueue_round(sh, d_x, bound, h->stream);
+    CU_CHECK(h, cudaGetLastError());
+    return PGM_OK;
+}
+
+// Step 2 (d_x now min-reduced over the ranks): commit; returns the live rows (identical on all ranks) and whether the
+// pair is finished.  Synchronises the stream (16 bytes read back).
+extern "C" int pgm_shard_commit(pgm_shard *sh, const uint32_t *d_x, int32_t bound, int32_t *live_rows, int32_t *done) {
+    if (!sh || !d_x || bound < 1) return PGM_E_INVALID_ARG;
     pgm_handle *h = sh->h;
     std::lock_guard<std::mutex> lk(h->mu);
     CU_CHECK(h, cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
+    shard_enqueue_commit(sh, d_x, bound, s);
+    CU_CHECK(h, cudaMemcpyAsync(sh->h_ctl, sh->ctl, sizeof(ShardCtl), cudaMemcpyDeviceToHost, s));
+    CU_CHECK(h, cudaStreamSynchronize(s));
+    if (live_rows) *live_rows = sh->h_ctl[0].live_rows;
+    if (done) *done = sh->h_ctl[0].done;
+    return PGM_OK;
+}
+
+static int shard_finish_locked(pgm_shard *sh, int32_t *d_out_qi, int32_t *d_out_tj, int32_t *d_out_dist, uint32_t flags,
+                               cudaStream_t s) {
+    pgm_handle *h = sh->h;
     // the order kernel derives the tail from min(n1, n2): it needs the TOTAL train size
     CU_CHECK(h, cudaMemcpyAsync((char *)sh->c.pairs + offsetof(PairDesc, n2), &sh->n2_total, 4, cudaMemcpyHostToDevice, s));
     const int nbins = 32 * sh->words + 1;     // padded width (see run_chunk)
@@ -1886,10 +1961,26 @@ extern "C" int pgm_shard_finish(pgm_shard *sh, int32_t *d_out_qi, int32_t *d_out
     }
     order_kernel<<<1, ORDER_THREADS_STANDALONE, order_smem_bytes(nbins, ORDER_THREADS_STANDALONE), s>>>(
         sh->c, nbins, flags, d_out_qi, d_out_tj, d_out_dist);
+    h->stats.kernel_launches += 1;
     CU_CHECK(h, cudaGetLastError());
+    return PGM_OK;
+}
+
+// Final step: every rank holds every accepted (row -> global column, distance); emit them in the
+// reference's order into device arrays of n1 triples (tail included with PGM_FLAG_REFERENCE_COMPAT_TAIL).
+extern "C" int pgm_shard_finish(pgm_shard *sh, int32_t *d_out_qi, int32_t *d_out_tj, int32_t *d_out_dist, uint32_t flags,
+                                int32_t *out_count, int32_t *out_rounds) {
+    if (!sh || !d_out_qi || !d_out_tj || !d_out_dist) return PGM_E_INVALID_ARG;
+    pgm_handle *h = sh->h;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU_CHECK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    int rc = shard_finish_locked(sh, d_out_qi, d_out_tj, d_out_dist, flags, s);
+    if (rc) return rc;
+    CU_CHECK(h, cudaMemcpyAsync(sh->h_ctl, sh->ctl, sizeof(ShardCtl), cudaMemcpyDeviceToHost, s));
     CU_CHECK(h, cudaStreamSynchronize(s));
     if (out_count) *out_count = out_count_for(sh->n1, sh->n2_total, flags);
-    if (out_rounds) *out_rounds = sh->round;
+    if (out_rounds) *out_rounds = sh->h_ctl[0].rounds;
     return PGM_OK;
 }
 
@@ -1900,9 +1991,221 @@ extern "C" int pgm_shard_destroy(pgm_shard *sh) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (sh->state.p) cudaFree(sh->state.p);
-    if (sh->h_counts) cudaFreeHost(sh->h_counts);
+    if (sh->h_ctl) cudaFreeHost(sh->h_ctl);
     delete sh;
     return PGM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// pgm_multi: one rank of a multi-GPU job, the library owning the NCCL communicator (threading
+// row).  NCCL is resolved at run time (dlopen): the single-GPU entry points carry no dependency on it, and a process
+// that already loaded NCCL (torch's bundled copy) shares that copy instead of loading a second one.
+// ---------------------------------------------------------------------------
+#include <dlfcn.h>
+namespace {
+struct NcclUniqueIdBlob { char internal[128]; };          // == ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128, stable across 2.x)
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(NcclUniqueIdBlob *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclUniqueIdBlob, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    std::string why;
+};
+constexpr int kNcclInt32 = 2, kNcclUint32 = 3, kNcclMin = 3;   // ncclDataType_t / ncclRedOp_t values (nccl.h, 2.x)
+NcclApi *nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) { api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
+        if (!api.lib) { api.why = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "?"); return; }
+        auto sym = [&](const char *n) { void *p = dlsym(api.lib, n); if (!p && api.why.empty()) api.why = std::string("missing NCCL symbol ") + n; return p; };
+        api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+        api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+        api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+        api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+        api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    });
+    return &api;
+}
+}  // namespace
+
+struct pgm_multi {
+    pgm_handle *h = nullptr;
+    void *comm = nullptr;
+    int rank = 0, world = 1;
+    DevBuf xbuf;                 // exchange buffer [2 * n1] / gathered keys
+    int64_t exchange_bytes = 0;  // payload this rank contributed to collectives in the last call
+    int32_t collectives = 0;
+};
+
+#define NCCL_CHECK(h, call)                                                                     \
+    do {                                                                                        \
+        int r__ = (call);                                                                       \
+        if (r__ != 0) {                                                                         \
+            (h)->err = std::string(#call " failed: ") + (nccl_api()->GetErrorString ? nccl_api()->GetErrorString(r__) : "?"); \
+            return PGM_E_NCCL;                                                                  \
+        }                                                                                       \
+    } while (0)
+
+extern "C" int pgm_multi_unique_id(uint8_t *out_id128) {
+    if (!out_id128) return PGM_E_INVALID_ARG;
+    NcclApi *a = nccl_api();
+    if (!a->lib || !a->why.empty()) return PGM_E_NCCL;
+    NcclUniqueIdBlob id;
+    if (a->GetUniqueId(&id) != 0) return PGM_E_NCCL;
+    memcpy(out_id128, id.internal, 128);
+    return PGM_OK;
+}
+
+extern "C" int pgm_multi_create(pgm_handle *h, const uint8_t *id128, int32_t rank, int32_t world, pgm_multi **out) {
+    if (!h || !out || world < 1 || rank < 0 || rank >= world || (world > 1 && !id128)) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    *out = nullptr;
+    pgm_multi *mh = new pgm_multi();
+    mh->h = h; mh->rank = rank; mh->world = world;
+    if (world > 1) {
+        NcclApi *a = nccl_api();
+        if (!a->lib || !a->why.empty()) { h->err = a->why.empty() ? "NCCL unavailable" : a->why; delete mh; return PGM_E_NCCL; }
+        if (cudaSetDevice(h->device) != cudaSuccess) { delete mh; return PGM_E_CUDA; }
+        NcclUniqueIdBlob id;
+        memcpy(id.internal, id128, 128);
+        const int r = a->CommInitRank(&mh->comm, world, id, rank);
+        if (r != 0) { h->err = std::string("ncclCommInitRank failed: ") + a->GetErrorString(r); delete mh; return PGM_E_NCCL; }
+    }
+    *out = mh;
+    return PGM_OK;
+}
+
+extern "C" int pgm_multi_destroy(pgm_multi *mh) {
+    if (!mh) return PGM_E_INVALID_ARG;
+    pgm_handle *h = mh->h;
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        cudaSetDevice(h->device);
+        cudaStreamSynchronize(h->stream);
+        if (mh->comm) nccl_api()->CommDestroy(mh->comm);
+        if (mh->xbuf.p) cudaFree(mh->xbuf.p);
+    }
+    delete mh;
+    return PGM_OK;
+}
+
+extern "C" int pgm_multi_get_exchange(pgm_multi *mh, int64_t *bytes, int32_t *collectives) {
+    if (!mh) return PGM_E_INVALID_ARG;
+    if (bytes) *bytes = mh->exchange_bytes;
+    if (collectives) *collectives = mh->collectives;
+    return PGM_OK;
+}
+
+// MatchKeypoints on ONE pair whose train set is sharded over the ranks: d_q = all queries, d_t_local = train rows
+// [col_offset, col_offset + n2_local).  Collective: every rank of the communicator must call it with the same n1,
+// n2_total, format and flags.  Writes the n1 (or min) triples, identical on every rank.
+extern "C" int pgm_multi_match_train_sharded_dev(pgm_multi *mh, const uint8_t *d_q, int32_t n1, const uint8_t *d_t_local,
+                                                 int32_t n2_local, int32_t col_offset, int32_t n2_total, int32_t desc_bits,
+                                                 int32_t stride_bytes, int32_t *d_out_qi, int32_t *d_out_tj,
+                                                 int32_t *d_out_dist, int32_t capacity, int32_t *out_count, uint32_t flags,
+                                                 int32_t *out_rounds) {
+    if (!mh || !d_out_qi || !d_out_tj || !d_out_dist) return PGM_E_INVALID_ARG;
+    pgm_handle *h = mh->h;
+    const int32_t cnt = out_count_for(n1, n2_total, flags);
+    if (out_count) *out_count = cnt;
+    if (capacity < cnt) return fail(h, PGM_E_CAPACITY, "capacity < number of triples");
+    pgm_shard *sh = nullptr;
+    int rc = pgm_shard_create(h, d_q, n1, d_t_local, n2_local, col_offset, n2_total, desc_bits, stride_bytes, &sh);
+    if (rc) return rc;
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        h->stats = pgm_stats{};
+        mh->exchange_bytes = 0; mh->collectives = 0;
+        if (cudaSetDevice(h->device) != cudaSuccess) { rc = PGM_E_CUDA; }
+        cudaStream_t s = h->stream;
+        if (!rc) rc = ensure_dev(h, mh->xbuf, (size_t)2 * n1 * 4);
+        uint32_t *X = (uint32_t *)mh->xbuf.p;
+        constexpr int BATCH = 4, RING = 8;
+        cudaEvent_t ev[RING];
+        for (auto &e : ev) e = nullptr;
+        for (int k = 0; k < RING && !rc; k++)
+            if (cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess) rc = PGM_E_CUDA;
+        int bound = n1, batch_no = 0;
+        bool done = false;
+        while (!rc && !done) {
+            for (int k = 0; k < BATCH && !rc; k++) {
+                shard_enqueue_round(sh, X, bound, s);
+                if (mh->world > 1) {
+                    const int r = nccl_api()->AllReduce(X, X, (size_t)2 * bound, kNcclUint32, kNcclMin, mh->comm, s);
+                    if (r != 0) { h->err = std::string("ncclAllReduce failed: ") + nccl_api()->GetErrorString(r); rc = PGM_E_NCCL; break; }
+                    mh->exchange_bytes += (int64_t)2 * bound * 4; mh->collectives++;
+                }
+                shard_enqueue_commit(sh, X, bound, s);
+            }
+            if (rc) break;
+            const int slot = batch_no % RING;
+            if (cudaMemcpyAsync(&sh->h_ctl[slot], sh->ctl, sizeof(ShardCtl), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                cudaEventRecord(ev[slot], s) != cudaSuccess) { rc = PGM_E_CUDA; break; }
+            // look at the status of the batch before the previous one: by now it has (almost always) completed, so the
+            // host never waits for the GPU and the GPU never waits for the host.  Every rank reads the same values at
+            // the same batch number, so all ranks enqueue the same collectives.
+            if (batch_no >= 1) {
+                const int old = (batch_no - 1) % RING;
+                if (cudaEventSynchronize(ev[old]) != cudaSuccess) { rc = PGM_E_CUDA; break; }
+                if (sh->h_ctl[old].done) done = true;
+                else bound = std::min(bound, std::max(SHARD_BLOCK, (sh->h_ctl[old].live_rows + SHARD_BLOCK - 1) / SHARD_BLOCK * SHARD_BLOCK));
+            }
+            batch_no++;
+            if (sh->round > 4 * MAX_N) { h->err = "train-sharded matcher failed to converge (internal error)"; rc = PGM_E_CUDA; }
+        }
+        if (!rc) rc = shard_finish_locked(sh, d_out_qi, d_out_tj, d_out_dist, flags, s);
+        if (!rc && cudaMemcpyAsync(&sh->h_ctl[0], sh->ctl, sizeof(ShardCtl), cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = PGM_E_CUDA;
+        if (!rc && cudaStreamSynchronize(s) != cudaSuccess) rc = PGM_E_CUDA;
+        if (!rc) {
+            h->stats.host_syncs++;
+            h->stats.rounds = sh->h_ctl[0].rounds;
+            h->stats.distance_evals = (int64_t)n1 * n2_local;
+            h->stats.matched = std::min(n1, n2_total);
+            h->stats.pairs = 1;
+            if (out_rounds) *out_rounds = sh->h_ctl[0].rounds;
+        } else if (rc == PGM_E_CUDA && h->err.empty()) {
+            h->err = std::string("CUDA error in the train-sharded matcher: ") + cudaGetErrorString(cudaGetLastError());
+        }
+        for (auto &e : ev) if (e) cudaEventDestroy(e);
+    }
+    pgm_shard_destroy(sh);
+    return rc;
+}
+
+// Nearest / second-nearest neighbour of every query over a train set sharded across the ranks: local search, packed
+// (distance << 20 | GLOBAL train index) keys, ONE all-gather of [2][n1] keys per rank, top-2 merge (north_star:
+// "train-set shard with a top-2 merge").  Identical results on every rank.
+extern "C" int pgm_multi_knn2_train_sharded_dev(pgm_multi *mh, const uint8_t *d_q, int32_t n1, const uint8_t *d_t_local,
+                                                int32_t n2_local, int32_t col_offset, int32_t desc_bits,
+                                                int32_t stride_bytes, int32_t *d_best_j, int32_t *d_best_d,
+                                                int32_t *d_second_j, int32_t *d_second_d) {
+    if (!mh || !d_best_j || !d_best_d || !d_second_j || !d_second_d) return PGM_E_INVALID_ARG;
+    pgm_handle *h = mh->h;
+    int rc = pgm_knn2_hamming_dev(h, d_q, n1, d_t_local, n2_local, desc_bits, stride_bytes, d_best_j, d_best_d, d_second_j, d_second_d);
+    if (rc) return rc;
+    if (n1 == 0) return PGM_OK;
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        CU_CHECK(h, cudaSetDevice(h->device));
+        if ((rc = ensure_dev(h, mh->xbuf, (size_t)(mh->world + 1) * 2 * n1 * 4))) return rc;
+        mh->exchange_bytes = 0; mh->collectives = 0;
+    }
+    uint32_t *mine = (uint32_t *)mh->xbuf.p, *all = mine + (size_t)2 * n1;
+    if ((rc = pgm_pack_top2_keys_dev(h, d_best_j, d_best_d, d_second_j, d_second_d, n1, col_offset, (int32_t *)mine))) return rc;
+    if (mh->world > 1) {
+        std::lock_guard<std::mutex> lk(h->mu);
+        NCCL_CHECK(h, nccl_api()->AllGather(mine, all, (size_t)2 * n1, kNcclInt32, mh->comm, h->stream));
+        mh->exchange_bytes = (int64_t)2 * n1 * 4; mh->collectives = 1;
+    } else {
+        all = mine;
+    }
+    return pgm_merge_top2_dev(h, (const int32_t *)all, mh->world, n1, d_best_j, d_best_d, d_second_j, d_second_d);
 }
 
 // ---------------------------------------------------------------------------

@@ -369,6 +369,32 @@ class Matcher:
             n = cnt.value
             return xy[:n], sc[:n], desc[:n]
 
+    def detect_describe_batch_dev(self, d_gray, threshold: float, pairs: np.ndarray, capacity: int = 4096,
+                                  stride: Optional[int] = None, python_generation: bool = False, read_counts: bool = True):
+        """FAST-12 -> BRIEF for a stack of device-resident images (torch float32 ``[K, H, W]``), one call, nothing read
+        back between the images.  Returns ``(xy int32[K, capacity, 2], score int32[K, capacity], desc uint8[K, capacity,
+        stride], counts)`` where ``counts`` is a numpy int32[K] (one synchronisation) or, with ``read_counts=False``,
+        a device tensor (no synchronisation at all).  A count above ``capacity`` means that image's list was truncated."""
+        import torch
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 4)
+        k, hgt, wid = (int(x) for x in d_gray.shape)
+        n_pairs = len(pairs)
+        stride = stride or ((n_pairs + 127) // 128) * 16
+        flags = PGM_FLAG_PYTHON_GENERATION if python_generation else 0
+        d_gray = d_gray.contiguous()
+        cap = max(int(capacity), 1)
+        xy = torch.empty((k, cap, 2), dtype=torch.int32, device=d_gray.device)
+        sc = torch.empty((k, cap), dtype=torch.int32, device=d_gray.device)
+        desc = torch.zeros((k, cap, stride), dtype=torch.uint8, device=d_gray.device)
+        d_cnt = torch.zeros(max(k, 1), dtype=torch.int32, device=d_gray.device)
+        h_cnt = np.zeros(max(k, 1), dtype=np.int32)
+        with self.torch_ordered(d_gray.device):
+            self._check(self._lib.pgm_detect_describe_batch_dev(
+                self._h, d_gray.data_ptr(), k, wid, hgt, float(threshold), pairs.ctypes.data, n_pairs, stride, flags,
+                xy.data_ptr(), sc.data_ptr(), desc.data_ptr(), cap, d_cnt.data_ptr(),
+                h_cnt.ctypes.data if read_counts else None))
+        return xy, sc, desc, (h_cnt[:k] if read_counts else d_cnt[:k])
+
     def nms(self, xy: np.ndarray, score: np.ndarray, radius: int) -> np.ndarray:
         """``RedundantKeypointEliminator.EliminateRedundantKeypoints`` (RedundantKeypointEliminator.cs:16-39):
         indices of the surviving keypoints in the reference's output order."""

@@ -133,14 +133,15 @@ def train_slices(n2_total: int, world_size: int) -> List[Tuple[int, int]]:
 
 
 class TrainShardedMatcher:
-    """MatchKeypoints on ONE pair whose train set is sharded over the ranks.
+    """MatchKeypoints on ONE pair whose train set is sharded over the ranks, with the exchange
+    left to the caller's transport (``pgm_shard_*``; :class:`MultiGpuMatcher` is the form where the library owns NCCL).
 
     ``d_q``: torch uint8 ``[n1, stride]`` (all queries, on this rank's GPU);
     ``d_t_local``: torch uint8 ``[n2_local, stride]`` = train rows ``[col_offset, col_offset + n2_local)``.
     ``reduce_min(tensor)`` performs an in-place MIN all-reduce of an int32 tensor across the ranks;
-    by default ``torch.distributed.all_reduce(op=MIN)`` on the default group.  Returns int32 ``[3, n1]``
-    (qi, tj, dist) in the reference's order -- identical on every rank and bit-identical to the
-    unsharded ``Matcher.match_greedy``.
+    by default ``torch.distributed.all_reduce(op=MIN)`` on the default group.  ONE exchange per round: ``x = [R | P]``,
+    ``2 * bound`` keys (include/pgmatch.h).  Returns int32 ``[3, n1]`` (qi, tj, dist) in the reference's order --
+    identical on every rank and bit-identical to the unsharded ``Matcher.match_greedy``.
     """
 
     def __init__(self, matcher, d_q, d_t_local, col_offset: int, n2_total: int, desc_bits: int = 256,
@@ -160,8 +161,8 @@ class TrainShardedMatcher:
                 matcher._h, d_q.data_ptr(), self.n1, d_t_local.data_ptr() if self.n2_local else None, self.n2_local,
                 int(col_offset), self.n2_total, int(desc_bits), self.stride, C.byref(self._sh)))
         dev = d_q.device
-        self.xkeys = torch.empty(self.n1, dtype=torch.int32, device=dev)
-        self.xacc = torch.empty(self.n1, dtype=torch.int32, device=dev)
+        self.x = torch.empty(2 * self.n1, dtype=torch.int32, device=dev)      # [R | P], the first 2 * bound entries in use
+        self.bound = self.n1
         self.out = torch.empty((3, self.n1), dtype=torch.int32, device=dev)
         self._reduce = reduce_min or self._dist_reduce
         self.rounds = 0
@@ -171,31 +172,29 @@ class TrainShardedMatcher:
         if dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
 
-    # the three local steps, exposed so a single process can drive several emulated ranks in lock-step
+    # the two local steps, exposed so a single process can drive several emulated ranks in lock-step
     # (every step runs on torch's current stream -- Matcher.torch_ordered -- unless the caller bound a stream, so
-    # the collectives torch enqueues between the steps are ordered against the library's kernels)
-    def step_round(self):
-        with self._m.torch_ordered(self.xkeys.device):
-            self._m._check(self._lib.pgm_shard_round(self._sh, self.xkeys.data_ptr()))
+    # the collective torch enqueues between the steps is ordered against the library's kernels)
+    def exchange_view(self):
+        return self.x[:2 * self.bound]
 
-    def step_propose(self):
-        with self._m.torch_ordered(self.xkeys.device):
-            self._m._check(self._lib.pgm_shard_propose(self._sh, self.xkeys.data_ptr(), self.xacc.data_ptr()))
+    def step_round(self):
+        with self._m.torch_ordered(self.x.device):
+            self._m._check(self._lib.pgm_shard_round(self._sh, self.x.data_ptr(), self.bound))
 
     def step_commit(self):
+        """-> (live rows, done).  The next round's exchange shrinks to the live rows (rounded up to 1024)."""
         import ctypes as C
-        lr, lc = C.c_int32(0), C.c_int32(0)
-        with self._m.torch_ordered(self.xkeys.device):
-            self._m._check(self._lib.pgm_shard_commit(self._sh, self.xacc.data_ptr(), C.byref(lr), C.byref(lc)))
-        return lr.value, lc.value
-
-    def done(self, live_rows: int) -> bool:
-        return live_rows == 0 or self.n2_total - (self.n1 - live_rows) == 0
+        lr, done = C.c_int32(0), C.c_int32(0)
+        with self._m.torch_ordered(self.x.device):
+            self._m._check(self._lib.pgm_shard_commit(self._sh, self.x.data_ptr(), self.bound, C.byref(lr), C.byref(done)))
+        self.bound = min(self.bound, max(1024, (lr.value + 1023) // 1024 * 1024))
+        return lr.value, bool(done.value)
 
     def finish(self, reference_compat_tail: bool = True):
         import ctypes as C
         cnt, rounds = C.c_int32(0), C.c_int32(0)
-        with self._m.torch_ordered(self.xkeys.device):
+        with self._m.torch_ordered(self.x.device):
             self._m._check(self._lib.pgm_shard_finish(
                 self._sh, self.out[0].data_ptr(), self.out[1].data_ptr(), self.out[2].data_ptr(),
                 1 if reference_compat_tail else 0, C.byref(cnt), C.byref(rounds)))
@@ -203,16 +202,14 @@ class TrainShardedMatcher:
         return self.out[:, :cnt.value]
 
     def match(self, reference_compat_tail: bool = True):
-        """Library steps and collectives alternate on torch's current stream (or on the stream the caller bound
+        """Library steps and the collective alternate on torch's current stream (or on the stream the caller bound
         with ``matcher.set_stream``, which must then also be torch's current stream)."""
         prev = self.n1 + 1
         while True:
             self.step_round()
-            self._reduce(self.xkeys)
-            self.step_propose()
-            self._reduce(self.xacc)
-            live_rows, _ = self.step_commit()
-            if self.done(live_rows):
+            self._reduce(self.exchange_view())
+            live_rows, done = self.step_commit()
+            if done:
                 break
             if live_rows >= prev:          # every round accepts at least the global minimum edge
                 raise RuntimeError("train-sharded matcher made no progress (internal error)")
@@ -229,6 +226,92 @@ class TrainShardedMatcher:
             self.close()
         except Exception:
             pass
+
+
+class MultiGpuMatcher:
+    """One rank of a multi-GPU job with the communicator inside the library (``pgm_multi_*``, NCCL over NVLink): what
+    a P/Invoke host gets.  ``unique_id`` (128 bytes from :func:`multi_unique_id` on rank 0) reaches the other ranks
+    by any channel -- here ``torch.distributed.broadcast`` if no id is given."""
+
+    def __init__(self, matcher, rank: int, world_size: int, unique_id: Optional[bytes] = None):
+        import ctypes as C
+        self._m, self._lib = matcher, matcher._lib
+        self.rank, self.world_size = int(rank), int(world_size)
+        if unique_id is None and self.world_size > 1:
+            unique_id = broadcast_unique_id(self._lib, self.rank)
+        self._mh = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+        matcher._check(self._lib.pgm_multi_create(matcher._h, buf, self.rank, self.world_size, C.byref(self._mh)))
+
+    def match_train_sharded(self, d_q, d_t_local, col_offset: int, n2_total: int, desc_bits: int = 256,
+                            reference_compat_tail: bool = True, out=None):
+        """int32 ``[3, count]`` device tensor (qi, tj, dist) in the reference's order, identical on every rank."""
+        import ctypes as C
+
+        import torch
+        n1, stride, n2_local = int(d_q.shape[0]), int(d_q.shape[1]), int(d_t_local.shape[0])
+        if out is None:
+            out = torch.empty((3, max(n1, 1)), dtype=torch.int32, device=d_q.device)
+        cnt, rounds = C.c_int32(0), C.c_int32(0)
+        with self._m.torch_ordered(d_q.device):
+            self._m._check(self._lib.pgm_multi_match_train_sharded_dev(
+                self._mh, d_q.data_ptr(), n1, d_t_local.data_ptr() if n2_local else None, n2_local, int(col_offset),
+                int(n2_total), int(desc_bits), stride, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), n1,
+                C.byref(cnt), 1 if reference_compat_tail else 0, C.byref(rounds)))
+        self.rounds = rounds.value
+        return out[:, :cnt.value]
+
+    def knn2_train_sharded(self, d_q, d_t_local, col_offset: int, desc_bits: int = 256):
+        import torch
+        n1, stride, n2_local = int(d_q.shape[0]), int(d_q.shape[1]), int(d_t_local.shape[0])
+        out = torch.empty((4, max(n1, 1)), dtype=torch.int32, device=d_q.device)
+        with self._m.torch_ordered(d_q.device):
+            self._m._check(self._lib.pgm_multi_knn2_train_sharded_dev(
+                self._mh, d_q.data_ptr(), n1, d_t_local.data_ptr() if n2_local else None, n2_local, int(col_offset),
+                int(desc_bits), stride, *(out[k].data_ptr() for k in range(4))))
+        return tuple(out[k, :n1] for k in range(4))
+
+    def exchange(self):
+        """(bytes this rank contributed to collectives, number of collectives) of the last call."""
+        import ctypes as C
+        b, n = C.c_int64(0), C.c_int32(0)
+        self._m._check(self._lib.pgm_multi_get_exchange(self._mh, C.byref(b), C.byref(n)))
+        return b.value, n.value
+
+    def close(self):
+        if getattr(self, "_mh", None) and self._mh.value:
+            self._lib.pgm_multi_destroy(self._mh)
+            self._mh = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def multi_unique_id(lib=None) -> bytes:
+    import ctypes as C
+
+    from . import _lib
+    lib = lib or _lib.load()
+    buf = (C.c_uint8 * 128)()
+    rc = lib.pgm_multi_unique_id(buf)
+    if rc != 0:
+        raise _lib.PgmatchError(rc, "pgm_multi_unique_id failed (NCCL not loadable?)")
+    return bytes(buf)
+
+
+def broadcast_unique_id(lib, rank: int) -> bytes:
+    """Rank 0 makes the communicator id, the others receive it over the default torch.distributed group."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(multi_unique_id(lib)), dtype=torch.uint8))
+    dist.broadcast(t, src=0)
+    return bytes(t.cpu().numpy().tobytes())
 
 
 class TrainShardedKnn:
@@ -322,42 +405,83 @@ def knn_train_sharded_emulated(matcher, d_q, d_t, n_shards: int, desc_bits: int 
 
 def match_train_sharded_emulated(matcher, q, t, n_shards: int, desc_bits: int = 256):
     """All ``n_shards`` ranks of the train-sharded mode emulated in ONE process on ONE GPU, run in
-    lock-step with the all-reduces replaced by element-wise minima (SURVEY.md section 4.4 item 5:
-    no inter-dependent concurrent kernels).  For tests and single-GPU validation."""
+    lock-step with the all-reduce replaced by an element-wise minimum (SURVEY.md section 4.4 item 5:
+    no inter-dependent concurrent kernels).  ``q`` / ``t``: numpy arrays or device tensors.  For tests and
+    single-GPU validation."""
     import torch
     dev = torch.device("cuda", matcher.device)
-    stream = torch.cuda.Stream(device=dev)
-    matcher.set_stream(stream.cuda_stream)
-    try:
-        with torch.cuda.stream(stream):
-            d_q = torch.from_numpy(np.ascontiguousarray(q)).to(dev)
-            d_t = torch.from_numpy(np.ascontiguousarray(t)).to(dev)
-            shards = [TrainShardedMatcher(matcher, d_q, d_t[lo:hi], lo, len(t), desc_bits, reduce_min=lambda x: None)
-                      for lo, hi in train_slices(len(t), n_shards)]
-            prev = len(q) + 1
-            while True:
-                for s in shards:
-                    s.step_round()
-                red = torch.stack([s.xkeys for s in shards]).min(dim=0).values
-                for s in shards:
-                    s.xkeys.copy_(red)
-                    s.step_propose()
-                red = torch.stack([s.xacc for s in shards]).min(dim=0).values
-                live = None
-                for s in shards:
-                    s.xacc.copy_(red)
-                    lr, _ = s.step_commit()
-                    assert live is None or live == lr, "ranks disagree on the live rows"
-                    live = lr
-                if shards[0].done(live):
-                    break
-                if live >= prev:
-                    raise RuntimeError("train-sharded matcher made no progress (internal error)")
-                prev = live
-            outs = [s.finish().T.contiguous().cpu().numpy() for s in shards]
-            rounds = shards[0].rounds
-            for s in shards:
-                s.close()
-    finally:
-        matcher.set_stream(None)
+    d_q = q if isinstance(q, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(q)).to(dev)
+    d_t = t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t)).to(dev)
+    n1, n2 = int(d_q.shape[0]), int(d_t.shape[0])
+    shards = [TrainShardedMatcher(matcher, d_q, d_t[lo:hi], lo, n2, desc_bits, reduce_min=lambda x: None)
+              for lo, hi in train_slices(n2, n_shards)]
+    prev = n1 + 1
+    while True:
+        for s in shards:
+            s.step_round()
+        red = torch.stack([s.exchange_view() for s in shards]).min(dim=0).values
+        live, done = None, None
+        for s in shards:
+            s.exchange_view().copy_(red)
+            lr, dn = s.step_commit()
+            assert live is None or (live, done) == (lr, dn), "ranks disagree on the live rows"
+            live, done = lr, dn
+        if done:
+            break
+        if live >= prev:
+            raise RuntimeError("train-sharded matcher made no progress (internal error)")
+        prev = live
+    outs = [s.finish().T.contiguous().cpu().numpy() for s in shards]
+    rounds = shards[0].rounds
+    for s in shards:
+        s.close()
     return outs, rounds
+
+
+def bench_train_sharded(matcher, stream, dev, rank: int, world: int, popc_peak: float, n: int = 200_000,
+                        dist_name: str = "U", reps: int = 2) -> dict:
+    """BASELINE configs[3]: one n x n pair, train set sharded over the ranks with the library-owned NCCL communicator
+    (every rank must call this).  Device time of the slowest rank; at world == 1 the same call runs unsharded."""
+    import torch
+    import torch.distributed as dist
+
+    from . import synthetic
+    q = synthetic.uniform_descriptors(1234, n, 256)
+    t = synthetic.uniform_descriptors(5678, n, 256) if dist_name == "U" else synthetic.noisy_copy_descriptors(42, q, 256)
+    lo, hi = train_slices(n, world)[rank]
+    mg = MultiGpuMatcher(matcher, rank, world)
+    with torch.cuda.stream(stream):
+        d_q = torch.from_numpy(q).to(dev)
+        d_t = torch.from_numpy(np.ascontiguousarray(t[lo:hi])).to(dev)
+        out = torch.empty((3, n), dtype=torch.int32, device=dev)
+        mg.match_train_sharded(d_q, d_t, lo, n, out=out)                      # warm-up (allocations, NCCL channels)
+        times = []
+        for _ in range(reps):
+            if world > 1:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            mg.match_train_sharded(d_q, d_t, lo, n, out=out)
+            e1.record(stream)
+            e1.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = float(min(times))
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        xb, xn = mg.exchange()
+        res = out.cpu().numpy()
+    ok = bool((np.sort(res[0]) == np.arange(n)).all() and (np.sort(res[1]) == np.arange(n)).all())
+    key = res[2].astype(np.int64) * (1 << 40) + res[0].astype(np.int64) * (1 << 20) + res[1]
+    ok &= bool((np.diff(key) > 0).all())
+    chk = np.linspace(0, n - 1, 2000).astype(np.int64)
+    ok &= bool((np.bitwise_count(q[res[0][chk]] ^ t[res[1][chk]]).sum(axis=1) == res[2][chk]).all())
+    rounds = mg.rounds
+    mg.close()
+    return {"workload": f"configs[3]: one {n}x{n} pair ({dist_name}), train set sharded x{world}", "ms": ms,
+            "evals_per_s": float(n) * n / (ms * 1e-3), "frac_of_popc_peak_per_gpu": float(n) * n * 8 / (ms * 1e-3) / popc_peak / world,
+            "rounds": rounds, "collective": "ncclAllReduce(min, uint32) of [R | P] = 2 x bound keys per round, inside the library"
+            if world > 1 else "none (1 rank)", "collectives": xn, "exchange_bytes_per_rank": xb,
+            "exchange_bytes_per_round": (xb / xn) if xn else 0.0,
+            "properties_ok": ok, "properties": "permutation of rows and columns, strict (d, i, j) order, recomputed distances"}

@@ -244,3 +244,22 @@ def test_python_twin_sorted_rows(matcher, lego):
     full = match_keypoints(kp1, kp2, -1)
     assert (full == orc.python_twin(lego["left"][:20], lego["right"][:30])).all()
     assert (full[:, :, 1] == ref[:20, :30, 1]).all() if False else True
+
+
+def test_multi_gpu_matcher_single_rank_equals_unsharded(matcher):
+    # the library-owned-communicator surface (pgm_multi_*) with a world of one: the batched, sync-free round loop and the
+    # shrinking exchange must give the unsharded result; NCCL itself is exercised by tools/bench_sharded.py on >= 2 GPUs
+    import torch
+
+    from photogrammetry_b200 import sharding
+    for n1, n2, dist in [(5000, 4200, "U"), (3000, 3000, "C"), (1500, 40, "U"), (1, 1, "U")]:
+        q = synthetic.uniform_descriptors(11, n1, 256)
+        t = synthetic.uniform_descriptors(12, n2, 256) if dist == "U" else synthetic.noisy_copy_descriptors(13, q, 256)[:n2]
+        mg = sharding.MultiGpuMatcher(matcher, 0, 1)
+        got = mg.match_train_sharded(torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda(), 0, n2).T.cpu().numpy()
+        assert (got == matcher.match_greedy(q, t, 256)).all()
+        knn = mg.knn2_train_sharded(torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda(), 0)
+        exp = matcher.knn2(q, t, 256)
+        assert all((a.cpu().numpy() == b).all() for a, b in zip(knn, exp))
+        assert mg.exchange() == (0, 0)
+        mg.close()

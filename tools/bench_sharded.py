@@ -1,17 +1,13 @@
 #!/usr/bin/env python
-"""BASELINE configs[3]: one huge synthetic pair, train set sharded over the ranks (torchrun).
+"""BASELINE configs[3]: one n x n pair with the train set sharded over the ranks (pgm_multi_*: NCCL inside the library).
 
+    python tools/bench_sharded.py [--size 200000] [--dist U] [--check]                                  # 1 GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port P \
-        tools/bench_sharded.py --size 200000 [--check]
+        tools/bench_sharded.py --check                                                              # G GPUs
 
-Every rank holds all N queries and 1/G of the train set; two NCCL `min` all-reduces of N packed keys per
-round.  With --check rank 0 also runs the unsharded single-GPU matcher and verifies bit-identity.
-
---mode knn: the nearest / second-nearest search with ratio test and cross-check on the same sharding
-(sharding.TrainShardedKnn): local searches, two NCCL all-gathers (packed (best, second) keys; per-slice column
-bests) and the device-side top-2 merge.
-"""
-import argparse, json, os, sys, time
+--check compares every rank's triples with the unsharded single-GPU call on rank 0 (bit-identity) and also runs the
+nearest / second-nearest search with the top-2 merge against the unsharded knn2."""
+import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
@@ -20,114 +16,48 @@ from photogrammetry_b200 import sharding, synthetic
 from photogrammetry_b200.keypoint_matching import Matcher
 
 
-def knn_mode(args, m, d_q, d_t, q, t, lo, n, world, rank, dev, stream):
-    sh = sharding.TrainShardedKnn(m, d_q, d_t, lo, n, 256, world_size=world)
-    times = []
-    for rep in range(args.reps + 1):
-        if world > 1: dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        kept = sh.match_ratio_crosscheck(0.8, True, -1)
-        e1.record(stream); e1.synchronize()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            tt = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
-        if rep > 0: times.append(ms)
-    res = kept.T.contiguous().cpu().numpy()
-    # both directions are searched (rows for knn2, columns for the cross-check): 2 N^2 distances
-    line = {"workload": f"configs[3] shape, knn2 + ratio 0.8 + cross-check: {n}x{n}, distribution {args.dist}, train set sharded x{world}",
-            "n_gpus": world, "ms": float(np.median(times)), "evals_per_s": 2.0 * n * n / (np.median(times) * 1e-3),
-            "kept": int(len(res)), "collectives": 2 if world > 1 else 0, "bytes_gathered_per_rank": 8 * n + 4 * (-(-n // world))}
-    if rank == 0:
-        assert (np.diff(res[:, 0]) > 0).all()
-        assert (np.bitwise_count(q[res[:, 0]] ^ t[res[:, 1]]).sum(axis=1) == res[:, 2]).all()
-        line["properties_ok"] = True
-        if args.check:
-            d_tf = torch.from_numpy(t).to(dev)
-            one = sharding.TrainShardedKnn(m, d_q, d_tf, 0, n, 256, world_size=1)
-            for _ in range(2):
-                torch.cuda.synchronize(); t0 = time.perf_counter()
-                ref = one.match_ratio_crosscheck(0.8, True, -1)
-                torch.cuda.synchronize(); dt = time.perf_counter() - t0
-            line["unsharded_1gpu_ms"] = dt * 1e3
-            line["bit_identical_to_unsharded"] = bool(torch.equal(ref, kept))
-        print(json.dumps(line), flush=True)
-
-
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--size", dest="n", type=int, default=200000)
-    ap.add_argument("--dist", default="U")
-    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--size", dest="n", type=int, default=200_000)
+    ap.add_argument("--dist", default="U", choices=["U", "C"])
     ap.add_argument("--check", action="store_true")
-    ap.add_argument("--stream", default="custom", choices=["custom", "default"])
-    ap.add_argument("--mode", default="greedy", choices=["greedy", "knn"])
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    torch.cuda.set_device(local); dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n = args.n
-    q = synthetic.uniform_descriptors(1234, n, 256)
-    t = synthetic.uniform_descriptors(5678, n, 256) if args.dist == "U" else synthetic.noisy_copy_descriptors(42, q, 256)
-    lo, hi = sharding.train_slices(n, world)[rank]
     m = Matcher(local)
-    # NCCL collectives are enqueued on torch's current stream: make that an explicit stream and hand
-    # the same stream to the matcher, so kernels and collectives are ordered without host syncs
-    if args.stream == "custom":
-        stream = torch.cuda.Stream(device=dev)
-        torch.cuda.set_stream(stream)
-    else:
-        stream = torch.cuda.current_stream(dev)
-    m.set_stream(stream.cuda_stream)
-    d_q = torch.from_numpy(q).to(dev); d_t = torch.from_numpy(t[lo:hi].copy()).to(dev)
-    if args.mode == "knn":
-        knn_mode(args, m, d_q, d_t, q, t, lo, n, world, rank, dev, stream)
-        m.close()
-        if world > 1:
-            dist.barrier(); dist.destroy_process_group()
-        return
-    times, rounds = [], 0
-    for rep in range(args.reps + 1):
-        sm = sharding.TrainShardedMatcher(m, d_q, d_t, lo, n, 256)
-        if world > 1: dist.barrier()
+    stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream); m.set_stream(stream.cuda_stream)
+    popc, _ = m.measure_popc_peak(200)
+    line = sharding.bench_train_sharded(m, stream, dev, rank, world, popc, n=args.n, dist_name=args.dist)
+    if args.check:
+        n = args.n
+        q = synthetic.uniform_descriptors(1234, n, 256)
+        t = synthetic.uniform_descriptors(5678, n, 256) if args.dist == "U" else synthetic.noisy_copy_descriptors(42, q, 256)
+        lo, hi = sharding.train_slices(n, world)[rank]
+        mg = sharding.MultiGpuMatcher(m, rank, world)
+        d_q, d_t = torch.from_numpy(q).to(dev), torch.from_numpy(np.ascontiguousarray(t[lo:hi])).to(dev)
+        got = mg.match_train_sharded(d_q, d_t, lo, n).clone()
+        knn = [x.clone() for x in mg.knn2_train_sharded(d_q, d_t, lo)]
+        xb, xn = mg.exchange()
+        d_tf = torch.from_numpy(t).to(dev)
+        ref = torch.empty((3, n), dtype=torch.int32, device=dev)
+        m.match_greedy_dev(d_q.data_ptr(), n, d_tf.data_ptr(), n, 256, 32, ref[0].data_ptr(), ref[1].data_ptr(), ref[2].data_ptr(), n)
+        ref_knn = m.knn2_hamming_dev(d_q, d_tf, 256)
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        out = sm.match()
-        e1.record(stream); e1.synchronize()
-        ms = e0.elapsed_time(e1)
+        same = torch.tensor([int(torch.equal(got, ref)), int(all(torch.equal(a, b) for a, b in zip(knn, ref_knn)))], device=dev)
         if world > 1:
-            tt = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
-        if rep > 0: times.append(ms)
-        rounds = sm.rounds
-        res = out.T.contiguous().cpu().numpy()
-        sm.close()
-    line = {"workload": f"configs[3]: single synthetic pair {n}x{n}, distribution {args.dist}, train set sharded x{world}",
-            "n_gpus": world, "ms": float(np.median(times)), "evals_per_s": float(n) * n / (np.median(times) * 1e-3),
-            "rounds": rounds, "collectives_per_round": 2 if world > 1 else 0, "bytes_per_collective": 4 * n}
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        line["every_rank_bit_identical_to_unsharded"] = bool(same[0].item())
+        line["knn2_top2_merge_bit_identical_to_unsharded"] = bool(same[1].item())
+        line["knn2_all_gather_bytes_per_rank"] = xb
+        mg.close()
     if rank == 0:
-        # size-independent properties: permutation, strict (d,i,j) order, true distances
-        assert sorted(res[:, 0].tolist()) == list(range(n)) and sorted(res[:, 1].tolist()) == list(range(n))
-        k = res[:, 2].astype(np.int64) * (1 << 40) + res[:, 0].astype(np.int64) * (1 << 20) + res[:, 1]
-        assert (np.diff(k) > 0).all()
-        assert (np.bitwise_count(q[res[:, 0]] ^ t[res[:, 1]]).sum(axis=1) == res[:, 2]).all()
-        line["properties_ok"] = True
-        if args.check:
-            d_tf = torch.from_numpy(t).to(dev)
-            o = torch.empty((3, n), dtype=torch.int32, device=dev)
-            for _ in range(2):
-                torch.cuda.synchronize(); t0 = time.perf_counter()
-                m.match_greedy_dev(d_q.data_ptr(), n, d_tf.data_ptr(), n, 256, 32, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), n)
-                torch.cuda.synchronize(); dt = time.perf_counter() - t0
-            line["unsharded_1gpu_ms"] = dt * 1e3
-            line["bit_identical_to_unsharded"] = bool((o.T.cpu().numpy() == res).all())
         print(json.dumps(line), flush=True)
     m.close()
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
+
 
 main()
