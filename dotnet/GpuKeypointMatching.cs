@@ -1,19 +1,17 @@
-// GpuKeypointMatching.cs -- drop-in replacement for ImageProcessing.KeypointMatching
-// (dotnet_src/ImageProcessing/KeypointMatching.cs:8-69) that P/Invokes libpgmatch.so.
+// GpuKeypointMatching.cs -- the P/Invoke engine behind dotnet/KeypointMatching.cs (the file that REPLACES
+// dotnet_src/ImageProcessing/KeypointMatching.cs:8-69).  It marshals two List<Keypoint> into packed little-endian
+// descriptor rows, calls pgm_match_hamming_greedy in libpgmatch.so and rebuilds the List<KeypointPair> from the returned
+// indices.  It is NOT itself a drop-in: the reference's KeypointMatching is a concrete, non-virtual class with no interface
+// (SURVEY D2), TestService takes a `KeypointMatching` parameter (TestService.cs:34), so a differently named or derived class
+// cannot be resolved in its place -- hence the same-named replacement class next to this file.
 //
-// NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no .NET SDK (see
-// DESIGN.md section 6).  The same C ABI is exercised from Python (ctypes) by
-// tests/test_gpu_parity.py, which mirrors this marshalling step for step.
+// NOT COMPILED IN THIS REPOSITORY: the build image has no .NET SDK (see DESIGN.md section 6).  The same C ABI is
+// exercised from Python (ctypes) by tests/test_gpu_parity.py, which mirrors this marshalling step for step.
 //
 // Integration (INTEGRATION.md):
-//   1. add this file to dotnet_src/ImageProcessing/ (it has no dependency beyond
-//      ImageProcessing.Abstractions);
-//   2. in dotnet_src/Photogrammetry/Program.cs:55 replace
-//          services.AddSingleton<KeypointMatching>();
-//      with
-//          services.AddSingleton<KeypointMatching, GpuKeypointMatching>();
-//      after making MatchKeypoints virtual, or inject GpuKeypointMatching directly
-//      into TestService (TestService.cs:34,43,96) -- the method signature is identical;
+//   1. copy this file and dotnet/KeypointMatching.cs into dotnet_src/ImageProcessing/, the latter OVER the reference's
+//      KeypointMatching.cs (add <AllowUnsafeBlocks>true</AllowUnsafeBlocks> to ImageProcessing.csproj);
+//   2. nothing else changes: Program.cs:55, TestService.cs:34,43,96 compile and run as they are;
 //   3. ship libpgmatch.so next to the executable (or on LD_LIBRARY_PATH).
 using System.Numerics;
 using System.Runtime.InteropServices;
