@@ -13,7 +13,7 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpgmatch.so")
+LIB_PATH = os.environ.get("PGM_LIB") or os.path.join(_HERE, "libpgmatch.so")     # PGM_LIB: e.g. the bounds-checked build
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 PGM_OK = 0

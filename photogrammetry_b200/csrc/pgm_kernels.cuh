@@ -33,6 +33,25 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include <cstdio>
+
+// Checked build (make checked -> libpgmatch_checked.so, loaded with PGM_LIB=...): every index a kernel derives from
+// data another kernel or CTA produced -- packed keys, candidate records, list positions, output slots -- is range
+// checked on the device and a violation traps.  compute-sanitizer is closed on this pool (it left GPUs needing a reset),
+// so this build, run on the small cases of tools/sanitize_cases.py, is the memory-safety evidence (profiles/r02_checked_build.log).
+#ifdef PGM_CHECKED
+#define PGM_ASSERT(cond)                                                                                          \
+    do {                                                                                                          \
+        if (!(cond)) {                                                                                            \
+            printf("PGM_ASSERT failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, \
+                   (int)threadIdx.x);                                                                             \
+            __trap();                                                                                             \
+        }                                                                                                         \
+    } while (0)
+#else
+#define PGM_ASSERT(cond) ((void)0)
+#endif
+
 namespace pgm {
 
 constexpr uint32_t KEY_IDX_BITS = 20;
@@ -75,7 +94,8 @@ constexpr int SP_SMEM_BYTES = 184 * 1024;   // shared memory of a sparse phase: 
                                             // and one min slot per live row and live column
 constexpr int SP_LCAP_MAX = SP_THREADS * SP_EPT;   // live edges per pair the global list is sized for
 constexpr int SP_MAX_SUB = 64;          // sub-rounds per sparse phase (each accepts >= 1 pair; the rest waits for the next pass)
-constexpr float CAND_TARGET = 4.0f;     // expected candidate edges per row of the smaller side
+constexpr float CAND_TARGET = 4.0f;     // expected candidate edges per row of the larger side and pass: a few pairs ...
+constexpr float CAND_TARGET_BATCH = 6.0f;   // ... and batches of pairs
 constexpr uint32_t KEY_DEAD = 0xFFFFFFFEu;  // sparse phase: row / column matched in an earlier sub-round
 
 enum PairStatus : uint8_t { PAIR_DONE = 0, PAIR_BIG = 1, PAIR_SMALL = 2 };
@@ -563,6 +583,33 @@ __device__ __forceinline__ uint32_t hamming_words(const uint32_t (&q)[WORDS], co
     return ones + 2u * twos;
 }
 
+// One compression level more: the three "twos" words go through a fourth full adder, leaving 4 POPC + 16 LOP3 per 8
+// words (popc(s3) + popc(x7) + 2 popc(t) + 4 popc(f)).  Alone it would make the ALU pipe the bottleneck (ptxas already
+// puts the additions on the FMA pipe as IMAD); alternated with the 5-POPC form over a thread's rows the two pipes come
+// out even: per distance 4.5 POPC x 8 = 36 cycles on the XU pipe vs ~17.7 ALU instructions x 2 = 35 cycles.
+template <int WORDS>
+__device__ __forceinline__ uint32_t hamming_words_deep(const uint32_t (&q)[WORDS], const uint32_t (&t)[WORDS]) {
+    if constexpr (WORDS % 8 != 0) {
+        return hamming_words<WORDS>(q, t);
+    } else {
+        uint32_t x[WORDS];
+#pragma unroll
+        for (int w = 0; w < WORDS; w++) x[w] = q[w] ^ t[w];
+        uint32_t ones = 0, twos = 0, fours = 0;
+#pragma unroll
+        for (int g = 0; g + 8 <= WORDS; g += 8) {
+            const uint32_t s1 = xor3(x[g], x[g + 1], x[g + 2]), c1 = maj3(x[g], x[g + 1], x[g + 2]);
+            const uint32_t s2 = xor3(x[g + 3], x[g + 4], x[g + 5]), c2 = maj3(x[g + 3], x[g + 4], x[g + 5]);
+            const uint32_t s3 = xor3(s1, s2, x[g + 6]), c3 = maj3(s1, s2, x[g + 6]);
+            const uint32_t tw = xor3(c1, c2, c3), fo = maj3(c1, c2, c3);
+            ones += __popc(s3) + __popc(x[g + 7]);
+            twos += __popc(tw);
+            fours += __popc(fo);
+        }
+        return ones + 2u * twos + 4u * fours;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // round kernel: live rows x live columns of every PAIR_BIG pair.
 // One thread owns RQ query descriptors in registers; the CTA streams train
@@ -647,6 +694,7 @@ __device__ __forceinline__ void round_tiles(const Chunk &c, int r, int total, in
             rowkey[k] = KEY_NONE;
             if (slot < nlr) {
                 const int i = __ldcg(live_rows + slot);
+                PGM_ASSERT(i >= 0 && i < pd.n1);
                 ikey[k] = (uint32_t)i;
                 const uint4 *src = reinterpret_cast<const uint4 *>(pd.q + (size_t)i * WORDS);
 #pragma unroll
@@ -671,6 +719,7 @@ __device__ __forceinline__ void round_tiles(const Chunk &c, int r, int total, in
                 uint32_t jk = KEY_INVALID;
                 if (y < c1) {
                     const int j = __ldcg(live_cols + y);
+                    PGM_ASSERT(j >= 0 && j < pd.n2);
                     x = __ldg(reinterpret_cast<const uint4 *>(pd.t + (size_t)j * WORDS) + part);
                     jk = (uint32_t)(j + pd.col_id_offset);
                 }
@@ -703,7 +752,8 @@ __device__ __forceinline__ void round_tiles(const Chunk &c, int r, int total, in
                         uint32_t cmin = KEY_NONE;
 #pragma unroll
                         for (int k = 0; k < RQ; k++) {
-                            const uint32_t d = hamming_words<WORDS>(q[k], t) << KEY_IDX_BITS;
+                            // (rows alternate between the 5-POPC and the 4-POPC popcount so that the XU and ALU pipes balance)
+                            const uint32_t d = ((k & 1) ? hamming_words_deep<WORDS>(q[k], t) : hamming_words<WORDS>(q[k], t)) << KEY_IDX_BITS;
                             rowkey[k] = min(rowkey[k], d + jk);
                             cmin = min(cmin, d + ikey[k]);
                         }
@@ -819,7 +869,9 @@ __device__ __forceinline__ void accept_blocks(const Chunk &c, int r, int vb, int
         if (is_row) {
             if (x < nlr) {
                 id = __ldcg(c.live_rows[cur] + pd.row_base + x);
+                PGM_ASSERT(id >= 0 && id < pd.n1);
                 const uint32_t rk = __ldcg(rowbest + id);
+                PGM_ASSERT(rk != KEY_NONE && (int)(rk & KEY_IDX_MASK) - pd.col_id_offset >= 0 && (int)(rk & KEY_IDX_MASK) - pd.col_id_offset < pd.n2);
                 const uint32_t ck = __ldcg(colbest + (rk & KEY_IDX_MASK));
                 if ((ck & KEY_IDX_MASK) == (uint32_t)id) c.match_key[pd.row_base + id] = rk;
                 else { survive = true; c.rowbest[nxt][pd.row_base + id] = KEY_NONE; }
@@ -827,7 +879,9 @@ __device__ __forceinline__ void accept_blocks(const Chunk &c, int r, int vb, int
         } else {
             if (x < nlc) {
                 id = __ldcg(c.live_cols[cur] + pd.col_base + x);
+                PGM_ASSERT(id >= 0 && id < pd.n2);
                 const uint32_t ck = __ldcg(colbest + id);
+                PGM_ASSERT(ck != KEY_NONE && (int)(ck & KEY_IDX_MASK) < pd.n1);
                 const uint32_t rk = __ldcg(rowbest + (ck & KEY_IDX_MASK));
                 if ((rk & KEY_IDX_MASK) != (uint32_t)id) { survive = true; c.colbest[nxt][pd.col_base + id] = KEY_NONE; }
             }
@@ -839,6 +893,7 @@ __device__ __forceinline__ void accept_blocks(const Chunk &c, int r, int vb, int
             base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
             if (survive) {
                 const int pos = base + __popc(m & ((1u << lane) - 1u));
+                PGM_ASSERT(pos >= 0 && pos < (is_row ? nlr : nlc));
                 if (is_row) { c.live_rows[nxt][pd.row_base + pos] = id; if (c.cand) c.row_pos[pd.row_base + id] = pos; }
                 else { c.live_cols[nxt][pd.col_base + pos] = id; if (c.cand) c.col_pos[pd.col_base + id] = pos; }
             }
@@ -875,6 +930,8 @@ __device__ __forceinline__ void filter_edges(const Chunk &c, int r, int p, int s
         if (e < n) {
             const unsigned long long key = __ldcg(raw + 2 * e);
             const uint32_t aux = (uint32_t)__ldcg(raw + 2 * e + 1);
+            PGM_ASSERT((int)((key >> KEY_IDX_BITS) & KEY_IDX_MASK) < pd.n1 && (int)(key & KEY_IDX_MASK) < pd.n2 && (key >> 40) <= 512);
+            PGM_ASSERT((aux >> KEY_IDX_BITS) == 1 || (aux >> KEY_IDX_BITS) == RQ_LARGE);
             ed[0] = key;
             const int rqn = (int)(aux >> KEY_IDX_BITS), slot0 = (int)(aux & KEY_IDX_MASK);
             if (rqn > 1) {
@@ -883,7 +940,10 @@ __device__ __forceinline__ void filter_edges(const Chunk &c, int r, int p, int s
                 const uint32_t i0 = (uint32_t)(key >> KEY_IDX_BITS) & KEY_IDX_MASK, j = (uint32_t)key & KEY_IDX_MASK;
                 uint32_t tw[16];
 #pragma unroll
-                for (int w = 0; w < 16; w++) tw[w] = w < words ? __ldg(td + (size_t)j * words + w) : 0u;
+                for (int v = 0; v < 4; v++) {            // rows are 16-byte aligned: 128-bit loads
+                    const uint4 x = 4 * v < words ? __ldg(reinterpret_cast<const uint4 *>(td + (size_t)j * words) + v) : make_uint4(0u, 0u, 0u, 0u);
+                    tw[4 * v] = x.x; tw[4 * v + 1] = x.y; tw[4 * v + 2] = x.z; tw[4 * v + 3] = x.w;
+                }
                 int used = 1;
                 for (int k = 0; k < rqn && k < RQ_LARGE; k++) {
                     const int slot = slot0 + k * ROUND_THREADS;
@@ -892,7 +952,12 @@ __device__ __forceinline__ void filter_edges(const Chunk &c, int r, int p, int s
                     if (i2 == i0) continue;
                     uint32_t d = 0;
 #pragma unroll
-                    for (int w = 0; w < 16; w++) if (w < words) d += __popc(__ldg(qd + (size_t)i2 * words + w) ^ tw[w]);
+                    for (int v = 0; v < 4; v++) {
+                        if (4 * v < words) {
+                            const uint4 x = __ldg(reinterpret_cast<const uint4 *>(qd + (size_t)i2 * words) + v);
+                            d += __popc(x.x ^ tw[4 * v]) + __popc(x.y ^ tw[4 * v + 1]) + __popc(x.z ^ tw[4 * v + 2]) + __popc(x.w ^ tw[4 * v + 3]);
+                        }
+                    }
                     if ((d << KEY_IDX_BITS) < thr) {
                         const unsigned long long k2 = ((unsigned long long)d << 40) | ((unsigned long long)i2 << 20) | j;
                         if (used == 1) ed[1] = k2; else if (used == 2) ed[2] = k2; else ed[3] = k2;
@@ -907,6 +972,7 @@ __device__ __forceinline__ void filter_edges(const Chunk &c, int r, int p, int s
             if (ed[x] != ~0ull) {
                 const uint32_t i = (uint32_t)(ed[x] >> KEY_IDX_BITS) & KEY_IDX_MASK, j = (uint32_t)ed[x] & KEY_IDX_MASK;
                 const uint32_t rk = __ldcg(rowbest + i), ck = __ldcg(colbest + j);
+                PGM_ASSERT((int)(rk & KEY_IDX_MASK) < pd.n2 && (int)(ck & KEY_IDX_MASK) < pd.n1);
                 const uint32_t ck_of_rk = __ldcg(colbest + (rk & KEY_IDX_MASK)), rk_of_ck = __ldcg(rowbest + (ck & KEY_IDX_MASK));
                 keep = (ck_of_rk & KEY_IDX_MASK) != i && (rk_of_ck & KEY_IDX_MASK) != j;
             }
@@ -972,6 +1038,7 @@ __device__ __forceinline__ int sparse_sub_rounds(uint32_t (&ek)[EPT], uint32_t (
                 // (a concurrent KEY_DEAD store by the accepting thread of another edge of this row / column can only
                 //  turn a mismatch into a mismatch: keys within a row, and within a column, are distinct)
                 if (ek[k] != KEY_NONE && rv[u] == ek[k] && cv[u] == kc[u]) {
+                    PGM_ASSERT(__ldcg(match_key + (kc[u] & KEY_IDX_MASK)) == KEY_NONE);      // a row is matched once
                     match_key[kc[u] & KEY_IDX_MASK] = ek[k];
                     rbest[ep[k] >> 16] = KEY_DEAD; cbest[ep[k] & 0xFFFFu] = KEY_DEAD;
                 }
@@ -1046,6 +1113,7 @@ __device__ __forceinline__ void sparse_body(const Chunk &c, int r, int p, unsign
                 const bool ok = key[u] != ~0ull;
                 const uint32_t i = ok ? (uint32_t)(key[u] >> KEY_IDX_BITS) & KEY_IDX_MASK : 0u, j = ok ? (uint32_t)key[u] & KEY_IDX_MASK : 0u;
                 pr[u] = by_id ? i : (uint32_t)__ldcg(row_pos + i); pc[u] = by_id ? j : (uint32_t)__ldcg(col_pos + j);
+                PGM_ASSERT(!ok || ((int)i < n1 && (int)j < n2 && (int)pr[u] < nr && (int)pc[u] < nc));
                 const uint32_t d = (uint32_t)(key[u] >> 40);
                 ek[k0 + u] = ok ? (d << KEY_IDX_BITS) | j : KEY_NONE;
                 ecs[(k0 + u) * NT] = (d << KEY_IDX_BITS) | i;
@@ -1111,6 +1179,7 @@ __device__ __forceinline__ void sparse_body(const Chunk &c, int r, int p, unsign
                     int base = 0;
                     if (lane == (__ffs(m) - 1)) base = atomicAdd(&s_cnt[side], __popc(m));
                     base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                    PGM_ASSERT(!keep[u] || base + __popc(m & ((1u << lane) - 1u)) < n);
                     if (keep[u]) live[base + __popc(m & ((1u << lane) - 1u))] = id[u];
                 }
             }
@@ -1506,6 +1575,7 @@ __device__ __forceinline__ void order_emit(const Chunk &c, int p, int slice, int
         __syncwarp();
         if (key != KEY_NONE) {
             const int64_t o = out_base + base + rank;
+            PGM_ASSERT(base + rank >= 0 && base + rank < min(n1, n2) && d < nbins);
             out_qi[o] = x; out_tj[o] = (int32_t)(key & KEY_IDX_MASK); out_dist[o] = d;
         }
     }
@@ -1731,6 +1801,7 @@ __global__ void shard_propose_cols_kernel(Chunk c, int r, uint32_t *__restrict__
         const uint32_t ck = __ldcg(colbest + j);
         if (ck == KEY_NONE) continue;
         const int pos = r == 0 ? (int)(ck & KEY_IDX_MASK) : __ldcg(c.row_pos + (ck & KEY_IDX_MASK));   // round 0: identity list
+        PGM_ASSERT((int)(ck & KEY_IDX_MASK) < pd.n1 && pos >= 0 && pos < bound);
         if (pos < bound) atomicMin(X + bound + pos, (ck & ~KEY_IDX_MASK) | (uint32_t)(j + off));
     }
 }
@@ -1794,6 +1865,7 @@ __global__ void __launch_bounds__(SHARD_BLOCK) shard_commit_scatter_kernel(Chunk
     for (int w = 0; w < wid; w++) woff += s_w[w];
     if (survive) {
         const int np = woff + __popc(m & ((1u << lane) - 1u));
+        PGM_ASSERT(np >= 0 && np <= pos && i >= 0 && i < n1);
         c.live_rows[nxt][np] = i;
         c.row_pos[i] = np;
         c.rowbest[nxt][i] = KEY_NONE;

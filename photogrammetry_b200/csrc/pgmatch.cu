@@ -408,7 +408,9 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
     // candidate edges (pgm_kernels.cuh): per pair a raw list of about 2 x CAND_TARGET entries per row and a list of the
     // edges that survive the accept, sized for the sparse phase's shared memory
     const bool use_cand = !h->no_cand;
-    float cand_target = CAND_TARGET;
+    // a few pairs (latency mode): the single-CTA sparse phase is on the critical path, keep its edge list short; batches:
+    // the sparse phases of different pairs run side by side, a longer list saves more recomputation than it costs
+    float cand_target = n_pairs <= LATENCY_MODE_MAX_PAIRS ? CAND_TARGET : CAND_TARGET_BATCH;
     if (const char *e = getenv("PGM_CAND_TARGET")) cand_target = std::max(0.1f, (float)atof(e));   // tuning experiments
     std::vector<int64_t> cand_off(n_pairs + 1, 0), ledge_off(n_pairs + 1, 0);
     if (use_cand) {
