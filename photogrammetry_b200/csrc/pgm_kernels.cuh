@@ -77,6 +77,7 @@ constexpr int FIN_MAX_EVALS = 49152;  // ... and nlr * nlc <= this (u16 distance
 constexpr int FIN_MAX_EVALS_TAIL = 65536;
 constexpr int FIN_D_STRIDE = FIN_MAX_EVALS_TAIL + 4 * FIN_MAX_DIM;   // u16 cells per pair incl. row-pitch padding
 constexpr uint32_t TAIL_FLAG_ACCEPT_FIRST = 0x80000000u;            // tail_kernel flags bit: run accept(r_start - 1) first
+constexpr int FIN_PREP_MIN_EVALS = 8192;                            // below this the finisher CTA computes its matrix itself
 constexpr int FIN_SEG = 128;                                        // entries of a row / column one warp handles
 constexpr int FIN_PARTS = FIN_MAX_DIM / FIN_SEG;                    // partial minima per row / column
 constexpr int ORDER_THREADS_STANDALONE = 1024;
@@ -246,35 +247,54 @@ __device__ __forceinline__ void plan_pair_emit(const Chunk &c, int p, uint8_t st
     c.ledge_cnt[p] = 0;
 }
 
-// Mean and standard deviation of 1024 sampled distances of pair p (32 rows x 32 columns spread over the pair), by one
-// warp.  Only the SIZE of the candidate lists depends on them, never a result.
+// Mean and standard deviation of 1024 sampled distances of pair p, by one CTA of ACCEPT_THREADS threads (four samples
+// per thread, all their descriptor loads in flight together: after an L2 flush each is an HBM round trip, and a serial
+// loop of them was 30 us on the critical path of the call).  Only the SIZE of the candidate lists depends on the
+// result, never a match.
 __device__ __forceinline__ void sample_pair_stats(const Chunk &c, int p, const PairDesc &pd) {
-    const int lane = threadIdx.x & 31;
-    if (!c.cand) return;
-    float mu = 0.0f, sd = 1.0f;
+    __shared__ unsigned s_sum, s_sum2;
+    if (!c.cand) return;                                    // (uniform)
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_sum = 0u; s_sum2 = 0u; }
+    __syncthreads();
+    unsigned sum = 0, sum2 = 0;
     if (pd.n1 > 0 && pd.n2 > 0) {
-        const int i = (int)(((long long)lane * pd.n1) >> 5);
-        uint32_t q[16];
+        constexpr int SPT = 1024 / ACCEPT_THREADS;
+        const int v4 = c.words >> 2;
+        uint4 a[SPT][4], b[SPT][4];
 #pragma unroll
-        for (int w = 0; w < 16; w++) q[w] = w < c.words ? __ldg(pd.q + (size_t)i * c.words + w) : 0u;
-        uint32_t sum = 0, sum2 = 0;
-        for (int k = 0; k < 32; k++) {
-            const int j = (int)(((long long)(k * 32 + ((lane * 7 + k) & 31)) * pd.n2) >> 10);
-            const uint32_t *t = pd.t + (size_t)j * c.words;
-            uint32_t d = 0;
+        for (int u = 0; u < SPT; u++) {
+            const unsigned sidx = (unsigned)(tid * SPT + u);
+            const int i = (int)(((unsigned long long)(sidx * 2654435761u) * (unsigned)pd.n1) >> 32);     // spread over the pair
+            const int j = (int)(((unsigned long long)(sidx * 2246822519u + 374761393u) * (unsigned)pd.n2) >> 32);
+            const uint4 *qa = reinterpret_cast<const uint4 *>(pd.q + (size_t)i * c.words);
+            const uint4 *tb = reinterpret_cast<const uint4 *>(pd.t + (size_t)j * c.words);
 #pragma unroll
-            for (int w = 0; w < 16; w++) if (w < c.words) d += __popc(q[w] ^ __ldg(t + w));
+            for (int v = 0; v < 4; v++) {
+                a[u][v] = v < v4 ? __ldg(qa + v) : make_uint4(0u, 0u, 0u, 0u);
+                b[u][v] = v < v4 ? __ldg(tb + v) : make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SPT; u++) {
+            unsigned d = 0;
+#pragma unroll
+            for (int v = 0; v < 4; v++)
+                d += __popc(a[u][v].x ^ b[u][v].x) + __popc(a[u][v].y ^ b[u][v].y) + __popc(a[u][v].z ^ b[u][v].z) + __popc(a[u][v].w ^ b[u][v].w);
             sum += d; sum2 += d * d;
         }
-        for (int o = 16; o; o >>= 1) {
-            sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            sum2 += __shfl_xor_sync(0xffffffffu, sum2, o);
-        }
-        mu = (float)sum * (1.0f / 1024.0f);
-        const float var = (float)sum2 * (1.0f / 1024.0f) - mu * mu;
-        sd = sqrtf(fmaxf(var, 1.0f));
     }
-    if (lane == 0) c.pstat[p] = PairStat{mu, sd, 1.0f, 0};
+    sum = __reduce_add_sync(0xffffffffu, sum); sum2 = __reduce_add_sync(0xffffffffu, sum2);
+    if ((tid & 31) == 0) { atomicAdd(&s_sum, sum); atomicAdd(&s_sum2, sum2); }
+    __syncthreads();
+    if (tid == 0) {
+        float mu = 0.0f, sd = 1.0f;
+        if (pd.n1 > 0 && pd.n2 > 0) {
+            mu = (float)s_sum * (1.0f / 1024.0f);
+            sd = sqrtf(fmaxf((float)s_sum2 * (1.0f / 1024.0f) - mu * mu, 1.0f));
+        }
+        c.pstat[p] = PairStat{mu, sd, 1.0f, 0};
+    }
 }
 
 // The same plan for at most 32 pairs, by ONE warp with everything in registers (no shared memory, no block
@@ -526,7 +546,7 @@ __global__ void __launch_bounds__(ACCEPT_THREADS) init_kernel(Chunk c, PairPack 
         c.status[p] = PAIR_BIG;                      // classified by plan(0)
         if (c.cand) { c.cand_cnt[p] = 0; c.ledge_cnt[p] = 0; c.thr[p] = 0u; }
     }
-    if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 64) sample_pair_stats(c, p, pd);
+    if (blockIdx.x == 0) sample_pair_stats(c, p, pd);      // (block-uniform)
     plan_in_last_block(c, 0, gridDim.x * gridDim.y);
 }
 
@@ -1150,37 +1170,43 @@ __device__ __forceinline__ void sparse_body(const Chunk &c, int r, int p, unsign
         }
         sparse_sub_rounds<NT, SP_EPC, false>(ck, cc, nullptr, cp, rbest, cbest, match_key, s_alive, sub, 0, c, p);
     }
-    // re-compact the live lists in place, SP_IPT ids per thread at a time (order is arbitrary).  A chunk's ids are all
-    // read before any of them is written back, and the kept ones land below the chunk's end: no unread slot is hit.
-#pragma unroll 1
-    for (int side = 0; side < 2; side++) {
-        const int n = side ? nlc : nlr;
-        int32_t *live = side ? c.live_cols[nxt] + col_base : c.live_rows[nxt] + row_base;
-        const uint32_t *best = side ? cbest : rbest;
-        if (tid == 0) s_cnt[side] = 0;
-        for (int k0 = 0; k0 < n; k0 += NT * SP_IPT) {
-            int32_t id[SP_IPT];
-            bool keep[SP_IPT];
+    // re-compact the live lists in place, SP_IPT ids per thread and side at a time (order is arbitrary).  A chunk's ids
+    // are all read before any of them is written back, and the kept ones land below the chunk's end: no unread slot is
+    // hit.  Rows and columns share the loop so that their loads are in flight together.
+    {
+        int32_t *live_r = c.live_rows[nxt] + row_base, *live_c = c.live_cols[nxt] + col_base;
+        if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
+        const int nmax = nlr > nlc ? nlr : nlc;
+        for (int k0 = 0; k0 < nmax; k0 += NT * SP_IPT) {
+            int32_t idr[SP_IPT], idc[SP_IPT];
+            bool kr[SP_IPT], kc[SP_IPT];
 #pragma unroll
             for (int u = 0; u < SP_IPT; u++) {
                 const int k = k0 + u * NT + tid;
-                id[u] = k < n ? __ldcg(live + k) : 0;
+                idr[u] = k < nlr ? __ldcg(live_r + k) : 0;
+                idc[u] = k < nlc ? __ldcg(live_c + k) : 0;
             }
 #pragma unroll
             for (int u = 0; u < SP_IPT; u++) {
                 const int k = k0 + u * NT + tid;
-                keep[u] = k < n && best[by_id ? id[u] : k] != KEY_DEAD;
+                kr[u] = k < nlr && rbest[by_id ? idr[u] : k] != KEY_DEAD;
+                kc[u] = k < nlc && cbest[by_id ? idc[u] : k] != KEY_DEAD;
             }
             __syncthreads();
 #pragma unroll
             for (int u = 0; u < SP_IPT; u++) {
-                const unsigned m = __ballot_sync(0xffffffffu, keep[u]);
-                if (m) {
-                    int base = 0;
-                    if (lane == (__ffs(m) - 1)) base = atomicAdd(&s_cnt[side], __popc(m));
-                    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-                    PGM_ASSERT(!keep[u] || base + __popc(m & ((1u << lane) - 1u)) < n);
-                    if (keep[u]) live[base + __popc(m & ((1u << lane) - 1u))] = id[u];
+#pragma unroll
+                for (int side = 0; side < 2; side++) {
+                    const bool keep = side ? kc[u] : kr[u];
+                    const unsigned m = __ballot_sync(0xffffffffu, keep);
+                    if (m) {
+                        int base = 0;
+                        if (lane == (__ffs(m) - 1)) base = atomicAdd(&s_cnt[side], __popc(m));
+                        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                        const int at = base + __popc(m & ((1u << lane) - 1u));
+                        PGM_ASSERT(!keep || at < (side ? nlc : nlr));
+                        if (keep) (side ? live_c : live_r)[at] = side ? idc[u] : idr[u];
+                    }
                 }
             }
         }
@@ -1718,21 +1744,34 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_kernel(Chunk c, int r_st
     }
     // every small pair's distance matrix and first-round minima, computed by all CTAs (finisher_prepare)
     // (the grid is split among the small pairs: CTA b works on the (b mod n_small)-th of them)
-    int n_small = 0, my_pair = -1;
+    // (a small pair whose matrix has at most FIN_PREP_MIN_EVALS cells is not worth the extra grid phase: its finisher
+    //  CTA computes the few distances itself -- after the sparse sub-rounds a pair usually arrives here with ~30 rows)
+    int n_small = 0, n_prep = 0, my_pair = -1;
     for (int p = 0; p < c.n_pairs; p++)
-        if (__ldcg(c.status + p) == PAIR_SMALL) n_small++;
-    if (n_small) {                                    // uniform: every CTA reads the same statuses
-        const int mine = (int)blockIdx.x % n_small;
+        if (__ldcg(c.status + p) == PAIR_SMALL) {
+            n_small++;
+            const int4 si = __ldcg(reinterpret_cast<const int4 *>(c.small + p));
+            if (si.x * si.y > FIN_PREP_MIN_EVALS) n_prep++;
+        }
+    if (n_prep) {                                     // uniform: every CTA reads the same statuses
+        const int mine = (int)blockIdx.x % n_prep;
         for (int p = 0, k = 0; p < c.n_pairs; p++)
-            if (__ldcg(c.status + p) == PAIR_SMALL && k++ == mine) my_pair = p;
-        finisher_prepare<WORDS>(c, my_pair, dyn_smem, (int)blockIdx.x / n_small,
-                                ((int)gridDim.x - mine + n_small - 1) / n_small);
+            if (__ldcg(c.status + p) == PAIR_SMALL) {
+                const int4 si = __ldcg(reinterpret_cast<const int4 *>(c.small + p));
+                if (si.x * si.y > FIN_PREP_MIN_EVALS && k++ == mine) my_pair = p;
+            }
+        finisher_prepare<WORDS>(c, my_pair, dyn_smem, (int)blockIdx.x / n_prep,
+                                ((int)gridDim.x - mine + n_prep - 1) / n_prep);
         __threadfence();
         grid_barrier(bar_counter, gridDim.x, epoch);
     }
     for (int p = blockIdx.x; p < c.n_pairs; p += gridDim.x) {
         stamp(c, slot);
-        if (__ldcg(c.status + p) == PAIR_SMALL) finisher_body<WORDS, true>(c, p, dyn_smem);
+        if (__ldcg(c.status + p) == PAIR_SMALL) {
+            const int4 si = __ldcg(reinterpret_cast<const int4 *>(c.small + p));
+            if (si.x * si.y > FIN_PREP_MIN_EVALS) finisher_body<WORDS, true>(c, p, dyn_smem);
+            else finisher_body<WORDS, false>(c, p, dyn_smem);
+        }
     }
     if (n_small) {                                    // the finishers' matches must be visible to every ordering CTA
         __threadfence();

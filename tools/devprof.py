@@ -20,9 +20,16 @@ def step():
 for _ in range(5): step()
 stream.synchronize()
 ts = []
-for _ in range(20):
+FLUSH = os.environ.get("FLUSH") == "1"
+if FLUSH:
+    with torch.cuda.stream(stream):
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+for k in range(20):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream); step(); e1.record(stream); e1.synchronize(); ts.append(e0.elapsed_time(e1))
+    with torch.cuda.stream(stream):
+        if FLUSH: flush.fill_(k & 0xFF)
+        e0.record(stream); step(); e1.record(stream)
+    e1.synchronize(); ts.append(e0.elapsed_time(e1))
 st = m.stats()
 m.set_profiling(True)
 r0 = []
