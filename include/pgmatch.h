@@ -310,22 +310,29 @@ int pgm_ransac_score(pgm_handle *h, const float *F, const uint8_t *valid, int32_
  *     pgm_multi_unique_id (made on rank 0) by whatever channel it has; nothing else crosses the ABI.  NCCL is loaded
  *     at run time (dlopen "libnccl.so.2"), so single-GPU users need no NCCL; failures return PGM_E_NCCL.
  *       pgm_multi_match_train_sharded_dev   the greedy matcher; per round ONE min all-reduce of 2 x bound 32-bit keys
- *                                           (bound = live rows, rounded up), no host synchronisation per round
+ *                                           (bound = live rows, rounded up) and ONE all-gather of the ranks' candidate
+ *                                           edges, no host synchronisation per round
  *       pgm_multi_knn2_train_sharded_dev    nearest / second nearest with the top-2 merge: one all-gather of [2][n1]
  *     Both are collective calls: every rank calls them with the same sizes / format / flags.
  *
- * (2) pgm_shard_*: the same steps with the exchange left to the caller (another transport, or several emulated ranks
+ * (2) pgm_shard_*: the same steps with the exchanges left to the caller (another transport, or several emulated ranks
  *     on one GPU in the tests):
- *       pgm_shard_create
+ *       pgm_shard_create;  pgm_shard_edge_capacity(n1, n2_total, n_ranks, &cap)      (same cap on every rank)
  *       repeat:
  *         pgm_shard_round(shard, x, bound)         local distances + row/column argmin; x[2 * bound] = [R | P]:
  *                                                  R[pos] best key of live row pos over this rank's columns,
  *                                                  P[pos] best key among this rank's columns that chose row pos
  *         x = element-wise MIN of x over the ranks (as int32 or uint32)
- *         pgm_shard_commit(shard, x, bound, &live_rows, &done)    row pos is matched iff R[pos] == P[pos]
+ *         pgm_shard_commit(shard, x, bound, edges, cap)    row pos is matched iff R[pos] == P[pos]; edges[1 + cap] (uint64,
+ *                                                  count first) = this rank's candidate edges (distance <= the pass's
+ *                                                  bound T) whose row and column are still unmatched
+ *         edges_all[n_ranks][1 + cap] = all-gather of edges
+ *         pgm_shard_finish_round(shard, edges_all, n_ranks, cap, &live_rows, &done)   mutual-best sub-rounds on the sparse
+ *                                                  edge list (every rank identically), compaction, next round's plan
  *       until done
  *       pgm_shard_finish                           reference-ordered triples on every rank
- *     bound >= the number of live rows (n1 always works; the value pgm_shard_commit returned is the tight one).
+ *     bound >= the number of live rows (n1 always works; the value pgm_shard_finish_round returned is the tight one).
+ *     Passing NULL for edges / edges_all gives the plain one-accept-per-round behaviour (no second exchange).
  *
  * Exchange keys are (distance << 20 | global train index); "none" is 0x7F7F7F7F, so a signed 32-bit MIN orders them
  * like the reference's (distance, i, j) tie-break.  The result is bit-identical to pgm_match_hamming_greedy on the
@@ -333,8 +340,11 @@ int pgm_ransac_score(pgm_handle *h, const float *F, const uint8_t *valid, int32_
 typedef struct pgm_shard pgm_shard;
 int pgm_shard_create(pgm_handle *h, const uint8_t *d_q, int32_t n1, const uint8_t *d_t_local, int32_t n2_local,
                      int32_t col_offset, int32_t n2_total, int32_t desc_bits, int32_t stride_bytes, pgm_shard **out);
+int pgm_shard_edge_capacity(int32_t n1, int32_t n2_total, int32_t n_ranks, int32_t *out_cap);
 int pgm_shard_round(pgm_shard *s, uint32_t *d_x, int32_t bound);
-int pgm_shard_commit(pgm_shard *s, const uint32_t *d_x, int32_t bound, int32_t *live_rows, int32_t *done);
+int pgm_shard_commit(pgm_shard *s, const uint32_t *d_x, int32_t bound, uint64_t *d_edges, int32_t edge_cap);
+int pgm_shard_finish_round(pgm_shard *s, const uint64_t *d_edges_all, int32_t n_ranks, int32_t edge_cap,
+                           int32_t *live_rows, int32_t *done);
 int pgm_shard_finish(pgm_shard *s, int32_t *d_out_qi, int32_t *d_out_tj, int32_t *d_out_dist, uint32_t flags,
                      int32_t *out_count, int32_t *out_rounds);
 int pgm_shard_destroy(pgm_shard *s);

@@ -39,7 +39,8 @@ EXPORTED_SYMBOLS = (
     "pgm_match_keypoints_sorted", "pgm_match_keypoints_sorted_dev", "pgm_knn2_l2", "pgm_knn2_l2_dev",
     "pgm_fast_detect", "pgm_brief_describe", "pgm_nms", "pgm_detect_describe_dev", "pgm_detect_describe_batch_dev",
     "pgm_ransac_score",
-    "pgm_shard_create", "pgm_shard_round", "pgm_shard_commit", "pgm_shard_finish", "pgm_shard_destroy",
+    "pgm_shard_create", "pgm_shard_edge_capacity", "pgm_shard_round", "pgm_shard_commit", "pgm_shard_finish_round",
+    "pgm_shard_finish", "pgm_shard_destroy",
     "pgm_multi_unique_id", "pgm_multi_create", "pgm_multi_destroy", "pgm_multi_match_train_sharded_dev",
     "pgm_multi_knn2_train_sharded_dev", "pgm_multi_get_exchange",
     "pgm_set_profiling", "pgm_get_round_profile", "pgm_measure_popc_peak",
@@ -152,7 +153,10 @@ def load() -> C.CDLL:
         lib.pgm_shard_create.argtypes = [C.c_void_p, u8p, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_int32, C.POINTER(C.c_void_p)]
         lib.pgm_shard_round.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
-        lib.pgm_shard_commit.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        lib.pgm_shard_commit.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
+        lib.pgm_shard_edge_capacity.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+        lib.pgm_shard_finish_round.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32),
+                                               C.POINTER(C.c_int32)]
         lib.pgm_multi_unique_id.argtypes = [C.c_void_p]
         lib.pgm_multi_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
         lib.pgm_multi_destroy.argtypes = [C.c_void_p]

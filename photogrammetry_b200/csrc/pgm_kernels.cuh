@@ -85,7 +85,7 @@ constexpr int TAIL_THREADS = 512;     // persistent tail kernel: 1 CTA per SM, f
 constexpr int ORDER_KEY_CACHE = 16384;  // match keys cached in smem by the order kernel
 static_assert(TAIL_THREADS == 512, "the sparse phase and the ordering slices assume 512-thread CTAs");
 // candidate edges / sparse sub-rounds
-constexpr int SCAND = 256;              // candidate edges a tile stages in shared memory before one global append
+constexpr int SCAND = 512;              // candidate records a tile stages in shared memory between two global appends
 constexpr int SP_THREADS = 512;         // threads of the CTA that runs a pair's sparse sub-rounds
 constexpr int SP_EPT = 32;              // live edges a thread of the sparse phase holds (two registers + one private smem word each)
 constexpr int SP_EPC = 4;               // ... and in the compact form, once at most SP_EPC x threads edges are left
@@ -95,7 +95,7 @@ constexpr int SP_SMEM_BYTES = 184 * 1024;   // shared memory of a sparse phase: 
                                             // and one min slot per live row and live column
 constexpr int SP_LCAP_MAX = SP_THREADS * SP_EPT;   // live edges per pair the global list is sized for
 constexpr int SP_MAX_SUB = 64;          // sub-rounds per sparse phase (each accepts >= 1 pair; the rest waits for the next pass)
-constexpr float CAND_TARGET = 4.0f;     // expected candidate edges per row of the larger side and pass: a few pairs ...
+constexpr float CAND_TARGET = 6.0f;     // expected candidate edges per row of the larger side and pass: a few pairs ...
 constexpr float CAND_TARGET_BATCH = 6.0f;   // ... and batches of pairs
 constexpr uint32_t KEY_DEAD = 0xFFFFFFFEu;  // sparse phase: row / column matched in an earlier sub-round
 
@@ -115,7 +115,8 @@ struct PairDesc {
     int32_t cand_cap, ledge_cap;
 };
 constexpr int PAIR_FLAG_NO_FINISHER = 1;   // never hand this pair to the single-CTA finisher
-constexpr int PAIR_FLAG_NO_EMIT = 2;       // no candidate edges for this pair (train-sharded mode: keys carry global ids)
+constexpr int PAIR_FLAG_NO_EMIT = 2;       // no candidate edges for this pair
+constexpr int PAIR_FLAG_SHARD = 4;         // one rank's slice of a train-sharded pair (keys carry global column ids)
 
 struct PairStat {            // per pair, written by the init kernel
     float mu, sd;            // mean / standard deviation of a sample of this pair's distances
@@ -175,6 +176,7 @@ struct Chunk {
     int32_t *row_pos, *col_pos;   // position of a surviving row / column in the next live list (written by accept)
     int32_t words;                // descriptor words (runtime copy of the kernels' template parameter)
     int32_t *order_cnt;           // latency mode: [n_pairs][ORDER_MAX_SLICES][ORDER_BIN_PITCH] per-slice distance histograms
+    int32_t shard_n2_total;       // train-sharded pair: columns of the whole pair
     float cand_target;            // expected candidate edges per row of the smaller side (CAND_TARGET; PGM_CAND_TARGET overrides)
 };
 
@@ -225,19 +227,34 @@ __device__ __forceinline__ float inv_norm_tail(float p) {
 // Per pair and pass: the candidate-edge bound T such that the pass emits about CAND_TARGET x max(nlr, nlc)
 // edges (distances taken as N(mu, sd) from the init kernel's sample).  Also resets the pair's edge counters and
 // reacts to an overflow of the previous pass.  Called by the planner thread that owns pair p.
-__device__ __forceinline__ void plan_pair_emit(const Chunk &c, int p, uint8_t st, int nlr, int nlc) {
+__device__ __forceinline__ void plan_pair_emit(const Chunk &c, int p, uint8_t st, int nlr, int nlc, int rq) {   // (nlr, nlc by value)
+    // a tile stages at most SCAND records between two flushes (one stage of columns): keep the expected number per stage
+    // below half of that, whatever the list budget would allow
+    const float p_max = 0.4f * (float)SCAND / (float)(ROUND_THREADS * rq * (rq == RQ_LARGE ? STAGE_LARGE : STAGE_SMALL));
     if (!c.cand) return;
     uint32_t thr = 0u;
     const PairDesc &pd = c.pairs[p];
-    if (__ldcg(c.cand_cnt + p) > pd.cand_cap) c.pstat[p].cscale *= 0.25f;       // the last pass overflowed
-    if (st == PAIR_BIG && pd.cand_cap > 0 && !(pd.flags & PAIR_FLAG_NO_EMIT)) {
+    if (!(pd.flags & PAIR_FLAG_SHARD) && __ldcg(c.cand_cnt + p) > pd.cand_cap) c.pstat[p].cscale *= 0.25f;   // the last pass overflowed
+    if (pd.flags & PAIR_FLAG_SHARD) {
+        // one rank of a train-sharded pair: every rank must arrive at the SAME bound, so it is computed from quantities
+        // all ranks share -- the live rows, the live columns of the whole pair (columns = total - matched rows) and a
+        // distance sample that does not involve the rank's train slice (init: queries against queries); no feedback
+        nlc = c.shard_n2_total - (pd.n1 - nlr);
+        if (nlr > 0 && nlc > 0 && pd.cand_cap > 0) {
+            const PairStat ps = c.pstat[p];
+            const float target = c.cand_target * (float)max(pd.n1, c.shard_n2_total) / (float)max(nlr, nlc);
+            const float z = inv_norm_tail(fminf(target / (float)min(nlr, nlc), p_max));
+            const float T = floorf(ps.mu - z * ps.sd - 0.5f);
+            if (T >= 0.0f) thr = ((uint32_t)fminf(T, 1022.0f) + 1u) << KEY_IDX_BITS;
+        }
+    } else if (st == PAIR_BIG && pd.cand_cap > 0 && !(pd.flags & PAIR_FLAG_NO_EMIT)) {
         const PairStat ps = c.pstat[p];
         // about cand_target x max(n1, n2) raw edges in EVERY pass: later passes have fewer live rows, so each row may
         // list more candidates for the same list size (8192 x 8192: 6 per row in pass 0, ~36 per row of the 1236 left
         // in pass 1, after which ~30 rows remain -- tools/sim_threshold_rounds.py)
         const float target = c.cand_target * ps.cscale * (float)max(pd.n1, pd.n2) / (float)max(nlr, nlc);
         if (target >= 0.09f) {
-            const float z = inv_norm_tail(fminf(target / (float)min(nlr, nlc), 0.25f));
+            const float z = inv_norm_tail(fminf(target / (float)min(nlr, nlc), p_max));
             const float T = floorf(ps.mu - z * ps.sd - 0.5f);                  // P(d <= T) ~ Phi((T + 0.5 - mu) / sd)
             if (T >= 0.0f) thr = ((uint32_t)fminf(T, 1022.0f) + 1u) << KEY_IDX_BITS;
         }
@@ -321,7 +338,6 @@ __device__ __forceinline__ void plan_warp(const Chunk &c, int r) {
         }
         int32_t *nx = cnt_ptr(c, (r + 1) % 3, p);   // accept(r) appends here
         nx[0] = 0; nx[1] = 0;
-        plan_pair_emit(c, p, st, nlr, nlc);
     }
     for (int o = 16; o; o >>= 1) {
         ev += __shfl_xor_sync(0xffffffffu, ev, o);
@@ -334,6 +350,7 @@ __device__ __forceinline__ void plan_warp(const Chunk &c, int r) {
     if (ev >= (unsigned long long)c.large_min_evals) { rq = RQ_LARGE; stage = STAGE_LARGE; }
     else { rq = RQ_SMALL; stage = STAGE_SMALL; }
     const int tile_rows = ROUND_THREADS * rq;
+    if (p < c.n_pairs) plan_pair_emit(c, p, st, nlr, nlc, rq);
     float per_tile = (float)ev / (2.0f * (float)slots);
     const float min_tile = (float)(tile_rows * stage);
     if (per_tile < min_tile) per_tile = min_tile;
@@ -420,7 +437,6 @@ __device__ void plan_device(const Chunk &c, int r) {
         }
         int32_t *nx = cnt_ptr(c, (r + 1) % 3, p);   // accept(r) appends here
         nx[0] = 0; nx[1] = 0;
-        plan_pair_emit(c, p, st, nlr, nlc);
     }
     for (int o = 16; o; o >>= 1) {
         ev += __shfl_xor_sync(0xffffffffu, ev, o);
@@ -456,6 +472,11 @@ __device__ void plan_device(const Chunk &c, int r) {
     }
     __syncthreads();
     const int cpt = s_cpt, tile_rows = s_tile_rows;
+    for (int p = tid; p < c.n_pairs; p += nt) {           // the pass's candidate bound of every pair (needs the tile shape)
+        const uint8_t st = c.status[p];
+        const int32_t *cp = cnt_ptr(c, buf, p);
+        plan_pair_emit(c, p, st, st == PAIR_BIG ? __ldcg(cp) : 0, st == PAIR_BIG ? __ldcg(cp + 1) : 0, tile_rows / ROUND_THREADS);
+    }
     // exclusive scan over pairs: each thread owns a contiguous slice
     const int per = (c.n_pairs + nt - 1) / nt;
     const int p0 = min(tid * per, c.n_pairs), p1 = min(p0 + per, c.n_pairs);
@@ -546,7 +567,11 @@ __global__ void __launch_bounds__(ACCEPT_THREADS) init_kernel(Chunk c, PairPack 
         c.status[p] = PAIR_BIG;                      // classified by plan(0)
         if (c.cand) { c.cand_cnt[p] = 0; c.ledge_cnt[p] = 0; c.thr[p] = 0u; }
     }
-    if (blockIdx.x == 0) sample_pair_stats(c, p, pd);      // (block-uniform)
+    if (blockIdx.x == 0) {                                 // (block-uniform)
+        PairDesc sp = pd;
+        if (pd.flags & PAIR_FLAG_SHARD) { sp.t = pd.q; sp.n2 = pd.n1; }      // rank-invariant sample (see plan_pair_emit)
+        sample_pair_stats(c, p, sp);
+    }
     plan_in_last_block(c, 0, gridDim.x * gridDim.y);
 }
 
@@ -1845,35 +1870,188 @@ __global__ void shard_propose_cols_kernel(Chunk c, int r, uint32_t *__restrict__
     }
 }
 
-// X: reduced over the ranks.  Pass 1 of the commit: record the matches, flag the owned matched columns dead, count the
-// surviving rows of each block of SHARD_BLOCK live-list positions.
+// X: reduced over the ranks.  Commit, step 1: record the matches and flag their columns dead (every rank sees every
+// match, so every rank keeps the dead flags of ALL columns: coldead[global j]).
 __global__ void __launch_bounds__(SHARD_BLOCK) shard_commit_mark_kernel(Chunk c, int r, const uint32_t *__restrict__ X, int bound,
-                                                                        uint8_t *__restrict__ coldead, int n2_local,
-                                                                        int32_t *__restrict__ blockcnt) {
-    const PairDesc &pd = c.pairs[0];
+                                                                        uint8_t *__restrict__ coldead) {
     const int nlr = __ldcg(cnt_ptr(c, r % 3, 0));
     const int pos = blockIdx.x * SHARD_BLOCK + threadIdx.x;
-    bool survive = false;
     if (pos < nlr && pos < bound) {
         const uint32_t R = __ldcg(X + pos), P = __ldcg(X + bound + pos);
         if (R != XKEY_NONE && R == P) {
             const int i = __ldcg(c.live_rows[r & 1] + pos);
             c.match_key[i] = R;
-            const int jl = (int)(R & KEY_IDX_MASK) - __ldg(&pd.col_id_offset);
-            if (jl >= 0 && jl < n2_local) coldead[jl] = 1;
-        } else {
-            survive = true;
+            coldead[R & KEY_IDX_MASK] = 1;
         }
     }
+}
+
+// Commit, step 2 (candidate edges, SURVEY-free extension of section 3.1 to the sharded pair): this rank's candidate
+// records of the pass -> the edges whose row and column are both still unmatched, with the emitting thread's sibling
+// rows verified.  out[0] = number of edges (SHARD_EDGE_OVERFLOW if this rank's lists cannot be trusted), out[1 + k] =
+// (d << 40 | i << 20 | GLOBAL j).
+constexpr unsigned long long SHARD_EDGE_OVERFLOW = 0x7FFFFFFFull;
+__global__ void __launch_bounds__(ACCEPT_THREADS) shard_filter_kernel(Chunk c, int r, const uint8_t *__restrict__ coldead,
+                                                                      unsigned long long *__restrict__ out, int out_cap,
+                                                                      int32_t *__restrict__ out_cnt) {
+    const PairDesc &pd = c.pairs[0];
+    const int n = __ldcg(c.cand_cnt), cap = __ldg(&pd.cand_cap);
+    if (n > cap) { if (blockIdx.x == 0 && threadIdx.x == 0) *out_cnt = 0x7FFFFFFF; return; }
+    const int lane = threadIdx.x & 31, words = c.words, off = __ldg(&pd.col_id_offset);
+    const int32_t *live_rows = c.live_rows[r & 1];
+    const int nlr = __ldcg(cnt_ptr(c, r % 3, 0));
+    const uint32_t thr = __ldcg(c.thr);
+    const uint32_t *qd = pd.q, *td = pd.t;
+    const unsigned long long *raw = c.cand + 2 * __ldg(&pd.cand_off);
+    const int start = (int)((blockIdx.x * ACCEPT_THREADS + threadIdx.x) & ~31u), step = (int)gridDim.x * ACCEPT_THREADS;
+    for (int e0 = start; e0 < n; e0 += step) {
+        const int e = e0 + lane;
+        unsigned long long ed[RQ_LARGE];
+#pragma unroll
+        for (int k = 0; k < RQ_LARGE; k++) ed[k] = ~0ull;
+        if (e < n) {
+            const unsigned long long key = __ldcg(raw + 2 * e);
+            const uint32_t aux = (uint32_t)__ldcg(raw + 2 * e + 1);
+            ed[0] = key;
+            const int rqn = (int)(aux >> KEY_IDX_BITS), slot0 = (int)(aux & KEY_IDX_MASK);
+            if (rqn > 1) {
+                const uint32_t i0 = (uint32_t)(key >> KEY_IDX_BITS) & KEY_IDX_MASK, j = (uint32_t)key & KEY_IDX_MASK;
+                PGM_ASSERT((int)j - off >= 0 && (int)j - off < pd.n2);
+                uint32_t tw[16];
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    const uint4 x = 4 * v < words ? __ldg(reinterpret_cast<const uint4 *>(td + (size_t)(j - off) * words) + v) : make_uint4(0u, 0u, 0u, 0u);
+                    tw[4 * v] = x.x; tw[4 * v + 1] = x.y; tw[4 * v + 2] = x.z; tw[4 * v + 3] = x.w;
+                }
+                int used = 1;
+                for (int k = 0; k < rqn && k < RQ_LARGE; k++) {
+                    const int slot = slot0 + k * ROUND_THREADS;
+                    if (slot >= nlr) break;
+                    const uint32_t i2 = (uint32_t)__ldcg(live_rows + slot);
+                    if (i2 == i0) continue;
+                    uint32_t d = 0;
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+                        if (4 * v < words) {
+                            const uint4 x = __ldg(reinterpret_cast<const uint4 *>(qd + (size_t)i2 * words) + v);
+                            d += __popc(x.x ^ tw[4 * v]) + __popc(x.y ^ tw[4 * v + 1]) + __popc(x.z ^ tw[4 * v + 2]) + __popc(x.w ^ tw[4 * v + 3]);
+                        }
+                    }
+                    if ((d << KEY_IDX_BITS) < thr) {
+                        const unsigned long long k2 = ((unsigned long long)d << 40) | ((unsigned long long)i2 << 20) | j;
+                        if (used == 1) ed[1] = k2; else if (used == 2) ed[2] = k2; else ed[3] = k2;
+                        used++;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int x = 0; x < RQ_LARGE; x++) {
+            bool keep = false;
+            if (ed[x] != ~0ull) {
+                const uint32_t i = (uint32_t)(ed[x] >> KEY_IDX_BITS) & KEY_IDX_MASK, j = (uint32_t)ed[x] & KEY_IDX_MASK;
+                keep = __ldcg(c.match_key + i) == KEY_NONE && !coldead[j];
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (m) {
+                int base = 0;
+                if (lane == (__ffs(m) - 1)) base = atomicAdd(out_cnt, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                const int pos = base + __popc(m & ((1u << lane) - 1u));
+                if (keep && pos < out_cap) out[1 + pos] = ed[x];
+            }
+        }
+    }
+}
+
+// publishes the edge count next to the edges (out[0]) once the filter has finished
+__global__ void shard_filter_finish_kernel(const int32_t *__restrict__ cnt, int out_cap, unsigned long long *__restrict__ out) {
+    const int n = *cnt;
+    out[0] = (n > out_cap) ? SHARD_EDGE_OVERFLOW : (unsigned long long)n;
+}
+
+// Commit, step 3: the sparse sub-rounds of section 3.1 over the edges of ALL ranks (gathered: all[g][1 + cap]), by the
+// whole grid (cooperative launch), every rank redundantly and identically.  One min slot per row and per GLOBAL column
+// in global memory, addressed by original id (a pair of this size does not fit one CTA's shared memory).  est[] holds
+// one live bit per edge slot.  Skipped altogether (uniformly on every rank) if any rank reported an overflow.
+__global__ void __launch_bounds__(TAIL_THREADS, 1) shard_sparse_kernel(Chunk c, const unsigned long long *__restrict__ all,
+                                                                       int n_ranks, int cap, uint32_t *__restrict__ rbest,
+                                                                       uint32_t *__restrict__ cbest, uint8_t *__restrict__ coldead,
+                                                                       uint8_t *__restrict__ est, unsigned *bar_counter,
+                                                                       int32_t *alive_cnt /*[2]*/) {
+    __shared__ int s_cnt[64];
+    const int tid = threadIdx.x;
+    unsigned epoch = 0;
+    for (int g = tid; g < n_ranks && g < 64; g += TAIL_THREADS) {
+        const unsigned long long v = __ldcg(all + (size_t)g * (1 + cap));
+        s_cnt[g] = v >= SHARD_EDGE_OVERFLOW ? -1 : (int)v;
+    }
+    __syncthreads();
+    for (int g = 0; g < n_ranks; g++) if (s_cnt[g] < 0) return;              // uniform: every CTA reads the same counts
+    const long long S = (long long)n_ranks * cap;
+    const long long gt = (long long)blockIdx.x * TAIL_THREADS + tid, gs = (long long)gridDim.x * TAIL_THREADS;
+    uint32_t *match_key = c.match_key;
+    for (long long s = gt; s < S; s += gs) {
+        const int g = (int)(s / cap), k = (int)(s - (long long)g * cap);
+        est[s] = k < s_cnt[g] ? 1 : 0;
+    }
+    if (blockIdx.x == 0 && tid == 0) { alive_cnt[0] = 0; alive_cnt[1] = 0; }
+    grid_barrier(bar_counter, gridDim.x, epoch);
+    for (int sub = 0; sub < SP_MAX_SUB; sub++) {
+        for (long long s = gt; s < S; s += gs) {
+            if (!est[s]) continue;
+            const int g = (int)(s / cap);
+            const unsigned long long key = __ldcg(all + (size_t)g * (1 + cap) + 1 + (s - (long long)g * cap));
+            const uint32_t d = (uint32_t)(key >> 40), i = (uint32_t)(key >> KEY_IDX_BITS) & KEY_IDX_MASK, j = (uint32_t)key & KEY_IDX_MASK;
+            atomicMin(rbest + i, (d << KEY_IDX_BITS) | j);
+            atomicMin(cbest + j, (d << KEY_IDX_BITS) | i);
+        }
+        grid_barrier(bar_counter, gridDim.x, epoch);
+        for (long long s = gt; s < S; s += gs) {
+            if (!est[s]) continue;
+            const int g = (int)(s / cap);
+            const unsigned long long key = __ldcg(all + (size_t)g * (1 + cap) + 1 + (s - (long long)g * cap));
+            const uint32_t d = (uint32_t)(key >> 40), i = (uint32_t)(key >> KEY_IDX_BITS) & KEY_IDX_MASK, j = (uint32_t)key & KEY_IDX_MASK;
+            // (the only writers of these two slots' owners are the threads of THE mutual edge: nobody else passes the test)
+            if (__ldcg(rbest + i) == ((d << KEY_IDX_BITS) | j) && __ldcg(cbest + j) == ((d << KEY_IDX_BITS) | i)) {
+                match_key[i] = (d << KEY_IDX_BITS) | j;
+                coldead[j] = 1;
+            }
+        }
+        if (blockIdx.x == 0 && tid == 0) alive_cnt[(sub + 1) & 1] = 0;
+        grid_barrier(bar_counter, gridDim.x, epoch);
+        int alive = 0;
+        for (long long s = gt; s < S; s += gs) {
+            if (!est[s]) continue;
+            const int g = (int)(s / cap);
+            const unsigned long long key = __ldcg(all + (size_t)g * (1 + cap) + 1 + (s - (long long)g * cap));
+            const uint32_t i = (uint32_t)(key >> KEY_IDX_BITS) & KEY_IDX_MASK, j = (uint32_t)key & KEY_IDX_MASK;
+            // every slot touched in this sub-round goes back to "none": a live row whose listed edges all died must not
+            // carry a stale minimum into the next pass
+            rbest[i] = KEY_NONE; cbest[j] = KEY_NONE;
+            if (__ldcg(match_key + i) != KEY_NONE || __ldcg(coldead + j)) est[s] = 0; else alive++;
+        }
+        alive = __reduce_add_sync(0xffffffffu, alive);
+        if ((tid & 31) == 0 && alive) atomicAdd(&alive_cnt[sub & 1], alive);
+        grid_barrier(bar_counter, gridDim.x, epoch);
+        if (__ldcg(&alive_cnt[sub & 1]) == 0) break;                         // uniform
+    }
+}
+
+// Commit, step 4: survivors of each block of SHARD_BLOCK live-list positions (a row survives iff it is still unmatched)
+__global__ void __launch_bounds__(SHARD_BLOCK) shard_count_kernel(Chunk c, int r, int32_t *__restrict__ blockcnt) {
+    const int nlr = __ldcg(cnt_ptr(c, r % 3, 0));
+    const int pos = blockIdx.x * SHARD_BLOCK + threadIdx.x;
+    const bool survive = pos < nlr && __ldcg(c.match_key + __ldcg(c.live_rows[r & 1] + pos)) == KEY_NONE;
     const int n = __syncthreads_count(survive);
     if (threadIdx.x == 0) blockcnt[blockIdx.x] = n;
 }
 
-// Pass 2: stable compaction of the surviving rows (block b starts behind the survivors of blocks 0 .. b-1), so every
-// rank ends up with the same list in the same order.  Also keeps row_pos and resets the survivors' keys.
-__global__ void __launch_bounds__(SHARD_BLOCK) shard_commit_scatter_kernel(Chunk c, int r, const uint32_t *__restrict__ X, int bound,
-                                                                           const int32_t *__restrict__ blockcnt, int n_blocks,
-                                                                           ShardCtl *__restrict__ ctl, int n1, int n2_total) {
+// Commit, step 5: stable compaction of the surviving rows (block b starts behind the survivors of blocks 0 .. b-1), so
+// every rank ends up with the same list in the same order.  Also keeps row_pos and resets the survivors' keys.
+__global__ void __launch_bounds__(SHARD_BLOCK) shard_commit_scatter_kernel(Chunk c, int r, const int32_t *__restrict__ blockcnt,
+                                                                           int n_blocks, ShardCtl *__restrict__ ctl, int n1,
+                                                                           int n2_total) {
     __shared__ int s_w[SHARD_BLOCK / 32], s_base, s_total;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int cur = r & 1, nxt = cur ^ 1;
@@ -1892,10 +2070,9 @@ __global__ void __launch_bounds__(SHARD_BLOCK) shard_commit_scatter_kernel(Chunk
     const int pos = blockIdx.x * SHARD_BLOCK + tid;
     bool survive = false;
     int i = 0;
-    if (pos < nlr && pos < bound) {
-        const uint32_t R = __ldcg(X + pos), P = __ldcg(X + bound + pos);
-        survive = !(R != XKEY_NONE && R == P);
+    if (pos < nlr) {
         i = __ldcg(c.live_rows[cur] + pos);
+        survive = __ldcg(c.match_key + i) == KEY_NONE;
     }
     const unsigned m = __ballot_sync(0xffffffffu, survive);
     if (lane == 0) s_w[wid] = __popc(m);
@@ -1919,16 +2096,18 @@ __global__ void __launch_bounds__(SHARD_BLOCK) shard_commit_scatter_kernel(Chunk
     }
 }
 
+// Commit, step 6: the rank's own columns (coldead is indexed by GLOBAL column id); the last block plans the next pass
 __global__ void __launch_bounds__(ACCEPT_THREADS) shard_commit_cols_kernel(Chunk c, int r, const uint8_t *coldead, ShardCtl *ctl) {
     const int cur = r & 1, nxt = cur ^ 1, lane = threadIdx.x & 31;
     const int nlc = __ldcg(cnt_ptr(c, r % 3, 0) + 1);
+    const int off = __ldg(&c.pairs[0].col_id_offset);
     const int nrounded = (nlc + 31) & ~31;
     for (int y = blockIdx.x * blockDim.x + threadIdx.x; y < nrounded; y += gridDim.x * blockDim.x) {
         bool survive = false;
         int j = 0;
         if (y < nlc) {
             j = __ldcg(c.live_cols[cur] + y);
-            if (!coldead[j]) { survive = true; c.colbest[nxt][j] = KEY_NONE; }
+            if (!coldead[j + off]) { survive = true; c.colbest[nxt][j] = KEY_NONE; }
         }
         const unsigned m = __ballot_sync(0xffffffffu, survive);
         if (m) {

@@ -1816,18 +1816,34 @@ extern "C" int pgm_ransac_score(pgm_handle *h, const float *F, const uint8_t *va
 //                 synchronisation per round: rounds are enqueued in batches and an 8-byte status read-back per batch,
 //                 checked two batches late, stops the loop and shrinks the exchange
 // ---------------------------------------------------------------------------
+struct ShardDev {                  // small device-resident control block of a shard (zeroed before every round)
+    unsigned bar;                  // grid-barrier counter of the cooperative sparse kernel
+    int32_t edge_cnt;              // filtered candidate edges of the round
+    int32_t alive[2];
+};
+
 struct pgm_shard {
     pgm_handle *h = nullptr;
-    DevBuf state;
+    DevBuf state, est;
     Chunk c{};
     int words = 8, desc_bits = 256, n1 = 0, n2_local = 0, n2_total = 0, col_offset = 0;
     int round = 0;
     int round_grid = 0;
-    uint8_t *coldead = nullptr;
+    int raw_cap = 0;               // candidate records this rank may emit per pass
+    uint8_t *coldead = nullptr;    // [n2_total] by GLOBAL column id
+    uint32_t *rbest_g = nullptr, *cbest_g = nullptr;   // [n1], [n2_total]: min slots of the grid-wide sparse phase
     int32_t *blockcnt = nullptr;
+    ShardDev *dev = nullptr;
     ShardCtl *ctl = nullptr;       // device
     ShardCtl *h_ctl = nullptr;     // pinned: [8] status read-backs (ring)
 };
+
+constexpr float CAND_TARGET_SHARD = 4.0f;
+// edges a rank may contribute per pass (identical on every rank for given sizes: the gathered layout is [ranks][1 + cap])
+static int shard_edge_capacity(int n1, int n2_total, int world) {
+    const int64_t m = std::max(n1, n2_total);
+    return (int)std::min<int64_t>((int64_t)(2.0f * CAND_TARGET_SHARD + 1.0f) * m * 5 / (4 * std::max(world, 1)) + 4096, (int64_t)1 << 28);
+}
 
 extern "C" int pgm_shard_create(pgm_handle *h, const uint8_t *d_q, int32_t n1, const uint8_t *d_t_local,
                                 int32_t n2_local, int32_t col_offset, int32_t n2_total, int32_t desc_bits,
@@ -1847,14 +1863,23 @@ extern "C" int pgm_shard_create(pgm_handle *h, const uint8_t *d_q, int32_t n1, c
     sh->n1 = n1; sh->n2_local = n2_local; sh->n2_total = n2_total; sh->col_offset = col_offset;
     const int64_t rows = n1, cols = std::max(n2_local, 1);
     const int n_blocks = (n1 + SHARD_BLOCK - 1) / SHARD_BLOCK;
+    const bool use_cand = !h->no_cand;
+    // this rank's share of the pass's candidate records (x 1.25 slack), by its share of the columns
+    sh->raw_cap = use_cand ? (int)std::min<int64_t>(
+        (int64_t)((2.0f * CAND_TARGET_SHARD + 1.0f) * 1.25f * (float)std::max(n1, n2_total) * ((float)cols / (float)n2_total)) + 4096,
+        (int64_t)n1 * cols) : 0;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t o_pairs = take(sizeof(PairDesc));
     const size_t o_rb0 = take(4 * rows), o_rb1 = take(4 * rows), o_cb0 = take(4 * cols), o_cb1 = take(4 * cols);
     const size_t o_lr0 = take(4 * rows), o_lr1 = take(4 * rows), o_lc0 = take(4 * cols), o_lc1 = take(4 * cols);
     const size_t o_cnt = take(sizeof(int32_t) * 6), o_mk = take(4 * rows), o_tb = take(8), o_ab = take(8);
-    const size_t o_st = take(1), o_small = take(sizeof(SmallInfo)), o_plan = take(sizeof(PlanInfo)), o_dead = take(cols);
+    const size_t o_st = take(1), o_small = take(sizeof(SmallInfo)), o_plan = take(sizeof(PlanInfo));
+    const size_t o_dead = take((size_t)n2_total);
     const size_t o_rpos = take(4 * rows), o_bcnt = take(4 * (size_t)n_blocks), o_ctl = take(sizeof(ShardCtl));
+    const size_t o_dev = take(sizeof(ShardDev));
+    const size_t o_rbg = take(4 * rows), o_cbg = take(4 * (size_t)n2_total);
+    const size_t o_cand = take(16 * (size_t)sh->raw_cap), o_ccnt = take(4), o_thr = take(4), o_pstat = take(sizeof(PairStat));
     if ((rc = ensure_dev(h, sh->state, off))) { delete sh; return rc; }
     if (cudaMallocHost((void **)&sh->h_ctl, sizeof(ShardCtl) * 8) != cudaSuccess) { cudaFree(sh->state.p); delete sh; return PGM_E_CUDA; }
     char *base = (char *)sh->state.p;
@@ -1866,6 +1891,9 @@ extern "C" int pgm_shard_create(pgm_handle *h, const uint8_t *d_q, int32_t n1, c
     c.fin_max_evals = FIN_MAX_EVALS;
     c.large_min_evals = large_tile_min_evals(h);
     c.words = sh->words;
+    c.shard_n2_total = n2_total;
+    c.cand_target = CAND_TARGET_SHARD;
+    if (const char *e = getenv("PGM_CAND_TARGET")) c.cand_target = std::max(0.1f, (float)atof(e));
     c.rowbest[0] = (uint32_t *)(base + o_rb0); c.rowbest[1] = (uint32_t *)(base + o_rb1);
     c.colbest[0] = (uint32_t *)(base + o_cb0); c.colbest[1] = (uint32_t *)(base + o_cb1);
     c.live_rows[0] = (int32_t *)(base + o_lr0); c.live_rows[1] = (int32_t *)(base + o_lr1);
@@ -1873,18 +1901,28 @@ extern "C" int pgm_shard_create(pgm_handle *h, const uint8_t *d_q, int32_t n1, c
     c.counts = (int32_t *)(base + o_cnt); c.match_key = (uint32_t *)(base + o_mk);
     c.tile_base = (int32_t *)(base + o_tb); c.ablock_base = (int32_t *)(base + o_ab);
     c.status = (uint8_t *)(base + o_st); c.small = (SmallInfo *)(base + o_small); c.plan = (PlanInfo *)(base + o_plan);
-    c.row_pos = (int32_t *)(base + o_rpos);      // (c.cand stays null: no candidate edges in this mode)
+    c.row_pos = (int32_t *)(base + o_rpos);
+    if (use_cand) {                // candidate records of the pass; the edges themselves live in the caller's exchange buffer
+        c.cand = (unsigned long long *)(base + o_cand);
+        c.cand_cnt = (int32_t *)(base + o_ccnt); c.ledge_cnt = c.cand_cnt;   // (ledge_cnt is only reset by the planner here)
+        c.thr = (uint32_t *)(base + o_thr); c.pstat = (PairStat *)(base + o_pstat);
+    }
     c.timeline = nullptr;
     sh->coldead = (uint8_t *)(base + o_dead);
     sh->blockcnt = (int32_t *)(base + o_bcnt);
     sh->ctl = (ShardCtl *)(base + o_ctl);
+    sh->dev = (ShardDev *)(base + o_dev);
+    sh->rbest_g = (uint32_t *)(base + o_rbg); sh->cbest_g = (uint32_t *)(base + o_cbg);
     PairPack pack{};
     pack.p[0].q = (const uint32_t *)d_q; pack.p[0].t = (const uint32_t *)d_t_local;
     pack.p[0].n1 = n1; pack.p[0].n2 = n2_local; pack.p[0].row_base = 0; pack.p[0].col_base = 0; pack.p[0].out_base = 0;
-    pack.p[0].col_id_offset = col_offset; pack.p[0].flags = PAIR_FLAG_NO_FINISHER | PAIR_FLAG_NO_EMIT;
+    pack.p[0].col_id_offset = col_offset; pack.p[0].flags = PAIR_FLAG_NO_FINISHER | PAIR_FLAG_SHARD;
+    pack.p[0].cand_off = 0; pack.p[0].cand_cap = sh->raw_cap;
     CU_CHECK(h, cudaMemsetAsync(c.plan, 0, sizeof(PlanInfo), s));
-    CU_CHECK(h, cudaMemsetAsync(sh->coldead, 0, cols, s));
+    CU_CHECK(h, cudaMemsetAsync(sh->coldead, 0, (size_t)n2_total, s));
     CU_CHECK(h, cudaMemsetAsync(sh->ctl, 0, sizeof(ShardCtl), s));
+    CU_CHECK(h, cudaMemsetAsync(sh->rbest_g, 0xFF, 4 * rows, s));
+    CU_CHECK(h, cudaMemsetAsync(sh->cbest_g, 0xFF, 4 * (size_t)n2_total, s));
     dim3 igrid(std::max(1, std::min((std::max(n1, n2_local) + ACCEPT_THREADS - 1) / ACCEPT_THREADS, 64)), 1);
     init_kernel<true><<<igrid, ACCEPT_THREADS, 0, s>>>(c, pack);
     CU_CHECK(h, cudaGetLastError());
@@ -1892,9 +1930,16 @@ extern "C" int pgm_shard_create(pgm_handle *h, const uint8_t *d_q, int32_t n1, c
     return PGM_OK;
 }
 
+extern "C" int pgm_shard_edge_capacity(int32_t n1, int32_t n2_total, int32_t n_ranks, int32_t *out_cap) {
+    if (!out_cap || n1 < 1 || n2_total < 1 || n_ranks < 1) return PGM_E_INVALID_ARG;
+    *out_cap = shard_edge_capacity(n1, n2_total, n_ranks);
+    return PGM_OK;
+}
+
 // enqueue: local round r, then this rank's contribution to the exchange into d_x[2 * bound] (bound >= live rows)
 static int shard_enqueue_round(pgm_shard *sh, uint32_t *d_x, int bound, cudaStream_t s) {
     pgm_handle *h = sh->h;
+    CU_CHECK(h, cudaMemsetAsync(sh->dev, 0, sizeof(ShardDev), s));
     dispatch_round(sh->words, sh->c, sh->round, sh->round_grid, s);
     const int g = std::max(1, std::min((bound + 255) / 256, h->num_sms * 8));
     shard_export_rows_kernel<<<g, 256, 0, s>>>(sh->c, sh->round, d_x, bound);
@@ -1904,13 +1949,47 @@ static int shard_enqueue_round(pgm_shard *sh, uint32_t *d_x, int bound, cudaStre
     return PGM_OK;
 }
 
-// enqueue: commit of round r from the reduced exchange buffer; advances the round counter
-static int shard_enqueue_commit(pgm_shard *sh, const uint32_t *d_x, int bound, cudaStream_t s) {
+// enqueue: commit step 1 + 2 from the reduced exchange buffer: matches, dead flags, this rank's filtered candidate edges
+// into d_edges[1 + edge_cap] (d_edges[0] = count, or the overflow marker)
+static int shard_enqueue_commit(pgm_shard *sh, const uint32_t *d_x, int bound, unsigned long long *d_edges, int edge_cap,
+                                cudaStream_t s) {
     pgm_handle *h = sh->h;
     const int r = sh->round;
     const int nb = std::max(1, (std::min(bound, sh->n1) + SHARD_BLOCK - 1) / SHARD_BLOCK);
-    shard_commit_mark_kernel<<<nb, SHARD_BLOCK, 0, s>>>(sh->c, r, d_x, bound, sh->coldead, sh->n2_local, sh->blockcnt);
-    shard_commit_scatter_kernel<<<nb, SHARD_BLOCK, 0, s>>>(sh->c, r, d_x, bound, sh->blockcnt, nb, sh->ctl, sh->n1, sh->n2_total);
+    shard_commit_mark_kernel<<<nb, SHARD_BLOCK, 0, s>>>(sh->c, r, d_x, bound, sh->coldead);
+    h->stats.kernel_launches += 1;
+    if (d_edges) {
+        if (sh->c.cand) {
+            shard_filter_kernel<<<h->num_sms * 4, ACCEPT_THREADS, 0, s>>>(sh->c, r, sh->coldead, d_edges, edge_cap, &sh->dev->edge_cnt);
+            shard_filter_finish_kernel<<<1, 1, 0, s>>>(&sh->dev->edge_cnt, edge_cap, d_edges);
+            h->stats.kernel_launches += 2;
+        } else {
+            CU_CHECK(h, cudaMemsetAsync(d_edges, 0, 8, s));       // no candidate edges: count 0
+        }
+    }
+    return PGM_OK;
+}
+
+// enqueue: commit steps 3-6: grid-wide sparse sub-rounds over every rank's edges, stable row compaction, columns, plan
+static int shard_enqueue_finish_round(pgm_shard *sh, const unsigned long long *d_edges_all, int n_ranks, int edge_cap,
+                                      cudaStream_t s) {
+    pgm_handle *h = sh->h;
+    const int r = sh->round;
+    if (d_edges_all && sh->c.cand && n_ranks >= 1) {
+        int rc = ensure_dev(h, sh->est, (size_t)n_ranks * edge_cap);
+        if (rc) return rc;
+        Chunk c = sh->c;
+        uint32_t *rb = sh->rbest_g, *cb = sh->cbest_g;
+        uint8_t *cd = sh->coldead, *est = (uint8_t *)sh->est.p;
+        unsigned *bar = &sh->dev->bar;
+        int32_t *alive = sh->dev->alive;
+        void *args[] = {&c, &d_edges_all, &n_ranks, &edge_cap, &rb, &cb, &cd, &est, &bar, &alive};
+        CU_CHECK(h, cudaLaunchCooperativeKernel((void *)shard_sparse_kernel, dim3(h->num_sms), dim3(TAIL_THREADS), args, 0, s));
+        h->stats.kernel_launches += 1;
+    }
+    const int nb = (sh->n1 + SHARD_BLOCK - 1) / SHARD_BLOCK;
+    shard_count_kernel<<<nb, SHARD_BLOCK, 0, s>>>(sh->c, r, sh->blockcnt);
+    shard_commit_scatter_kernel<<<nb, SHARD_BLOCK, 0, s>>>(sh->c, r, sh->blockcnt, nb, sh->ctl, sh->n1, sh->n2_total);
     const int g2 = std::max(1, std::min((sh->n2_local + ACCEPT_THREADS - 1) / ACCEPT_THREADS, h->num_sms * 8));
     shard_commit_cols_kernel<<<g2, ACCEPT_THREADS, 0, s>>>(sh->c, r, sh->coldead, sh->ctl);
     h->stats.kernel_launches += 3;
@@ -1924,20 +2003,37 @@ extern "C" int pgm_shard_round(pgm_shard *sh, uint32_t *d_x, int32_t bound) {
     pgm_handle *h = sh->h;
     std::lock_guard<std::mutex> lk(h->mu);
     CU_CHECK(h, cudaSetDevice(h->device));
-    shard_enqueue_round(sh, d_x, bound, h->stream);
+    int rc = shard_enqueue_round(sh, d_x, bound, h->stream);
+    if (rc) return rc;
     CU_CHECK(h, cudaGetLastError());
     return PGM_OK;
 }
 
-// Step 2 (d_x now min-reduced over the ranks): commit; returns the live rows (identical on all ranks) and whether the
-// pair is finished.  Synchronises the stream (16 bytes read back).
-extern "C" int pgm_shard_commit(pgm_shard *sh, const uint32_t *d_x, int32_t bound, int32_t *live_rows, int32_t *done) {
-    if (!sh || !d_x || bound < 1) return PGM_E_INVALID_ARG;
+// Step 2 (d_x now min-reduced over the ranks): matches of the round; this rank's surviving candidate edges go to
+// d_edges[1 + edge_cap] (count first).  d_edges may be NULL (no candidate edges: plain one-accept-per-round behaviour).
+extern "C" int pgm_shard_commit(pgm_shard *sh, const uint32_t *d_x, int32_t bound, uint64_t *d_edges, int32_t edge_cap) {
+    if (!sh || !d_x || bound < 1 || (d_edges && edge_cap < 1)) return PGM_E_INVALID_ARG;
+    pgm_handle *h = sh->h;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU_CHECK(h, cudaSetDevice(h->device));
+    int rc = shard_enqueue_commit(sh, d_x, bound, (unsigned long long *)d_edges, edge_cap, h->stream);
+    if (rc) return rc;
+    CU_CHECK(h, cudaGetLastError());
+    return PGM_OK;
+}
+
+// Step 3 (d_edges_all[n_ranks][1 + edge_cap] = every rank's edges, gathered; NULL skips the sparse phase): sparse
+// sub-rounds, compaction, plan of the next round.  Returns the live rows (identical on all ranks) and whether the pair is
+// finished.  Synchronises the stream (16 bytes read back).
+extern "C" int pgm_shard_finish_round(pgm_shard *sh, const uint64_t *d_edges_all, int32_t n_ranks, int32_t edge_cap,
+                                      int32_t *live_rows, int32_t *done) {
+    if (!sh || (d_edges_all && (n_ranks < 1 || n_ranks > 64 || edge_cap < 1))) return PGM_E_INVALID_ARG;
     pgm_handle *h = sh->h;
     std::lock_guard<std::mutex> lk(h->mu);
     CU_CHECK(h, cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
-    shard_enqueue_commit(sh, d_x, bound, s);
+    int rc = shard_enqueue_finish_round(sh, (const unsigned long long *)d_edges_all, n_ranks, edge_cap, s);
+    if (rc) return rc;
     CU_CHECK(h, cudaMemcpyAsync(sh->h_ctl, sh->ctl, sizeof(ShardCtl), cudaMemcpyDeviceToHost, s));
     CU_CHECK(h, cudaStreamSynchronize(s));
     if (live_rows) *live_rows = sh->h_ctl[0].live_rows;
@@ -1993,6 +2089,7 @@ extern "C" int pgm_shard_destroy(pgm_shard *sh) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (sh->state.p) cudaFree(sh->state.p);
+    if (sh->est.p) cudaFree(sh->est.p);
     if (sh->h_ctl) cudaFreeHost(sh->h_ctl);
     delete sh;
     return PGM_OK;
@@ -2016,7 +2113,7 @@ struct NcclApi {
     const char *(*GetErrorString)(int) = nullptr;
     std::string why;
 };
-constexpr int kNcclInt32 = 2, kNcclUint32 = 3, kNcclMin = 3;   // ncclDataType_t / ncclRedOp_t values (nccl.h, 2.x)
+constexpr int kNcclInt32 = 2, kNcclUint32 = 3, kNcclUint64 = 5, kNcclMin = 3;   // ncclDataType_t / ncclRedOp_t values (nccl.h, 2.x)
 NcclApi *nccl_api() {
     static NcclApi api;
     static std::once_flag once;
@@ -2126,9 +2223,14 @@ extern "C" int pgm_multi_match_train_sharded_dev(pgm_multi *mh, const uint8_t *d
         mh->exchange_bytes = 0; mh->collectives = 0;
         if (cudaSetDevice(h->device) != cudaSuccess) { rc = PGM_E_CUDA; }
         cudaStream_t s = h->stream;
-        if (!rc) rc = ensure_dev(h, mh->xbuf, (size_t)2 * n1 * 4);
+        const int edge_cap = shard_edge_capacity(n1, n2_total, mh->world);
+        const bool edges_on = sh->c.cand != nullptr && mh->world <= 64;
+        const size_t x_bytes = align_up((size_t)2 * n1 * 4, 256);
+        if (!rc) rc = ensure_dev(h, mh->xbuf, x_bytes + (edges_on ? (size_t)mh->world * (1 + (size_t)edge_cap) * 8 : 0));
         uint32_t *X = (uint32_t *)mh->xbuf.p;
-        constexpr int BATCH = 4, RING = 8;
+        unsigned long long *E_all = edges_on ? (unsigned long long *)((char *)mh->xbuf.p + x_bytes) : nullptr;
+        unsigned long long *E_mine = edges_on ? E_all + (size_t)mh->rank * (1 + (size_t)edge_cap) : nullptr;
+        constexpr int BATCH = 2, RING = 8;
         cudaEvent_t ev[RING];
         for (auto &e : ev) e = nullptr;
         for (int k = 0; k < RING && !rc; k++)
@@ -2137,13 +2239,19 @@ extern "C" int pgm_multi_match_train_sharded_dev(pgm_multi *mh, const uint8_t *d
         bool done = false;
         while (!rc && !done) {
             for (int k = 0; k < BATCH && !rc; k++) {
-                shard_enqueue_round(sh, X, bound, s);
+                if ((rc = shard_enqueue_round(sh, X, bound, s))) break;
                 if (mh->world > 1) {
                     const int r = nccl_api()->AllReduce(X, X, (size_t)2 * bound, kNcclUint32, kNcclMin, mh->comm, s);
                     if (r != 0) { h->err = std::string("ncclAllReduce failed: ") + nccl_api()->GetErrorString(r); rc = PGM_E_NCCL; break; }
                     mh->exchange_bytes += (int64_t)2 * bound * 4; mh->collectives++;
                 }
-                shard_enqueue_commit(sh, X, bound, s);
+                if ((rc = shard_enqueue_commit(sh, X, bound, E_mine, edge_cap, s))) break;
+                if (edges_on && mh->world > 1) {      // in place: this rank's block already sits at its slot of the gathered buffer
+                    const int r = nccl_api()->AllGather(E_mine, E_all, (size_t)(1 + edge_cap), kNcclUint64, mh->comm, s);
+                    if (r != 0) { h->err = std::string("ncclAllGather failed: ") + nccl_api()->GetErrorString(r); rc = PGM_E_NCCL; break; }
+                    mh->exchange_bytes += (int64_t)(1 + edge_cap) * 8; mh->collectives++;
+                }
+                if ((rc = shard_enqueue_finish_round(sh, E_all, mh->world, edge_cap, s))) break;
             }
             if (rc) break;
             const int slot = batch_no % RING;

@@ -133,19 +133,20 @@ def train_slices(n2_total: int, world_size: int) -> List[Tuple[int, int]]:
 
 
 class TrainShardedMatcher:
-    """MatchKeypoints on ONE pair whose train set is sharded over the ranks, with the exchange
+    """MatchKeypoints on ONE pair whose train set is sharded over the ranks, with the exchanges
     left to the caller's transport (``pgm_shard_*``; :class:`MultiGpuMatcher` is the form where the library owns NCCL).
 
     ``d_q``: torch uint8 ``[n1, stride]`` (all queries, on this rank's GPU);
     ``d_t_local``: torch uint8 ``[n2_local, stride]`` = train rows ``[col_offset, col_offset + n2_local)``.
-    ``reduce_min(tensor)`` performs an in-place MIN all-reduce of an int32 tensor across the ranks;
-    by default ``torch.distributed.all_reduce(op=MIN)`` on the default group.  ONE exchange per round: ``x = [R | P]``,
-    ``2 * bound`` keys (include/pgmatch.h).  Returns int32 ``[3, n1]`` (qi, tj, dist) in the reference's order --
+    ``reduce_min(tensor)``: in-place MIN all-reduce of an int32 tensor across the ranks (default
+    ``torch.distributed.all_reduce(op=MIN)``); ``all_gather(tensor) -> tensor[world, ...]`` (default
+    ``torch.distributed.all_gather_into_tensor``).  Two exchanges per round: ``x = [R | P]`` (``2 * bound`` keys) and the
+    ranks' candidate edges (include/pgmatch.h).  Returns int32 ``[3, n1]`` (qi, tj, dist) in the reference's order --
     identical on every rank and bit-identical to the unsharded ``Matcher.match_greedy``.
     """
 
     def __init__(self, matcher, d_q, d_t_local, col_offset: int, n2_total: int, desc_bits: int = 256,
-                 reduce_min=None):
+                 reduce_min=None, all_gather=None, world_size: Optional[int] = None):
         import ctypes as C
 
         import torch
@@ -155,16 +156,25 @@ class TrainShardedMatcher:
         self.n1, self.stride = int(d_q.shape[0]), int(d_q.shape[1])
         self.n2_local, self.n2_total = int(d_t_local.shape[0]), int(n2_total)
         self._keep = (d_q, d_t_local)
+        if world_size is None:
+            import torch.distributed as dist
+            world_size = dist.get_world_size() if dist.is_initialized() else 1
+        self.world_size = int(world_size)
         self._sh = C.c_void_p()
         with matcher.torch_ordered(d_q.device):
             matcher._check(self._lib.pgm_shard_create(
                 matcher._h, d_q.data_ptr(), self.n1, d_t_local.data_ptr() if self.n2_local else None, self.n2_local,
                 int(col_offset), self.n2_total, int(desc_bits), self.stride, C.byref(self._sh)))
         dev = d_q.device
+        cap = C.c_int32(0)
+        matcher._check(self._lib.pgm_shard_edge_capacity(self.n1, self.n2_total, self.world_size, C.byref(cap)))
+        self.edge_cap = cap.value
         self.x = torch.empty(2 * self.n1, dtype=torch.int32, device=dev)      # [R | P], the first 2 * bound entries in use
+        self.edges = torch.zeros(1 + self.edge_cap, dtype=torch.int64, device=dev)   # count, then (d << 40 | i << 20 | global j)
         self.bound = self.n1
         self.out = torch.empty((3, self.n1), dtype=torch.int32, device=dev)
         self._reduce = reduce_min or self._dist_reduce
+        self._gather = all_gather or self._dist_gather
         self.rounds = 0
 
     def _dist_reduce(self, t):
@@ -172,9 +182,18 @@ class TrainShardedMatcher:
         if dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
 
-    # the two local steps, exposed so a single process can drive several emulated ranks in lock-step
+    def _dist_gather(self, t):
+        import torch
+        import torch.distributed as dist
+        if self.world_size == 1:
+            return t.unsqueeze(0)
+        out = torch.empty((self.world_size,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out.view(-1), t.contiguous())
+        return out
+
+    # the three local steps, exposed so a single process can drive several emulated ranks in lock-step
     # (every step runs on torch's current stream -- Matcher.torch_ordered -- unless the caller bound a stream, so
-    # the collective torch enqueues between the steps is ordered against the library's kernels)
+    # the collectives torch enqueues between the steps are ordered against the library's kernels)
     def exchange_view(self):
         return self.x[:2 * self.bound]
 
@@ -183,11 +202,18 @@ class TrainShardedMatcher:
             self._m._check(self._lib.pgm_shard_round(self._sh, self.x.data_ptr(), self.bound))
 
     def step_commit(self):
-        """-> (live rows, done).  The next round's exchange shrinks to the live rows (rounded up to 1024)."""
+        with self._m.torch_ordered(self.x.device):
+            self._m._check(self._lib.pgm_shard_commit(self._sh, self.x.data_ptr(), self.bound, self.edges.data_ptr(), self.edge_cap))
+
+    def step_finish_round(self, edges_all):
+        """``edges_all``: int64 ``[n_ranks, 1 + edge_cap]`` -> (live rows, done).  The next round's exchange shrinks to the
+        live rows (rounded up to 1024)."""
         import ctypes as C
         lr, done = C.c_int32(0), C.c_int32(0)
+        edges_all = edges_all.contiguous()
         with self._m.torch_ordered(self.x.device):
-            self._m._check(self._lib.pgm_shard_commit(self._sh, self.x.data_ptr(), self.bound, C.byref(lr), C.byref(done)))
+            self._m._check(self._lib.pgm_shard_finish_round(self._sh, edges_all.data_ptr(), int(edges_all.shape[0]),
+                                                            self.edge_cap, C.byref(lr), C.byref(done)))
         self.bound = min(self.bound, max(1024, (lr.value + 1023) // 1024 * 1024))
         return lr.value, bool(done.value)
 
@@ -202,13 +228,14 @@ class TrainShardedMatcher:
         return self.out[:, :cnt.value]
 
     def match(self, reference_compat_tail: bool = True):
-        """Library steps and the collective alternate on torch's current stream (or on the stream the caller bound
+        """Library steps and the collectives alternate on torch's current stream (or on the stream the caller bound
         with ``matcher.set_stream``, which must then also be torch's current stream)."""
         prev = self.n1 + 1
         while True:
             self.step_round()
             self._reduce(self.exchange_view())
-            live_rows, done = self.step_commit()
+            self.step_commit()
+            live_rows, done = self.step_finish_round(self._gather(self.edges))
             if done:
                 break
             if live_rows >= prev:          # every round accepts at least the global minimum edge
@@ -405,25 +432,29 @@ def knn_train_sharded_emulated(matcher, d_q, d_t, n_shards: int, desc_bits: int 
 
 def match_train_sharded_emulated(matcher, q, t, n_shards: int, desc_bits: int = 256):
     """All ``n_shards`` ranks of the train-sharded mode emulated in ONE process on ONE GPU, run in
-    lock-step with the all-reduce replaced by an element-wise minimum (SURVEY.md section 4.4 item 5:
-    no inter-dependent concurrent kernels).  ``q`` / ``t``: numpy arrays or device tensors.  For tests and
+    lock-step with the all-reduce replaced by an element-wise minimum and the all-gather by a stack (SURVEY.md section
+    4.4 item 5: no inter-dependent concurrent kernels).  ``q`` / ``t``: numpy arrays or device tensors.  For tests and
     single-GPU validation."""
     import torch
     dev = torch.device("cuda", matcher.device)
     d_q = q if isinstance(q, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(q)).to(dev)
     d_t = t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t)).to(dev)
     n1, n2 = int(d_q.shape[0]), int(d_t.shape[0])
-    shards = [TrainShardedMatcher(matcher, d_q, d_t[lo:hi], lo, n2, desc_bits, reduce_min=lambda x: None)
+    shards = [TrainShardedMatcher(matcher, d_q, d_t[lo:hi], lo, n2, desc_bits, reduce_min=lambda x: None,
+                                  all_gather=lambda x: None, world_size=n_shards)
               for lo, hi in train_slices(n2, n_shards)]
     prev = n1 + 1
     while True:
         for s in shards:
             s.step_round()
         red = torch.stack([s.exchange_view() for s in shards]).min(dim=0).values
-        live, done = None, None
         for s in shards:
             s.exchange_view().copy_(red)
-            lr, dn = s.step_commit()
+            s.step_commit()
+        edges_all = torch.stack([s.edges for s in shards])
+        live, done = None, None
+        for s in shards:
+            lr, dn = s.step_finish_round(edges_all)
             assert live is None or (live, done) == (lr, dn), "ranks disagree on the live rows"
             live, done = lr, dn
         if done:
@@ -481,7 +512,7 @@ def bench_train_sharded(matcher, stream, dev, rank: int, world: int, popc_peak: 
     mg.close()
     return {"workload": f"configs[3]: one {n}x{n} pair ({dist_name}), train set sharded x{world}", "ms": ms,
             "evals_per_s": float(n) * n / (ms * 1e-3), "frac_of_popc_peak_per_gpu": float(n) * n * 8 / (ms * 1e-3) / popc_peak / world,
-            "rounds": rounds, "collective": "ncclAllReduce(min, uint32) of [R | P] = 2 x bound keys per round, inside the library"
+            "rounds": rounds, "collective": "per round ncclAllReduce(min, uint32) of [R | P] = 2 x bound keys + ncclAllGather of the ranks' candidate edges, inside the library"
             if world > 1 else "none (1 rank)", "collectives": xn, "exchange_bytes_per_rank": xb,
             "exchange_bytes_per_round": (xb / xn) if xn else 0.0,
             "properties_ok": ok, "properties": "permutation of rows and columns, strict (d, i, j) order, recomputed distances"}
