@@ -300,6 +300,19 @@ int pgm_ransac_score(pgm_handle *h, const float *F, const uint8_t *valid, int32_
                      const int32_t *xy2, int32_t n, float threshold, int32_t *out_counts, int32_t *out_best,
                      uint8_t *out_best_mask);
 
+/* Nearest neighbour + ratio test + mutual cross-check (+ optional distance bound) for MANY small pairs in one launch --
+ * the consecutive frames of a sequence (BASELINE configs[2]; per pair the same result as pgm_match_ratio_crosscheck, which
+ * extends the nearest-neighbour-within-a-threshold use of python_src/scripts/match_keypoints.py:112-134).  Layout as for
+ * pgm_match_pairs_batch_dev: d_all_desc holds every image's descriptors, image_offsets[n_images + 1] (host) delimits
+ * them, pair_list[n_pairs][2] (host) names the pairs; pair p's kept triples (ascending query index) start at the sum
+ * of the query sizes of the pairs before it, out_counts[p] (host) says how many.  One CTA per pair with both descriptor
+ * sets in shared memory: (n1 + n2) * stride_bytes + 4 * n2 must not exceed 200 KB, else PGM_E_INVALID_ARG. */
+int pgm_match_ratio_crosscheck_batch_dev(pgm_handle *h, const uint8_t *d_all_desc, const int64_t *image_offsets,
+                                         int32_t n_images, const int32_t *pair_list, int32_t n_pairs, int32_t desc_bits,
+                                         int32_t stride_bytes, float ratio, int32_t cross_check, int32_t max_dist,
+                                         int32_t *d_out_qi, int32_t *d_out_tj, int32_t *d_out_dist, int64_t capacity,
+                                         int32_t *out_counts);
+
 /* ---- train-sharded single pair (multi-GPU) ----------
  * For ONE huge pair (BASELINE configs[3]: 200k x 200k; the call it shards is MatchKeypoints,
  * KeypointMatching.cs:14-69) every rank holds all n1 queries and a contiguous slice

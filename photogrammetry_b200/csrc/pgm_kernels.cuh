@@ -1893,10 +1893,10 @@ __global__ void __launch_bounds__(SHARD_BLOCK) shard_commit_mark_kernel(Chunk c,
 constexpr unsigned long long SHARD_EDGE_OVERFLOW = 0x7FFFFFFFull;
 __global__ void __launch_bounds__(ACCEPT_THREADS) shard_filter_kernel(Chunk c, int r, const uint8_t *__restrict__ coldead,
                                                                       unsigned long long *__restrict__ out, int out_cap,
-                                                                      int32_t *__restrict__ out_cnt) {
+                                                                      int32_t *__restrict__ out_cnt, unsigned *__restrict__ ticket) {
     const PairDesc &pd = c.pairs[0];
     const int n = __ldcg(c.cand_cnt), cap = __ldg(&pd.cand_cap);
-    if (n > cap) { if (blockIdx.x == 0 && threadIdx.x == 0) *out_cnt = 0x7FFFFFFF; return; }
+    if (n > cap) { if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = SHARD_EDGE_OVERFLOW; return; }     // (uniform)
     const int lane = threadIdx.x & 31, words = c.words, off = __ldg(&pd.col_id_offset);
     const int32_t *live_rows = c.live_rows[r & 1];
     const int nlr = __ldcg(cnt_ptr(c, r % 3, 0));
@@ -1962,12 +1962,17 @@ __global__ void __launch_bounds__(ACCEPT_THREADS) shard_filter_kernel(Chunk c, i
             }
         }
     }
-}
-
-// publishes the edge count next to the edges (out[0]) once the filter has finished
-__global__ void shard_filter_finish_kernel(const int32_t *__restrict__ cnt, int out_cap, unsigned long long *__restrict__ out) {
-    const int n = *cnt;
-    out[0] = (n > out_cap) ? SHARD_EDGE_OVERFLOW : (unsigned long long)n;
+    // the last block to finish publishes the edge count next to the edges
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        const int total = __ldcg(out_cnt);
+        out[0] = total > out_cap ? SHARD_EDGE_OVERFLOW : (unsigned long long)total;
+    }
 }
 
 // Commit, step 3: the sparse sub-rounds of section 3.1 over the edges of ALL ranks (gathered: all[g][1 + cap]), by the
@@ -1979,7 +1984,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) shard_sparse_kernel(Chunk c, 
                                                                        uint32_t *__restrict__ cbest, uint8_t *__restrict__ coldead,
                                                                        uint8_t *__restrict__ est, unsigned *bar_counter,
                                                                        int32_t *alive_cnt /*[2]*/) {
-    __shared__ int s_cnt[64];
+    __shared__ int s_cnt[64], s_pre[65];
     const int tid = threadIdx.x;
     unsigned epoch = 0;
     for (int g = tid; g < n_ranks && g < 64; g += TAIL_THREADS) {
@@ -1988,31 +1993,34 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) shard_sparse_kernel(Chunk c, 
     }
     __syncthreads();
     for (int g = 0; g < n_ranks; g++) if (s_cnt[g] < 0) return;              // uniform: every CTA reads the same counts
-    const long long S = (long long)n_ranks * cap;
-    const long long gt = (long long)blockIdx.x * TAIL_THREADS + tid, gs = (long long)gridDim.x * TAIL_THREADS;
+    if (tid == 0) { int a = 0; for (int g = 0; g < n_ranks; g++) { s_pre[g] = a; a += s_cnt[g]; } s_pre[n_ranks] = a; }
+    __syncthreads();
+    const int E = s_pre[n_ranks];                                            // edges of all ranks, addressed 0 .. E-1
+    if (E == 0) return;
+    const int gt = (int)blockIdx.x * TAIL_THREADS + tid, gs = (int)gridDim.x * TAIL_THREADS;
     uint32_t *match_key = c.match_key;
-    for (long long s = gt; s < S; s += gs) {
-        const int g = (int)(s / cap), k = (int)(s - (long long)g * cap);
-        est[s] = k < s_cnt[g] ? 1 : 0;
-    }
+    auto edge_at = [&](int e) -> unsigned long long {
+        int g = 0;
+        while (g + 1 < n_ranks && s_pre[g + 1] <= e) g++;
+        return __ldcg(all + (size_t)g * (1 + cap) + 1 + (e - s_pre[g]));
+    };
+    for (int e = gt; e < E; e += gs) est[e] = 1;
     if (blockIdx.x == 0 && tid == 0) { alive_cnt[0] = 0; alive_cnt[1] = 0; }
     grid_barrier(bar_counter, gridDim.x, epoch);
     for (int sub = 0; sub < SP_MAX_SUB; sub++) {
-        for (long long s = gt; s < S; s += gs) {
-            if (!est[s]) continue;
-            const int g = (int)(s / cap);
-            const unsigned long long key = __ldcg(all + (size_t)g * (1 + cap) + 1 + (s - (long long)g * cap));
+        for (int e = gt; e < E; e += gs) {
+            if (!est[e]) continue;
+            const unsigned long long key = edge_at(e);
             const uint32_t d = (uint32_t)(key >> 40), i = (uint32_t)(key >> KEY_IDX_BITS) & KEY_IDX_MASK, j = (uint32_t)key & KEY_IDX_MASK;
             atomicMin(rbest + i, (d << KEY_IDX_BITS) | j);
             atomicMin(cbest + j, (d << KEY_IDX_BITS) | i);
         }
         grid_barrier(bar_counter, gridDim.x, epoch);
-        for (long long s = gt; s < S; s += gs) {
-            if (!est[s]) continue;
-            const int g = (int)(s / cap);
-            const unsigned long long key = __ldcg(all + (size_t)g * (1 + cap) + 1 + (s - (long long)g * cap));
+        for (int e = gt; e < E; e += gs) {
+            if (!est[e]) continue;
+            const unsigned long long key = edge_at(e);
             const uint32_t d = (uint32_t)(key >> 40), i = (uint32_t)(key >> KEY_IDX_BITS) & KEY_IDX_MASK, j = (uint32_t)key & KEY_IDX_MASK;
-            // (the only writers of these two slots' owners are the threads of THE mutual edge: nobody else passes the test)
+            // (only the threads of THE mutual edge of a row / column pass this test, so nobody races on these stores)
             if (__ldcg(rbest + i) == ((d << KEY_IDX_BITS) | j) && __ldcg(cbest + j) == ((d << KEY_IDX_BITS) | i)) {
                 match_key[i] = (d << KEY_IDX_BITS) | j;
                 coldead[j] = 1;
@@ -2021,15 +2029,14 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) shard_sparse_kernel(Chunk c, 
         if (blockIdx.x == 0 && tid == 0) alive_cnt[(sub + 1) & 1] = 0;
         grid_barrier(bar_counter, gridDim.x, epoch);
         int alive = 0;
-        for (long long s = gt; s < S; s += gs) {
-            if (!est[s]) continue;
-            const int g = (int)(s / cap);
-            const unsigned long long key = __ldcg(all + (size_t)g * (1 + cap) + 1 + (s - (long long)g * cap));
+        for (int e = gt; e < E; e += gs) {
+            if (!est[e]) continue;
+            const unsigned long long key = edge_at(e);
             const uint32_t i = (uint32_t)(key >> KEY_IDX_BITS) & KEY_IDX_MASK, j = (uint32_t)key & KEY_IDX_MASK;
             // every slot touched in this sub-round goes back to "none": a live row whose listed edges all died must not
             // carry a stale minimum into the next pass
             rbest[i] = KEY_NONE; cbest[j] = KEY_NONE;
-            if (__ldcg(match_key + i) != KEY_NONE || __ldcg(coldead + j)) est[s] = 0; else alive++;
+            if (__ldcg(match_key + i) != KEY_NONE || __ldcg(coldead + j)) est[e] = 0; else alive++;
         }
         alive = __reduce_add_sync(0xffffffffu, alive);
         if ((tid & 31) == 0 && alive) atomicAdd(&alive_cnt[sub & 1], alive);
@@ -2290,6 +2297,79 @@ __global__ void ratio_crosscheck_kernel(int n1, int n2, const int32_t *best_j, c
     if (k && cross_check && col_best_i[best_j[i]] != i) k = false;
     if (k && max_dist >= 0 && best_d[i] > max_dist) k = false;
     keep[i] = k ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------
+// Many small pairs at once (a frame sequence, BASELINE configs[2]): nearest / second nearest of every query, best query
+// of every train descriptor, ratio test, cross-check and max-distance filter, ordered compaction -- one CTA per pair,
+// both descriptor sets in shared memory (read as broadcasts), a thread's own descriptor in registers.  Same keys,
+// same tie-break and the same filter expression as knn2_kernel + ratio_crosscheck_kernel.
+// ---------------------------------------------------------------------------
+constexpr int RCB_THREADS = 512;
+struct RcbPair { const uint32_t *q, *t; int32_t n1, n2; int64_t out_base; };
+
+template <int WORDS>
+__global__ void __launch_bounds__(RCB_THREADS) ratio_crosscheck_batch_kernel(const RcbPair *__restrict__ pairs, float ratio,
+                                                                             int cross_check, int max_dist,
+                                                                             int32_t *__restrict__ out_qi, int32_t *__restrict__ out_tj,
+                                                                             int32_t *__restrict__ out_dist, int32_t *__restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    constexpr int V4 = WORDS / 4;
+    __shared__ int s_w[RCB_THREADS / 32], s_base;
+    const RcbPair pr = pairs[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, n1 = pr.n1, n2 = pr.n2;
+    uint4 *sq = reinterpret_cast<uint4 *>(dyn_smem), *st = sq + (size_t)n1 * V4;
+    uint32_t *colbest = reinterpret_cast<uint32_t *>(st + (size_t)n2 * V4);          // [n2] (d << 20 | i)
+    for (int k = tid; k < n1 * V4; k += RCB_THREADS) sq[k] = __ldg(reinterpret_cast<const uint4 *>(pr.q) + k);
+    for (int k = tid; k < n2 * V4; k += RCB_THREADS) st[k] = __ldg(reinterpret_cast<const uint4 *>(pr.t) + k);
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    auto load = [&](const uint4 *base, int idx, uint32_t (&x)[WORDS]) {
+#pragma unroll
+        for (int v = 0; v < V4; v++) { const uint4 a = base[idx * V4 + v]; x[4 * v] = a.x; x[4 * v + 1] = a.y; x[4 * v + 2] = a.z; x[4 * v + 3] = a.w; }
+    };
+    if (cross_check) {
+        for (int j = tid; j < n2; j += RCB_THREADS) {
+            uint32_t mine[WORDS], other[WORDS], best = KEY_NONE;
+            load(st, j, mine);
+            for (int i = 0; i < n1; i++) { load(sq, i, other); best = min(best, (hamming_words<WORDS>(mine, other) << KEY_IDX_BITS) + (uint32_t)i); }
+            colbest[j] = best;
+        }
+    }
+    __syncthreads();
+    for (int i0 = 0; i0 < n1; i0 += RCB_THREADS) {
+        const int i = i0 + tid;
+        bool keep = false;
+        uint32_t best = KEY_NONE, second = KEY_NONE;
+        if (i < n1) {
+            uint32_t mine[WORDS], other[WORDS];
+            load(sq, i, mine);
+            for (int j = 0; j < n2; j++) {
+                load(st, j, other);
+                const uint32_t key = (hamming_words<WORDS>(mine, other) << KEY_IDX_BITS) + (uint32_t)j;
+                second = min(second, max(best, key));
+                best = min(best, key);
+            }
+            const int bj = (int)(best & KEY_IDX_MASK), bd = (int)(best >> KEY_IDX_BITS), sd = second == KEY_NONE ? -1 : (int)(second >> KEY_IDX_BITS);
+            keep = n2 > 0;
+            if (keep && ratio > 0.0f && n2 >= 2 && !((float)bd < ratio * (float)sd)) keep = false;
+            if (keep && cross_check && (int)(colbest[bj] & KEY_IDX_MASK) != i) keep = false;
+            if (keep && max_dist >= 0 && bd > max_dist) keep = false;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_w[wid] = __popc(m);
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < wid; w++) off += s_w[w];
+        if (keep) {
+            const int64_t o = pr.out_base + off + __popc(m & ((1u << lane) - 1u));
+            out_qi[o] = i; out_tj[o] = (int32_t)(best & KEY_IDX_MASK); out_dist[o] = (int32_t)(best >> KEY_IDX_BITS);
+        }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int w = 0; w < RCB_THREADS / 32; w++) t += s_w[w]; s_base += t; }
+        __syncthreads();
+    }
+    if (tid == 0) counts[blockIdx.x] = s_base;
 }
 
 // ---------------------------------------------------------------------------

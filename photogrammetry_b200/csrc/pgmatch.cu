@@ -1044,6 +1044,77 @@ extern "C" int pgm_match_ratio_crosscheck(pgm_handle *h, const uint8_t *q, int32
 }
 
 // ---------------------------------------------------------------------------
+// many small pairs: nearest neighbour + ratio test + cross-check in ONE launch (BASELINE configs[2]: the consecutive
+// frames of a sequence).  Pair p's kept triples (ascending query index) start at sum of n1 over the pairs before it.
+// ---------------------------------------------------------------------------
+constexpr size_t RCB_SMEM_MAX = 200 * 1024;
+template <int WORDS>
+static cudaError_t launch_rcb(pgm_handle *h, const RcbPair *d_pairs, int n_pairs, size_t smem, float ratio, int cross_check,
+                              int max_dist, int32_t *oq, int32_t *ot, int32_t *od, int32_t *d_counts, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(ratio_crosscheck_batch_kernel<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCB_SMEM_MAX);
+    if (e != cudaSuccess) return e;
+    (void)h;
+    ratio_crosscheck_batch_kernel<WORDS><<<n_pairs, RCB_THREADS, smem, s>>>(d_pairs, ratio, cross_check, max_dist, oq, ot, od, d_counts);
+    return cudaGetLastError();
+}
+
+extern "C" int pgm_match_ratio_crosscheck_batch_dev(pgm_handle *h, const uint8_t *d_all_desc, const int64_t *image_offsets,
+                                                    int32_t n_images, const int32_t *pair_list, int32_t n_pairs,
+                                                    int32_t desc_bits, int32_t stride_bytes, float ratio, int32_t cross_check,
+                                                    int32_t max_dist, int32_t *d_out_qi, int32_t *d_out_tj,
+                                                    int32_t *d_out_dist, int64_t capacity, int32_t *out_counts) {
+    if (!h || !out_counts || n_pairs < 0 || n_images < 0 || (n_pairs > 0 && (!image_offsets || !pair_list))) return PGM_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    int rc = check_format(h, desc_bits, stride_bytes);
+    if (rc) return rc;
+    h->stats = pgm_stats{};
+    h->stats_pending = false;
+    if (n_pairs == 0) return PGM_OK;
+    if (!d_all_desc || !d_out_qi || !d_out_tj || !d_out_dist) return fail(h, PGM_E_INVALID_ARG, "null pointer");
+    CU_CHECK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    std::vector<RcbPair> hp(n_pairs);
+    int64_t total = 0;
+    size_t smem = 0;
+    for (int p = 0; p < n_pairs; p++) {
+        const int a = pair_list[2 * p], b = pair_list[2 * p + 1];
+        if (a < 0 || a >= n_images || b < 0 || b >= n_images) return fail(h, PGM_E_INVALID_ARG, "pair index out of range");
+        const int64_t n1 = image_offsets[a + 1] - image_offsets[a], n2 = image_offsets[b + 1] - image_offsets[b];
+        if (n1 < 0 || n2 < 0 || n1 >= MAX_N || n2 >= MAX_N) return fail(h, PGM_E_INVALID_ARG, "bad image sizes");
+        hp[p] = RcbPair{(const uint32_t *)(d_all_desc + (size_t)image_offsets[a] * stride_bytes),
+                        (const uint32_t *)(d_all_desc + (size_t)image_offsets[b] * stride_bytes), (int32_t)n1, (int32_t)n2, total};
+        total += n1;
+        smem = std::max(smem, (size_t)(n1 + n2) * stride_bytes + (size_t)n2 * 4 + 16);
+    }
+    if (capacity < total) return fail(h, PGM_E_CAPACITY, "capacity < sum of query sizes");
+    if (smem > RCB_SMEM_MAX)
+        return fail(h, PGM_E_INVALID_ARG, "a pair is too large for the small-pair batch kernel (use pgm_match_ratio_crosscheck per pair)");
+    const size_t pb = align_up(sizeof(RcbPair) * n_pairs, 256);
+    if ((rc = ensure_dev(h, h->misc, pb + (size_t)n_pairs * 4))) return rc;
+    if ((rc = ensure_host(h, h->pin_in, pb + (size_t)n_pairs * 4))) return rc;
+    CU_CHECK(h, cudaStreamSynchronize(s));                 // the staging buffer may still feed an earlier call's copy
+    memcpy(h->pin_in.p, hp.data(), sizeof(RcbPair) * n_pairs);
+    CU_CHECK(h, cudaMemcpyAsync(h->misc.p, h->pin_in.p, sizeof(RcbPair) * n_pairs, cudaMemcpyHostToDevice, s));
+    const RcbPair *d_pairs = (const RcbPair *)h->misc.p;
+    int32_t *d_counts = (int32_t *)((char *)h->misc.p + pb);
+    cudaError_t e;
+    switch (stride_bytes / 4) {
+        case 4: e = launch_rcb<4>(h, d_pairs, n_pairs, smem, ratio, cross_check, max_dist, d_out_qi, d_out_tj, d_out_dist, d_counts, s); break;
+        case 8: e = launch_rcb<8>(h, d_pairs, n_pairs, smem, ratio, cross_check, max_dist, d_out_qi, d_out_tj, d_out_dist, d_counts, s); break;
+        case 12: e = launch_rcb<12>(h, d_pairs, n_pairs, smem, ratio, cross_check, max_dist, d_out_qi, d_out_tj, d_out_dist, d_counts, s); break;
+        default: e = launch_rcb<16>(h, d_pairs, n_pairs, smem, ratio, cross_check, max_dist, d_out_qi, d_out_tj, d_out_dist, d_counts, s); break;
+    }
+    CU_CHECK(h, e);
+    CU_CHECK(h, cudaMemcpyAsync((char *)h->pin_in.p + pb, d_counts, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(h, cudaStreamSynchronize(s));
+    memcpy(out_counts, (char *)h->pin_in.p + pb, (size_t)n_pairs * 4);
+    h->stats.kernel_launches += 1; h->stats.host_syncs += 2; h->stats.pairs = n_pairs;
+    for (int p = 0; p < n_pairs; p++) { h->stats.distance_evals += (int64_t)hp[p].n1 * hp[p].n2; h->stats.matched += out_counts[p]; }
+    h->stats.evals_computed = h->stats.distance_evals * (cross_check ? 2 : 1);
+    return PGM_OK;
+}
+
+// ---------------------------------------------------------------------------
 // train-sharded nearest neighbours: key exchange format, top-2 merge, device-side filter
 // ---------------------------------------------------------------------------
 extern "C" int pgm_pack_top2_keys_dev(pgm_handle *h, const int32_t *d_best_j, const int32_t *d_best_d,
@@ -1820,6 +1891,7 @@ struct ShardDev {                  // small device-resident control block of a s
     unsigned bar;                  // grid-barrier counter of the cooperative sparse kernel
     int32_t edge_cnt;              // filtered candidate edges of the round
     int32_t alive[2];
+    unsigned ticket;               // last-block-done counter of the edge filter
 };
 
 struct pgm_shard {
@@ -1960,9 +2032,9 @@ static int shard_enqueue_commit(pgm_shard *sh, const uint32_t *d_x, int bound, u
     h->stats.kernel_launches += 1;
     if (d_edges) {
         if (sh->c.cand) {
-            shard_filter_kernel<<<h->num_sms * 4, ACCEPT_THREADS, 0, s>>>(sh->c, r, sh->coldead, d_edges, edge_cap, &sh->dev->edge_cnt);
-            shard_filter_finish_kernel<<<1, 1, 0, s>>>(&sh->dev->edge_cnt, edge_cap, d_edges);
-            h->stats.kernel_launches += 2;
+            shard_filter_kernel<<<h->num_sms * 4, ACCEPT_THREADS, 0, s>>>(sh->c, r, sh->coldead, d_edges, edge_cap, &sh->dev->edge_cnt,
+                                                                         &sh->dev->ticket);
+            h->stats.kernel_launches += 1;
         } else {
             CU_CHECK(h, cudaMemsetAsync(d_edges, 0, 8, s));       // no candidate edges: count 0
         }
@@ -2230,43 +2302,41 @@ extern "C" int pgm_multi_match_train_sharded_dev(pgm_multi *mh, const uint8_t *d
         uint32_t *X = (uint32_t *)mh->xbuf.p;
         unsigned long long *E_all = edges_on ? (unsigned long long *)((char *)mh->xbuf.p + x_bytes) : nullptr;
         unsigned long long *E_mine = edges_on ? E_all + (size_t)mh->rank * (1 + (size_t)edge_cap) : nullptr;
-        constexpr int BATCH = 2, RING = 8;
+        // The host runs LOOK rounds ahead of the status it inspects: round r's 16-byte status (done, live rows) is copied
+        // back asynchronously and looked at when round r + LOOK has been enqueued.  The GPU therefore never waits for a
+        // launch (the late rounds are a few microseconds of work each, less than the host needs to enqueue one), the
+        // host never waits for the GPU except to stay LOOK rounds ahead, and at most LOOK empty rounds follow the last
+        // one.  Every rank reads the same values at the same round, so all ranks enqueue the same collectives.
+        constexpr int LOOK = 4, RING = 8;
         cudaEvent_t ev[RING];
         for (auto &e : ev) e = nullptr;
         for (int k = 0; k < RING && !rc; k++)
             if (cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess) rc = PGM_E_CUDA;
-        int bound = n1, batch_no = 0;
+        int bound = n1;
         bool done = false;
-        while (!rc && !done) {
-            for (int k = 0; k < BATCH && !rc; k++) {
-                if ((rc = shard_enqueue_round(sh, X, bound, s))) break;
-                if (mh->world > 1) {
-                    const int r = nccl_api()->AllReduce(X, X, (size_t)2 * bound, kNcclUint32, kNcclMin, mh->comm, s);
-                    if (r != 0) { h->err = std::string("ncclAllReduce failed: ") + nccl_api()->GetErrorString(r); rc = PGM_E_NCCL; break; }
-                    mh->exchange_bytes += (int64_t)2 * bound * 4; mh->collectives++;
-                }
-                if ((rc = shard_enqueue_commit(sh, X, bound, E_mine, edge_cap, s))) break;
-                if (edges_on && mh->world > 1) {      // in place: this rank's block already sits at its slot of the gathered buffer
-                    const int r = nccl_api()->AllGather(E_mine, E_all, (size_t)(1 + edge_cap), kNcclUint64, mh->comm, s);
-                    if (r != 0) { h->err = std::string("ncclAllGather failed: ") + nccl_api()->GetErrorString(r); rc = PGM_E_NCCL; break; }
-                    mh->exchange_bytes += (int64_t)(1 + edge_cap) * 8; mh->collectives++;
-                }
-                if ((rc = shard_enqueue_finish_round(sh, E_all, mh->world, edge_cap, s))) break;
+        for (int rno = 0; !rc && !done; rno++) {
+            if ((rc = shard_enqueue_round(sh, X, bound, s))) break;
+            if (mh->world > 1) {
+                const int r = nccl_api()->AllReduce(X, X, (size_t)2 * bound, kNcclUint32, kNcclMin, mh->comm, s);
+                if (r != 0) { h->err = std::string("ncclAllReduce failed: ") + nccl_api()->GetErrorString(r); rc = PGM_E_NCCL; break; }
+                mh->exchange_bytes += (int64_t)2 * bound * 4; mh->collectives++;
             }
-            if (rc) break;
-            const int slot = batch_no % RING;
+            if ((rc = shard_enqueue_commit(sh, X, bound, E_mine, edge_cap, s))) break;
+            if (edges_on && mh->world > 1) {      // in place: this rank's block already sits at its slot of the gathered buffer
+                const int r = nccl_api()->AllGather(E_mine, E_all, (size_t)(1 + edge_cap), kNcclUint64, mh->comm, s);
+                if (r != 0) { h->err = std::string("ncclAllGather failed: ") + nccl_api()->GetErrorString(r); rc = PGM_E_NCCL; break; }
+                mh->exchange_bytes += (int64_t)(1 + edge_cap) * 8; mh->collectives++;
+            }
+            if ((rc = shard_enqueue_finish_round(sh, E_all, mh->world, edge_cap, s))) break;
+            const int slot = rno % RING;
             if (cudaMemcpyAsync(&sh->h_ctl[slot], sh->ctl, sizeof(ShardCtl), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
                 cudaEventRecord(ev[slot], s) != cudaSuccess) { rc = PGM_E_CUDA; break; }
-            // look at the status of the batch before the previous one: by now it has (almost always) completed, so the
-            // host never waits for the GPU and the GPU never waits for the host.  Every rank reads the same values at
-            // the same batch number, so all ranks enqueue the same collectives.
-            if (batch_no >= 1) {
-                const int old = (batch_no - 1) % RING;
+            if (rno >= LOOK) {
+                const int old = (rno - LOOK) % RING;
                 if (cudaEventSynchronize(ev[old]) != cudaSuccess) { rc = PGM_E_CUDA; break; }
                 if (sh->h_ctl[old].done) done = true;
                 else bound = std::min(bound, std::max(SHARD_BLOCK, (sh->h_ctl[old].live_rows + SHARD_BLOCK - 1) / SHARD_BLOCK * SHARD_BLOCK));
             }
-            batch_no++;
             if (sh->round > 4 * MAX_N) { h->err = "train-sharded matcher failed to converge (internal error)"; rc = PGM_E_CUDA; }
         }
         if (!rc) rc = shard_finish_locked(sh, d_out_qi, d_out_tj, d_out_dist, flags, s);

@@ -279,6 +279,27 @@ class Matcher:
                 C.byref(cnt)))
         return out[:, :cnt.value]
 
+    def match_ratio_crosscheck_batch_dev(self, d_all_desc, image_offsets, pair_list, desc_bits: int = 256, ratio: float = 0.8,
+                                         cross_check: bool = True, max_dist: int = -1):
+        """Nearest neighbour + ratio test + cross-check for many small pairs in ONE launch (a frame sequence).
+        ``d_all_desc``: torch uint8 ``[sum, stride]`` on the GPU.  Returns ``(out int32[3, sum of n1], starts int64[n_pairs],
+        counts int32[n_pairs])``; pair ``p`` owns ``out[:, starts[p]:starts[p] + counts[p]]`` (ascending query index)."""
+        import torch
+        offs = np.ascontiguousarray(image_offsets, dtype=np.int64)
+        pairs = np.ascontiguousarray(pair_list, dtype=np.int32).reshape(-1, 2)
+        sizes = np.diff(offs)
+        n1s = sizes[pairs[:, 0]] if len(pairs) else np.zeros(0, np.int64)
+        starts = np.concatenate([[0], np.cumsum(n1s)]).astype(np.int64)
+        total = int(starts[-1])
+        out = torch.empty((3, max(total, 1)), dtype=torch.int32, device=d_all_desc.device)
+        counts = np.zeros(max(len(pairs), 1), dtype=np.int32)
+        with self.torch_ordered(d_all_desc.device):
+            self._check(self._lib.pgm_match_ratio_crosscheck_batch_dev(
+                self._h, d_all_desc.data_ptr(), offs.ctypes.data, len(offs) - 1, pairs.ctypes.data, len(pairs), int(desc_bits),
+                int(d_all_desc.shape[1]), float(ratio), int(bool(cross_check)), int(max_dist), out[0].data_ptr(),
+                out[1].data_ptr(), out[2].data_ptr(), total, counts.ctypes.data))
+        return out, starts[:-1], counts[:len(pairs)]
+
     def match_keypoints_sorted(self, q: np.ndarray, t: np.ndarray, desc_bits: Optional[int] = None) -> np.ndarray:
         """``int64[n1, n2, 2]`` = (idx2, dist), rows sorted by (dist, idx2) (keypoint_matching.py:7-33)."""
         q, bits_q = as_descriptor_rows(q, desc_bits)

@@ -8,7 +8,8 @@ the Python generation, which the reference tree can execute): detector -> descri
 
     frames (one H2D) -> pgm_detect_describe_batch_dev (6 kernels for all frames, one read-back of K counts)
                      -> pgm_match_pairs_batch_dev over the K - 1 consecutive pairs (greedy, the reference's MatchKeypoints)
-                     -> per pair nearest / second nearest + ratio test + cross-check (the north_star extension)
+                     -> pgm_match_ratio_crosscheck_batch_dev: nearest / second nearest + ratio test + cross-check of every
+                        consecutive pair in one launch (the north_star extension)
 """
 from __future__ import annotations
 
@@ -93,15 +94,11 @@ def match_sequence_dev(matcher, d_frames, threshold: float, pairs: np.ndarray, r
                                                 out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), total)
     torch.cuda.current_stream(d_frames.device).synchronize()
     t2 = time.perf_counter()
-    filtered = []
-    for a, b in plist:
-        qa, tb = d_desc[offs[a]:offs[a + 1]], d_desc[offs[b]:offs[b + 1]]
-        if len(qa) == 0 or len(tb) == 0:
-            filtered.append(torch.zeros((3, 0), dtype=torch.int32, device=d_frames.device))
-            continue
-        bj, bd, _sj, sd = matcher.knn2_hamming_dev(qa, tb, desc_bits)
-        col = matcher.knn2_hamming_dev(tb, qa, desc_bits)[0] if cross_check else None
-        filtered.append(matcher.ratio_crosscheck_filter_dev(len(tb), bj, bd, sd, col, ratio, cross_check, -1))
+    if len(plist):
+        fo, fstarts, fcounts = matcher.match_ratio_crosscheck_batch_dev(d_desc, offs, plist, desc_bits, ratio, cross_check, -1)
+        filtered = [fo[:, int(fstarts[k]):int(fstarts[k]) + int(fcounts[k])] for k in range(len(plist))]
+    else:
+        filtered = []
     torch.cuda.current_stream(d_frames.device).synchronize()
     t3 = time.perf_counter()
     if timings is not None:
@@ -133,4 +130,4 @@ def bench_star_sequence(matcher, stream, dev, n_frames: int = 32, step: int = 5,
             "ratio_crosscheck_matches": int(sum(int(f.shape[1]) for f in res.filtered)),
             "note": "proxy for the un-rendered Blender pan (SURVEY D5): 15pt_star shifted 5 px per frame as "
                     "scripts/image_editing.py:8-15; FAST-12 threshold 50 + BRIEF-256 of the Python generation on the "
-                    "device; greedy MatchKeypoints per consecutive pair in one batch call, then ratio 0.8 + cross-check"}
+                    "device; greedy MatchKeypoints of all consecutive pairs in one batch call, ratio 0.8 + cross-check of all pairs in one launch"}

@@ -63,3 +63,26 @@ def test_batched_detector_equals_per_image_calls(matcher):
         # truncation is reported, not silent
         _, _, _, c2 = matcher.detect_describe_batch_dev(torch.from_numpy(frames).cuda(), th, pairs, capacity=3, python_generation=pg)
         assert (c2 == counts).all()
+
+
+def test_ratio_crosscheck_batch_equals_per_pair_calls(matcher):
+    import torch
+    rng = np.random.default_rng(9)
+    sizes = [37, 1, 64, 200, 5, 129]
+    for bits, stride in ((256, 32), (100, 16), (512, 64)):
+        desc = [rng.integers(0, 256, size=(n, stride), dtype=np.uint8) for n in sizes]
+        if bits == 100:
+            for d in desc:
+                d[:, 13:] = 0
+                d[:, 12] &= 0x0F
+        offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        pairs = np.array([(0, 1), (1, 0), (2, 3), (3, 2), (4, 5), (5, 5), (3, 3)], dtype=np.int32)
+        d_all = torch.from_numpy(np.concatenate(desc)).cuda()
+        for ratio, cc, md in ((0.8, True, -1), (0.0, True, -1), (0.9, False, 120), (0.0, False, -1)):
+            out, starts, counts = matcher.match_ratio_crosscheck_batch_dev(d_all, offs, pairs, bits, ratio, cc, md)
+            out = out.cpu().numpy()
+            for p, (a, b) in enumerate(pairs):
+                exp = matcher.match_ratio_crosscheck(desc[a], desc[b], ratio, cc, md, bits)
+                got = out[:, starts[p]:starts[p] + counts[p]].T
+                assert got.shape == exp.shape and (got == exp).all(), (bits, ratio, cc, md, p)
+                assert (exp == orc.match_ratio_crosscheck(desc[a], desc[b], ratio, cc, md)).all()
