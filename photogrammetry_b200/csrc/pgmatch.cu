@@ -2301,7 +2301,6 @@ extern "C" int pgm_multi_match_train_sharded_dev(pgm_multi *mh, const uint8_t *d
         if (!rc) rc = ensure_dev(h, mh->xbuf, x_bytes + (edges_on ? (size_t)mh->world * (1 + (size_t)edge_cap) * 8 : 0));
         uint32_t *X = (uint32_t *)mh->xbuf.p;
         unsigned long long *E_all = edges_on ? (unsigned long long *)((char *)mh->xbuf.p + x_bytes) : nullptr;
-        unsigned long long *E_mine = edges_on ? E_all + (size_t)mh->rank * (1 + (size_t)edge_cap) : nullptr;
         // The host runs LOOK rounds ahead of the status it inspects: round r's 16-byte status (done, live rows) is copied
         // back asynchronously and looked at when round r + LOOK has been enqueued.  The GPU therefore never waits for a
         // launch (the late rounds are a few microseconds of work each, less than the host needs to enqueue one), the
@@ -2321,13 +2320,18 @@ extern "C" int pgm_multi_match_train_sharded_dev(pgm_multi *mh, const uint8_t *d
                 if (r != 0) { h->err = std::string("ncclAllReduce failed: ") + nccl_api()->GetErrorString(r); rc = PGM_E_NCCL; break; }
                 mh->exchange_bytes += (int64_t)2 * bound * 4; mh->collectives++;
             }
-            if ((rc = shard_enqueue_commit(sh, X, bound, E_mine, edge_cap, s))) break;
+            // the pass cannot list more than p_max x (live rows)^2 edges (plan_pair_emit's density clamp, <= 0.05): late
+            // rounds exchange small edge blocks.  `bound` is the same on every rank, hence so is the block size.
+            const double live_cols_max = (double)bound + (double)std::max(0, n2_total - n1);     // live columns = total - matched rows
+            const int cap_r = (int)std::min<int64_t>(edge_cap, (int64_t)(0.06 * (double)bound * live_cols_max) + 4096);
+            unsigned long long *E_mine_r = edges_on ? E_all + (size_t)mh->rank * (1 + (size_t)cap_r) : nullptr;
+            if ((rc = shard_enqueue_commit(sh, X, bound, E_mine_r, cap_r, s))) break;
             if (edges_on && mh->world > 1) {      // in place: this rank's block already sits at its slot of the gathered buffer
-                const int r = nccl_api()->AllGather(E_mine, E_all, (size_t)(1 + edge_cap), kNcclUint64, mh->comm, s);
+                const int r = nccl_api()->AllGather(E_mine_r, E_all, (size_t)(1 + cap_r), kNcclUint64, mh->comm, s);
                 if (r != 0) { h->err = std::string("ncclAllGather failed: ") + nccl_api()->GetErrorString(r); rc = PGM_E_NCCL; break; }
-                mh->exchange_bytes += (int64_t)(1 + edge_cap) * 8; mh->collectives++;
+                mh->exchange_bytes += (int64_t)(1 + cap_r) * 8; mh->collectives++;
             }
-            if ((rc = shard_enqueue_finish_round(sh, E_all, mh->world, edge_cap, s))) break;
+            if ((rc = shard_enqueue_finish_round(sh, E_all, mh->world, cap_r, s))) break;
             const int slot = rno % RING;
             if (cudaMemcpyAsync(&sh->h_ctl[slot], sh->ctl, sizeof(ShardCtl), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
                 cudaEventRecord(ev[slot], s) != cudaSuccess) { rc = PGM_E_CUDA; break; }
