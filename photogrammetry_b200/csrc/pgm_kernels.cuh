@@ -2128,6 +2128,84 @@ __global__ void __launch_bounds__(ACCEPT_THREADS) shard_commit_cols_kernel(Chunk
     (void)ctl;
 }
 
+// ---- replicated finish of a train-sharded pair (pgm_multi): once few rows are left, every rank collects the descriptors
+// of all surviving rows and columns and finishes the remaining (small) problem itself with the single-GPU engine ----
+__global__ void shard_gather_rows_kernel(const uint32_t *__restrict__ q, const int32_t *__restrict__ live, int n, int words,
+                                         uint32_t *__restrict__ out) {
+    const int v4 = words >> 2;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n * v4; k += gridDim.x * blockDim.x) {
+        const int row = k / v4, part = k - row * v4;
+        reinterpret_cast<uint4 *>(out)[k] = __ldg(reinterpret_cast<const uint4 *>(q + (size_t)__ldcg(live + row) * words) + part);
+    }
+}
+
+// this rank's surviving columns in ASCENDING order (one block, ordered compaction over the dead flags):
+// block[0] = count (16-byte header), then ids (global) int32[cap], then descriptors uint32[cap][words] (16-byte aligned)
+__global__ void __launch_bounds__(1024) shard_pack_cols_kernel(const uint32_t *__restrict__ t, int n2_local, int off, int words,
+                                                               const uint8_t *__restrict__ coldead, int cap,
+                                                               unsigned long long *__restrict__ block) {
+    __shared__ int s_w[32], s_base;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, v4 = words >> 2;
+    int32_t *ids = reinterpret_cast<int32_t *>(block + 2);
+    uint4 *desc = reinterpret_cast<uint4 *>(reinterpret_cast<char *>(block + 2) + (((size_t)cap * 4 + 15) & ~(size_t)15));
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int j0 = 0; j0 < n2_local; j0 += 1024) {
+        const int j = j0 + tid;
+        const bool alive = j < n2_local && !coldead[j + off];
+        const unsigned m = __ballot_sync(0xffffffffu, alive);
+        if (lane == 0) s_w[wid] = __popc(m);
+        __syncthreads();
+        int o = s_base;
+        for (int w = 0; w < wid; w++) o += s_w[w];
+        if (alive) {
+            const int at = o + __popc(m & ((1u << lane) - 1u));
+            if (at < cap) {
+                ids[at] = j + off;
+                for (int v = 0; v < v4; v++) desc[(size_t)at * v4 + v] = __ldg(reinterpret_cast<const uint4 *>(t + (size_t)j * words) + v);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) { int tot = 0; for (int w = 0; w < 32; w++) tot += s_w[w]; s_base += tot; }
+        __syncthreads();
+    }
+    if (tid == 0) block[0] = (unsigned long long)s_base;
+}
+
+// the ranks' column blocks (rank order = ascending global id) -> one dense train set + its global ids
+__global__ void shard_merge_cols_kernel(const unsigned long long *__restrict__ all, size_t block_words64, int n_ranks, int cap,
+                                        int words, uint32_t *__restrict__ t_sub, int32_t *__restrict__ gid, int total_expected,
+                                        int32_t *__restrict__ mismatch) {
+    __shared__ int s_pre[65];
+    const int v4 = words >> 2;
+    if (threadIdx.x == 0) {
+        int a = 0;
+        for (int g = 0; g < n_ranks; g++) { s_pre[g] = a; a += (int)min((unsigned long long)cap, __ldcg(all + (size_t)g * block_words64)); }
+        s_pre[n_ranks] = a;
+        if (blockIdx.x == 0 && a != total_expected) *mismatch = 1;
+    }
+    __syncthreads();
+    const int total = min(s_pre[n_ranks], total_expected);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+        int g = 0;
+        while (g + 1 < n_ranks && s_pre[g + 1] <= k) g++;
+        const unsigned long long *blk = all + (size_t)g * block_words64;
+        const int32_t *ids = reinterpret_cast<const int32_t *>(blk + 2);
+        const uint4 *desc = reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(blk + 2) + (((size_t)cap * 4 + 15) & ~(size_t)15));
+        const int e = k - s_pre[g];
+        gid[k] = __ldcg(ids + e);
+        for (int v = 0; v < v4; v++) reinterpret_cast<uint4 *>(t_sub)[(size_t)k * v4 + v] = __ldcg(desc + (size_t)e * v4 + v);
+    }
+}
+
+// triples of the sub-problem (indices into the gathered rows / columns) -> match keys of the original rows
+__global__ void shard_map_matches_kernel(const int32_t *__restrict__ sq, const int32_t *__restrict__ st, const int32_t *__restrict__ sd,
+                                         int n, const int32_t *__restrict__ live_rows, const int32_t *__restrict__ gid,
+                                         uint32_t *__restrict__ match_key) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+        match_key[__ldcg(live_rows + sq[k])] = ((uint32_t)sd[k] << KEY_IDX_BITS) | (uint32_t)__ldcg(gid + st[k]);
+}
+
 // ---------------------------------------------------------------------------
 // nearest / second nearest (no masks): same tiling, two keys per row in
 // registers; column splits write partial top-2 that a merge kernel combines.

@@ -1901,6 +1901,7 @@ struct pgm_shard {
     int words = 8, desc_bits = 256, n1 = 0, n2_local = 0, n2_total = 0, col_offset = 0;
     int round = 0;
     int round_grid = 0;
+    const uint32_t *q_host_ptr = nullptr, *t_host_ptr = nullptr;   // the pair's descriptors (device pointers)
     int raw_cap = 0;               // candidate records this rank may emit per pass
     uint8_t *coldead = nullptr;    // [n2_total] by GLOBAL column id
     uint32_t *rbest_g = nullptr, *cbest_g = nullptr;   // [n1], [n2_total]: min slots of the grid-wide sparse phase
@@ -1933,6 +1934,7 @@ extern "C" int pgm_shard_create(pgm_handle *h, const uint8_t *d_q, int32_t n1, c
     pgm_shard *sh = new pgm_shard();
     sh->h = h; sh->words = stride_bytes / 4; sh->desc_bits = desc_bits;
     sh->n1 = n1; sh->n2_local = n2_local; sh->n2_total = n2_total; sh->col_offset = col_offset;
+    sh->q_host_ptr = (const uint32_t *)d_q; sh->t_host_ptr = (const uint32_t *)d_t_local;
     const int64_t rows = n1, cols = std::max(n2_local, 1);
     const int n_blocks = (n1 + SHARD_BLOCK - 1) / SHARD_BLOCK;
     const bool use_cand = !h->no_cand;
@@ -2210,6 +2212,7 @@ struct pgm_multi {
     void *comm = nullptr;
     int rank = 0, world = 1;
     DevBuf xbuf;                 // exchange buffer [2 * n1] / gathered keys
+    DevBuf fin;                  // replicated finish: gathered rows / columns, sub-problem output
     int64_t exchange_bytes = 0;  // payload this rank contributed to collectives in the last call
     int32_t collectives = 0;
 };
@@ -2261,6 +2264,7 @@ extern "C" int pgm_multi_destroy(pgm_multi *mh) {
         cudaStreamSynchronize(h->stream);
         if (mh->comm) nccl_api()->CommDestroy(mh->comm);
         if (mh->xbuf.p) cudaFree(mh->xbuf.p);
+        if (mh->fin.p) cudaFree(mh->fin.p);
     }
     delete mh;
     return PGM_OK;
@@ -2270,6 +2274,61 @@ extern "C" int pgm_multi_get_exchange(pgm_multi *mh, int64_t *bytes, int32_t *co
     if (!mh) return PGM_E_INVALID_ARG;
     if (bytes) *bytes = mh->exchange_bytes;
     if (collectives) *collectives = mh->collectives;
+    return PGM_OK;
+}
+
+// Once at most SHARD_FINISH_MAX rows and columns are left, the remaining rounds would be a few microseconds of work each
+// behind two collectives and a dozen launches.  Instead every rank gathers the descriptors of ALL surviving rows (it holds
+// every query) and columns (one all-gather of the ranks' surviving train rows, ascending) and finishes the remaining small
+// problem itself with the single-GPU engine -- identical input on every rank, hence identical matches.  The gathered
+// indices are order-preserving (the row list is compacted stably, the columns are packed ascending), so the engine's
+// (distance, i, j) tie-break in sub-problem indices is the reference's tie-break in original indices.
+constexpr int SHARD_FINISH_MAX = 12288;
+static int shard_replicated_finish(pgm_multi *mh, pgm_shard *sh, int live_rows, cudaStream_t s) {
+    pgm_handle *h = sh->h;
+    const int words = sh->words, stride = words * 4;
+    const int Lr = live_rows, Lc = sh->n2_total - (sh->n1 - live_rows);
+    if (Lr <= 0 || Lc <= 0) return PGM_OK;
+    const int r = sh->round;                                   // the lists of the NEXT round hold the survivors
+    const size_t blk_bytes = align_up(16 + align_up((size_t)Lc * 4, 16) + (size_t)Lc * stride, 256);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_q = take((size_t)Lr * stride), o_t = take((size_t)Lc * stride), o_gid = take((size_t)Lc * 4);
+    const size_t o_out = take((size_t)3 * Lr * 4), o_flag = take(4), o_all = take(blk_bytes * mh->world);
+    int rc = ensure_dev(h, mh->fin, off);
+    if (rc) return rc;
+    char *base = (char *)mh->fin.p;
+    uint32_t *q_sub = (uint32_t *)(base + o_q), *t_sub = (uint32_t *)(base + o_t);
+    int32_t *gid = (int32_t *)(base + o_gid), *oq = (int32_t *)(base + o_out), *ot = oq + Lr, *od = ot + Lr;
+    int32_t *d_flag = (int32_t *)(base + o_flag);
+    unsigned long long *all = (unsigned long long *)(base + o_all);
+    unsigned long long *mine = (unsigned long long *)((char *)all + blk_bytes * mh->rank);
+    CU_CHECK(h, cudaMemsetAsync(d_flag, 0, 4, s));
+    const uint32_t *qd = sh->q_host_ptr, *td = sh->t_host_ptr;
+    shard_gather_rows_kernel<<<std::min((Lr * (words / 4) + 255) / 256, h->num_sms * 8), 256, 0, s>>>(
+        qd, sh->c.live_rows[r & 1], Lr, words, q_sub);
+    shard_pack_cols_kernel<<<1, 1024, 0, s>>>(td, sh->n2_local, sh->col_offset, words, sh->coldead, Lc, mine);
+    if (mh->world > 1) {
+        NCCL_CHECK(h, nccl_api()->AllGather(mine, all, blk_bytes / 8, kNcclUint64, mh->comm, s));
+        mh->exchange_bytes += (int64_t)blk_bytes; mh->collectives++;
+    }
+    shard_merge_cols_kernel<<<std::min((Lc + 255) / 256, h->num_sms * 8), 256, 0, s>>>(all, blk_bytes / 8, mh->world, Lc, words,
+                                                                                   t_sub, gid, Lc, d_flag);
+    h->stats.kernel_launches += 3;
+    HostPair hp{(const uint8_t *)q_sub, (const uint8_t *)t_sub, Lr, Lc, 0};
+    const pgm_stats keep = h->stats;
+    rc = run_chunk(h, &hp, 1, sh->desc_bits, stride, 0u, oq, ot, od);
+    if (rc) return rc;
+    const int launches = h->stats.kernel_launches;
+    h->stats = keep; h->stats.kernel_launches = launches; h->stats_pending = false;
+    const int nm = std::min(Lr, Lc);
+    shard_map_matches_kernel<<<std::min((nm + 255) / 256, h->num_sms * 8), 256, 0, s>>>(oq, ot, od, nm, sh->c.live_rows[r & 1], gid,
+                                                                                    sh->c.match_key);
+    h->stats.kernel_launches += 1;
+    int32_t flag = 0;
+    CU_CHECK(h, cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(h, cudaStreamSynchronize(s));
+    if (flag) return fail(h, PGM_E_CUDA, "train-sharded finish: the ranks' surviving columns do not add up (internal error)");
     return PGM_OK;
 }
 
@@ -2301,27 +2360,29 @@ extern "C" int pgm_multi_match_train_sharded_dev(pgm_multi *mh, const uint8_t *d
         if (!rc) rc = ensure_dev(h, mh->xbuf, x_bytes + (edges_on ? (size_t)mh->world * (1 + (size_t)edge_cap) * 8 : 0));
         uint32_t *X = (uint32_t *)mh->xbuf.p;
         unsigned long long *E_all = edges_on ? (unsigned long long *)((char *)mh->xbuf.p + x_bytes) : nullptr;
-        // The host runs LOOK rounds ahead of the status it inspects: round r's 16-byte status (done, live rows) is copied
-        // back asynchronously and looked at when round r + LOOK has been enqueued.  The GPU therefore never waits for a
-        // launch (the late rounds are a few microseconds of work each, less than the host needs to enqueue one), the
-        // host never waits for the GPU except to stay LOOK rounds ahead, and at most LOOK empty rounds follow the last
-        // one.  Every rank reads the same values at the same round, so all ranks enqueue the same collectives.
-        constexpr int LOOK = 4, RING = 8;
-        cudaEvent_t ev[RING];
-        for (auto &e : ev) e = nullptr;
-        for (int k = 0; k < RING && !rc; k++)
-            if (cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess) rc = PGM_E_CUDA;
+        // Rounds while many rows are live (each is milliseconds of work: one 16-byte status read-back per round costs
+        // nothing), then the replicated finish.  Every rank reads the same status, so all ranks take the same path.
         int bound = n1;
         bool done = false;
-        for (int rno = 0; !rc && !done; rno++) {
+        const bool no_fin = getenv("PGM_SHARD_NO_REPLICATED_FINISH") != nullptr;
+        const bool timing = getenv("PGM_SHARD_TIMING") != nullptr;      // debug: host wall time of every round (stream is idle at each mark)
+        auto t_prev = std::chrono::steady_clock::now();
+        auto mark = [&](const char *what, int a) {
+            if (!timing) return;
+            const auto now = std::chrono::steady_clock::now();
+            fprintf(stderr, "[pgm shard rank %d] %s %d: %.3f ms\n", mh->rank, what, a, std::chrono::duration<double, std::milli>(now - t_prev).count());
+            t_prev = now;
+        };
+        if (timing) { cudaStreamSynchronize(s); mark("create", 0); }
+        while (!rc && !done) {
             if ((rc = shard_enqueue_round(sh, X, bound, s))) break;
             if (mh->world > 1) {
                 const int r = nccl_api()->AllReduce(X, X, (size_t)2 * bound, kNcclUint32, kNcclMin, mh->comm, s);
                 if (r != 0) { h->err = std::string("ncclAllReduce failed: ") + nccl_api()->GetErrorString(r); rc = PGM_E_NCCL; break; }
                 mh->exchange_bytes += (int64_t)2 * bound * 4; mh->collectives++;
             }
-            // the pass cannot list more than p_max x (live rows)^2 edges (plan_pair_emit's density clamp, <= 0.05): late
-            // rounds exchange small edge blocks.  `bound` is the same on every rank, hence so is the block size.
+            // the pass cannot list more than p_max x live rows x live columns edges (plan_pair_emit's density clamp,
+            // <= 0.05): late rounds exchange small edge blocks.  `bound` is the same on every rank, hence so is the block size.
             const double live_cols_max = (double)bound + (double)std::max(0, n2_total - n1);     // live columns = total - matched rows
             const int cap_r = (int)std::min<int64_t>(edge_cap, (int64_t)(0.06 * (double)bound * live_cols_max) + 4096);
             unsigned long long *E_mine_r = edges_on ? E_all + (size_t)mh->rank * (1 + (size_t)cap_r) : nullptr;
@@ -2332,14 +2393,17 @@ extern "C" int pgm_multi_match_train_sharded_dev(pgm_multi *mh, const uint8_t *d
                 mh->exchange_bytes += (int64_t)(1 + cap_r) * 8; mh->collectives++;
             }
             if ((rc = shard_enqueue_finish_round(sh, E_all, mh->world, cap_r, s))) break;
-            const int slot = rno % RING;
-            if (cudaMemcpyAsync(&sh->h_ctl[slot], sh->ctl, sizeof(ShardCtl), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-                cudaEventRecord(ev[slot], s) != cudaSuccess) { rc = PGM_E_CUDA; break; }
-            if (rno >= LOOK) {
-                const int old = (rno - LOOK) % RING;
-                if (cudaEventSynchronize(ev[old]) != cudaSuccess) { rc = PGM_E_CUDA; break; }
-                if (sh->h_ctl[old].done) done = true;
-                else bound = std::min(bound, std::max(SHARD_BLOCK, (sh->h_ctl[old].live_rows + SHARD_BLOCK - 1) / SHARD_BLOCK * SHARD_BLOCK));
+            if (cudaMemcpyAsync(&sh->h_ctl[0], sh->ctl, sizeof(ShardCtl), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                cudaStreamSynchronize(s) != cudaSuccess) { rc = PGM_E_CUDA; break; }
+            h->stats.host_syncs++;
+            const int live = sh->h_ctl[0].live_rows;
+            done = sh->h_ctl[0].done != 0;
+            mark("round, live rows after", live);
+            bound = std::min(bound, std::max(SHARD_BLOCK, (live + SHARD_BLOCK - 1) / SHARD_BLOCK * SHARD_BLOCK));
+            if (!done && !no_fin && live <= SHARD_FINISH_MAX && (int64_t)n2_total - (n1 - live) <= SHARD_FINISH_MAX) {
+                rc = shard_replicated_finish(mh, sh, live, s);
+                done = true;
+                mark("replicated finish of rows", live);
             }
             if (sh->round > 4 * MAX_N) { h->err = "train-sharded matcher failed to converge (internal error)"; rc = PGM_E_CUDA; }
         }
@@ -2356,7 +2420,6 @@ extern "C" int pgm_multi_match_train_sharded_dev(pgm_multi *mh, const uint8_t *d
         } else if (rc == PGM_E_CUDA && h->err.empty()) {
             h->err = std::string("CUDA error in the train-sharded matcher: ") + cudaGetErrorString(cudaGetLastError());
         }
-        for (auto &e : ev) if (e) cudaEventDestroy(e);
     }
     pgm_shard_destroy(sh);
     return rc;

@@ -263,3 +263,34 @@ def test_multi_gpu_matcher_single_rank_equals_unsharded(matcher):
         assert all((a.cpu().numpy() == b).all() for a, b in zip(knn, exp))
         assert mg.exchange() == (0, 0)
         mg.close()
+
+
+def _bimodal(seed, n, dup_frac=0.5):
+    """Half the rows are copies of ONE descriptor (every distance among them is 0), the rest uniform: the sampled mean and
+    deviation put the candidate bound T above 0, so the duplicate block alone lists ~n^2/4 edges -- far more than any
+    candidate list holds.  Exercises the overflow paths (tile staging, raw list, live-edge list, sharded edge blocks)."""
+    a = synthetic.uniform_descriptors(seed, n, 256)
+    k = int(n * dup_frac)
+    a[:k] = a[0]
+    rng = np.random.default_rng(seed)
+    return a[rng.permutation(n)]
+
+
+@pytest.mark.parametrize("n1,n2", [(3000, 3000), (2500, 1800), (700, 900)])
+def test_candidate_list_overflow_falls_back_to_plain_rounds(matcher, n1, n2):
+    q, t = _bimodal(5, n1), _bimodal(6, n2)
+    t[: n2 // 2] = q[0]                                       # the duplicate blocks of both sides coincide: distance 0
+    exp = orc.match_sweep(q, t)
+    assert (matcher.match_greedy(q, t, 256) == exp).all()
+    # throughput mode (more than 16 pairs), and the train-sharded steps
+    from photogrammetry_b200 import sharding
+    imgs = np.concatenate([q[:600], t[:600]] + [_bimodal(20 + k, 600) for k in range(5)])
+    offs = np.arange(8, dtype=np.int64) * 600
+    pairs = sharding.all_pairs(7)
+    tr, starts, counts = matcher.match_pairs_batch(imgs, offs, pairs, 256)
+    for p in (0, 1, 7, 20):
+        a, b = pairs[p]
+        e = orc.match_sweep(imgs[offs[a]:offs[a + 1]], imgs[offs[b]:offs[b + 1]])
+        assert (tr[starts[p]:starts[p] + counts[p]] == e).all(), p
+    outs, _ = sharding.match_train_sharded_emulated(matcher, q, t, 3)
+    assert all((o == exp).all() for o in outs)
