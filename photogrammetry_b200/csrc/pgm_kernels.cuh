@@ -361,18 +361,24 @@ __device__ __forceinline__ void plan_warp(const Chunk &c, int r) {
     // wave-aware refinement: a round takes ~ceil(tiles / slots) x cpt; a slightly wider tile often saves a whole,
     // mostly empty, second wave (2301 x 2301 live: 648 tiles of 64 columns on 592 slots -> 432 tiles of 96)
     if (c.n_pairs == 1) {
-        // one pair: 32 candidate widths at once, one per lane (a tile's column extent only has to be a multiple of 8);
-        // 8192 x 8192 on 592 slots: 224 columns -> 16 x 37 = 592 tiles, exactly one wave
-        const unsigned cand = min(cpt + 8u * (unsigned)lane, (unsigned)MAX_N);
+        // one pair: 32 candidate tilings at once, one per lane.  Lane l tries (n0 - 8 + l) column tiles per row tile
+        // (n0 from the heuristic width), i.e. widths from far wider to far narrower than the heuristic one; a tile's
+        // column extent only has to be a multiple of 8.  8192 x 8192 on 888 slots: 152 columns -> 16 x 54 = 864 tiles, one
+        // wave; 200 000 x 25 000: 9 column tiles -> 3519 tiles = 3.96 waves instead of 5 tiles -> 2.2 waves paid as 3.
         const int nlr0 = __shfl_sync(0xffffffffu, nlr, 0), nlc0 = __shfl_sync(0xffffffffu, nlc, 0);
         const int big0 = __shfl_sync(0xffffffffu, (int)(st == PAIR_BIG), 0);
+        const int n0 = (nlc0 + (int)cpt - 1) / (int)cpt;
+        const int nct = max(1, n0 - 8 + lane);
+        unsigned cand = (unsigned)((nlc0 + nct - 1) / nct);
+        cand = min(max((cand + 7u) & ~7u, 8u), (unsigned)MAX_N);
         const unsigned t = big0 ? (unsigned)tiles_of(nlr0, nlc0, tile_rows, (int)cand) : 0u;
         unsigned long long key = ((unsigned long long)(((t + slots - 1) / slots)) * (cand + 16u) << 8) | (unsigned)lane;
+        unsigned long long best = key;
         for (int o = 16; o; o >>= 1) {
-            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-            key = other < key ? other : key;
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other < best ? other : best;
         }
-        cpt = min(cpt + 8u * (unsigned)(key & 0xFFu), (unsigned)MAX_N);
+        cpt = __shfl_sync(0xffffffffu, cand, (int)(best & 0xFFu));
     } else {
         unsigned best_cpt = cpt, best_cost = 0xFFFFFFFFu;
         for (unsigned k = 0; k < 4; k++) {

@@ -252,9 +252,13 @@ def test_multi_gpu_matcher_single_rank_equals_unsharded(matcher):
     import torch
 
     from photogrammetry_b200 import sharding
-    for n1, n2, dist in [(5000, 4200, "U"), (3000, 3000, "C"), (1500, 40, "U"), (1, 1, "U")]:
+    # (30000 x 29000: two rounds, then the replicated finish; 3000 x 40000: too many columns stay live for the replicated
+    #  finish, the rounds run to the end; the small ones finish right after round 0)
+    for n1, n2, dist in [(5000, 4200, "U"), (3000, 3000, "C"), (1500, 40, "U"), (1, 1, "U"), (30000, 29000, "U"), (3000, 40000, "U")]:
         q = synthetic.uniform_descriptors(11, n1, 256)
         t = synthetic.uniform_descriptors(12, n2, 256) if dist == "U" else synthetic.noisy_copy_descriptors(13, q, 256)[:n2]
+        if n1 * n2 > 10 ** 8:                                   # the literal-free oracle for the big shapes
+            assert (matcher.match_greedy(q, t, 256) == orc.match_rounds(q, t)).all()
         mg = sharding.MultiGpuMatcher(matcher, 0, 1)
         got = mg.match_train_sharded(torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda(), 0, n2).T.cpu().numpy()
         assert (got == matcher.match_greedy(q, t, 256)).all()
