@@ -202,3 +202,76 @@ def test_train_sharded_knn_emulated_ranks_cpu(n1, n2, shards, bits):
             assert (a.numpy() == b).all()
         exp = orc.match_ratio_crosscheck(q, t, ratio, cc, md)
         assert kept.numpy().T.shape == exp.shape and (kept.numpy().T == exp).all()
+
+
+# ---- train-sharded greedy matcher: the [R | P] exchange rule of one round (gloo, world_size 2) -------------------
+# include/pgmatch.h: R[i] = row i's best key (d << 20 | global j) over the rank's columns, P[i] = the best key among the
+# rank's columns that chose row i as their best row; after an element-wise MIN over the ranks row i is matched iff
+# R[i] == P[i].  The device kernels (shard_export_rows / shard_propose_cols / shard_commit_mark) compute exactly this; the
+# test restates the rank-local part in numpy, runs the exchange through gloo and checks the rule against the unsharded
+# definition of a locally dominant edge (mutual best under the reference's (d, i, j) order).
+NONE_KEY = 0x7F7F7F7F
+
+
+def _local_rp(q, t_local, col_offset):
+    d = np.bitwise_count(q[:, None, :] ^ t_local[None, :, :]).sum(axis=2).astype(np.int64)
+    n1, n2l = d.shape
+    R = np.full(n1, NONE_KEY, dtype=np.int64)
+    P = np.full(n1, NONE_KEY, dtype=np.int64)
+    if n2l:
+        keys_rows = (d << 20) | (np.arange(n2l)[None, :] + col_offset)
+        R = keys_rows.min(axis=1)
+        keys_cols = (d << 20) | np.arange(n1)[:, None]                    # a column's key over the rows: (d, i)
+        best_row = (keys_cols.min(axis=0) & 0xFFFFF).astype(np.int64)       # each local column's choice is final
+        for j in range(n2l):
+            i = best_row[j]
+            P[i] = min(P[i], (d[i, j] << 20) | (j + col_offset))
+    return R.astype(np.int32), P.astype(np.int32)
+
+
+def _rp_worker(rank, world, port, q, t, out_q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = sharding.train_slices(len(t), world)[rank]
+        R, P = _local_rp(q, t[lo:hi], lo)
+        x = torch.from_numpy(np.concatenate([R, P]))
+        dist.all_reduce(x, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            out_q.put(x.numpy())
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rp_exchange_rule_world2_gloo():
+    import torch.multiprocessing as mp
+    q = synthetic.uniform_descriptors(3, 90, 16)            # 16-bit descriptors: plenty of tied distances
+    t = synthetic.uniform_descriptors(4, 71, 16)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    procs = [ctx.Process(target=_rp_worker, args=(r, 2, port, q, t, queue)) for r in range(2)]
+    for p in procs:
+        p.start()
+    x = queue.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n1 = len(q)
+    R, P = x[:n1].astype(np.int64), x[n1:].astype(np.int64)
+    assert (P >= R).all()
+    d = np.bitwise_count(q[:, None, :] ^ t[None, :, :]).sum(axis=2).astype(np.int64)
+    row_best = ((d << 20) | np.arange(len(t))[None, :]).min(axis=1)            # (d, j) order
+    col_best = ((d << 20) | np.arange(n1)[:, None]).min(axis=0)                # (d, i) order
+    mutual = np.array([(col_best[row_best[i] & 0xFFFFF] & 0xFFFFF) == i for i in range(n1)])
+    assert (R == row_best).all()
+    assert ((R == P) == mutual).all() and mutual.sum() >= 1
+    # and those are the first accepts of the reference's greedy loop: every mutual pair is in the literal result
+    exp = {(int(a), int(b)) for a, b, _ in orc.match_literal(q, t, kernighan=True)[:min(n1, len(t))]}
+    assert all((i, int(R[i] & 0xFFFFF)) in exp for i in np.flatnonzero(mutual))
