@@ -550,15 +550,25 @@ def extra_knn_l2(m, stream, dev, popc_peak):
             rel = float(((fd[0][rows].double() - ref_d).abs() / ref_d.clamp_min(1e-30)).max().item())
         stream.synchronize()
         tf_alg = 2.0 * dim * nf * nf / (ms * 1e-3) / 1e12
+        st = m.stats()
+        fallback_rows = m.l2_last_fallback_rows()
+        fp16 = fallback_rows >= 0
+        terms = 1.0 if fp16 else 3.0
         out[f"l2_knn2_{nf // 1024}k_d{dim}"] = {
-            "ms": ms, "evals_per_s": nf * float(nf) / (ms * 1e-3), "launches": 3,
+            "ms": ms, "evals_per_s": nf * float(nf) / (ms * 1e-3), "launches": st["kernel_launches"],
+            "ranking": ("one fp16 term under a global power-of-two scale, certified band, exhaustive fallback for "
+                        "uncertified rows" if fp16 else "three-term bf16 split (PGM_L2_MODE=bf16x3)"),
+            "rows_recomputed_exhaustively": fallback_rows,
             "nearest_index_mismatch_rate_vs_fp64": mism, "nearest_distance_max_rel_err_vs_fp64": rel,
             "roofline": {"bound": "tensor", "achieved": tf_alg, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf_alg / peak_tf,
                          "peak_source": peak_src,
                          "algorithmic": "2 x D flops per distance (SURVEY 8d)",
-                         "executed_frac": 3.0 * tf_alg / peak_tf,
-                         "executed": "2 x 3 x D per distance: three bf16 split terms (hi.hi + lo.hi + hi.lo) keep the "
-                                     "1e-4 relative tolerance; the norm MMA adds 4 %"}}
+                         "executed_frac": terms * (dim + 16.0) / dim * tf_alg / peak_tf if fp16 else terms * tf_alg / peak_tf,
+                         "executed": ("2 x (D + 16) per distance: one fp16 GEMM pass + the K = 16 norm step; the kernel is "
+                                      "bound by the epilogue's TMEM reads and the operand feed, not by the tensor pipe "
+                                      "(DESIGN 4.2)" if fp16 else
+                                      "2 x 3 x D per distance: three bf16 split terms (hi.hi + lo.hi + hi.lo); the norm "
+                                      "MMA adds 4 %")}}
         del fq, ft, fj, fd
     return out
 

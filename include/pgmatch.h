@@ -223,17 +223,25 @@ int pgm_match_ratio_crosscheck(pgm_handle *h,
  * q: float[n1][dim], t: float[n2][dim], 1 <= dim <= 128.  The reference has no float
  * descriptor; semantics are those of oracle/pgm_oracle.c orc_l2_knn2: exact squared
  * Euclidean distance, best and second-best train index under (distance, index), -1 where
- * absent.  Computed as ||q||^2 + ||t||^2 - 2 q.t on the tcgen05 tensor cores (split-bf16
- * operands, fp32 accumulation in TMEM) to rank candidates, then the top candidates are
- * re-evaluated exactly in fp32: distances are exact to fp32 rounding (<= 1e-5 relative);
- * indices equal the oracle's except where two candidates' distances differ by less than
- * ~1e-5 relative (near-ties).  d_debug_dist (optional, device float[n1][n2]) receives
- * the approximate GEMM distances. */
+ * absent.  Computed as ||q||^2 + ||t||^2 - 2 q.t on the tcgen05 tensor cores (fp32
+ * accumulation in TMEM) to RANK candidates, then every candidate inside the error band of the
+ * ranking is re-evaluated exactly in fp32: distances are exact to fp32 rounding (<= 1e-5
+ * relative); indices equal the oracle's except where two candidates' exact fp32 distances
+ * differ only by summation order (near-ties).  Ranking operands: one fp16 term per component
+ * under a global power-of-two scale (band 2^-9 (3|q|^2 + 2d)); a query whose band could hide a
+ * train row that the kernel's per-column-group top-4 lists dropped is recomputed exhaustively on
+ * the device, so the guarantee does not depend on the data (pgm_l2_last_fallback_rows counts
+ * them).  PGM_L2_MODE=bf16x3 selects the round-1 three-term bf16 split (three GEMM passes),
+ * which n1 <= 128 always uses.  d_debug_dist (optional, device float[n1][n2]) receives the
+ * approximate GEMM distances. */
 int pgm_knn2_l2(pgm_handle *h, const float *q, int32_t n1, const float *t, int32_t n2, int32_t dim,
                 int32_t *best_j, float *best_d, int32_t *second_j, float *second_d);
 int pgm_knn2_l2_dev(pgm_handle *h, const float *d_q, int32_t n1, const float *d_t, int32_t n2, int32_t dim,
                     int32_t *d_best_j, float *d_best_d, int32_t *d_second_j, float *d_second_d,
                     float *d_debug_dist);
+/* Rows of the handle's last float call that took the exhaustive fallback (synchronises the stream);
+ * -1 if that call did not run in the fp16 ranking mode. */
+int pgm_l2_last_fallback_rows(pgm_handle *h);
 
 /* ---- the producer of the matcher's inputs ----------
  * gray: float[height][width] = Grayscale.K (Images.Abstractions/Pixels/Grayscale.cs:19-23),

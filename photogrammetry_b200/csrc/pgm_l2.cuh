@@ -36,6 +36,7 @@
 #include <cstdint>
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 namespace pgm_l2 {
@@ -46,9 +47,15 @@ constexpr int CHUNK_K = 64;        // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K = 16;         // K of one tcgen05.mma for 16-bit inputs
 constexpr int MAX_CHUNKS = 5;      // resident A' chunks: [hi | lo | norm], Dp <= 128
 constexpr int STAGES = 8;          // B' ring of chunk slots: two whole tiles deep at Dp = 128
-constexpr int THREADS = 384;        // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: two epilogue warpgroups (four were 8 % slower)
-constexpr int EPI_GROUPS = 2;       // each epilogue warpgroup reduces half of the accumulator's columns
-constexpr int TOPK = 4;             // candidates kept per (query, column split, epilogue warpgroup)
+#ifndef PGM_L2_EPI_GROUPS
+#define PGM_L2_EPI_GROUPS 2
+#endif
+constexpr int EPI_GROUPS = PGM_L2_EPI_GROUPS;   // each epilogue warpgroup reduces an equal share of the accumulator's columns
+constexpr int THREADS = 128 + 128 * EPI_GROUPS; // warps 0-3: TMA / MMA / TMEM alloc / spare; then the epilogue warpgroups
+#ifndef PGM_L2_TOPK
+#define PGM_L2_TOPK 8
+#endif
+constexpr int TOPK = PGM_L2_TOPK;   // candidates kept per (query, column split, epilogue warpgroup)
 constexpr int CAND = TOPK * EPI_GROUPS;
 constexpr uint32_t CHUNK_BYTES = TILE_N * CHUNK_K * 2;   // 16 KB (A' and B' chunks have the same shape)
 constexpr uint32_t TMEM_COLS = 256;                      // two fp32 accumulators of 128 columns
@@ -69,8 +76,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"     // suspend-time hint: the thread
-        "selp.u32 %0, 1, 0, p;\n\t}"                                         // sleeps in hardware, no issue slots
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"     // suspend-time hint: the thread sleeps in
+        "selp.u32 %0, 1, 0, p;\n\t}"                                         // hardware, no issue slots (a pure spin measured 4-8 % slower)
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
     return ok != 0;
 }
@@ -109,6 +116,13 @@ __device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[3
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tc_ld_32x32b_x64(uint32_t taddr, uint32_t (&v)[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+        : "r"(taddr) : "memory");
+}
 // Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may
 // start (prologue: barriers, TMEM allocation) while its predecessor drains; pdl_wait() blocks until the
 // predecessor grid has completed and its memory is visible.  pdl_trigger() lets the successor start early.
@@ -134,14 +148,18 @@ constexpr uint32_t IDESC_BF16_M128_N128 =
 __global__ void __launch_bounds__(256) split_kernel(const float *__restrict__ q, int n1, const float *__restrict__ t, int n2,
                                                     int dim, int dp, __nv_bfloat16 *__restrict__ a,
                                                     __nv_bfloat16 *__restrict__ b, int32_t *__restrict__ cand_j,
-                                                    int slots) {
+                                                    int slots, float *__restrict__ qnorm, float *__restrict__ cand_drop) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     pdl_trigger();                                   // the GEMM kernel's prologue may overlap this kernel
     if (w >= n1 + n2) return;
     const bool train = w >= n1;
     const int row = train ? w - n1 : w;
     if (!train)                                      // candidate slots no segment of the GEMM kernel fills stay "absent"
+    {
         for (int e = lane; e < slots * CAND; e += 32) cand_j[((size_t)(e / CAND) * n1 + row) * CAND + (e % CAND)] = -1;
+        for (int e = lane; e < slots * EPI_GROUPS; e += 32)
+            cand_drop[((size_t)(e / EPI_GROUPS) * n1 + row) * EPI_GROUPS + (e % EPI_GROUPS)] = 3.4e38f;
+    }
     const float *x = (train ? t : q) + (size_t)row * dim;
     __nv_bfloat16 *o = (train ? b : a) + (size_t)row * (2 * dp + CHUNK_K);
     float acc = 0.f;
@@ -169,6 +187,7 @@ __global__ void __launch_bounds__(256) split_kernel(const float *__restrict__ q,
         for (int e = 0; e < 4; e++) acc = fmaf(v[e], v[e], acc);
     }
     for (int sh = 16; sh; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
+    if (!train && lane == 0) qnorm[row] = acc;
     const float hn = -0.5f * acc;
     const __nv_bfloat16 e0 = __float2bfloat16_rn(hn);
     const float r1 = hn - __bfloat162float(e0);
@@ -184,12 +203,137 @@ __global__ void __launch_bounds__(256) split_kernel(const float *__restrict__ q,
     *reinterpret_cast<__nv_bfloat162 *>(o + 2 * dp + 2 * lane) = ext;
 }
 
+
+// ---- single-term fp16 ranking (round 2) ---------------------------------------------------------
+// The three-term bf16 split costs three GEMM passes for a ranking that the refinement kernel re-derives
+// exactly anyway.  One fp16 term ranks as well as needed: fp16 rounds to 2^-11 relative, so
+//     |h_q.h_t - q.t| <= (2 * 2^-11 + 2^-22) sum |q_i t_i| <= 2^-10 |q| |t|,   i.e.  |d_approx - d| <= 2^-10 (|q|^2 + |t|^2)
+// and the refinement keeps every candidate within that band of the second-best approximation (typically
+// one extra train row per query).  A query whose band could hide a train row the epilogue's top-4 lists
+// dropped is recomputed exhaustively (l2_exact_rows_kernel), so the result does not depend on the data
+// being well spread.  fp16 has a narrow exponent range, hence a global power-of-two scale s (exact in
+// fp32) that maps max |x| over both sets into [2^9, 2^10): squared norms stay below 2^27 and components down
+// to 2^-24 of the maximum keep their full relative precision.  The norm chunk carries -|x s|^2 / 2 as
+// 4096 * (h0 + h1 + h2) -- three fp16 terms, 33 bits -- against (4096, 4096, 4096) on the other side.
+constexpr float NORM_C = 4096.f;
+__device__ __forceinline__ void l2_scale_from_bits(unsigned bits, float &s, float &inv_s2, float &mprime) {
+    int eb = (int)(bits >> 23);                      // biased exponent of max |x| (sign bit is clear)
+    if (bits == 0u) { s = 1.f; inv_s2 = 1.f; mprime = 0.f; return; }
+    eb = max(eb, 1);
+    const int sb = min(max(263 - eb, 127 - 60), 127 + 60);   // s = 2^(136 - eb), clamped to 2^+-60 so that 1/s^2 stays finite
+    s = __uint_as_float((unsigned)sb << 23);
+    const float is = __uint_as_float((unsigned)(254 - sb) << 23);
+    inv_s2 = is * is;
+    mprime = __uint_as_float((unsigned)min(eb + 1, 254) << 23);
+}
+
+// hdr[0] = max |x| bits, one atomicMax per block.  hdr lives in a buffer of its own that is zeroed when allocated; every
+// call leaves hdr[0] = 0 behind (l2_exact_rows_kernel, the last kernel of the chain) and its ticket hdr[2] self-cleans, so no
+// memset sits in front of the chain.
+__global__ void __launch_bounds__(256) absmax_kernel(const float *__restrict__ q, size_t nq, const float *__restrict__ t, size_t nt,
+                                                     unsigned *__restrict__ hdr) {
+    pdl_trigger();
+    if (blockIdx.x == 0 && threadIdx.x == 0) hdr[1] = 0;      // flagged-row count of this call (the refinement fills it)
+    unsigned m = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int side = 0; side < 2; side++) {
+        const float *x = side ? t : q;
+        const size_t n = side ? nt : nq;
+        if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+            const size_t n4 = n >> 2;
+            const uint4 *x4 = reinterpret_cast<const uint4 *>(x);
+            for (size_t i = tid; i < n4; i += stride) {
+                const uint4 v = __ldg(x4 + i);
+                m = max(max(m, v.x & 0x7FFFFFFFu), max(max(v.y & 0x7FFFFFFFu, v.z & 0x7FFFFFFFu), v.w & 0x7FFFFFFFu));
+            }
+            for (size_t i = (n4 << 2) + tid; i < n; i += stride) m = max(m, __float_as_uint(__ldg(x + i)) & 0x7FFFFFFFu);
+        } else {
+            for (size_t i = tid; i < n; i += stride) m = max(m, __float_as_uint(__ldg(x + i)) & 0x7FFFFFFFu);
+        }
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    __shared__ unsigned sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = max(m, sm[w]);
+        if (m) atomicMax(hdr, m);
+    }
+}
+
+// Row layout in fp16 mode: [x16 (Dp) | norm chunk (64)].  One warp per row, as split_kernel.
+__global__ void __launch_bounds__(256) split16_kernel(const float *__restrict__ q, int n1, const float *__restrict__ t, int n2,
+                                                      int dim, int dp, __half *__restrict__ a, __half *__restrict__ b,
+                                                      int32_t *__restrict__ cand_j, int slots, const unsigned *__restrict__ hdr,
+                                                      float *__restrict__ qnorm, float *__restrict__ cand_drop) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
+    if (w >= n1 + n2) return;
+    const bool train = w >= n1;
+    const int row = train ? w - n1 : w;
+    if (!train)
+    {
+        for (int e = lane; e < slots * CAND; e += 32) cand_j[((size_t)(e / CAND) * n1 + row) * CAND + (e % CAND)] = -1;
+        for (int e = lane; e < slots * EPI_GROUPS; e += 32)
+            cand_drop[((size_t)(e / EPI_GROUPS) * n1 + row) * EPI_GROUPS + (e % EPI_GROUPS)] = 3.4e38f;
+    }
+    const float *x = (train ? t : q) + (size_t)row * dim;
+    __half *o = (train ? b : a) + (size_t)row * (dp + CHUNK_K);
+    const bool vec = (dim & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    const int k = 4 * lane;                          // Dp <= 128: one group of four components per lane
+    if (k < dp) {
+        if (vec && k + 3 < dim) {
+            const float4 f = __ldg(reinterpret_cast<const float4 *>(x + k));
+            v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++) v[e] = k + e < dim ? __ldg(x + k + e) : 0.f;
+        }
+    }
+    pdl_wait();                                      // the scale comes from absmax_kernel
+    float s, inv_s2, mprime;
+    l2_scale_from_bits(__ldcg(hdr), s, inv_s2, mprime);
+    float acc = 0.f;
+    if (k < dp) {
+        __half2 h[2];
+#pragma unroll
+        for (int e = 0; e < 4; e++) v[e] *= s;
+        h[0] = __floats2half2_rn(v[0], v[1]);
+        h[1] = __floats2half2_rn(v[2], v[3]);
+        *reinterpret_cast<uint2 *>(o + k) = make_uint2(*reinterpret_cast<uint32_t *>(&h[0]), *reinterpret_cast<uint32_t *>(&h[1]));
+#pragma unroll
+        for (int e = 0; e < 4; e++) acc = fmaf(v[e], v[e], acc);
+    }
+    for (int sh = 16; sh; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
+    if (!train && lane == 0) qnorm[row] = acc;       // scaled, like the accumulator
+    const float hn = -0.5f * acc * (1.f / NORM_C);
+    const __half e0 = __float2half_rn(hn);
+    const float r1 = hn - __half2float(e0);
+    const __half e1 = __float2half_rn(r1);
+    const __half e2 = __float2half_rn(r1 - __half2float(e1));
+    const __half cc = __float2half_rn(NORM_C), zero = __float2half_rn(0.f);
+    const __half n0 = train ? cc : e0, n1v = train ? cc : e1, n2v = train ? cc : e2;
+    const __half n3 = train ? e0 : cc, n4 = train ? e1 : cc, n5 = train ? e2 : cc;
+    __half2 ext;
+    ext.x = lane == 0 ? n0 : lane == 1 ? n2v : lane == 2 ? n4 : zero;
+    ext.y = lane == 0 ? n1v : lane == 1 ? n3 : lane == 2 ? n5 : zero;
+    *reinterpret_cast<__half2 *>(o + dp + 2 * lane) = ext;
+}
+
 // ---- the GEMM + top-4 kernel ----------------------------------------------------------------
 struct L2Params {
     int n1, n2, dpc;               // dpc = Dp / 64: chunks per operand part (hi or lo)
     int tiles_per_split;           // single-CTA kernel: column tiles handled by one blockIdx.y
     int col_tiles, items, flat;    // pair kernel: column tiles per row pair, row pairs x column tiles, work distribution
     uint32_t key_mask;             // 0x7FFFFFE0, passed as data so that (acc & mask) | column is ONE LOP3
+    int dbg_flags;                 // developer experiments (PGM_L2_DBG): 1 = the epilogue releases accumulators without reading them
+    int nparts;                    // operand parts per row: 2 = bf16 hi + lo (three GEMM passes), 1 = one fp16 term (one pass)
+    uint32_t idesc;                // tcgen05 instruction descriptor of the pair kernel (bf16 or fp16 inputs)
+    const unsigned *absmax_bits;   // fp16 mode: bit pattern of max |x| over both operand sets (the scale derives from it), else null
+    float band_rel, band_abs_sqrt, band_abs_const;   // error band of one accumulator comparison (see RowTop)
+    const float *qnorm;            // [n1] |q|^2 in the accumulator's units (written by the split kernel)
+    float *cand_drop;              // [splits][n1][EPI_GROUPS] approximate distance of a FULL list's last entry (3.4e38: list not full)
     int32_t *cand_j;               // [splits][n1][CAND]
     float *cand_d;                 // [splits][n1][CAND] approximate distances (diagnostic)
     float *dbg_dist;               // optional [n1][n2] approximate distance matrix (tests)
@@ -204,17 +348,58 @@ __device__ __forceinline__ void l2_stamp(const L2Params &p, int slot) {
     }
 }
 
-// Epilogue reducer shared by both kernels: NCOLS accumulator columns of this thread's row, starting at TMEM
-// address `taddr` = global train index `jbase`.  The accumulator holds -d/2 (see the header), so the rank
-// key of a column is |acc|'s bit pattern (non-negative floats order like unsigned integers) with the
-// column-in-group in its 5 low mantissa bits: one LOP3 per element, an integer min tree per 32 columns, and
-// only a group that can improve the row's top-4 takes the insertion loop.  The 2^-18 relative perturbation
-// only affects candidate ranking; distances are refined exactly afterwards.  bk[] = keys of the row's top-4
-// (ascending, index bits cleared), bj[] their train indices.  Rows that do not exist pass bk[] = 0 and
-// never insert; columns >= n2 (zero rows from the TMA's out-of-bounds fill, key ~ 0) are skipped on insertion.
+// Epilogue reducer shared by both kernels.  The accumulator holds -d/2 (see the header); one query row per thread.
+//
+// Hot path, per 32 accumulator columns: a float max tree (3-input FMNMX, half an instruction per element) and ONE
+// compare against the row's trigger level -- nothing else.  Only a chunk holding a column that can still matter takes
+// the slow path, which rebuilds tagged integer keys (|acc| bits with the column-in-chunk in the 5 low mantissa bits,
+// one LOP3 per element; the 2^-18 relative perturbation only affects ranking) and inserts into the row's sorted
+// top-K list.
+//
+// "Can still matter": the refinement only ever needs the columns whose approximate distance lies within the ranking's
+// error band of the SECOND best one (pgm_l2.cuh header).  The band of the current second best only shrinks as the
+// stream goes on, so a column outside it now is outside it at the end: trigger level = min(K-th best key, second best
+// + band).  That makes the slow path rare (about 3 ln n visits per row instead of K ln n) without weakening what the
+// lists certify.  A column that a FULL list turned away or evicted has a key >= the list's final last entry, which is
+// what the refinement's certificate looks at (cand_drop).
+//
+// Rows that do not exist never trigger (trigger level +inf); columns >= n2 (zero rows from the TMA's out-of-bounds
+// fill) are skipped on insertion.
+struct RowTop {
+    uint32_t bk[TOPK];     // ascending keys, index bits cleared; 0xFFFFFFFF = empty
+    int bj[TOPK];
+    uint32_t thr_key;      // slow-path insertion bound (tagged keys below it are inserted)
+    float thr_acc;         // hot-path trigger: some accumulator of the chunk > thr_acc
+    float qn3;             // 3 |q|^2 in the accumulator's units (scaled in fp16 mode)
+};
+struct BandParams { float rel, abs_sqrt, abs_const; };   // band of an accumulator a: rel (3|q|^2 + 4|a|) + abs_sqrt sqrt(.) + abs_const
+
+__device__ __forceinline__ void rowtop_reset(RowTop &r, bool exists, float qn) {
+#pragma unroll
+    for (int k = 0; k < TOPK; k++) { r.bk[k] = 0xFFFFFFFFu; r.bj[k] = -1; }
+    r.thr_key = exists ? 0xFFFFFFFFu : 0u;
+    r.thr_acc = exists ? -__int_as_float(0x7F800000) : __int_as_float(0x7F800000);
+    r.qn3 = 3.f * qn;
+}
+__device__ __forceinline__ void rowtop_update_trigger(RowTop &r, const BandParams &bp) {
+    uint32_t tk = r.bk[TOPK - 1];
+    if (r.bk[1] != 0xFFFFFFFFu) {
+        const float a2 = __uint_as_float(r.bk[1]);
+        const float span = r.qn3 + 4.f * a2;
+        const float lim = a2 + bp.rel * span + bp.abs_sqrt * sqrtf(span) + bp.abs_const;
+        tk = min(tk, (__float_as_uint(lim) + 64u) & 0xFFFFFFE0u);
+        r.thr_key = tk;
+        r.thr_acc = -__uint_as_float(tk);
+    }
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
 template <int NCOLS, bool DBG>
-__device__ __forceinline__ void epilogue_reduce(uint32_t taddr, int jbase, int n2, uint32_t mask, uint32_t (&bk)[TOPK],
-                                                int (&bj)[TOPK], float *dbg_row) {
+__device__ __forceinline__ void epilogue_reduce(uint32_t taddr, int jbase, int n2, uint32_t mask, RowTop &r, const BandParams &bp,
+                                                float *dbg_row, float dbg_scale) {
     uint32_t va[32], vb[32];
     constexpr int GROUPS = NCOLS / 32;
     tc_ld_32x32b_x32(taddr, va);
@@ -224,43 +409,60 @@ __device__ __forceinline__ void epilogue_reduce(uint32_t taddr, int jbase, int n
         tc_wait_ld();
         if (g + 1 < GROUPS) tc_ld_32x32b_x32(taddr + (uint32_t)((g + 1) * 32), (g & 1) ? va : vb);
         const int jg = jbase + g * 32;
-#pragma unroll
-        for (int c = 0; c < 32; c++) v[c] = (v[c] & mask) | (uint32_t)c;
         if (DBG && dbg_row) {
 #pragma unroll
             for (int c = 0; c < 32; c++)
-                if (jg + c < n2) dbg_row[jg + c] = 2.f * __uint_as_float(v[c] & 0xFFFFFFE0u);
+                if (jg + c < n2) dbg_row[jg + c] = dbg_scale * __uint_as_float(v[c] & 0x7FFFFFE0u);
         }
-        uint32_t k0 = v[0], k1 = v[1], k2 = v[2], k3 = v[3];
+        float m0 = fmax3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+        float m1 = fmax3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
+        float m2 = fmax3(__uint_as_float(v[6]), __uint_as_float(v[7]), __uint_as_float(v[8]));
+        float m3 = fmax3(__uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
 #pragma unroll
-        for (int c = 4; c < 32; c += 4) {
-            k0 = min(k0, v[c]); k1 = min(k1, v[c + 1]); k2 = min(k2, v[c + 2]); k3 = min(k3, v[c + 3]);
+        for (int c = 12; c < 28; c += 8) {
+            m0 = fmax3(m0, __uint_as_float(v[c]), __uint_as_float(v[c + 1]));
+            m1 = fmax3(m1, __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+            m2 = fmax3(m2, __uint_as_float(v[c + 4]), __uint_as_float(v[c + 5]));
+            m3 = fmax3(m3, __uint_as_float(v[c + 6]), __uint_as_float(v[c + 7]));
         }
-        uint32_t kmin = min(min(k0, k1), min(k2, k3));
-        uint32_t thr = bk[TOPK - 1];
-        while (kmin < thr) {                            // usually zero or one iteration
-            const int j = jg + (int)(kmin & 31u);
-            if (j < n2) {
-                bk[3] = kmin & 0xFFFFFFE0u; bj[3] = j;
+        m0 = fmax3(m0, __uint_as_float(v[28]), __uint_as_float(v[29]));
+        m1 = fmax3(m1, __uint_as_float(v[30]), __uint_as_float(v[31]));
+        const float mx = fmaxf(fmax3(m0, m1, m2), m3);
+        if (mx > r.thr_acc) {
+            // tagged keys of the chunk, then the sorted insertion (usually one iteration)
+            uint32_t key[32];
 #pragma unroll
-                for (int k = 3; k > 0; k--)
-                    if (bk[k] < bk[k - 1]) {
-                        const uint32_t tk = bk[k]; bk[k] = bk[k - 1]; bk[k - 1] = tk;
-                        const int tj = bj[k]; bj[k] = bj[k - 1]; bj[k - 1] = tj;
-                    }
-                thr = bk[TOPK - 1];
-            }
-            // next key strictly above the one just taken: keys at or below it wrap to >= 2^31 under the
-            // unsigned subtraction (all keys are < 2^31), so one add+min per element finds it
-            const uint32_t k1p = kmin + 1u;
-            uint32_t d0 = 0xFFFFFFFFu, d1 = 0xFFFFFFFFu, d2 = 0xFFFFFFFFu, d3 = 0xFFFFFFFFu;   // four independent chains
+            for (int c = 0; c < 32; c++) key[c] = (v[c] & mask) | (uint32_t)c;
+            uint32_t k0 = key[0], k1 = key[1], k2 = key[2], k3 = key[3];
 #pragma unroll
-            for (int c = 0; c < 32; c += 4) {
-                d0 = min(d0, v[c] - k1p); d1 = min(d1, v[c + 1] - k1p); d2 = min(d2, v[c + 2] - k1p); d3 = min(d3, v[c + 3] - k1p);
+            for (int c = 4; c < 32; c += 4) {
+                k0 = min(k0, key[c]); k1 = min(k1, key[c + 1]); k2 = min(k2, key[c + 2]); k3 = min(k3, key[c + 3]);
             }
-            const uint32_t dlt = min(min(d0, d1), min(d2, d3));
-            if (dlt >= 0x80000000u) break;
-            kmin = k1p + dlt;
+            uint32_t kmin = min(min(k0, k1), min(k2, k3));
+            while (kmin < r.thr_key) {
+                const int j = jg + (int)(kmin & 31u);
+                if (j < n2) {
+                    r.bk[TOPK - 1] = kmin & 0xFFFFFFE0u; r.bj[TOPK - 1] = j;
+#pragma unroll
+                    for (int k = TOPK - 1; k > 0; k--)
+                        if (r.bk[k] < r.bk[k - 1]) {
+                            const uint32_t tk = r.bk[k]; r.bk[k] = r.bk[k - 1]; r.bk[k - 1] = tk;
+                            const int tj = r.bj[k]; r.bj[k] = r.bj[k - 1]; r.bj[k - 1] = tj;
+                        }
+                    rowtop_update_trigger(r, bp);
+                }
+                // next key strictly above the one just taken: keys at or below it wrap to >= 2^31 under the
+                // unsigned subtraction (all keys are < 2^31), so one add+min per element finds it
+                const uint32_t k1p = kmin + 1u;
+                uint32_t d0 = 0xFFFFFFFFu, d1 = 0xFFFFFFFFu, d2 = 0xFFFFFFFFu, d3 = 0xFFFFFFFFu;
+#pragma unroll
+                for (int c = 0; c < 32; c += 4) {
+                    d0 = min(d0, key[c] - k1p); d1 = min(d1, key[c + 1] - k1p); d2 = min(d2, key[c + 2] - k1p); d3 = min(d3, key[c + 3] - k1p);
+                }
+                const uint32_t dlt = min(min(d0, d1), min(d2, d3));
+                if (dlt >= 0x80000000u) break;
+                kmin = k1p + dlt;
+            }
         }
     }
 }
@@ -356,9 +558,9 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int ew = warp & 3;                                // the TMEM lane quarter this warp may read (warp % 4)
         const int eg = (warp - 4) >> 2;                         // which half of the accumulator's columns
         const int row = m0 + ew * 32 + lane;
-        uint32_t bk[TOPK]; int bj[TOPK];
-#pragma unroll
-        for (int k = 0; k < TOPK; k++) { bk[k] = row < p.n1 ? 0xFFFFFFFFu : 0u; bj[k] = -1; }
+        RowTop rt;
+        const BandParams bp{p.band_rel, p.band_abs_sqrt, p.band_abs_const};
+        rowtop_reset(rt, row < p.n1, row < p.n1 ? __ldcg(p.qnorm + row) : 0.f);
         constexpr int NCOLS = TILE_N / EPI_GROUPS;
         for (int t = 0; t < ntiles; t++) {
             const int acc = t & 1;
@@ -366,8 +568,8 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tc_fence_after();
             const int jbase = (ct0 + t) * TILE_N + eg * NCOLS;
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TILE_N + eg * NCOLS);
-            epilogue_reduce<NCOLS, DBG>(taddr, jbase, p.n2, p.key_mask, bk, bj,
-                                        DBG && p.dbg_dist && row < p.n1 ? p.dbg_dist + (size_t)row * p.n2 : nullptr);
+            epilogue_reduce<NCOLS, DBG>(taddr, jbase, p.n2, p.key_mask, rt, bp,
+                                        DBG && p.dbg_dist && row < p.n1 ? p.dbg_dist + (size_t)row * p.n2 : nullptr, 2.f);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -376,9 +578,11 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const size_t o = ((size_t)blockIdx.y * p.n1 + row) * CAND + (size_t)eg * TOPK;
 #pragma unroll
             for (int k = 0; k < TOPK; k++) {
-                p.cand_j[o + k] = bk[k] != 0xFFFFFFFFu ? bj[k] : -1;
-                p.cand_d[o + k] = bk[k] != 0xFFFFFFFFu ? 2.f * __uint_as_float(bk[k]) : 3.4e38f;
+                p.cand_j[o + k] = rt.bk[k] != 0xFFFFFFFFu ? rt.bj[k] : -1;
+                p.cand_d[o + k] = rt.bk[k] != 0xFFFFFFFFu ? 2.f * __uint_as_float(rt.bk[k]) : 3.4e38f;
             }
+            p.cand_drop[((size_t)blockIdx.y * p.n1 + row) * EPI_GROUPS + eg] =
+                rt.bk[TOPK - 1] != 0xFFFFFFFFu ? 2.f * __uint_as_float(rt.bk[TOPK - 1]) : 3.4e38f;
         }
     }
     pdl_trigger();                                   // the refinement kernel may be scheduled
@@ -437,7 +641,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank)
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
         ::"r"(smem_u32(bar)), "r"(rank) : "memory");
 }
 __device__ __forceinline__ void tc_commit_pair(uint64_t *bar) {      // arrives on both CTAs' barrier at this offset
@@ -511,7 +715,7 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer (both CTAs): own A' rows, own half of every B' tile =====
-        const int nch = 2 * p.dpc + 1;                    // hi chunks, lo chunks, norm chunk
+        const int nch = p.nparts * p.dpc + 1;             // hi chunks, lo chunks (three-pass mode only), norm chunk
         int s = 0; uint32_t ph = 0;
         int cur_rp = -1; uint32_t n_a = 0;
         for (int it = it0; it < it1; it++) {
@@ -552,8 +756,11 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             tc_fence_after();
             if (t < 36) l2_stamp(p, 4 + t);
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * TILE_N2;
-            // pass 0: q_hi . t_hi (waits for the hi slots), pass 1: q_lo . t_hi (frees them), pass 2: q_hi . t_lo
-            for (int pass = 0; pass < 3; pass++) {
+            // three-pass mode: pass 0 q_hi . t_hi (waits for the hi slots), pass 1 q_lo . t_hi (frees them), pass 2 q_hi . t_lo;
+            // fp16 mode: the one pass waits for and frees its slots
+            const int np = p.nparts, npass = np == 2 ? 3 : 1;
+            const uint32_t idesc = p.idesc;
+            for (int pass = 0; pass < npass; pass++) {
                 for (int c = 0; c < dpc; c++) {
                     const uint32_t i = g + (uint32_t)(pass == 2 ? dpc + c : c), s = i % STAGES2, ph = (i / STAGES2) & 1u;
                     if (pass != 1) { mbar_wait(&full[s], ph); tc_fence_after(); }
@@ -562,19 +769,19 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     const uint64_t bdesc = umma_desc_sw128(smem_u32(sb + (size_t)s * B_CHUNK_BYTES2));
 #pragma unroll
                     for (int k = 0; k < CHUNK_K / UMMA_K; k++)
-                        tc_mma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC_BF16_M256_N2,
+                        tc_mma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
                                          (uint32_t)((pass | c | k) != 0));
-                    if (pass != 0) tc_commit_pair(&empty[s]);
+                    if (pass != 0 || np == 1) tc_commit_pair(&empty[s]);
                 }
             }
             {   // norm chunk: one K = 16 step adds -(||q||^2 + ||t||^2) / 2
-                const uint32_t i = g + 2u * (uint32_t)dpc, s = i % STAGES2, ph = (i / STAGES2) & 1u;
+                const uint32_t i = g + (uint32_t)(np * dpc), s = i % STAGES2, ph = (i / STAGES2) & 1u;
                 mbar_wait(&full[s], ph); tc_fence_after();
-                tc_mma_bf16_pair(d_tmem, umma_desc_sw128(smem_u32(sa + (size_t)(2 * dpc) * CHUNK_BYTES)),
-                                 umma_desc_sw128(smem_u32(sb + (size_t)s * B_CHUNK_BYTES2)), IDESC_BF16_M256_N2, 1u);
+                tc_mma_bf16_pair(d_tmem, umma_desc_sw128(smem_u32(sa + (size_t)(np * dpc) * CHUNK_BYTES)),
+                                 umma_desc_sw128(smem_u32(sb + (size_t)s * B_CHUNK_BYTES2)), idesc, 1u);
                 tc_commit_pair(&empty[s]);
             }
-            g += 2u * (uint32_t)dpc + 1u;
+            g += (uint32_t)(np * dpc) + 1u;
             tc_commit_pair(&tfull[acc]);
             if (it + 1 < it1 && (it + 1) / CT != rp) tc_commit_pair(a_empty);   // A' may be overwritten once these retire
         }
@@ -582,18 +789,23 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // ===== epilogue: one query row per thread, this CTA's 128 rows x 256 columns =====
         const int ew = warp & 3;
         const int eg = (warp - 4) >> 2;
-        uint32_t bk[TOPK]; int bj[TOPK];
+        RowTop rt;
+        const BandParams bp{p.band_rel, p.band_abs_sqrt, p.band_abs_const};
         constexpr int NCOLS = TILE_N2 / EPI_GROUPS;
         int cur_rp = -1, row = 0;
+        float out_scale = 2.f;                                  // accumulator -> distance: -2, and 1/s^2 in fp16 mode
+        if (p.absmax_bits) { float s_, is2, mp; l2_scale_from_bits(__ldcg(p.absmax_bits), s_, is2, mp); out_scale = 2.f * is2; }
         auto flush = [&]() {
             if (cur_rp < 0 || row >= p.n1) return;
             const int slot = p.flat ? cid - l2_segment_of_item(cur_rp * CT, items, clusters) : (int)blockIdx.y;
             const size_t o = ((size_t)slot * p.n1 + row) * CAND + (size_t)eg * TOPK;
 #pragma unroll
             for (int k = 0; k < TOPK; k++) {
-                p.cand_j[o + k] = bk[k] != 0xFFFFFFFFu ? bj[k] : -1;
-                p.cand_d[o + k] = bk[k] != 0xFFFFFFFFu ? 2.f * __uint_as_float(bk[k]) : 3.4e38f;
+                p.cand_j[o + k] = rt.bk[k] != 0xFFFFFFFFu ? rt.bj[k] : -1;
+                p.cand_d[o + k] = rt.bk[k] != 0xFFFFFFFFu ? out_scale * __uint_as_float(rt.bk[k]) : 3.4e38f;
             }
+            p.cand_drop[((size_t)slot * p.n1 + row) * EPI_GROUPS + eg] =
+                rt.bk[TOPK - 1] != 0xFFFFFFFFu ? out_scale * __uint_as_float(rt.bk[TOPK - 1]) : 3.4e38f;
         };
         for (int it = it0; it < it1; it++) {
             const int t = it - it0, rp = it / CT, ct = it - rp * CT;
@@ -601,8 +813,7 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 flush();
                 cur_rp = rp;
                 row = (2 * rp + (int)rank) * TILE_M + ew * 32 + lane;
-#pragma unroll
-                for (int k = 0; k < TOPK; k++) { bk[k] = row < p.n1 ? 0xFFFFFFFFu : 0u; bj[k] = -1; }
+                rowtop_reset(rt, row < p.n1, row < p.n1 ? __ldcg(p.qnorm + row) : 0.f);
             }
             const int acc = t % NACC2;
             mbar_wait(&tfull[acc], (t / NACC2) & 1);
@@ -610,8 +821,9 @@ l2_topk_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             if (warp == 4 && lane == 0 && t < 36) l2_stamp(p, 40 + t);
             const int jbase = ct * TILE_N2 + eg * NCOLS;
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TILE_N2 + eg * NCOLS);
-            epilogue_reduce<NCOLS, DBG>(taddr, jbase, p.n2, p.key_mask, bk, bj,
-                                        DBG && p.dbg_dist && row < p.n1 ? p.dbg_dist + (size_t)row * p.n2 : nullptr);
+            if (!(p.dbg_flags & 1))
+            epilogue_reduce<NCOLS, DBG>(taddr, jbase, p.n2, p.key_mask, rt, bp,
+                                        DBG && p.dbg_dist && row < p.n1 ? p.dbg_dist + (size_t)row * p.n2 : nullptr, out_scale);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(&tempty[acc], 0);      // the leader's barrier counts both CTAs' warps
@@ -651,8 +863,9 @@ inline size_t l2_smem_bytes() {
 // Summation order per distance: each lane's strided partial sum, then a butterfly.
 __global__ void __launch_bounds__(256, 7) l2_refine_kernel(const float *__restrict__ q, int n1, const float *__restrict__ t, int n2,
                                                         int dim, const int32_t *__restrict__ cand_j,
-                                                        const float *__restrict__ cand_d, int splits,
-                                                        int32_t *best_j, float *best_d, int32_t *second_j, float *second_d) {
+                                                        const float *__restrict__ cand_d, const float *__restrict__ cand_drop, int splits,
+                                                        int32_t *best_j, float *best_d, int32_t *second_j, float *second_d,
+                                                        float slack_rel, unsigned *hdr, int32_t *ovf_rows) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n1) return;
     const int i = warp;
@@ -665,6 +878,16 @@ __global__ void __launch_bounds__(256, 7) l2_refine_kernel(const float *__restri
     for (int o = 16; o; o >>= 1) qn += __shfl_xor_sync(0xffffffffu, qn, o);
     pdl_wait();                                      // candidates are written by the GEMM kernel
     const int ncand = splits * CAND;
+    // fp16 mode (hdr != null): absolute terms of the band -- fp16 subnormals (components below 2^-24 of the scaled
+    // maximum round to 2^-25 absolute) and the norm chunk's last term
+    float slack_abs = 0.f, slack_const = 0.f;
+    if (hdr) {
+        float s_, is2, mp;
+        l2_scale_from_bits(__ldcg(hdr), s_, is2, mp);
+        slack_abs = 4.656612873e-10f * mp * sqrtf((float)dim);     // 2^-31 M' sqrt(D), times sqrt(3|q|^2 + 2d) below
+        slack_const = 4.8828125e-4f * is2;                          // 2^-11 / s^2
+    }
+    bool overflow = false;
     // second-smallest approximate distance over all candidates (two warp minima per 32 candidates)
     float m1 = 3.4e38f, m2 = 3.4e38f;
     for (int c0 = 0; c0 < ncand; c0 += 32) {
@@ -688,8 +911,10 @@ __global__ void __launch_bounds__(256, 7) l2_refine_kernel(const float *__restri
         const size_t o = ((size_t)sp * n1 + i) * CAND + k;
         const int jc = c < ncand ? __ldg(cand_j + o) : -1;
         const float dc = (jc >= 0 && jc < n2) ? __ldg(cand_d + o) : 3.4e38f;
-        const bool keep = jc >= 0 && jc < n2 && dc <= m2 + 0.000244140625f * (3.f * qn + 2.f * dc);
+        const float span = 3.f * qn + 2.f * dc;
+        const bool keep = jc >= 0 && jc < n2 && dc <= m2 + slack_rel * span + slack_abs * sqrtf(span) + slack_const;
         unsigned todo = __ballot_sync(0xffffffffu, keep);
+
         while (todo) {                                               // ascending candidate order, four per batch
             int j[4]; float acc[4];
 #pragma unroll
@@ -732,6 +957,145 @@ __global__ void __launch_bounds__(256, 7) l2_refine_kernel(const float *__restri
         best_j[i] = bj; best_d[i] = bj < 0 ? -1.f : b;
         second_j[i] = sj; second_d[i] = sj < 0 ? -1.f : s;
     }
+    // Certificate.  A train row x that the GEMM kernel's lists do not hold either lay outside the band of the second
+    // best approximation when it was seen (and the band only shrinks), or was turned away / evicted by a full list --
+    // then approx(x) >= that list's last entry (cand_drop).  If x belonged to the exact top two, exact(x) <= s (the
+    // exact second best of the kept candidates) and |t_x|^2 <= 2|q|^2 + 2 exact(x), so approx(x) <= s + err (3|q|^2 + 2 s).
+    // A full list whose last entry lies above that hid nothing; otherwise the row is recomputed exhaustively.
+    if (ovf_rows && sj >= 0) {
+        const float span = 3.f * qn + 2.f * s;
+        const float lim = s + 0.5f * slack_rel * span + slack_abs * sqrtf(span) + slack_const;
+        const int nlists = splits * EPI_GROUPS;
+        for (int c = lane; c < nlists; c += 32) {
+            const int sp = c / EPI_GROUPS, g = c - sp * EPI_GROUPS;
+            overflow |= __ldg(cand_drop + ((size_t)sp * n1 + i) * EPI_GROUPS + g) <= lim;
+        }
+        if (__any_sync(0xffffffffu, overflow) && lane == 0) ovf_rows[atomicAdd(hdr + 1, 1u)] = i;
+    }
+}
+
+// ---- exhaustive fallback for the rows the refinement could not certify ----------------------------
+// Every CTA owns slices of the train set and evaluates ALL flagged queries against them, EX_R queries at a time
+// (queries in shared memory, a train row is loaded once per EX_R queries): exact fp32 distances with the
+// refinement's summation order (so a distance has the same bits whichever kernel computed it), top-2 by
+// (distance, index) per warp, merged per CTA into part[row][slice]; the CTA that finishes last (one ticket,
+// returned to zero) merges the slices of every flagged row.  A handful of flagged rows -- the usual case when there
+// are any -- costs one pass over the train set (16 MB at 32k x 128: ~5 us); with nothing flagged every CTA reads
+// the count and leaves.  slices = min(grid, n2 / 64, EX_MAX_SLICES_PER_ROW * n1 / rows), the last term being the
+// capacity of `part`.
+constexpr int EX_MAX_SLICES_PER_ROW = 16;   // capacity of `part`: n1 * this many float4
+constexpr int EX_THREADS = 256;
+constexpr int EX_R = 8;                     // flagged queries evaluated per pass over a slice
+struct Top2 { float b, s; int bj, sj; };
+__device__ __forceinline__ void top2_insert(Top2 &x, float d, int j) {
+    if (j < 0) return;
+    const bool lt_b = x.bj < 0 || d < x.b || (d == x.b && j < x.bj);
+    const bool lt_s = x.sj < 0 || d < x.s || (d == x.s && j < x.sj);
+    if (lt_b) { x.s = x.b; x.sj = x.bj; x.b = d; x.bj = j; }
+    else if (lt_s) { x.s = d; x.sj = j; }
+}
+__device__ __forceinline__ Top2 top2_warp_merge(Top2 x) {
+#pragma unroll
+    for (int sh = 16; sh; sh >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, x.b, sh), os = __shfl_xor_sync(0xffffffffu, x.s, sh);
+        const int obj = __shfl_xor_sync(0xffffffffu, x.bj, sh), osj = __shfl_xor_sync(0xffffffffu, x.sj, sh);
+        top2_insert(x, ob, obj);
+        top2_insert(x, os, osj);
+    }
+    return x;
+}
+__global__ void __launch_bounds__(EX_THREADS) l2_exact_rows_kernel(const float *__restrict__ q, int n1, const float *__restrict__ t,
+                                                                   int n2, int dim, unsigned *__restrict__ hdr,
+                                                                   const int32_t *__restrict__ ovf_rows,
+                                                                   float4 *__restrict__ part, int32_t *best_j, float *best_d,
+                                                                   int32_t *second_j, float *second_d) {
+    pdl_wait();
+    const int count = (int)__ldcg(hdr + 1);
+    if (blockIdx.x == 0 && threadIdx.x == 0) hdr[0] = 0;       // every reader of the scale has finished: reset for the next call
+    if (count == 0) return;
+    long long want = min((long long)gridDim.x, (long long)EX_MAX_SLICES_PER_ROW * n1 / count);
+    want = max(1ll, min(want, (long long)(n2 + 63) / 64));
+    const int slice = (int)(((n2 + want - 1) / want + 31) / 32 * 32);
+    const int n_slices = (n2 + slice - 1) / slice;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ float s_q[EX_R][128];
+    __shared__ Top2 s_top[EX_THREADS / 32][EX_R];
+    __shared__ unsigned s_ticket;
+    for (int sl = blockIdx.x; sl < n_slices; sl += gridDim.x) {
+        const int j0 = sl * slice, j1 = min(n2, j0 + slice);
+        for (int r0 = 0; r0 < count; r0 += EX_R) {
+            const int nr = min(EX_R, count - r0);
+            for (int e = threadIdx.x; e < EX_R * 128; e += EX_THREADS) {
+                const int r = e >> 7, k = e & 127;
+                s_q[r][k] = (r < nr && k < dim) ? __ldg(q + (size_t)__ldcg(ovf_rows + r0 + r) * dim + k) : 0.f;
+            }
+            __syncthreads();
+            Top2 x[EX_R];
+#pragma unroll
+            for (int r = 0; r < EX_R; r++) x[r] = Top2{0.f, 0.f, -1, -1};
+            for (int jb = j0 + 4 * warp; jb < j1; jb += 4 * (EX_THREADS / 32)) {      // four train rows per warp step
+                float tv[4][4];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+#pragma unroll
+                    for (int k2 = 0; k2 < 4; k2++)
+                        tv[u][k2] = (jb + u < j1 && lane + 32 * k2 < dim) ? __ldg(t + (size_t)(jb + u) * dim + lane + 32 * k2) : 0.f;
+#pragma unroll
+                for (int r = 0; r < EX_R; r++) {
+                    if (r >= nr) break;                                                   // uniform
+                    float acc[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        acc[u] = 0.f;
+#pragma unroll
+                        for (int k2 = 0; k2 < 4; k2++) {
+                            const float df = s_q[r][lane + 32 * k2] - tv[u][k2];
+                            if (lane + 32 * k2 < dim) acc[u] = fmaf(df, df, acc[u]);
+                        }
+                    }
+#pragma unroll
+                    for (int sh = 16; sh; sh >>= 1)
+#pragma unroll
+                        for (int u = 0; u < 4; u++) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], sh);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) top2_insert(x[r], acc[u], jb + u < j1 ? jb + u : -1);
+                }
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int r = 0; r < EX_R; r++) s_top[warp][r] = x[r];
+            }
+            __syncthreads();
+            if ((int)threadIdx.x < nr) {
+                const int r = threadIdx.x;
+                Top2 m = s_top[0][r];
+                for (int w = 1; w < EX_THREADS / 32; w++) { top2_insert(m, s_top[w][r].b, s_top[w][r].bj); top2_insert(m, s_top[w][r].s, s_top[w][r].sj); }
+                part[(size_t)(r0 + r) * n_slices + sl] = make_float4(m.b, __int_as_float(m.bj), m.s, __int_as_float(m.sj));
+            }
+            __syncthreads();
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(hdr + 2, 1u);
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    __threadfence();                                                               // last CTA: merge the slices of every flagged row
+    for (int r = warp; r < count; r += EX_THREADS / 32) {
+        Top2 m{0.f, 0.f, -1, -1};
+        for (int k = lane; k < n_slices; k += 32) {
+            const float4 v = __ldcg(part + (size_t)r * n_slices + k);
+            top2_insert(m, v.x, __float_as_int(v.y));
+            top2_insert(m, v.z, __float_as_int(v.w));
+        }
+        m = top2_warp_merge(m);
+        if (lane == 0) {
+            const int i = __ldcg(ovf_rows + r);
+            best_j[i] = m.bj; best_d[i] = m.bj < 0 ? -1.f : m.b;
+            second_j[i] = m.sj; second_d[i] = m.sj < 0 ? -1.f : m.s;
+        }
+    }
+    if (threadIdx.x == 0) hdr[2] = 0;                                              // ticket ready for the next call
 }
 
 }  // namespace pgm_l2

@@ -53,6 +53,7 @@ struct pgm_handle {
     cudaEvent_t ev_done[2] = {nullptr, nullptr};   // chunk's kernels finished (main stream)
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}; // chunk's triples sit in pinned memory (copy stream)
     DevBuf misc;      // knn2 partials etc.
+    DevBuf l2_state;  // float path, fp16 ranking: [max |x| bits, flagged rows, fallback ticket]; zeroed on allocation, self-cleaning
     HostBuf pin_in;   // pinned staging, host -> device
     HostBuf pin_out;  // pinned staging, device -> host
     HostBuf pin_meta; // pinned PairDesc array + PlanInfo readback
@@ -64,6 +65,7 @@ struct pgm_handle {
     bool l2_attr_set = false;         // cudaFuncSetAttribute is per device, hence per handle
     int l2_max_clusters = 1;          // co-resident CTA pairs of the float pair kernel (persistent grid)
     bool l2_force_single = false;     // PGM_L2_SINGLE=1: never use the CTA-pair (cta_group::2) float kernel
+    unsigned *l2_hdr = nullptr;       // fp16 ranking mode of the last float call: [max |x| bits, rows recomputed exhaustively]
     bool force_multilaunch = false;   // PGM_FORCE_MULTILAUNCH=1: never use the persistent tail kernel
     bool stats_pending = false;   // rounds / evals of the last latency-mode call still sit in pin_meta
     const void *pending_plan = nullptr;
@@ -213,7 +215,7 @@ extern "C" int pgm_destroy(pgm_handle *h) {
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     for (cudaEvent_t e : {h->ev_done[0], h->ev_done[1], h->ev_copied[0], h->ev_copied[1]})
         if (e) cudaEventDestroy(e);
-    for (DevBuf *b : {&h->state, &h->desc, &h->out, &h->out2, &h->misc})
+    for (DevBuf *b : {&h->state, &h->desc, &h->out, &h->out2, &h->misc, &h->l2_state})
         if (b->p) cudaFree(b->p);
     for (HostBuf *b : {&h->pin_in, &h->pin_out, &h->pin_out2, &h->pin_meta, &h->pin_prof})
         if (b->p) cudaFreeHost(b->p);
@@ -1279,10 +1281,15 @@ static int l2_dev_impl(pgm_handle *h, const float *d_q, int32_t n1, const float 
                        int32_t *d_bj, float *d_bd, int32_t *d_sj, float *d_sd, float *d_dbg) {
     using namespace pgm_l2;
     cudaStream_t s = h->stream;
-    const int dp = (dim + CHUNK_K - 1) / CHUNK_K * CHUNK_K, kprime = 2 * dp + CHUNK_K, dpc = dp / CHUNK_K;   // rows = [hi | lo | norm]
+    const int dp = (dim + CHUNK_K - 1) / CHUNK_K * CHUNK_K, dpc = dp / CHUNK_K;
     const int row_tiles = (n1 + TILE_M - 1) / TILE_M;
     // CTA pairs (cta_group::2, M = 256 x N = 256) whenever there are at least two row tiles
     const bool pair = row_tiles >= 2 && !h->l2_force_single;
+    // ranking precision: one fp16 term + certified band + exhaustive fallback (pair kernel, default), or the
+    // three-term bf16 split (PGM_L2_MODE=bf16x3, and always for the single-CTA kernel)
+    const char *mode_env = getenv("PGM_L2_MODE");
+    const bool fp16 = pair && !(mode_env && !strcmp(mode_env, "bf16x3"));
+    const int kprime = fp16 ? dp + CHUNK_K : 2 * dp + CHUNK_K;   // rows = [x16 | norm] or [hi | lo | norm]
     if (!h->l2_attr_set) {
         CU_CHECK(h, cudaFuncSetAttribute(l2_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l2_smem_bytes()));
         CU_CHECK(h, cudaFuncSetAttribute(l2_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l2_smem_bytes()));
@@ -1344,13 +1351,38 @@ static int l2_dev_impl(pgm_handle *h, const float *d_q, int32_t n1, const float 
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
     const size_t o_a = take((size_t)n1 * kprime * 2), o_b = take((size_t)n2 * kprime * 2);
     const size_t o_cj = take((size_t)splits * n1 * CAND * 4), o_cd = take((size_t)splits * n1 * CAND * 4);
+    // fp16 mode: [max |x| bits, flagged-row count | ticket per flagged row] (one memset), flagged rows, slice partials
+    const size_t o_ovf = take(fp16 ? (size_t)n1 * 4 : 0);
+    const size_t o_part = take(fp16 ? (size_t)n1 * EX_MAX_SLICES_PER_ROW * 16 : 0);
+    const size_t o_qn = take((size_t)n1 * 4), o_drop = take((size_t)splits * n1 * EPI_GROUPS * 4);
     int rc = ensure_dev(h, h->misc, off);
     if (rc) return rc;
+    if (fp16 && h->l2_state.cap < 16) {
+        if ((rc = ensure_dev(h, h->l2_state, 16))) return rc;
+        CU_CHECK(h, cudaMemsetAsync(h->l2_state.p, 0, h->l2_state.cap, s));
+    }
     char *base = (char *)h->misc.p;
     __nv_bfloat16 *a = (__nv_bfloat16 *)(base + o_a), *b = (__nv_bfloat16 *)(base + o_b);
     L2Params p{};
     p.n1 = n1; p.n2 = n2; p.dpc = dpc; p.tiles_per_split = tps; p.col_tiles = col_tiles; p.items = items; p.flat = flat;
     p.key_mask = 0x7FFFFFE0u;
+    unsigned *hdr = fp16 ? (unsigned *)h->l2_state.p : nullptr;
+    int32_t *ovf_rows = fp16 ? (int32_t *)(base + o_ovf) : nullptr;
+    float *qnorm = (float *)(base + o_qn);
+    p.qnorm = qnorm; p.cand_drop = (float *)(base + o_drop);
+    // band of the ranking (d-domain, two approximations compared): 2^-12 (3|q|^2 + 2d) covers the three-term bf16 split
+    // 2.8 times over; one fp16 term needs 2 x 2^-10, taken with 25 % to spare.  The accumulator holds -d s^2 / 2, hence
+    // half of it there; the absolute terms (fp16 subnormals under the global scale, the norm chunk's last term) are
+    // expressed in scaled units, where max |x| < 2^10.
+    const float slack_rel = fp16 ? 0.00244140625f : 0.000244140625f;
+    p.band_rel = 0.5f * slack_rel;
+    p.band_abs_sqrt = fp16 ? 4.8828125e-7f * sqrtf((float)dp) : 0.f;     // 2^-21 sqrt(D) sqrt(3|q|^2 + 4|a|)
+    p.band_abs_const = fp16 ? 2.44140625e-4f : 0.f;                        // 2^-12
+    { const char *df = getenv("PGM_L2_DBG"); p.dbg_flags = df ? atoi(df) : 0; }
+    p.nparts = fp16 ? 1 : 2;
+    p.idesc = fp16 ? (IDESC_BF16_M256_N2 & ~((1u << 7) | (1u << 10))) : IDESC_BF16_M256_N2;   // A/B format field 0 = F16, 1 = BF16
+    p.absmax_bits = hdr;
+    h->l2_hdr = hdr;
     p.cand_j = (int32_t *)(base + o_cj); p.cand_d = (float *)(base + o_cd); p.dbg_dist = d_dbg;
     const bool tl = getenv("PGM_L2_TIMELINE") != nullptr;
     if (tl) {
@@ -1358,16 +1390,27 @@ static int l2_dev_impl(pgm_handle *h, const float *d_q, int32_t n1, const float 
         CU_CHECK(h, cudaMemsetAsync(h->timeline.p, 0, 1000 * 8, s));
         p.timeline = (unsigned long long *)h->timeline.p;
     }
-    split_kernel<<<(int)(((size_t)(n1 + n2) * 32 + 255) / 256), 256, 0, s>>>(d_q, n1, d_t, n2, dim, dp, a, b, p.cand_j, splits);
-    CUtensorMap map_a, map_b;
-    if ((rc = make_operand_map(h, &map_a, a, n1, kprime))) return rc;
-    if ((rc = make_operand_map(h, &map_b, b, n2, kprime, pair ? B_ROWS2 : TILE_N))) return rc;
     // the GEMM kernel and the refinement are programmatic dependents of their predecessors (griddepcontrol)
     cudaLaunchAttribute pdl{};
     pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
     pdl.val.programmaticStreamSerializationAllowed = 1;
     cudaLaunchConfig_t cfg{};
-    cfg.blockDim = dim3(THREADS); cfg.stream = s; cfg.attrs = &pdl; cfg.numAttrs = 1;
+    cfg.stream = s; cfg.attrs = &pdl; cfg.numAttrs = 1;
+    const int split_blocks = (int)(((size_t)(n1 + n2) * 32 + 255) / 256);
+    if (fp16) {
+        const size_t nq = (size_t)n1 * dim, nt = (size_t)n2 * dim;
+        const int ab = (int)std::min<size_t>((size_t)h->num_sms * 8, (nq + nt + 4095) / 4096 + 1);
+        absmax_kernel<<<ab, 256, 0, s>>>(d_q, nq, d_t, nt, hdr);
+        cfg.gridDim = dim3((unsigned)split_blocks); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0;
+        CU_CHECK(h, cudaLaunchKernelEx(&cfg, split16_kernel, d_q, (int)n1, d_t, (int)n2, (int)dim, dp, (__half *)a, (__half *)b,
+                                       p.cand_j, splits, (const unsigned *)hdr, qnorm, p.cand_drop));
+    } else {
+        split_kernel<<<split_blocks, 256, 0, s>>>(d_q, n1, d_t, n2, dim, dp, a, b, p.cand_j, splits, qnorm, p.cand_drop);
+    }
+    CUtensorMap map_a, map_b;
+    if ((rc = make_operand_map(h, &map_a, a, n1, kprime))) return rc;
+    if ((rc = make_operand_map(h, &map_b, b, n2, kprime, pair ? B_ROWS2 : TILE_N))) return rc;
+    cfg.blockDim = dim3(THREADS);
     if (pair) {
         cfg.gridDim = flat ? dim3(2 * (unsigned)clusters) : dim3(2 * (unsigned)row_pairs, (unsigned)splits);
         cfg.dynamicSmemBytes = l2_pair_smem_bytes();
@@ -1380,7 +1423,15 @@ static int l2_dev_impl(pgm_handle *h, const float *d_q, int32_t n1, const float 
     }
     cfg.gridDim = dim3((unsigned)(((size_t)n1 * 32 + 255) / 256)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0;
     CU_CHECK(h, cudaLaunchKernelEx(&cfg, l2_refine_kernel, d_q, n1, d_t, n2, dim, (const int32_t *)p.cand_j,
-                                   (const float *)p.cand_d, splits, d_bj, d_bd, d_sj, d_sd));
+                                   (const float *)p.cand_d, (const float *)p.cand_drop, splits, d_bj, d_bd, d_sj, d_sd,
+                                   slack_rel, hdr, ovf_rows));
+    if (fp16 && getenv("PGM_L2_NO_FALLBACK")) {        // (debug switch: time the call without the exhaustive fallback)
+        CU_CHECK(h, cudaMemsetAsync(hdr, 0, 4, s));
+    } else if (fp16) {
+        cfg.gridDim = dim3((unsigned)h->num_sms * 4); cfg.blockDim = dim3(EX_THREADS);
+        CU_CHECK(h, cudaLaunchKernelEx(&cfg, l2_exact_rows_kernel, d_q, (int)n1, d_t, (int)n2, (int)dim, hdr,
+                                       (const int32_t *)ovf_rows, (float4 *)(base + o_part), d_bj, d_bd, d_sj, d_sd));
+    }
     if (tl) {                                        // debug: phase timeline of cluster 0's leader CTA, us since kernel start
         std::vector<unsigned long long> v(256);
         CU_CHECK(h, cudaMemcpyAsync(v.data(), h->timeline.p, 256 * 8, cudaMemcpyDeviceToHost, s));
@@ -1399,7 +1450,7 @@ static int l2_dev_impl(pgm_handle *h, const float *d_q, int32_t n1, const float 
         for (int t = 1; t < 36 && v[40 + t]; t++) fprintf(stderr, " %llu", v[128 + 40 + t] - v[128 + 40 + t - 1]);
         fprintf(stderr, "\n");
     }
-    h->stats.kernel_launches += 3;
+    h->stats.kernel_launches += fp16 ? 5 : 3;
     h->stats.distance_evals += (int64_t)n1 * n2;
     h->stats.evals_computed += (int64_t)n1 * n2;
     CU_CHECK(h, cudaGetLastError());
@@ -1438,6 +1489,17 @@ extern "C" int pgm_knn2_l2_dev(pgm_handle *h, const float *d_q, int32_t n1, cons
         return PGM_OK;
     }
     return l2_dev_impl(h, d_q, n1, d_t, n2, dim, d_best_j, d_best_d, d_second_j, d_second_d, d_debug_dist);
+}
+
+extern "C" int pgm_l2_last_fallback_rows(pgm_handle *h) {
+    if (!h) return -1;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->l2_hdr) return -1;
+    unsigned v[2] = {0, 0};
+    if (cudaSetDevice(h->device) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(v, h->l2_hdr, 8, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
+    return (int)v[1];
 }
 
 extern "C" int pgm_knn2_l2(pgm_handle *h, const float *q, int32_t n1, const float *t, int32_t n2, int32_t dim,

@@ -323,6 +323,11 @@ class Matcher:
                                           sj.ctypes.data, sd.ctypes.data))
         return bj[:n1], bd[:n1], sj[:n1], sd[:n1]
 
+    def l2_last_fallback_rows(self) -> int:
+        """Queries of the last float call that were recomputed exhaustively (their candidate band could not be
+        certified from the kernel's top-4 lists); -1 if that call used the three-term bf16 ranking."""
+        return int(self._lib.pgm_l2_last_fallback_rows(self._h))
+
     # -- the producer of the matcher's inputs: FAST-12, BRIEF, NMS ----------
     def fast_detect(self, gray: np.ndarray, threshold: float, python_generation: bool = False):
         """``KeypointDetection.Detect`` without the descriptors (KeypointDetection.cs:42-133).

@@ -101,3 +101,73 @@ def test_l2_underfilled_grid_shape(matcher):
     q = rng.random((10240, 64), dtype=np.float32)
     t = rng.random((2048, 64), dtype=np.float32)
     _check(matcher, q, t)
+
+
+# ---- ranking modes (round 2): one fp16 term + certified band + exhaustive fallback (default for n1 > 128) vs the
+# ---- three-term bf16 split ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n1,n2,dim", [(300, 500, 128), (2600, 1300, 128), (1000, 2100, 64)])
+def test_l2_bf16x3_mode_still_agrees(matcher, monkeypatch, n1, n2, dim):
+    monkeypatch.setenv("PGM_L2_MODE", "bf16x3")
+    rng = np.random.default_rng(n1 + 3 * n2 + dim)
+    q = rng.standard_normal((n1, dim)).astype(np.float32)
+    t = rng.standard_normal((n2, dim)).astype(np.float32)
+    _check(matcher, q, t)
+    assert matcher.l2_last_fallback_rows() == -1
+
+
+def test_l2_fp16_mode_is_the_default_and_certifies_random_data(matcher):
+    rng = np.random.default_rng(31)
+    q = rng.random((4096, 128), dtype=np.float32)
+    t = rng.random((6000, 128), dtype=np.float32)
+    _check(matcher, q, t)
+    assert 0 <= matcher.l2_last_fallback_rows() <= 4            # well-spread data: (almost) nothing needs the fallback
+
+
+def test_l2_fallback_crowded_band(matcher):
+    # twelve train rows within 2e-3 of query 7, adjacent (one column group): more than the group's candidate list
+    # holds, so the list cannot prove it has the whole band and row 7 is recomputed exhaustively; the answers must
+    # still be the oracle's
+    rng = np.random.default_rng(32)
+    q = rng.standard_normal((600, 128)).astype(np.float32)
+    t = rng.standard_normal((3000, 128)).astype(np.float32)
+    e = np.zeros(128, dtype=np.float32); e[3] = 1
+    for k in range(12):
+        t[100 + k] = q[7] + np.float32(0.01 * (12 - k)) * e         # closest copy has the LARGEST index of the twelve
+    bj, bd, sj, sd = _check(matcher, q, t)
+    assert bj[7] == 111 and sj[7] == 110
+    assert matcher.l2_last_fallback_rows() >= 1
+
+
+def test_l2_fallback_all_identical_train_rows(matcher):
+    # every train row is the same vector: every query's band holds the whole train set -> every row takes the
+    # fallback; exact ties resolve to the smallest indices
+    rng = np.random.default_rng(33)
+    q = rng.standard_normal((300, 96)).astype(np.float32)
+    t = np.tile(rng.standard_normal((1, 96)).astype(np.float32), (5000, 1))
+    bj, bd, sj, sd = _check(matcher, q, t)
+    assert (bj == 0).all() and (sj == 1).all()
+    assert matcher.l2_last_fallback_rows() == 300
+
+
+@pytest.mark.parametrize("scale", [1e-18, 3e-6, 1.0, 4e4, 1e15])
+def test_l2_fp16_global_scale(matcher, scale):
+    # the fp16 operands live under a global power-of-two scale: tiny and huge magnitudes rank like unit ones
+    rng = np.random.default_rng(34)
+    q = (rng.standard_normal((700, 128)) * scale).astype(np.float32)
+    t = (rng.standard_normal((900, 128)) * scale).astype(np.float32)
+    bj, bd, sj, sd = matcher.knn2_l2(q, t)
+    d = ((q[:, None, :].astype(np.float64) - t[None].astype(np.float64)) ** 2).sum(-1)
+    ej = d.argmin(1)
+    assert (bj == ej).mean() > 0.99
+    np.testing.assert_allclose(bd, d[np.arange(700), bj], rtol=RTOL)
+    np.testing.assert_allclose(bd, d.min(1), rtol=RTOL)
+
+
+def test_l2_wide_dynamic_range_within_rows(matcher):
+    # components spanning 2^-30 .. 1 inside every row: the small ones fall below fp16's range under the global scale
+    # and only the band's absolute term covers them
+    rng = np.random.default_rng(35)
+    mag = 2.0 ** rng.uniform(-30, 0, size=(1, 128))
+    q = (rng.standard_normal((500, 128)) * mag).astype(np.float32)
+    t = (rng.standard_normal((800, 128)) * mag).astype(np.float32)
+    _check(matcher, q, t)
