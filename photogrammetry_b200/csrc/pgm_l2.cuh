@@ -6,31 +6,29 @@
 //
 //     ||q - t||^2 = ||q||^2 + ||t||^2 - 2 q.t          (N1 x N2 x D GEMM)
 //
-// Precision: every fp32 component is split into bf16 hi + bf16 lo (x = hi + lo up to 2^-17
-// relative) and the dot product is evaluated as hi.hi + lo.hi + hi.lo -- three bf16 GEMM passes
-// of K = Dp accumulated into the same fp32 TMEM accumulator.  Operand rows are stored once as
-// [x_hi | x_lo | norm] (2*Dp + 64 bf16); the train-side hi chunks are staged once per tile and used
-// by two of the passes.  The norm chunk folds ||q||^2 and ||t||^2 into the SAME accumulator: the
-// query row carries -||q||^2/2 as three bf16 terms (24 bits, exact) against ones on the train side
-// and vice versa, so one extra K = 16 MMA per tile leaves  q.t - (||q||^2 + ||t||^2)/2 = -d/2  in
-// TMEM and the epilogue needs no arithmetic at all: a distance's rank is its bit pattern with the
-// sign masked off.  A tile costs 5 chunk loads for 6 chunk MMAs + 1 MMA instruction.
-// The GEMM ranks the candidates (top-4 per query and column split); a refinement kernel
-// recomputes those few distances exactly in fp32 (sum of squared differences) and picks
-// best/second, so reported distances are exact to fp32 rounding and only candidates whose
-// approximate distances differ by < ~1e-5 relative (near-ties) can be mis-selected.
+// The GEMM only RANKS.  Default (CTA-pair kernel): every component becomes ONE fp16 value under a global
+// power-of-two scale (absmax_kernel + split16_kernel), one GEMM pass of K = Dp.  PGM_L2_MODE=bf16x3 (and the
+// single-CTA kernel, n1 <= 128): bf16 hi + lo split, q.t ~ hi.hi + lo.hi + hi.lo as three passes into the same
+// fp32 TMEM accumulator.  Operand rows are stored once as [x16 | norm] (resp. [x_hi | x_lo | norm]).  The norm
+// chunk folds ||q||^2 and ||t||^2 into the SAME accumulator: the query row carries -||q||^2/2 as three 16-bit
+// terms against constants on the train side and vice versa, so one extra K = 16 MMA per tile leaves
+// q.t - (||q||^2 + ||t||^2)/2 = -d/2 in TMEM and the epilogue needs no arithmetic at all: a distance's rank is
+// its bit pattern.  The epilogue keeps, per query and column group, the columns within the ranking's error band
+// of the second best one (RowTop below); l2_refine_kernel recomputes those few distances exactly in fp32 (sum of
+// squared differences), picks best/second and certifies that the lists cannot have hidden a better column; rows
+// it cannot certify are recomputed exhaustively by l2_exact_rows_kernel.  Reported distances are exact to fp32
+// rounding; indices can differ from the oracle only where exact fp32 distances tie up to summation order.
 //
 // Kernel anatomy (sm_100a, hand-written PTX; layouts follow the canonical K-major
 // SWIZZLE_128B UMMA atoms):
 //   warp 0   TMA producer: A' tile (128 queries x K', resident) once, then B' tiles
 //            (128 train rows x 64) through a ring of mbarrier-guarded stages
-//   warp 1   one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=128, K=16) into
-//            one of two 128-column TMEM accumulators, tcgen05.commit frees stages / publishes
-//            the accumulator
-//   warp 2   TMEM alloc / dealloc (256 columns)
+//   warp 1   one thread issues tcgen05.mma.kind::f16 (K = 16) into one of two TMEM accumulators,
+//            tcgen05.commit frees stages / publishes the accumulator
+//   warp 2   TMEM alloc / dealloc
 //   warps 4-11 epilogue (two warpgroups, half the columns each): tcgen05.ld (32 lanes x 32
-//            columns per instruction), key = |acc| bits with the column in the 5 low bits (one
-//            LOP3), integer min tree, per-row top-4 in registers
+//            columns per instruction), float max tree + one compare per 32 columns, slow path only for
+//            chunks that can still matter
 #pragma once
 
 #include <cstdint>
@@ -114,13 +112,6 @@ __device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[3
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tc_ld_32x32b_x64(uint32_t taddr, uint32_t (&v)[64]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
         : "r"(taddr) : "memory");
 }
 // Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may
