@@ -53,6 +53,8 @@ struct pgm_handle {
     cudaEvent_t ev_done[2] = {nullptr, nullptr};   // chunk's kernels finished (main stream)
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}; // chunk's triples sit in pinned memory (copy stream)
     DevBuf misc;      // knn2 partials etc.
+    DevBuf shard_pool_state, shard_pool_est;   // a destroyed pgm_shard parks its device buffers here: the next one reuses them
+    void *shard_pool_hctl = nullptr;           // (cudaMalloc / cudaMallocHost / cudaFree cost ~1.5 ms per train-sharded call)
     DevBuf l2_state;  // float path, fp16 ranking: [max |x| bits, flagged rows, fallback ticket]; zeroed on allocation, self-cleaning
     HostBuf pin_in;   // pinned staging, host -> device
     HostBuf pin_out;  // pinned staging, device -> host
@@ -215,7 +217,8 @@ extern "C" int pgm_destroy(pgm_handle *h) {
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     for (cudaEvent_t e : {h->ev_done[0], h->ev_done[1], h->ev_copied[0], h->ev_copied[1]})
         if (e) cudaEventDestroy(e);
-    for (DevBuf *b : {&h->state, &h->desc, &h->out, &h->out2, &h->misc, &h->l2_state})
+    if (h->shard_pool_hctl) cudaFreeHost(h->shard_pool_hctl);
+    for (DevBuf *b : {&h->state, &h->desc, &h->out, &h->out2, &h->misc, &h->l2_state, &h->shard_pool_state, &h->shard_pool_est})
         if (b->p) cudaFree(b->p);
     for (HostBuf *b : {&h->pin_in, &h->pin_out, &h->pin_out2, &h->pin_meta, &h->pin_prof})
         if (b->p) cudaFreeHost(b->p);
@@ -2016,8 +2019,13 @@ extern "C" int pgm_shard_create(pgm_handle *h, const uint8_t *d_q, int32_t n1, c
     const size_t o_dev = take(sizeof(ShardDev));
     const size_t o_rbg = take(4 * rows), o_cbg = take(4 * (size_t)n2_total);
     const size_t o_cand = take(16 * (size_t)sh->raw_cap), o_ccnt = take(4), o_thr = take(4), o_pstat = take(sizeof(PairStat));
-    if ((rc = ensure_dev(h, sh->state, off))) { delete sh; return rc; }
-    if (cudaMallocHost((void **)&sh->h_ctl, sizeof(ShardCtl) * 8) != cudaSuccess) { cudaFree(sh->state.p); delete sh; return PGM_E_CUDA; }
+    std::swap(sh->state, h->shard_pool_state);      // buffers parked by the previous shard of this handle, if any
+    std::swap(sh->est, h->shard_pool_est);
+    if ((rc = ensure_dev(h, sh->state, off))) { if (sh->est.p) cudaFree(sh->est.p); delete sh; return rc; }
+    if (h->shard_pool_hctl) { sh->h_ctl = (ShardCtl *)h->shard_pool_hctl; h->shard_pool_hctl = nullptr; }
+    else if (cudaMallocHost((void **)&sh->h_ctl, sizeof(ShardCtl) * 8) != cudaSuccess) {
+        cudaFree(sh->state.p); if (sh->est.p) cudaFree(sh->est.p); delete sh; return PGM_E_CUDA;
+    }
     char *base = (char *)sh->state.p;
     if (h->ctas_per_sm[sh->words / 4] == 0) h->ctas_per_sm[sh->words / 4] = std::max(1, dispatch_occupancy(sh->words));
     sh->round_grid = h->num_sms * h->ctas_per_sm[sh->words / 4];
@@ -2223,10 +2231,17 @@ extern "C" int pgm_shard_destroy(pgm_shard *sh) {
     pgm_handle *h = sh->h;
     std::lock_guard<std::mutex> lk(h->mu);
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
-    if (sh->state.p) cudaFree(sh->state.p);
-    if (sh->est.p) cudaFree(sh->est.p);
-    if (sh->h_ctl) cudaFreeHost(sh->h_ctl);
+    // park the buffers in the handle for the next shard (stream order protects them: every later use is enqueued on
+    // the same stream); free only what the pool already holds
+    if (sh->state.p && !h->shard_pool_state.p) { h->shard_pool_state = sh->state; sh->state = DevBuf{}; }
+    if (sh->est.p && !h->shard_pool_est.p) { h->shard_pool_est = sh->est; sh->est = DevBuf{}; }
+    if (sh->h_ctl && !h->shard_pool_hctl) { h->shard_pool_hctl = sh->h_ctl; sh->h_ctl = nullptr; }
+    if (sh->state.p || sh->est.p || sh->h_ctl) {
+        cudaStreamSynchronize(h->stream);
+        if (sh->state.p) cudaFree(sh->state.p);
+        if (sh->est.p) cudaFree(sh->est.p);
+        if (sh->h_ctl) cudaFreeHost(sh->h_ctl);
+    }
     delete sh;
     return PGM_OK;
 }
