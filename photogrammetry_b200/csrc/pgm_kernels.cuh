@@ -178,6 +178,7 @@ struct Chunk {
     int32_t *order_cnt;           // latency mode: [n_pairs][ORDER_MAX_SLICES][ORDER_BIN_PITCH] per-slice distance histograms
     int32_t shard_n2_total;       // train-sharded pair: columns of the whole pair
     float cand_target;            // expected candidate edges per row of the smaller side (CAND_TARGET; PGM_CAND_TARGET overrides)
+    float cand_row_max;           // upper bound of the per-row target of a pass (later passes: few live rows share the list budget)
 };
 
 __device__ __forceinline__ int32_t *cnt_ptr(const Chunk &c, int buf3, int p) {
@@ -252,7 +253,7 @@ __device__ __forceinline__ void plan_pair_emit(const Chunk &c, int p, uint8_t st
         // about cand_target x max(n1, n2) raw edges in EVERY pass: later passes have fewer live rows, so each row may
         // list more candidates for the same list size (8192 x 8192: 6 per row in pass 0, ~36 per row of the 1236 left
         // in pass 1, after which ~30 rows remain -- tools/sim_threshold_rounds.py)
-        const float target = c.cand_target * ps.cscale * (float)max(pd.n1, pd.n2) / (float)max(nlr, nlc);
+        const float target = fminf(c.cand_target * ps.cscale * (float)max(pd.n1, pd.n2) / (float)max(nlr, nlc), c.cand_row_max);
         if (target >= 0.09f) {
             const float z = inv_norm_tail(fminf(target / (float)min(nlr, nlc), p_max));
             const float T = floorf(ps.mu - z * ps.sd - 0.5f);                  // P(d <= T) ~ Phi((T + 0.5 - mu) / sd)
