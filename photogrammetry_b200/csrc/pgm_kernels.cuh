@@ -87,11 +87,11 @@ static_assert(TAIL_THREADS == 512, "the sparse phase and the ordering slices ass
 // candidate edges / sparse sub-rounds
 constexpr int SCAND = 512;              // candidate records a tile stages in shared memory between two global appends
 constexpr int SP_THREADS = 512;         // threads of the CTA that runs a pair's sparse sub-rounds
-constexpr int SP_EPT = 32;              // live edges a thread of the sparse phase holds (two registers + one private smem word each)
-constexpr int SP_EPC = 4;               // ... and in the compact form, once at most SP_EPC x threads edges are left
+constexpr int SP_EPT = 32;              // live edges a thread of the sparse phase holds at most (its private column of shared memory)
 constexpr int SP_B = 4;                 // edges are processed in batches of SP_B: loads of a batch first, then its stores
+constexpr int SP_LB = 8;                // edges a thread loads from the global list at a time
 constexpr int SP_IPT = 8;               // ids a thread re-compacts at a time
-constexpr int SP_SMEM_BYTES = 184 * 1024;   // shared memory of a sparse phase: the edges' column-side keys (SP_EPT x threads words)
+constexpr int SP_SMEM_BYTES = 224 * 1024;   // shared memory of a sparse phase: the edges (8 or 12 bytes each)
                                             // and one min slot per live row and live column
 constexpr int SP_LCAP_MAX = SP_THREADS * SP_EPT;   // live edges per pair the global list is sized for
 constexpr int SP_MAX_SUB = 64;          // sub-rounds per sparse phase (each accepts >= 1 pair; the rest waits for the next pass)
@@ -179,6 +179,7 @@ struct Chunk {
     int32_t shard_n2_total;       // train-sharded pair: columns of the whole pair
     float cand_target;            // expected candidate edges per row of the smaller side (CAND_TARGET; PGM_CAND_TARGET overrides)
     float cand_row_max;           // upper bound of the per-row target of a pass (later passes: few live rows share the list budget)
+    int32_t sp_slots_max;         // edge slots per thread a sparse phase may use (SP_EPT; smaller values force its truncation path in tests)
 };
 
 __device__ __forceinline__ int32_t *cnt_ptr(const Chunk &c, int buf3, int p) {
@@ -1050,78 +1051,8 @@ __device__ __forceinline__ void filter_edges(const Chunk &c, int r, int p, int s
 // mutual ones, drop the edges that lost an endpoint; repeat until no edge is left.  Rows whose listed edges all died
 // simply stay live for the next distance pass.  Afterwards the pair's live lists (already compacted by the accept)
 // are re-compacted in place and its counts updated.
-// Edges live in REGISTERS (SP_EPT per thread, every loop fully unrolled so the loads / atomics of a phase are all in
-// flight together -- a single CTA is latency-bound, not throughput-bound); shared memory holds one min slot per live
-// row and column, addressed by the position the accept gave the row / column in the next live list.
+// Shared memory holds the edges and one min slot per row and column (layout: sparse_body).
 // ---------------------------------------------------------------------------
-// The sub-round loop over EPT edges per thread.  ek = (d << 20 | j) or KEY_NONE (dead / absent), ep = (row slot << 16 |
-// column slot); the column-side key (d << 20 | i) sits in registers (ec) or, in the wide form, in the thread's private
-// shared-memory column ecs[k * NT].  Returns the number of live edges left; stops early once it is <= stop_at.
-template <int NT, int EPT, bool EC_SMEM>
-__device__ __forceinline__ int sparse_sub_rounds(uint32_t (&ek)[EPT], uint32_t (&ec)[EC_SMEM ? 1 : EPT], const uint32_t *ecs,
-                                                 const uint32_t (&ep)[EPT], uint32_t *rbest, uint32_t *cbest,
-                                                 uint32_t *match_key, int *s_alive, int &sub, int stop_at,
-                                                 const Chunk &c, int p) {
-    constexpr int B = EPT < SP_B ? EPT : SP_B;
-    const int tid = threadIdx.x;
-    int total = 0;
-    for (; sub < SP_MAX_SUB; sub++) {
-        if (tid == 0) s_alive[(sub + 1) & 1] = 0;
-#pragma unroll
-        for (int k = 0; k < EPT; k++)
-            if (ek[k] != KEY_NONE) {
-                atomicMin(&rbest[ep[k] >> 16], ek[k]);
-                atomicMin(&cbest[ep[k] & 0xFFFFu], EC_SMEM ? ecs[k * NT] : ec[EC_SMEM ? 0 : k]);
-            }
-        __syncthreads();
-        // loads first, stores after, in batches of B edges: a shared-memory store between two loads makes ptxas order
-        // them (possible alias), and the phase would pay one memory round trip per edge instead of one per batch
-#pragma unroll
-        for (int k0 = 0; k0 < EPT; k0 += B) {
-            uint32_t rv[B], cv[B], kc[B];
-#pragma unroll
-            for (int u = 0; u < B; u++) {
-                rv[u] = rbest[ep[k0 + u] >> 16]; cv[u] = cbest[ep[k0 + u] & 0xFFFFu];
-                kc[u] = EC_SMEM ? ecs[(k0 + u) * NT] : ec[EC_SMEM ? 0 : k0 + u];
-            }
-#pragma unroll
-            for (int u = 0; u < B; u++) {
-                const int k = k0 + u;
-                // (a concurrent KEY_DEAD store by the accepting thread of another edge of this row / column can only
-                //  turn a mismatch into a mismatch: keys within a row, and within a column, are distinct)
-                if (ek[k] != KEY_NONE && rv[u] == ek[k] && cv[u] == kc[u]) {
-                    PGM_ASSERT(__ldcg(match_key + (kc[u] & KEY_IDX_MASK)) == KEY_NONE);      // a row is matched once
-                    match_key[kc[u] & KEY_IDX_MASK] = ek[k];
-                    rbest[ep[k] >> 16] = KEY_DEAD; cbest[ep[k] & 0xFFFFu] = KEY_DEAD;
-                }
-            }
-        }
-        __syncthreads();
-        int alive = 0;
-#pragma unroll
-        for (int k0 = 0; k0 < EPT; k0 += B) {
-            uint32_t rv[B], cv[B];
-#pragma unroll
-            for (int u = 0; u < B; u++) { rv[u] = rbest[ep[k0 + u] >> 16]; cv[u] = cbest[ep[k0 + u] & 0xFFFFu]; }
-#pragma unroll
-            for (int u = 0; u < B; u++) {
-                const int k = k0 + u;
-                if (ek[k] != KEY_NONE) {
-                    if (rv[u] == KEY_DEAD || cv[u] == KEY_DEAD) ek[k] = KEY_NONE;
-                    else { rbest[ep[k] >> 16] = KEY_NONE; cbest[ep[k] & 0xFFFFu] = KEY_NONE; alive++; }   // (never overwrites KEY_DEAD)
-                }
-            }
-        }
-        alive = __reduce_add_sync(0xffffffffu, alive);
-        if ((tid & 31) == 0 && alive) atomicAdd(&s_alive[sub & 1], alive);
-        tstamp(c, p, tid, 22);
-        __syncthreads();
-        total = s_alive[sub & 1];
-        if (total <= stop_at) { sub++; break; }
-    }
-    return total;
-}
-
 template <int NT>
 __device__ __forceinline__ void sparse_body(const Chunk &c, int r, int p, unsigned char *smem) {
     if (!c.cand || __ldcg(c.status + p) != PAIR_BIG) return;
@@ -1133,75 +1064,192 @@ __device__ __forceinline__ void sparse_body(const Chunk &c, int r, int p, unsign
     const int nlr = __ldcg(cnt), nlc = __ldcg(cnt + 1);
     const int n1 = __ldg(&pdr.n1), n2 = __ldg(&pdr.n2);
     if (nL <= 0 || nL > __ldg(&pdr.ledge_cap) || nL > NT * SP_EPT || nlr <= 0 || nlc <= 0) return;
-    // min slots addressed by the ORIGINAL row / column id when the pair is small enough (no position look-ups: they
-    // are 2 random 32-byte sectors per edge, and one SM's L2 bandwidth is what bounds the loading of the edges),
-    // else by the position the accept gave the survivor in the next live list
-    constexpr size_t FIXED = 4 * (size_t)SP_EPT * NT + 12 * (size_t)SP_EPC * NT;
-    const bool by_id = FIXED + 4 * (size_t)(n1 + n2) <= (size_t)SP_SMEM_BYTES && n1 <= 65535 && n2 <= 65535;
+    // Edges live in SHARED memory, `slots` per thread in the thread's private column E[k * NT] (conflict-free), kept
+    // compact: a thread's live edges are E[0 .. ne).  Every loop below is a real loop over the live edges -- the phase
+    // runs once per pass on one SM, its code is fetched cold, and the register-resident, fully unrolled form it replaces
+    // (138 KB of SASS) was bound by instruction fetch, not by the edges.
+    // Min slots are addressed by the ORIGINAL row / column id when the pair is small enough (no position look-ups: they
+    // are 2 random 32-byte sectors per edge, and one SM's L2 bandwidth is what bounds the loading of the edges), else by
+    // the position the accept gave the survivor in the next live list (one more word per edge).
+    // When the pass listed more edges than shared memory holds, the phase keeps the edges with distance <= T' for the
+    // largest T' that fits: a set that is complete up to T' is as valid as one complete up to T (it is what a smaller
+    // candidate bound would have produced), the rows it does not resolve wait for the next distance pass.
+    static_assert(NT == 512, "the distance histogram of the truncation gives one bin to every thread");
+    const int need = (nL + NT - 1) / NT;
+    const int slots_id = (int)min((long long)c.sp_slots_max, max(0ll, ((long long)SP_SMEM_BYTES - 4ll * (n1 + n2)) / (8 * NT)));
+    const int slots_pos = nlr <= 65535 && nlc <= 65535 ? (int)min((long long)c.sp_slots_max, max(0ll, ((long long)SP_SMEM_BYTES - 4ll * (nlr + nlc)) / (12 * NT))) : 0;
+    // (positions cost two random L2 sectors per edge when the list is loaded -- ~20 us for 13 000 edges on one SM -- so
+    //  ids are preferred even when they leave room for somewhat fewer edges)
+    const bool by_id = slots_id >= need || 2 * slots_id >= slots_pos;
+    const int slots = min(need, by_id ? slots_id : slots_pos);
+    if (slots <= 0) return;
+    const bool truncated = slots < need;
     const int nr = by_id ? n1 : nlr, nc = by_id ? n2 : nlc;
-    if (FIXED + 4 * (size_t)(nr + nc) > (size_t)SP_SMEM_BYTES || nr > 65535 || nc > 65535) return;
     const int64_t row_base = __ldg(&pdr.row_base), col_base = __ldg(&pdr.col_base);
-    uint32_t *ecs = reinterpret_cast<uint32_t *>(smem) + tid;     // this thread's column-side keys: ecs[k * NT], conflict-free
-    uint32_t *cbuf = reinterpret_cast<uint32_t *>(smem) + SP_EPT * NT;   // [3][SP_EPC * NT] staging of the compact form
-    uint32_t *rbest = cbuf + 3 * SP_EPC * NT;
+    uint2 *E = reinterpret_cast<uint2 *>(smem);                             // .x = (d << 20 | j), .y = i; thread t owns E[t + k * NT]
+    uint32_t *P = reinterpret_cast<uint32_t *>(smem + 8 * (size_t)slots * NT);   // !by_id: (row slot << 16 | column slot)
+    uint32_t *rbest = reinterpret_cast<uint32_t *>(smem + (by_id ? 8 : 12) * (size_t)slots * NT);
     uint32_t *cbest = rbest + nr;
-    __shared__ int s_cnt[2], s_alive[2], s_nc;
+    __shared__ int s_cnt[2], s_alive[3], s_fill, s_nsel, s_wsum[NT / 32];
+    const unsigned long long *edges = c.ledge + __ldg(&pdr.ledge_off);
 
     tstamp(c, p, tid, 20);
+    uint32_t dmax = 0xFFFFFFFFu;                                            // edges with distance <= dmax take part
+    int n_sel = nL;
+    if (truncated) {                                                        // (block-uniform)
+        int *hist = reinterpret_cast<int *>(smem);                          // (the edge arrays are written after this block)
+        for (int k = tid; k < NT + 1; k += NT) hist[k] = 0;
+        if (tid == 0) s_fill = 0;
+        __syncthreads();
+        for (int e0 = 0; e0 < nL; e0 += NT * SP_LB) {
+            unsigned long long key[SP_LB];
+#pragma unroll
+            for (int u = 0; u < SP_LB; u++) { const int e = e0 + u * NT + tid; key[u] = e < nL ? __ldcg(edges + e) : ~0ull; }
+#pragma unroll
+            for (int u = 0; u < SP_LB; u++) {
+                // (the list holds a handful of distinct distances: one atomic per warp and distance, not per edge)
+                const uint32_t d = min((uint32_t)(key[u] >> 40), (uint32_t)NT + 1u);       // NT + 1: no edge
+                const unsigned peers = __match_any_sync(0xffffffffu, d);
+                if (d <= (uint32_t)NT && lane == __ffs(peers) - 1) atomicAdd(&hist[d], __popc(peers));
+            }
+        }
+        __syncthreads();
+        int cum = hist[tid];                                                // thread t: edges with distance <= t
+        for (int o = 1; o < 32; o <<= 1) { const int a = __shfl_up_sync(0xffffffffu, cum, o); if (lane >= o) cum += a; }
+        if (lane == 31) s_wsum[tid >> 5] = cum;
+        __syncthreads();
+        for (int w = 0; w < (tid >> 5); w++) cum += s_wsum[w];
+        const int keep = __syncthreads_count(cum <= slots * NT);            // cum never decreases: the kept distances are a prefix
+        if (keep == 0) return;
+        if (tid == keep - 1) s_nsel = cum;
+        __syncthreads();
+        dmax = (uint32_t)(keep - 1);
+        n_sel = s_nsel;
+        if (n_sel <= 0) return;
+    }
     for (int k = tid; k < nr + nc; k += NT) rbest[k] = KEY_NONE;        // (rbest and cbest are contiguous)
-    if (tid == 0) { s_alive[0] = 0; s_alive[1] = 0; s_nc = 0; }
-    uint32_t ek[SP_EPT], ep[SP_EPT], ec_none[1] = {0u};
+    if (tid == 0) { s_alive[0] = 0; s_alive[1] = 0; s_alive[2] = 0; }
     {
-        const unsigned long long *edges = c.ledge + __ldg(&pdr.ledge_off);
         const int32_t *row_pos = c.row_pos + row_base, *col_pos = c.col_pos + col_base;
+        for (int k0 = 0; k0 < need; k0 += SP_LB) {                      // SP_LB independent L2 loads in flight per thread
+            unsigned long long key[SP_LB];
 #pragma unroll
-        for (int k0 = 0; k0 < SP_EPT; k0 += SP_B) {
-            unsigned long long key[SP_B];
+            for (int u = 0; u < SP_LB; u++) {
+                const int e = tid + (k0 + u) * NT;
+                key[u] = e < nL ? __ldcg(edges + e) : ~0ull;
+                if ((uint32_t)(key[u] >> 40) > dmax) key[u] = ~0ull;        // (~0 >> 40 exceeds every distance)
+            }
+            uint32_t pp[SP_LB];
 #pragma unroll
-            for (int u = 0; u < SP_B; u++) { const int e = tid + (k0 + u) * NT; key[u] = e < nL ? __ldcg(edges + e) : ~0ull; }
-            uint32_t pr[SP_B], pc[SP_B];
-#pragma unroll
-            for (int u = 0; u < SP_B; u++) {
-                const bool ok = key[u] != ~0ull;
-                const uint32_t i = ok ? (uint32_t)(key[u] >> KEY_IDX_BITS) & KEY_IDX_MASK : 0u, j = ok ? (uint32_t)key[u] & KEY_IDX_MASK : 0u;
-                pr[u] = by_id ? i : (uint32_t)__ldcg(row_pos + i); pc[u] = by_id ? j : (uint32_t)__ldcg(col_pos + j);
-                PGM_ASSERT(!ok || ((int)i < n1 && (int)j < n2 && (int)pr[u] < nr && (int)pc[u] < nc));
-                const uint32_t d = (uint32_t)(key[u] >> 40);
-                ek[k0 + u] = ok ? (d << KEY_IDX_BITS) | j : KEY_NONE;
-                ecs[(k0 + u) * NT] = (d << KEY_IDX_BITS) | i;
+            for (int u = 0; u < SP_LB; u++) {
+                pp[u] = 0u;
+                if (!by_id && key[u] != ~0ull) {
+                    const uint32_t i = (uint32_t)(key[u] >> KEY_IDX_BITS) & KEY_IDX_MASK, j = (uint32_t)key[u] & KEY_IDX_MASK;
+                    PGM_ASSERT((int)i < n1 && (int)j < n2);
+                    pp[u] = ((uint32_t)__ldcg(row_pos + i) << 16) | (uint32_t)__ldcg(col_pos + j);
+                }
             }
 #pragma unroll
-            for (int u = 0; u < SP_B; u++) ep[k0 + u] = ek[k0 + u] != KEY_NONE ? (pr[u] << 16) | pc[u] : 0u;
+            for (int u = 0; u < SP_LB; u++) {
+                const bool sel = key[u] != ~0ull;
+                int pos = tid + (k0 + u) * NT;                              // nothing cut: list position = layout position
+                if (truncated) {                                            // (uniform; the loop bound is uniform too)
+                    const unsigned m = __ballot_sync(0xffffffffu, sel);
+                    int base = 0;
+                    if (m && lane == (__ffs(m) - 1)) base = atomicAdd(&s_fill, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, m ? __ffs(m) - 1 : 0);
+                    pos = base + __popc(m & ((1u << lane) - 1u));
+                }
+                if (sel) {
+                    const uint32_t i = (uint32_t)(key[u] >> KEY_IDX_BITS) & KEY_IDX_MASK, j = (uint32_t)key[u] & KEY_IDX_MASK;
+                    PGM_ASSERT((int)i < n1 && (int)j < n2 && pos < slots * NT && (by_id || ((int)(pp[u] >> 16) < nr && (int)(pp[u] & 0xFFFFu) < nc)));
+                    E[pos] = make_uint2(((uint32_t)(key[u] >> 40) << KEY_IDX_BITS) | j, i);
+                    if (!by_id) P[pos] = pp[u];
+                }
+            }
         }
     }
+    E += tid; P += tid;                                                     // from here on: the thread's own column
+    int ne = n_sel > tid ? (n_sel - tid + NT - 1) / NT : 0;                 // its live edges are E[0 .. ne) (x NT)
     __syncthreads();
     tstamp(c, p, tid, 21);
     uint32_t *match_key = c.match_key + row_base;
-    int sub = 0;
-    // wide form until few enough edges are left, then the survivors are dealt out again SP_EPC per thread: the cost of
-    // a sub-round is the unrolled per-slot code every thread runs, not the number of live edges
-    int left = nL;
-    if (nL > SP_EPC * NT)
-        left = sparse_sub_rounds<NT, SP_EPT, true>(ek, ec_none, ecs, ep, rbest, cbest, match_key, s_alive, sub, SP_EPC * NT, c, p);
-    if (left > 0 && sub < SP_MAX_SUB) {
+    // slot indices of an edge
+#define PGM_SP_RS(e, q) (by_id ? (e).y : (q) >> 16)
+#define PGM_SP_CS(e, q) (by_id ? ((e).x & KEY_IDX_MASK) : ((q) & 0xFFFFu))
+#define PGM_SP_CKEY(e) (((e).x & ~KEY_IDX_MASK) | (e).y)
+    for (int sub = 0; sub < SP_MAX_SUB; sub++) {
+        // (three counters: the one reset here was last read two barriers ago -- with two, a warp late to read the
+        //  previous sub-round's total could see the reset)
+        if (tid == 0) s_alive[(sub + 1) % 3] = 0;
+        // A. every live edge goes to the min slot of its row (key d, j) and of its column (key d, i)
+        for (int k0 = 0; k0 < ne; k0 += SP_B) {
+            uint2 e[SP_B]; uint32_t q[SP_B];
 #pragma unroll
-        for (int k = 0; k < SP_EPT; k++)
-            if (ek[k] != KEY_NONE) {
-                const int at = atomicAdd(&s_nc, 1);
-                cbuf[at] = ek[k]; cbuf[SP_EPC * NT + at] = ecs[k * NT]; cbuf[2 * SP_EPC * NT + at] = ep[k];
+            for (int u = 0; u < SP_B; u++) {
+                const int k = min(k0 + u, ne - 1);
+                e[u] = E[k * NT]; q[u] = by_id ? 0u : P[k * NT];
             }
-        __syncthreads();
-        const int ncomp = s_nc;
-        uint32_t ck[SP_EPC], cc[SP_EPC], cp[SP_EPC];
 #pragma unroll
-        for (int k = 0; k < SP_EPC; k++) {
-            const int e = tid + k * NT;
-            ck[k] = e < ncomp ? cbuf[e] : KEY_NONE;
-            cc[k] = e < ncomp ? cbuf[SP_EPC * NT + e] : KEY_NONE;
-            cp[k] = e < ncomp ? cbuf[2 * SP_EPC * NT + e] : 0u;
+            for (int u = 0; u < SP_B; u++)
+                if (k0 + u < ne) { atomicMin(&rbest[PGM_SP_RS(e[u], q[u])], e[u].x); atomicMin(&cbest[PGM_SP_CS(e[u], q[u])], PGM_SP_CKEY(e[u])); }
         }
-        sparse_sub_rounds<NT, SP_EPC, false>(ck, cc, nullptr, cp, rbest, cbest, match_key, s_alive, sub, 0, c, p);
+        __syncthreads();
+        // B. an edge that is the minimum of both its row and its column is accepted.  Loads first, stores after, in
+        // batches: a shared-memory store between two loads makes ptxas order them (possible alias)
+        for (int k0 = 0; k0 < ne; k0 += SP_B) {
+            uint2 e[SP_B]; uint32_t q[SP_B], rv[SP_B], cv[SP_B];
+#pragma unroll
+            for (int u = 0; u < SP_B; u++) {
+                const int k = min(k0 + u, ne - 1);
+                e[u] = E[k * NT]; q[u] = by_id ? 0u : P[k * NT];
+            }
+#pragma unroll
+            for (int u = 0; u < SP_B; u++) { rv[u] = rbest[PGM_SP_RS(e[u], q[u])]; cv[u] = cbest[PGM_SP_CS(e[u], q[u])]; }
+#pragma unroll
+            for (int u = 0; u < SP_B; u++) {
+                // (a concurrent KEY_DEAD store by the accepting thread of another edge of this row / column can only
+                //  turn a mismatch into a mismatch: keys within a row, and within a column, are distinct)
+                if (k0 + u < ne && rv[u] == e[u].x && cv[u] == PGM_SP_CKEY(e[u])) {
+                    PGM_ASSERT(__ldcg(match_key + e[u].y) == KEY_NONE);      // a row is matched once
+                    match_key[e[u].y] = e[u].x;
+                    rbest[PGM_SP_RS(e[u], q[u])] = KEY_DEAD; cbest[PGM_SP_CS(e[u], q[u])] = KEY_DEAD;
+                }
+            }
+        }
+        __syncthreads();
+        // C. edges that lost an endpoint leave the thread's list (survivors move to the front: a batch is read before any
+        // of it is written, and the write position never passes the read position); live slots are reset for the next
+        // sub-round (never overwrites KEY_DEAD: a dead slot has no live edge)
+        int w = 0;
+        for (int k0 = 0; k0 < ne; k0 += SP_B) {
+            uint2 e[SP_B]; uint32_t q[SP_B], rv[SP_B], cv[SP_B];
+#pragma unroll
+            for (int u = 0; u < SP_B; u++) {
+                const int k = min(k0 + u, ne - 1);
+                e[u] = E[k * NT]; q[u] = by_id ? 0u : P[k * NT];
+            }
+#pragma unroll
+            for (int u = 0; u < SP_B; u++) { rv[u] = rbest[PGM_SP_RS(e[u], q[u])]; cv[u] = cbest[PGM_SP_CS(e[u], q[u])]; }
+#pragma unroll
+            for (int u = 0; u < SP_B; u++) {
+                if (k0 + u < ne && rv[u] != KEY_DEAD && cv[u] != KEY_DEAD) {
+                    rbest[PGM_SP_RS(e[u], q[u])] = KEY_NONE; cbest[PGM_SP_CS(e[u], q[u])] = KEY_NONE;
+                    if (w != k0 + u) { E[w * NT] = e[u]; if (!by_id) P[w * NT] = q[u]; }
+                    w++;
+                }
+            }
+        }
+        ne = w;
+        const int alive = __reduce_add_sync(0xffffffffu, ne);
+        if (lane == 0 && alive) atomicAdd(&s_alive[sub % 3], alive);
+        tstamp(c, p, tid, 22);
+        __syncthreads();
+        if (s_alive[sub % 3] == 0) break;
     }
+#undef PGM_SP_RS
+#undef PGM_SP_CS
+#undef PGM_SP_CKEY
     // re-compact the live lists in place, SP_IPT ids per thread and side at a time (order is arbitrary).  A chunk's ids
     // are all read before any of them is written back, and the kept ones land below the chunk's end: no unread slot is
     // hit.  Rows and columns share the loop so that their loads are in flight together.
@@ -1225,20 +1273,25 @@ __device__ __forceinline__ void sparse_body(const Chunk &c, int r, int p, unsign
                 kc[u] = k < nlc && cbest[by_id ? idc[u] : k] != KEY_DEAD;
             }
             __syncthreads();
+            // one shared-memory atomic per warp, side and chunk (not per 32 ids: 16 warps queueing on two counters was
+            // most of this step's time)
 #pragma unroll
-            for (int u = 0; u < SP_IPT; u++) {
+            for (int side = 0; side < 2; side++) {
+                unsigned m[SP_IPT];
+                int tot = 0;
 #pragma unroll
-                for (int side = 0; side < 2; side++) {
-                    const bool keep = side ? kc[u] : kr[u];
-                    const unsigned m = __ballot_sync(0xffffffffu, keep);
-                    if (m) {
-                        int base = 0;
-                        if (lane == (__ffs(m) - 1)) base = atomicAdd(&s_cnt[side], __popc(m));
-                        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-                        const int at = base + __popc(m & ((1u << lane) - 1u));
-                        PGM_ASSERT(!keep || at < (side ? nlc : nlr));
-                        if (keep) (side ? live_c : live_r)[at] = side ? idc[u] : idr[u];
+                for (int u = 0; u < SP_IPT; u++) { m[u] = __ballot_sync(0xffffffffu, side ? kc[u] : kr[u]); tot += __popc(m[u]); }
+                int at = 0;
+                if (lane == 0 && tot) at = atomicAdd(&s_cnt[side], tot);
+                at = __shfl_sync(0xffffffffu, at, 0);
+#pragma unroll
+                for (int u = 0; u < SP_IPT; u++) {
+                    if (side ? kc[u] : kr[u]) {
+                        const int o = at + __popc(m[u] & ((1u << lane) - 1u));
+                        PGM_ASSERT(o < (side ? nlc : nlr));
+                        (side ? live_c : live_r)[o] = side ? idc[u] : idr[u];
                     }
+                    at += __popc(m[u]);
                 }
             }
         }

@@ -471,6 +471,8 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
     c.plan = (PlanInfo *)(base + o_plan);
     c.words = words;
     c.cand_target = cand_target;
+    c.sp_slots_max = SP_EPT;
+    if (const char *e = getenv("PGM_SP_SLOTS_MAX")) c.sp_slots_max = std::min(SP_EPT, std::max(1, atoi(e)));   // tests: force the truncation path
     c.cand_row_max = 1e9f;
     if (const char *e = getenv("PGM_CAND_ROW_MAX")) c.cand_row_max = std::max(0.1f, (float)atof(e));   // tuning experiments
     if (use_cand) {
@@ -2040,6 +2042,7 @@ extern "C" int pgm_shard_create(pgm_handle *h, const uint8_t *d_q, int32_t n1, c
     c.shard_n2_total = n2_total;
     c.cand_target = CAND_TARGET_SHARD;
     c.cand_row_max = 1e9f;
+    c.sp_slots_max = SP_EPT;
     if (const char *e = getenv("PGM_CAND_TARGET")) c.cand_target = std::max(0.1f, (float)atof(e));
     c.rowbest[0] = (uint32_t *)(base + o_rb0); c.rowbest[1] = (uint32_t *)(base + o_rb1);
     c.colbest[0] = (uint32_t *)(base + o_cb0); c.colbest[1] = (uint32_t *)(base + o_cb1);

@@ -298,3 +298,24 @@ def test_candidate_list_overflow_falls_back_to_plain_rounds(matcher, n1, n2):
         assert (tr[starts[p]:starts[p] + counts[p]] == e).all(), p
     outs, _ = sharding.match_train_sharded_emulated(matcher, q, t, 3)
     assert all((o == exp).all() for o in outs)
+
+
+@pytest.mark.parametrize("slots_max", [1, 2, 5])
+@pytest.mark.parametrize("n1,n2,dist", [(3000, 2800, "U"), (2048, 2048, "C"), (4096, 4096, "U")])
+def test_sparse_phase_truncated_edge_list(matcher, monkeypatch, n1, n2, dist, slots_max):
+    """A sparse phase whose edge list exceeds its shared memory keeps the edges up to the largest distance that fits
+    (pgm_kernels.cuh, sparse_body).  PGM_SP_SLOTS_MAX shrinks the capacity so that small pairs take that path (the 16k+
+    pairs of test_gpu_fullsize.py take it on their own); only list sizes change, never a match (KeypointMatching.cs:44-65)."""
+    q, t = synthetic.config2_pair(max(n1, n2), dist)
+    q, t = q[:n1], t[:n2]
+    exp = orc.match_sweep(q, t)
+    monkeypatch.setenv("PGM_SP_SLOTS_MAX", str(slots_max))
+    got = matcher.match_greedy(q, t, 256)
+    assert got.shape == exp.shape and (got == exp).all()
+    # the same through the batch engine (throughput mode: standalone sparse kernel)
+    imgs = np.concatenate([q, t])
+    offs = np.array([0, n1, n1 + n2], dtype=np.int64)
+    pairs = np.array([(0, 1)] * 17, dtype=np.int32)            # > 16 pairs: not the latency mode
+    tr, starts, counts = matcher.match_pairs_batch(imgs, offs, pairs, 256)
+    for p in (0, 16):
+        assert (tr[starts[p]:starts[p] + counts[p]] == exp).all()
