@@ -1832,12 +1832,14 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_kernel(Chunk c, int r_st
     // (a small pair whose matrix has at most FIN_PREP_MIN_EVALS cells is not worth the extra grid phase: its finisher
     //  CTA computes the few distances itself -- after the sparse sub-rounds a pair usually arrives here with ~30 rows)
     int n_small = 0, n_prep = 0, my_pair = -1;
+    stamp(c, slot);
     for (int p = 0; p < c.n_pairs; p++)
         if (__ldcg(c.status + p) == PAIR_SMALL) {
             n_small++;
             const int4 si = __ldcg(reinterpret_cast<const int4 *>(c.small + p));
             if (si.x * si.y > FIN_PREP_MIN_EVALS) n_prep++;
         }
+    stamp(c, slot);
     if (n_prep) {                                     // uniform: every CTA reads the same statuses
         const int mine = (int)blockIdx.x % n_prep;
         for (int p = 0, k = 0; p < c.n_pairs; p++)

@@ -473,7 +473,9 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
     c.cand_target = cand_target;
     c.sp_slots_max = SP_EPT;
     if (const char *e = getenv("PGM_SP_SLOTS_MAX")) c.sp_slots_max = std::min(SP_EPT, std::max(1, atoi(e)));   // tests: force the truncation path
-    c.cand_row_max = 1e9f;
+    // a few pairs: later passes list at most 16 candidates per row (the sparse phase of a pass runs on ONE SM and sits on
+    // the call's critical path; measured best at 4096^2 ... 16384^2); batches: the list budget alone decides
+    c.cand_row_max = latency_mode ? 16.0f : 1e9f;
     if (const char *e = getenv("PGM_CAND_ROW_MAX")) c.cand_row_max = std::max(0.1f, (float)atof(e));   // tuning experiments
     if (use_cand) {
         c.cand = (unsigned long long *)(base + o_cand); c.ledge = (unsigned long long *)(base + o_ledge);
