@@ -985,12 +985,18 @@ __device__ __forceinline__ void filter_edges(const Chunk &c, int r, int p, int s
             const uint32_t aux = (uint32_t)__ldcg(raw + 2 * e + 1);
             PGM_ASSERT((int)((key >> KEY_IDX_BITS) & KEY_IDX_MASK) < pd.n1 && (int)(key & KEY_IDX_MASK) < pd.n2 && (key >> 40) <= 512);
             PGM_ASSERT((aux >> KEY_IDX_BITS) == 1 || (aux >> KEY_IDX_BITS) == RQ_LARGE);
-            ed[0] = key;
+            const uint32_t i0 = (uint32_t)(key >> KEY_IDX_BITS) & KEY_IDX_MASK, j = (uint32_t)key & KEY_IDX_MASK;
+            // the column first: it is shared by the record's edge and its siblings, and about half of the columns are
+            // matched by this very accept -- those records cost two sectors instead of a dozen
+            const uint32_t ck = __ldcg(colbest + j);
+            PGM_ASSERT((int)(ck & KEY_IDX_MASK) < pd.n1);
+            const uint32_t rk_of_ck = __ldcg(rowbest + (ck & KEY_IDX_MASK));
             const int rqn = (int)(aux >> KEY_IDX_BITS), slot0 = (int)(aux & KEY_IDX_MASK);
-            if (rqn > 1) {
+            if ((rk_of_ck & KEY_IDX_MASK) != j) {
+              ed[0] = key;
+              if (rqn > 1) {
                 // the emitting thread held rqn rows (live-list slots slot0 + k * ROUND_THREADS) and reported the best
                 // of them in this column: check the others against the bound
-                const uint32_t i0 = (uint32_t)(key >> KEY_IDX_BITS) & KEY_IDX_MASK, j = (uint32_t)key & KEY_IDX_MASK;
                 uint32_t tw[16];
 #pragma unroll
                 for (int v = 0; v < 4; v++) {            // rows are 16-byte aligned: 128-bit loads
@@ -1001,7 +1007,7 @@ __device__ __forceinline__ void filter_edges(const Chunk &c, int r, int p, int s
                 for (int k = 0; k < rqn && k < RQ_LARGE; k++) {
                     const int slot = slot0 + k * ROUND_THREADS;
                     if (slot >= nlr) break;
-                    const uint32_t i2 = (uint32_t)__ldcg(live_rows + slot);
+                    const uint32_t i2 = r == 0 ? (uint32_t)slot : (uint32_t)__ldcg(live_rows + slot);   // (pass 0: the live list is the identity)
                     if (i2 == i0) continue;
                     uint32_t d = 0;
 #pragma unroll
@@ -1017,17 +1023,18 @@ __device__ __forceinline__ void filter_edges(const Chunk &c, int r, int p, int s
                         used++;
                     }
                 }
+              }
             }
         }
 #pragma unroll
         for (int x = 0; x < RQ_LARGE; x++) {
             bool keep = false;
-            if (ed[x] != ~0ull) {
-                const uint32_t i = (uint32_t)(ed[x] >> KEY_IDX_BITS) & KEY_IDX_MASK, j = (uint32_t)ed[x] & KEY_IDX_MASK;
-                const uint32_t rk = __ldcg(rowbest + i), ck = __ldcg(colbest + j);
-                PGM_ASSERT((int)(rk & KEY_IDX_MASK) < pd.n2 && (int)(ck & KEY_IDX_MASK) < pd.n1);
-                const uint32_t ck_of_rk = __ldcg(colbest + (rk & KEY_IDX_MASK)), rk_of_ck = __ldcg(rowbest + (ck & KEY_IDX_MASK));
-                keep = (ck_of_rk & KEY_IDX_MASK) != i && (rk_of_ck & KEY_IDX_MASK) != j;
+            if (ed[x] != ~0ull) {                              // (the column survives: checked above)
+                const uint32_t i = (uint32_t)(ed[x] >> KEY_IDX_BITS) & KEY_IDX_MASK;
+                const uint32_t rk = __ldcg(rowbest + i);
+                PGM_ASSERT((int)(rk & KEY_IDX_MASK) < pd.n2);
+                const uint32_t ck_of_rk = __ldcg(colbest + (rk & KEY_IDX_MASK));
+                keep = (ck_of_rk & KEY_IDX_MASK) != i;
             }
             const unsigned m = __ballot_sync(0xffffffffu, keep);
             if (m) {
@@ -1302,11 +1309,17 @@ __device__ __forceinline__ void sparse_body(const Chunk &c, int r, int p, unsign
 }
 
 // standalone forms (throughput mode): accept + edge filter, then one sparse CTA per pair whose last block plans
-__global__ void __launch_bounds__(ACCEPT_THREADS) accept_kernel(Chunk c, int r) {
+// (5 CTAs per SM: the kernel is a chain of dependent L2 / HBM accesses per record, more resident warps is what it needs)
+__global__ void __launch_bounds__(ACCEPT_THREADS, 5) accept_kernel(Chunk c, int r) {
     accept_blocks(c, r, blockIdx.x, gridDim.x, threadIdx.x);
     if (c.cand) {
-        for (int p = blockIdx.x; p < c.n_pairs; p += gridDim.x)
-            filter_edges(c, r, p, (int)(threadIdx.x & ~31u), ACCEPT_THREADS);
+        // a pair's raw list is dealt out in FILTER_SEGS interleaved segments: with one CTA per pair a grid of ~1200
+        // CTAs walked 2016 lists as two unequal waves of ~100 dependent iterations each
+        constexpr int FILTER_SEGS = 8;
+        for (int item = blockIdx.x; item < c.n_pairs * FILTER_SEGS; item += gridDim.x) {
+            const int p = item / FILTER_SEGS, seg = item - p * FILTER_SEGS;
+            filter_edges(c, r, p, seg * ACCEPT_THREADS + (int)(threadIdx.x & ~31u), ACCEPT_THREADS * FILTER_SEGS);
+        }
     } else {
         plan_in_last_block(c, r + 1, gridDim.x);
     }
