@@ -464,9 +464,18 @@ def extra_single_pair(m, stream, dev, popc_peak):
         stream.synchronize()
         ms = float(np.median([a.elapsed_time(b) for a, b in ts]))
         st = m.stats()
+        tb = []
+        with torch.cuda.stream(stream):                                 # the same call back to back (state and code stay in L2)
+            for k in range(20):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream); step(); e1.record(stream)
+                tb.append((e0, e1))
+        stream.synchronize()
+        ms_b2b = float(np.median([a.elapsed_time(b) for a, b in tb]))
         rec = {"ms": ms, "evals_per_s": n * n / (ms * 1e-3), "whole_call_frac_of_popc_peak": n * n * 8 / (ms * 1e-3) / popc_peak,
+               "ms_back_to_back": ms_b2b, "whole_call_frac_back_to_back": n * n * 8 / (ms_b2b * 1e-3) / popc_peak,
                "distance_passes": st["rounds"], "recompute_factor": st["evals_computed"] / st["distance_evals"],
-               "launches": st["kernel_launches"], "l2": "flushed between timed calls"}
+               "launches": st["kernel_launches"], "l2": "ms: flushed between timed calls; ms_back_to_back: not flushed"}
         if dist_name == "U":
             m.set_profiling(True)
             r0 = []

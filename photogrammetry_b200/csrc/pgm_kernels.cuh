@@ -142,6 +142,17 @@ struct PlanInfo {                 // device resident, rewritten every round
     unsigned long long evals;     // XOR+popcount evaluations planned so far (grid rounds)
 };
 
+// Latency mode keeps its PlanInfo in a per-handle allocation that the tail kernel leaves CLEAN (all zero) for the next
+// call and reports the call's statistics through: a cudaMemsetAsync before and a 48-byte cudaMemcpyAsync after the
+// three launches cost 5-8 us and 9-14 us of a 0.24 ms call.
+struct LatState {
+    PlanInfo plan;
+    unsigned exit_cnt;                // CTAs of the tail kernel that have finished
+    unsigned pad;
+    unsigned long long last_rounds;   // statistics of the last call (read back on demand: pgm_get_stats)
+    unsigned long long last_evals;
+};
+
 struct Chunk {
     PairDesc *pairs;
     int32_t n_pairs;
@@ -179,6 +190,7 @@ struct Chunk {
     int32_t shard_n2_total;       // train-sharded pair: columns of the whole pair
     float cand_target;            // expected candidate edges per row of the smaller side (CAND_TARGET; PGM_CAND_TARGET overrides)
     float cand_row_max;           // upper bound of the per-row target of a pass (later passes: few live rows share the list budget)
+    LatState *lat;                // latency mode: the self-cleaning plan + statistics block (plan == &lat->plan), else nullptr
     int32_t sp_slots_max;         // edge slots per thread a sparse phase may use (SP_EPT; smaller values force its truncation path in tests)
 };
 
@@ -363,14 +375,16 @@ __device__ __forceinline__ void plan_warp(const Chunk &c, int r) {
     // wave-aware refinement: a round takes ~ceil(tiles / slots) x cpt; a slightly wider tile often saves a whole,
     // mostly empty, second wave (2301 x 2301 live: 648 tiles of 64 columns on 592 slots -> 432 tiles of 96)
     if (c.n_pairs == 1) {
-        // one pair: 32 candidate tilings at once, one per lane.  Lane l tries (n0 - 8 + l) column tiles per row tile
-        // (n0 from the heuristic width), i.e. widths from far wider to far narrower than the heuristic one; a tile's
-        // column extent only has to be a multiple of 8.  8192 x 8192 on 888 slots: 152 columns -> 16 x 54 = 864 tiles, one
-        // wave; 200 000 x 25 000: 9 column tiles -> 3519 tiles = 3.96 waves instead of 5 tiles -> 2.2 waves paid as 3.
+        // one pair: 32 candidate tilings at once, one per lane.  Under the cost model below (waves x (width + 16)) the best
+        // tiling for a given number of waves is the NARROWEST one that still fits them, so lane l tries the tiling with
+        // floor((l + 1) x slots / row tiles) column tiles; a tile's column extent only has to be a multiple of 8.
+        // 8192 x 8192 on 888 slots: 55 -> 54 column tiles of 152 columns = 864 tiles, one wave; 1817 x 1817 (small tiles,
+        // 592 slots): 38 column tiles of 48 = 570 tiles, one wave (a search around the heuristic width found two waves of
+        // 40-column tiles: 14 us instead of 9); 200 000 x 25 000: 9 column tiles -> 3519 tiles = 3.96 waves.
         const int nlr0 = __shfl_sync(0xffffffffu, nlr, 0), nlc0 = __shfl_sync(0xffffffffu, nlc, 0);
         const int big0 = __shfl_sync(0xffffffffu, (int)(st == PAIR_BIG), 0);
-        const int n0 = (nlc0 + (int)cpt - 1) / (int)cpt;
-        const int nct = max(1, n0 - 8 + lane);
+        const int row_tiles = max(1, (nlr0 + tile_rows - 1) / tile_rows);
+        const int nct = max(1, (int)(((unsigned)(lane + 1) * slots) / (unsigned)row_tiles));
         unsigned cand = (unsigned)((nlc0 + nct - 1) / nct);
         cand = min(max((cand + 7u) & ~7u, 8u), (unsigned)MAX_N);
         const unsigned t = big0 ? (unsigned)tiles_of(nlr0, nlc0, tile_rows, (int)cand) : 0u;
@@ -1889,6 +1903,19 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_kernel(Chunk c, int r_st
     if (ordering) order_emit<TAIL_THREADS>(c, op, oslice, S, nbins, flags, out_qi, out_tj, out_dist,
                                            reinterpret_cast<int32_t *>(dyn_smem), c.order_cnt);
     stamp(c, slot);
+    // the last CTA out publishes the call's statistics and zeroes the plan for the next call (every CTA is past its last
+    // grid barrier once it counts itself out, so the barrier counter can be reset)
+    if (c.lat && tid == 0) {
+        if (atomicAdd(&c.lat->exit_cnt, 1u) == gridDim.x - 1) {
+            PlanInfo *pl = &c.lat->plan;
+            const int done = __ldcg(&pl->done_round_p1), rnd = __ldcg(&pl->round);
+            c.lat->last_rounds = (unsigned long long)(done > 0 ? done - 1 : rnd);
+            c.lat->last_evals = __ldcg(&pl->evals);
+            pl->total_tiles = 0; pl->cols_per_tile = 0; pl->total_ablocks = 0; pl->n_big = 0; pl->n_small = 0; pl->round = 0;
+            pl->ticket = 0u; pl->done_round_p1 = 0; pl->rq = 0; pl->grid_bar = 0u; pl->evals = 0ull;
+            c.lat->exit_cnt = 0u;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------

@@ -69,8 +69,11 @@ struct pgm_handle {
     bool l2_force_single = false;     // PGM_L2_SINGLE=1: never use the CTA-pair (cta_group::2) float kernel
     unsigned *l2_hdr = nullptr;       // fp16 ranking mode of the last float call: [max |x| bits, rows recomputed exhaustively]
     bool force_multilaunch = false;   // PGM_FORCE_MULTILAUNCH=1: never use the persistent tail kernel
-    bool stats_pending = false;   // rounds / evals of the last latency-mode call still sit in pin_meta
-    const void *pending_plan = nullptr;
+    DevBuf lat_state;             // LatState of latency mode (pgm_kernels.cuh): zeroed on allocation, left clean by every call
+    bool lat_dirty = false;       // a latency-mode call was cut short between its launches: zero lat_state before the next
+    bool stats_pending = false;   // rounds / evals of the last latency-mode call still sit in lat_state (device) ...
+    bool stats_copied = false;    // ... or, once a read-back has been enqueued, in the pinned slot pending_plan points at
+    void *pending_plan = nullptr;
     bool tail_plain_launch = false;  // PGM_TAIL_PLAIN_LAUNCH=1 (experiment): non-cooperative launch of the tail kernel
     bool tail_timeline = false;      // PGM_TAIL_TIMELINE=1: dump the tail kernel's phase timeline to stderr (debug)
     DevBuf timeline;
@@ -136,6 +139,7 @@ static int ensure_host(pgm_handle *h, HostBuf &b, size_t bytes) {
 }
 
 static void resolve_pending_stats(pgm_handle *h);
+static void enqueue_stats_readback(pgm_handle *h);
 
 // Page-locked host memory (cudaHostAlloc / cudaHostRegister) can be the source or target of an asynchronous
 // copy directly; pageable memory is staged through the handle's pinned buffers.
@@ -218,7 +222,7 @@ extern "C" int pgm_destroy(pgm_handle *h) {
     for (cudaEvent_t e : {h->ev_done[0], h->ev_done[1], h->ev_copied[0], h->ev_copied[1]})
         if (e) cudaEventDestroy(e);
     if (h->shard_pool_hctl) cudaFreeHost(h->shard_pool_hctl);
-    for (DevBuf *b : {&h->state, &h->desc, &h->out, &h->out2, &h->misc, &h->l2_state, &h->shard_pool_state, &h->shard_pool_est})
+    for (DevBuf *b : {&h->state, &h->desc, &h->out, &h->out2, &h->misc, &h->l2_state, &h->lat_state, &h->shard_pool_state, &h->shard_pool_est})
         if (b->p) cudaFree(b->p);
     for (HostBuf *b : {&h->pin_in, &h->pin_out, &h->pin_out2, &h->pin_meta, &h->pin_prof})
         if (b->p) cudaFreeHost(b->p);
@@ -469,6 +473,15 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
     c.status = (uint8_t *)(base + o_st);
     c.small = (SmallInfo *)(base + o_small);
     c.plan = (PlanInfo *)(base + o_plan);
+    c.lat = nullptr;
+    if (latency_mode) {           // the plan lives in the handle's self-cleaning block: no memset, no read-back per call
+        if (!h->lat_state.p) {
+            if ((rc = ensure_dev(h, h->lat_state, sizeof(LatState)))) return rc;
+            h->lat_dirty = true;
+        }
+        c.lat = (LatState *)h->lat_state.p;
+        c.plan = &c.lat->plan;
+    }
     c.words = words;
     c.cand_target = cand_target;
     c.sp_slots_max = SP_EPT;
@@ -510,7 +523,13 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
     h->stats.pairs += n_pairs;
     // live sets only shrink, so the initial block count bounds every later accept launch
     const int accept_grid = (int)std::max<int64_t>(1, std::min<int64_t>(ablocks, (int64_t)h->num_sms * 8));
-    CU_CHECK(h, cudaMemsetAsync(c.plan, 0, sizeof(PlanInfo), s));
+    // PGM_LAT_SPLIT=1 (debug): events between the launches of a latency-mode call, printed after a synchronisation
+    static const bool lat_split = getenv("PGM_LAT_SPLIT") != nullptr;
+    cudaEvent_t sev[4] = {};
+    if (lat_split) { for (auto &e : sev) cudaEventCreate(&e); cudaEventRecord(sev[0], s); }
+    if (!latency_mode) CU_CHECK(h, cudaMemsetAsync(c.plan, 0, sizeof(PlanInfo), s));
+    else if (h->lat_dirty) CU_CHECK(h, cudaMemsetAsync(c.lat, 0, sizeof(LatState), s));
+    if (latency_mode) h->lat_dirty = true;      // until the tail kernel is enqueued
     dim3 igrid(std::max(1, std::min((max_n + ACCEPT_THREADS - 1) / ACCEPT_THREADS, 64)), n_pairs);
     if (latency_mode) {
         PairPack pack{};
@@ -543,7 +562,9 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
                 CU_CHECK(h, cudaMemcpyAsync(&pp[0], c.plan, sizeof(PlanInfo), cudaMemcpyDeviceToHost, s));
                 CU_CHECK(h, cudaEventRecord(h->prof_events[0], s));
             }
+            if (lat_split) cudaEventRecord(sev[1], s);
             dispatch_round(words, c, 0, round_grid, s);
+            if (lat_split) cudaEventRecord(sev[2], s);
             if (prof) CU_CHECK(h, cudaEventRecord(h->prof_events[1], s));
             if (prof) h->prof_rounds = 1;
             h->stats.kernel_launches += 1;
@@ -552,8 +573,17 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
         CU_CHECK(h, dispatch_tail(h, words, c, r_start, nbins, (flags & ~TAIL_FLAG_ACCEPT_FIRST) | (any_big ? TAIL_FLAG_ACCEPT_FIRST : 0u), d_out_qi,
                                   d_out_tj, d_out_dist, s));
         h->stats.kernel_launches += 1;
-        CU_CHECK(h, cudaMemcpyAsync(h_plan, c.plan, sizeof(PlanInfo), cudaMemcpyDeviceToHost, s));
-        h->stats_pending = true;          // resolved by pgm_get_stats / the host-buffer entry points after their sync
+        h->lat_dirty = false;
+        if (lat_split) {
+            cudaEventRecord(sev[3], s);
+            cudaStreamSynchronize(s);
+            float d[3] = {};
+            for (int k = 0; k < 3; k++) cudaEventElapsedTime(&d[k], sev[k], sev[k + 1]);
+            fprintf(stderr, "[pgm lat split, us] init %.1f  round0 %.1f  tail %.1f\n", d[0] * 1e3, d[1] * 1e3, d[2] * 1e3);
+            for (auto &e : sev) cudaEventDestroy(e);
+        }
+        h->stats_pending = true;          // resolved by pgm_get_stats / the host-buffer entry points (with their own read-back)
+        h->stats_copied = false;
         h->pending_plan = h_plan;
         CU_CHECK(h, cudaGetLastError());
         if (h->tail_timeline) {
@@ -624,12 +654,23 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
     return PGM_OK;
 }
 
-// Folds the PlanInfo read back by a latency-mode call into the stats (the stream must be idle).
+// Statistics of the last latency-mode call: the tail kernel left them in lat_state.  enqueue_stats_readback adds the
+// 16-byte copy to the stream (host-buffer entry points: ahead of the synchronisation they do anyway);
+// resolve_pending_stats folds the values into the stats, fetching them first if nobody has.
+static void enqueue_stats_readback(pgm_handle *h) {
+    if (!h->stats_pending || h->stats_copied || !h->lat_state.p) return;
+    const LatState *ls = (const LatState *)h->lat_state.p;
+    if (cudaMemcpyAsync(h->pending_plan, &ls->last_rounds, 16, cudaMemcpyDeviceToHost, h->stream) == cudaSuccess) h->stats_copied = true;
+}
 static void resolve_pending_stats(pgm_handle *h) {
     if (!h->stats_pending) return;
-    const PlanInfo *pl = (const PlanInfo *)h->pending_plan;
-    h->stats.rounds += pl->done_round_p1 > 0 ? pl->done_round_p1 - 1 : pl->round;
-    h->stats.evals_computed += (int64_t)pl->evals;
+    if (!h->stats_copied) {
+        enqueue_stats_readback(h);
+        if (!h->stats_copied || cudaStreamSynchronize(h->stream) != cudaSuccess) { h->stats_pending = false; return; }
+    }
+    const unsigned long long *v = (const unsigned long long *)h->pending_plan;
+    h->stats.rounds += (int64_t)v[0];
+    h->stats.evals_computed += (int64_t)v[1];
     h->stats_pending = false;
 }
 
@@ -710,12 +751,14 @@ extern "C" int pgm_match_hamming_greedy(pgm_handle *h, const uint8_t *q, int32_t
         CU_CHECK(h, cudaMemcpyAsync(out_qi, d_qi, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s));
         CU_CHECK(h, cudaMemcpyAsync(out_tj, d_tj, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s));
         CU_CHECK(h, cudaMemcpyAsync(out_dist, d_dd, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s));
+        enqueue_stats_readback(h);
         CU_CHECK(h, cudaStreamSynchronize(s));
         h->stats.host_syncs++;
         resolve_pending_stats(h);
     } else {
         if ((rc = ensure_host(h, h->pin_out, (size_t)3 * n1 * 4))) return rc;
         CU_CHECK(h, cudaMemcpyAsync(h->pin_out.p, h->out.p, (size_t)3 * n1 * 4, cudaMemcpyDeviceToHost, s));
+        enqueue_stats_readback(h);
         CU_CHECK(h, cudaStreamSynchronize(s));
         h->stats.host_syncs++;
         resolve_pending_stats(h);
@@ -816,7 +859,8 @@ static int batch_impl(pgm_handle *h, const uint8_t *d_all_desc, const int64_t *i
         }
         int rc = run_chunk(h, chunk.data(), (int)chunk.size(), desc_bits, stride_bytes, flags, d_qi, d_tj, d_dd);
         if (rc) return rc;
-        if (h->stats_pending) {       // latency-mode chunk: its plan read-back shares pin_meta with the next chunk
+        if (h->stats_pending) {       // latency-mode chunk: its statistics slot is shared with the next chunk
+            enqueue_stats_readback(h);
             CU_CHECK(h, cudaStreamSynchronize(s));
             h->stats.host_syncs++;
             resolve_pending_stats(h);
