@@ -103,6 +103,8 @@ int pgm_set_stream(pgm_handle *h, void *cuda_stream);
 int pgm_host_alloc(size_t bytes, void **out);
 int pgm_host_free(void *p);
 int pgm_synchronize(pgm_handle *h);
+/* Statistics of the last call.  After an asynchronous (_dev) call on a few pairs the round / evaluation counts still sit
+ * on the device: the function then synchronises the handle's stream and fetches them (nothing is copied per call). */
 int pgm_get_stats(pgm_handle *h, pgm_stats *out);
 
 /* ---- MatchKeypoints (KeypointMatching.cs:14-69) -------------------------
