@@ -100,3 +100,51 @@ def test_topk_subround_formulation_equals_reference(K):
         exp = orc.match_sweep(q, t)[:min(n1, n2)]
         assert got.shape == exp.shape and (got == exp).all(), (seed, K)
         assert len(passes) >= 1
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5])
+def test_candidate_edges_with_arbitrary_bounds_equal_reference(seed):
+    """a distance pass keeps every edge with distance <= T, mutual-best sub-rounds on that list
+    accept exactly what the reference's argmin scans (KeypointMatching.cs:38-66) emit next, and ANY bound is correct --
+    the planner's Gaussian fit, the quartered bound after an overflow, or the smaller T' a sparse phase truncates its
+    list to when the edges do not fit its shared memory (pgm_kernels.cuh, sparse_body).  Restated here in numpy with a
+    random bound per pass (including passes that list nothing) against the sweep oracle."""
+    rng = np.random.default_rng(seed)
+    n1, n2, bits = [(300, 280, 256), (220, 360, 256), (260, 130, 16), (180, 180, 8), (350, 350, 64)][seed - 1]
+    q = orc.gen_uniform(seed, n1, bits)
+    t = orc.gen_uniform(seed + 50, n2, bits)
+    if seed == 5:
+        t[40:90] = q[7]                                   # a block of exact duplicates: heavy ties
+    qb = np.unpackbits(q, axis=1).astype(np.int64)
+    tb = np.unpackbits(t, axis=1).astype(np.int64)
+    D = qb.sum(1)[:, None] + tb.sum(1)[None, :] - 2 * qb @ tb.T
+    lr, lc = np.ones(n1, bool), np.ones(n2, bool)
+    out = []
+    while lr.any() and lc.any():
+        ri, ci = np.flatnonzero(lr), np.flatnonzero(lc)
+        sub = D[np.ix_(ri, ci)]
+        # the classic accept of the pass: rows and columns that chose each other
+        rb = (sub * (1 << 20) + ci[None, :]).argmin(1)
+        cb = (sub * (1 << 20) + ri[:, None]).argmin(0)
+        mutual = cb[rb] == np.arange(len(ri))
+        ai, aj = ri[mutual], ci[rb[mutual]]
+        out += [(int(D[i, j]), int(i), int(j)) for i, j in zip(ai, aj)]
+        # candidate edges under a random bound, filtered by the accept
+        T = int(rng.integers(-1, int(np.quantile(sub, 0.2)) + 2))
+        ei, ej = np.nonzero(sub <= T)
+        ei, ej = ri[ei], ci[ej]
+        lr[ai] = False; lc[aj] = False
+        keep = lr[ei] & lc[ej]
+        ei, ej = ei[keep], ej[keep]
+        while len(ei):                                    # sparse sub-rounds
+            key = (D[ei, ej] << 40) | (ei.astype(np.int64) << 20) | ej
+            rbest = np.full(n1, np.iinfo(np.int64).max); cbest = rbest[:n2].copy() if n2 <= n1 else np.full(n2, np.iinfo(np.int64).max)
+            np.minimum.at(rbest, ei, key); np.minimum.at(cbest, ej, key)
+            ok = (rbest[ei] == key) & (cbest[ej] == key)
+            out += [(int(D[i, j]), int(i), int(j)) for i, j in zip(ei[ok], ej[ok])]
+            lr[ei[ok]] = False; lc[ej[ok]] = False
+            keep = lr[ei] & lc[ej]
+            ei, ej = ei[keep], ej[keep]
+    exp = orc.match_sweep(q, t)[:min(n1, n2)]
+    got = np.array([(i, j, d) for d, i, j in sorted(out)], dtype=np.int32)
+    assert got.shape == exp.shape and (got == exp).all()
