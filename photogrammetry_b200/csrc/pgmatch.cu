@@ -69,7 +69,7 @@ struct pgm_handle {
     bool l2_force_single = false;     // PGM_L2_SINGLE=1: never use the CTA-pair (cta_group::2) float kernel
     unsigned *l2_hdr = nullptr;       // fp16 ranking mode of the last float call: [max |x| bits, rows recomputed exhaustively]
     bool force_multilaunch = false;   // PGM_FORCE_MULTILAUNCH=1: never use the persistent tail kernel
-    DevBuf lat_state;             // LatState of latency mode (pgm_kernels.cuh): zeroed on allocation, left clean by every call
+    DevBuf lat_state;             // LatState of latency mode (pgm_kernels.cuh): zeroed before its first use, left clean by every call
     bool lat_dirty = false;       // a latency-mode call was cut short between its launches: zero lat_state before the next
     bool stats_pending = false;   // rounds / evals of the last latency-mode call still sit in lat_state (device) ...
     bool stats_copied = false;    // ... or, once a read-back has been enqueued, in the pinned slot pending_plan points at
@@ -524,7 +524,8 @@ static int run_chunk(pgm_handle *h, const HostPair *pairs, int n_pairs, int desc
     // live sets only shrink, so the initial block count bounds every later accept launch
     const int accept_grid = (int)std::max<int64_t>(1, std::min<int64_t>(ablocks, (int64_t)h->num_sms * 8));
     // PGM_LAT_SPLIT=1 (debug): events between the launches of a latency-mode call, printed after a synchronisation
-    static const bool lat_split = getenv("PGM_LAT_SPLIT") != nullptr;
+    static const bool lat_split_env = getenv("PGM_LAT_SPLIT") != nullptr;
+    const bool lat_split = lat_split_env && latency_mode;
     cudaEvent_t sev[4] = {};
     if (lat_split) { for (auto &e : sev) cudaEventCreate(&e); cudaEventRecord(sev[0], s); }
     if (!latency_mode) CU_CHECK(h, cudaMemsetAsync(c.plan, 0, sizeof(PlanInfo), s));
